@@ -1,0 +1,129 @@
+"""ctypes binding of libespm_b200.so (the C ABI declared in include/espm_b200.h).
+
+The product path has NO CPU fallback: importing this module never builds anything silently and
+``load()`` raises if the CUDA library is missing or cannot be loaded.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIBPATH = os.path.join(HERE, "lib", "libespm_b200.so")
+
+F32, F64 = 0, 1
+TILE_PX = 128
+MAX_K = 16
+NSCALARS = 24
+MAXIT_DICHOTOMY = 100
+
+# espm_state.flags
+FLAG_SIMPLEX_H = 1 << 0
+FLAG_SIMPLEX_W = 1 << 1
+FLAG_G_IDENTITY = 1 << 2
+FLAG_CLAMP_Y = 1 << 3
+FLAG_LOSS_DUAL = 1 << 4
+FLAG_FIXED_H = 1 << 5
+FLAG_FIXED_W = 1 << 6
+FLAG_MU = 1 << 7
+FLAG_LAPLACIAN = 1 << 8
+FLAG_HAVE_HPREV = 1 << 9
+FLAG_SIMPLEX_ROWS = 1 << 10
+FLAG_HQ = 1 << 11
+
+# device error word
+DEV_NONFINITE = 1 << 0
+DEV_BRACKET = 1 << 1
+DEV_NEGATIVE = 1 << 2
+DEV_GW_BELOW_LS = 1 << 3
+DEV_GW_ZERO_ROW = 1 << 4
+
+# scalar record slots
+S_XLOGY, S_SUMY, S_LOGREG, S_LAPL, S_REL_H, S_REL_W, S_BISECT_ITS_H, S_BISECT_ITS_W, S_DEV_FLAGS, \
+    S_MEAN_H, S_MEAN_W, S_GW_FLAGS = range(12)
+
+_i32, _u32, _i64, _f64, _vp = ctypes.c_int32, ctypes.c_uint32, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
+
+
+class EspmState(ctypes.Structure):
+    """Mirror of ``struct espm_state`` (include/espm_b200.h) -- keep the field order identical."""
+    _fields_ = [
+        ("n", _i32), ("n_pad", _i32), ("m", _i32), ("k", _i32), ("kp", _i32),
+        ("p_loc", _i32), ("p_pad", _i32), ("n_tiles", _i32), ("nx", _i32), ("ny", _i32),
+        ("row0", _i32), ("halo", _i32), ("ldh", _i32), ("x_dtype", _i32), ("c_dtype", _i32),
+        ("flags", _u32), ("n_simplex_rows", _i32), ("maxit", _i32),
+        ("n_sms", _i32), ("h_grid", _i32), ("h_nsplit", _i32), ("w_nb", _i32), ("w_nr", _i32),
+        ("px_blocks", _i32), ("h_depth", _i32), ("w_depth", _i32), ("w_sacc_rows", _i32),
+        ("h_smem", _i32), ("w_smem", _i32), ("reserved0", _i32),
+        ("p_total", _i64),
+        ("lambda_L", _f64), ("sigma", _f64), ("eps_reg", _f64), ("log_shift", _f64),
+        ("dicotomy_tol", _f64), ("dicotomy_tol_w", _f64), ("tol", _f64),
+        ("mu", _f64 * MAX_K),
+        ("Xt", _vp), ("G", _vp), ("Gt", _vp), ("colsum_G", _vp),
+        ("W_cur", _vp), ("W_next", _vp),
+        ("GW_cur", _vp), ("GWc_cur", _vp), ("GW_next", _vp), ("GWc_next", _vp),
+        ("gwstats_cur", _vp), ("gwstats_next", _vp),
+        ("H_prev", _vp), ("H_cur", _vp), ("H_next", _vp),
+        ("hstats_cur", _vp), ("hstats_next", _vp),
+        ("fixed_H", _vp), ("fixed_W", _vp), ("simplex_rows", _vp),
+        ("numraw", _vp), ("num", _vp), ("den", _vp),
+        ("s_part", _vp), ("s_sum", _vp), ("t_mk", _vp), ("w_num", _vp), ("w_den", _vp),
+        ("xlogy_part", _vp), ("px_part", _vp), ("bisect_mask", _vp), ("dev_flags", _vp), ("scalars", _vp),
+    ]
+
+
+class EspmError(RuntimeError):
+    pass
+
+
+_EXPORTS = {
+    # name: (restype, argtypes)
+    "espm_last_error": (ctypes.c_char_p, []),
+    "espm_version": (ctypes.c_int, []),
+    "espm_state_layout": (ctypes.c_int, [ctypes.POINTER(_i64)]),
+    "espm_device_count": (ctypes.c_int, []),
+    "espm_plan": (ctypes.c_int, [ctypes.POINTER(EspmState)]),
+    "espm_plan_info": (ctypes.c_int, [ctypes.POINTER(EspmState), ctypes.POINTER(_i32)]),
+    "espm_retile_x": (ctypes.c_int, [ctypes.POINTER(EspmState), _vp, _i32, _i64, _i64, _i64, _f64, _vp]),
+    "espm_gw_prepare": (ctypes.c_int, [ctypes.POINTER(EspmState), _vp]),
+    "espm_colsum_g": (ctypes.c_int, [ctypes.POINTER(EspmState), _vp, _vp]),
+    "espm_h_stats": (ctypes.c_int, [ctypes.POINTER(EspmState), _vp]),
+    "espm_h_pass": (ctypes.c_int, [ctypes.POINTER(EspmState), _vp]),
+    "espm_h_finish": (ctypes.c_int, [ctypes.POINTER(EspmState), _vp]),
+    "espm_h_apply": (ctypes.c_int, [ctypes.POINTER(EspmState), _vp]),
+    "espm_h_scalars": (ctypes.c_int, [ctypes.POINTER(EspmState), _vp]),
+    "espm_w_pass": (ctypes.c_int, [ctypes.POINTER(EspmState), _vp]),
+    "espm_w_reduce": (ctypes.c_int, [ctypes.POINTER(EspmState), _vp]),
+    "espm_w_finish": (ctypes.c_int, [ctypes.POINTER(EspmState), _vp]),
+    "espm_dichotomy_simplex": (ctypes.c_int, [_i32, _i32, _i64, _vp, _vp, _f64, _f64, _i32, _vp, _vp, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+def exported_symbols():
+    """Names every entry point include/espm_b200.h declares (used by the CPU symbol test)."""
+    return sorted(_EXPORTS)
+
+
+def load():
+    """Load libespm_b200.so.  Raises EspmError if it is missing -- there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIBPATH):
+        raise EspmError(
+            "espm_b200: %s is missing. Build it with `python -m espm_b200.build` (needs nvcc); "
+            "there is no CPU fallback." % LIBPATH)
+    lib = ctypes.CDLL(LIBPATH)
+    for name, (restype, argtypes) in _EXPORTS.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc < 0:
+        msg = load().espm_last_error()
+        raise EspmError("espm_b200 error %d: %s" % (rc, msg.decode() if msg else "?"))
+    return rc

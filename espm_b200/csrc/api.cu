@@ -1,0 +1,328 @@
+// C ABI of libespm_b200.so (see include/espm_b200.h): argument checking, launch planning and kernel
+// dispatch.  No device memory is owned here; the host passes every buffer.
+#include <cstdarg>
+#include <cstddef>
+#include <cstdio>
+#include <cstring>
+
+#include "small_inst.cuh"
+#include "xpass_inst.cuh"
+
+namespace espm {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static int pad_k(int k) {
+    static const int widths[] = {2, 3, 4, 5, 6, 8, 12, 16};
+    for (int w : widths)
+        if (k <= w) return w;
+    return -1;
+}
+
+typedef int (*xpass_fn)(const XPassLaunch&, const XPassArgs*, int*, cudaStream_t);
+
+static xpass_fn pick_xpass(const espm_state* st) {
+    if (st->x_dtype == ESPM_F32 && st->c_dtype == ESPM_F32) return xpass_f32f32;
+    if (st->x_dtype == ESPM_F32 && st->c_dtype == ESPM_F64) return xpass_f32f64;
+    if (st->x_dtype == ESPM_F64 && st->c_dtype == ESPM_F64) return xpass_f64f64;
+    return nullptr;
+}
+
+static void sizes_of(const espm_state* st, int safe, int* stride, int* red, int* fixed, int* cs, int* halves) {
+    if (st->x_dtype == ESPM_F32 && st->c_dtype == ESPM_F32)
+        xpass_sizes<float, float>(st->kp, safe, stride, red, fixed, cs, halves);
+    else if (st->x_dtype == ESPM_F32 && st->c_dtype == ESPM_F64)
+        xpass_sizes<float, double>(st->kp, safe, stride, red, fixed, cs, halves);
+    else
+        xpass_sizes<double, double>(st->kp, safe, stride, red, fixed, cs, halves);
+}
+
+static bool is_safe(const espm_state* st) { return (st->flags & (ESPM_FLAG_CLAMP_Y | ESPM_FLAG_LOSS_DUAL)) != 0; }
+
+static int check_state(const espm_state* st) {
+    if (!st) {
+        set_error("null state");
+        return ESPM_ERR_BAD_ARG;
+    }
+    if (!pick_xpass(st)) {
+        set_error("unsupported dtype pair x=%d c=%d (f64 storage requires f64 arithmetic)", st->x_dtype, st->c_dtype);
+        return ESPM_ERR_UNSUPPORTED;
+    }
+    if (st->k < 1 || st->k > ESPM_MAX_K) {
+        set_error("n_components=%d is outside the supported range 1..%d", st->k, ESPM_MAX_K);
+        return ESPM_ERR_UNSUPPORTED;
+    }
+    if (st->n < 1 || st->p_loc < 1 || st->m < 1) {
+        set_error("empty problem n=%d p_loc=%d m=%d", st->n, st->p_loc, st->m);
+        return ESPM_ERR_BAD_ARG;
+    }
+    if (st->flags & ESPM_FLAG_HQ) {
+        set_error("algo=l2_surrogate is not implemented on the device yet");
+        return ESPM_ERR_UNSUPPORTED;
+    }
+    return ESPM_OK;
+}
+
+static XPassArgs make_args(const espm_state* st, bool w_pass) {
+    XPassArgs a;
+    memset(&a, 0, sizeof(a));
+    int stride, red, fixed, cs, halves;
+    sizes_of(st, is_safe(st), &stride, &red, &fixed, &cs, &halves);
+    a.Xt = st->Xt;
+    a.GW = st->GW_cur;
+    a.GWc = st->GWc_cur;
+    a.H = w_pass ? st->H_next : st->H_cur;
+    a.numraw = st->numraw;
+    a.xlogy_part = st->xlogy_part;
+    a.s_part = st->s_part;
+    a.n_pad = st->n_pad;
+    a.k = st->k;
+    a.n_tiles = st->n_tiles;
+    a.ldh = st->ldh;
+    a.p_pad = st->p_pad;
+    a.nstages_tile = st->n_pad / cs;
+    a.nsplit = st->h_nsplit;
+    a.w_nb = st->w_nb;
+    a.w_nr = st->w_nr;
+    a.depth = w_pass ? st->w_depth : st->h_depth;
+    a.sacc_rows = st->w_sacc_rows;
+    a.clamp_y = (st->flags & ESPM_FLAG_CLAMP_Y) ? 1 : 0;
+    a.dual = (st->flags & ESPM_FLAG_LOSS_DUAL) ? 1 : 0;
+    a.log_shift = st->log_shift;
+    return a;
+}
+
+}  // namespace espm
+
+using namespace espm;
+
+extern "C" {
+
+const char* espm_last_error(void) { return g_err; }
+
+int espm_version(void) { return 100; }
+
+int espm_state_layout(int64_t* out8) {
+    if (!out8) return ESPM_ERR_BAD_ARG;
+    out8[0] = (int64_t)sizeof(espm_state);
+    out8[1] = (int64_t)offsetof(espm_state, p_total);
+    out8[2] = (int64_t)offsetof(espm_state, lambda_L);
+    out8[3] = (int64_t)offsetof(espm_state, mu);
+    out8[4] = (int64_t)offsetof(espm_state, Xt);
+    out8[5] = (int64_t)offsetof(espm_state, H_prev);
+    out8[6] = (int64_t)offsetof(espm_state, numraw);
+    out8[7] = (int64_t)offsetof(espm_state, scalars);
+    return ESPM_OK;
+}
+
+int espm_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        set_error("no CUDA device available (%s); espm_b200 has no CPU fallback",
+                  e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return ESPM_ERR_NO_DEVICE;
+    }
+    return n;
+}
+
+int espm_plan(espm_state* st) {
+    if (!st) {
+        set_error("null state");
+        return ESPM_ERR_BAD_ARG;
+    }
+    st->kp = pad_k(st->k);
+    int rc = check_state(st);
+    if (rc) return rc;
+    int dev = 0;
+    ESPM_CUDA_CHECK(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    ESPM_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10) {
+        set_error("device %s is sm_%d%d; espm_b200 is built for sm_100a only", prop.name, prop.major, prop.minor);
+        return ESPM_ERR_NO_DEVICE;
+    }
+    st->n_sms = prop.multiProcessorCount;
+    st->n_pad = (st->n + 31) / 32 * 32;
+    st->n_tiles = (st->p_loc + TILE_PX - 1) / TILE_PX;
+    st->p_pad = st->n_tiles * TILE_PX;
+    st->px_blocks = (st->p_loc + PX_THREADS - 1) / PX_THREADS;
+    if (st->maxit <= 0 || st->maxit > 127) st->maxit = ESPM_MAXIT_DICHOTOMY;
+
+    // The plan is made for the SAFE variant's shared-memory footprint so that switching on the
+    // clamp / dual-loss fallbacks mid-fit never needs a re-plan.
+    int stride, red, fixed, cs, halves;
+    sizes_of(st, 1, &stride, &red, &fixed, &cs, &halves);
+    const int NS = st->n_pad / cs;
+    const int tc_bytes = st->c_dtype == ESPM_F64 ? 8 : 4;
+    const int want_occ = (st->kp * tc_bytes <= 32) ? 2 : 1;
+    const int smem_cap = (int)prop.sharedMemPerBlockOptin;                      // 227 KiB on B200
+    const int per_cta = (int)(prop.sharedMemPerMultiprocessor / want_occ) - 1024;  // 1 KiB reserved per CTA
+    const int budget = per_cta < smem_cap ? per_cta : smem_cap;
+    xpass_fn fn = pick_xpass(st);
+
+    // ---- H pass ----
+    int depth = (budget - fixed - red) / stride;
+    if (depth > 8) depth = 8;
+    if (depth < 2) {
+        set_error("shared memory budget too small for the H pass (kp=%d)", st->kp);
+        return ESPM_ERR_UNSUPPORTED;
+    }
+    st->h_depth = depth;
+    st->h_smem = fixed + depth * stride + red;
+    int occ = 0;
+    {
+        XPassLaunch l{XPASS_H, st->kp, 1, 1, st->h_smem};
+        rc = fn(l, nullptr, &occ, 0);
+        if (rc) return rc;
+        if (occ < 1) {
+            set_error("H pass kernel does not fit on an SM (smem=%d)", st->h_smem);
+            return ESPM_ERR_UNSUPPORTED;
+        }
+    }
+    const int cap_h = st->n_sms * occ;
+    {
+        // channel splits: smallest split count whose static schedule keeps >= 95 % of the CTAs busy
+        static const int cand[] = {1, 2, 3, 4, 6, 8, 12, 16};
+        int best = 1;
+        double best_eff = -1.0;
+        for (int s : cand) {
+            if (s > NS) break;
+            const long long items = (long long)st->n_tiles * s;
+            const long long grid = items < cap_h ? items : cap_h;
+            const long long rounds = (items + grid - 1) / grid;
+            // small problems: also reward filling the machine
+            const double eff = (double)items / (double)(rounds * cap_h);
+            if (eff > best_eff + 1e-9) {
+                best_eff = eff;
+                best = s;
+            }
+            if (eff >= 0.95) break;
+        }
+        st->h_nsplit = best;
+        const long long items = (long long)st->n_tiles * best;
+        st->h_grid = (int)(items < cap_h ? items : cap_h);
+    }
+
+    // ---- W pass ----
+    {
+        int wdepth = depth;
+        // channel blocks: accumulator <= 32 KiB, and enough CTAs to fill the machine on small images
+        const int acc_cap = 32 * 1024;
+        int nb = 1;
+        while (nb < NS) {
+            const int rows = ((NS + nb - 1) / nb) * cs;
+            if (halves * rows * st->kp * tc_bytes <= acc_cap) break;
+            ++nb;
+        }
+        const int want = (cap_h + st->n_tiles - 1) / st->n_tiles;  // blocks needed to reach cap with few tiles
+        if (want > nb) nb = want < NS ? want : NS;
+        const int rows = ((NS + nb - 1) / nb) * cs;
+        const int acc = halves * rows * st->kp * tc_bytes;
+        while (wdepth > 2 && fixed + wdepth * stride + acc > budget) --wdepth;
+        st->w_nb = nb;
+        st->w_sacc_rows = rows;
+        st->w_depth = wdepth;
+        st->w_smem = fixed + wdepth * stride + acc;
+        int wocc = 0;
+        XPassLaunch l{XPASS_W, st->kp, 1, 1, st->w_smem};
+        rc = fn(l, nullptr, &wocc, 0);
+        if (rc) return rc;
+        if (wocc < 1) {
+            set_error("W pass kernel does not fit on an SM (smem=%d)", st->w_smem);
+            return ESPM_ERR_UNSUPPORTED;
+        }
+        int nr = (st->n_sms * wocc) / nb;
+        if (nr < 1) nr = 1;
+        if (nr > st->n_tiles) nr = st->n_tiles;
+        st->w_nr = nr;
+    }
+    return ESPM_OK;
+}
+
+int espm_plan_info(const espm_state* st, int32_t* info8) {
+    if (!st || !info8) return ESPM_ERR_BAD_ARG;
+    int stride, red, fixed, cs, halves;
+    sizes_of(st, 1, &stride, &red, &fixed, &cs, &halves);
+    info8[0] = stride;
+    info8[1] = red;
+    info8[2] = cs;
+    info8[3] = halves;
+    info8[4] = st->h_smem;
+    info8[5] = st->w_smem;
+    info8[6] = st->h_grid;
+    info8[7] = st->w_nb * st->w_nr;
+    return ESPM_OK;
+}
+
+int espm_retile_x(const espm_state* st, const void* src, int32_t src_dtype, int64_t stride_c, int64_t stride_p,
+                  int64_t j0, double scale, void* stream) {
+    int rc = check_state(st);
+    if (rc) return rc;
+    return retile_launch(st, src, src_dtype, stride_c, stride_p, j0, scale, (cudaStream_t)stream);
+}
+
+static int small(int op, const espm_state* st, void* stream) {
+    int rc = check_state(st);
+    if (rc) return rc;
+    return st->c_dtype == ESPM_F64 ? small_launch_f64(op, st, (cudaStream_t)stream)
+                                   : small_launch_f32(op, st, (cudaStream_t)stream);
+}
+
+int espm_gw_prepare(const espm_state* st, void* stream) { return small(OP_GW_PREPARE, st, stream); }
+int espm_h_stats(const espm_state* st, void* stream) { return small(OP_H_STATS, st, stream); }
+int espm_h_finish(const espm_state* st, void* stream) { return small(OP_H_FINISH, st, stream); }
+int espm_h_apply(const espm_state* st, void* stream) { return small(OP_H_APPLY, st, stream); }
+int espm_h_scalars(const espm_state* st, void* stream) { return small(OP_H_SCALARS, st, stream); }
+int espm_w_reduce(const espm_state* st, void* stream) { return small(OP_W_REDUCE, st, stream); }
+int espm_w_finish(const espm_state* st, void* stream) { return small(OP_W_FINISH, st, stream); }
+
+int espm_colsum_g(const espm_state* st, void* colsum_out, void* stream) {
+    int rc = check_state(st);
+    if (rc) return rc;
+    if (!st->Gt) {
+        set_error("colsum_g needs Gt");
+        return ESPM_ERR_BAD_ARG;
+    }
+    return st->c_dtype == ESPM_F64 ? colsum_launch_f64(st, colsum_out, (cudaStream_t)stream)
+                                   : colsum_launch_f32(st, colsum_out, (cudaStream_t)stream);
+}
+
+int espm_h_pass(const espm_state* st, void* stream) {
+    int rc = check_state(st);
+    if (rc) return rc;
+    // the trace mask of the coming h_finish is cleared here, ahead of it on the same stream
+    ESPM_CUDA_CHECK(cudaMemsetAsync(st->bisect_mask, 0, 4 * sizeof(uint32_t), (cudaStream_t)stream));
+    XPassArgs a = make_args(st, false);
+    XPassLaunch l{XPASS_H, st->kp, is_safe(st) ? 1 : 0, st->h_grid, st->h_smem};
+    return pick_xpass(st)(l, &a, nullptr, (cudaStream_t)stream);
+}
+
+int espm_w_pass(const espm_state* st, void* stream) {
+    int rc = check_state(st);
+    if (rc) return rc;
+    XPassArgs a = make_args(st, true);
+    XPassLaunch l{XPASS_W, st->kp, is_safe(st) ? 1 : 0, st->w_nb * st->w_nr, st->w_smem};
+    return pick_xpass(st)(l, &a, nullptr, (cudaStream_t)stream);
+}
+
+int espm_dichotomy_simplex(int32_t c_dtype, int32_t k, int64_t p, const void* num, const void* den, double log_shift,
+                           double tol, int32_t maxit, void* nu_out, uint32_t* mask4, uint32_t* dev_flags,
+                           int32_t* its_out, void* stream) {
+    const int kp = pad_k(k);
+    if (kp < 0 || p < 1) {
+        set_error("dichotomy_simplex: unsupported shape k=%d p=%lld", k, (long long)p);
+        return ESPM_ERR_BAD_ARG;
+    }
+    DichoArgs d{k, kp, maxit, (long long)p, num, den, log_shift, tol, nu_out, mask4, dev_flags, its_out};
+    return c_dtype == ESPM_F64 ? dicho_launch_f64(d, (cudaStream_t)stream) : dicho_launch_f32(d, (cudaStream_t)stream);
+}
+
+}  // extern "C"

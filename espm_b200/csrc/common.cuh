@@ -1,0 +1,159 @@
+// Shared device helpers for the espm_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/espm_b200.h"
+
+#ifndef __CUDA_ARCH__
+#define ESPM_DEVICE_ARCH 0
+#else
+#define ESPM_DEVICE_ARCH __CUDA_ARCH__
+#endif
+
+namespace espm {
+
+constexpr int TILE_PX = ESPM_TILE_PX;        // pixels per tile
+constexpr int STAGE_BYTES = ESPM_STAGE_BYTES; // X bytes per pipeline stage
+constexpr int N_CONSUMER_WARPS = 8;
+constexpr int N_CONSUMER_THREADS = N_CONSUMER_WARPS * 32;
+constexpr int XPASS_THREADS = N_CONSUMER_THREADS + 32;  // + one TMA producer warp
+
+// ---------------------------------------------------------------- error plumbing (host)
+void set_error(const char* fmt, ...);
+#define ESPM_CUDA_CHECK(expr)                                                               \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            espm::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                            __LINE__);                                                      \
+            return ESPM_ERR_CUDA;                                                           \
+        }                                                                                   \
+    } while (0)
+
+// ---------------------------------------------------------------- mbarrier / bulk-copy PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// TMA bulk copy global -> shared (contiguous bytes, 16 B aligned, size % 16 == 0); completion is
+// signalled on `bar` through complete_tx.  SASS: UBLKCP.
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                             uint64_t* bar, uint64_t l2_policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+            "r"(smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(l2_policy)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// ---------------------------------------------------------------- arithmetic traits
+template <typename T>
+struct Num;
+template <>
+struct Num<float> {
+    // x / y for the streaming passes: MUFU.RCP + FMUL (<= 2 ulp; the fp32 mode's bar is 1e-5)
+    static __device__ __forceinline__ float ratio(float x, float y) { return __fdividef(x, y); }
+    static __device__ __forceinline__ float log2_fast(float y) { return __log2f(y); }
+    static __device__ __forceinline__ float vmax(float a, float b) { return fmaxf(a, b); }
+    static __device__ __forceinline__ float vmin(float a, float b) { return fminf(a, b); }
+    static __device__ __forceinline__ float vabs(float a) { return fabsf(a); }
+    static __device__ __forceinline__ float vsqrt(float a) { return sqrtf(a); }
+    static __device__ __forceinline__ float vlog(float a) { return logf(a); }
+    static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
+};
+template <>
+struct Num<double> {
+    // fp64 ratio: fp32 MUFU.RCP seed + two Newton steps in fp64 (full double accuracy, ~1 ulp),
+    // falls back to IEEE division when y is outside the fp32 range.
+    static __device__ __forceinline__ double ratio(double x, double y) {
+        float yf = __double2float_rn(y);
+        if (yf > 1e-30f && yf < 1e30f) {
+            double r = (double)__frcp_rn(yf);
+            double e = fma(-y, r, 1.0);
+            r = fma(r, e, r);
+            e = fma(-y, r, 1.0);
+            r = fma(r, e, r);
+            return x * r;
+        }
+        return x / y;
+    }
+    static __device__ __forceinline__ double log2_fast(double y) { return log2(y); }
+    static __device__ __forceinline__ double vmax(double a, double b) { return fmax(a, b); }
+    static __device__ __forceinline__ double vmin(double a, double b) { return fmin(a, b); }
+    static __device__ __forceinline__ double vabs(double a) { return fabs(a); }
+    static __device__ __forceinline__ double vsqrt(double a) { return sqrt(a); }
+    static __device__ __forceinline__ double vlog(double a) { return log(a); }
+    static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+};
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <typename T>
+__device__ __forceinline__ T warp_max(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        T u = __shfl_xor_sync(0xffffffffu, v, o);
+        v = v > u ? v : u;
+    }
+    return v;
+}
+
+// Geometry of the X-pass kernels for a (storage, compute) type pair.
+template <typename TX, typename TC>
+struct PassGeom {
+    static constexpr int PPL = (sizeof(TC) == 8) ? 2 : 4;          // pixels per lane
+    static constexpr int HALVES = 4 / PPL;                         // warps covering one 128-px row
+    static constexpr int NSLOT = N_CONSUMER_WARPS / HALVES;        // channel rows processed at once
+    static constexpr int CS = STAGE_BYTES / (TILE_PX * (int)sizeof(TX));  // channels per stage
+    static constexpr int CPW = CS / NSLOT;                         // channels per warp per stage
+};
+
+// host-side helpers implemented in api.cu
+int plan_stage_channels(int x_dtype);
+
+}  // namespace espm

@@ -1,0 +1,815 @@
+// Kernels that only touch k x p / m x k data (L2 resident): per-pixel assembly of the H update, the
+// lock-step simplex bisection (trace + replay), the W update, and the scalar reductions.
+#pragma once
+#include "common.cuh"
+
+namespace espm {
+
+constexpr int PX_THREADS = 256;
+constexpr int PX_WARPS = PX_THREADS / 32;
+
+// px_part row layout (doubles), sums first, maxima last:
+//   [0] log-reg  [1] laplacian trace  [2 + kk] rowsum(H_next)  [2 + kp + kk] rowsum(max(H_next, ls))
+//   [2 + 2kp] rel_H max   [3 + 2kp + kk] rowmax(H_next)
+__host__ __device__ inline int px_part_stride(int kp) { return 3 + 3 * kp; }
+__host__ __device__ inline int px_part_nsum(int kp) { return 2 + 2 * kp; }
+
+// ------------------------------------------------------------------------------------------------
+// simplex function  f(x) = sum_k max(num_k / (x + den_k), ls) - 1   (dicotomy.py:51-53)
+// Sequential sum over k, IEEE division: the same arithmetic as the NumPy reference.
+// ------------------------------------------------------------------------------------------------
+template <typename TC, int KP>
+__device__ __forceinline__ TC simplex_f(const TC (&num)[KP], const TC (&den)[KP], TC x, int k, TC ls) {
+    TC s = Num<TC>::vmax(num[0] / (x + den[0]), ls);
+#pragma unroll
+    for (int kk = 1; kk < KP; ++kk)
+        if (kk < k) s += Num<TC>::vmax(num[kk] / (x + den[kk]), ls);
+    return s - TC(1);
+}
+
+// bracket of dicotomy.py:29-49
+template <typename TC, int KP>
+__device__ __forceinline__ void simplex_bracket(const TC (&num)[KP], const TC (&den)[KP], int k, TC& a, TC& b) {
+    TC amax = -Num<TC>::inf(), nmax = num[0], dmin = den[0];
+#pragma unroll
+    for (int kk = 0; kk < KP; ++kk)
+        if (kk < k) {
+            if (num[kk] > TC(0)) amax = Num<TC>::vmax(amax, num[kk] / TC(2) - den[kk]);
+            nmax = Num<TC>::vmax(nmax, num[kk]);
+            dmin = Num<TC>::vmin(dmin, den[kk]);
+        }
+    a = amax;
+    b = (TC)k * nmax / TC(0.5) - dmin;
+}
+
+struct Mask128 {
+    uint32_t w[4];
+    __device__ __forceinline__ void clear() { w[0] = w[1] = w[2] = w[3] = 0u; }
+    __device__ __forceinline__ void set(int j) {
+        const uint32_t bit = 1u << (j & 31);
+        const int wi = j >> 5;
+        w[0] |= (wi == 0) ? bit : 0u;
+        w[1] |= (wi == 1) ? bit : 0u;
+        w[2] |= (wi == 2) ? bit : 0u;
+        w[3] |= (wi == 3) ? bit : 0u;
+    }
+    __device__ __forceinline__ void set_from(int j, int end) {  // bits [j, end)
+        for (int i = j; i < end; ++i) set(i);
+    }
+};
+
+// first clear bit in [0, maxit) of the global trace mask, or maxit (dicotomy.py:152,169-171)
+__device__ __forceinline__ int first_clear_bit(const uint32_t* mask, int maxit) {
+    for (int wv = 0; wv < 4; ++wv) {
+        const uint32_t inv = ~mask[wv];
+        if (inv) {
+            const int j = wv * 32 + (__ffs((int)inv) - 1);
+            return j < maxit ? j : maxit;
+        }
+    }
+    return maxit;
+}
+
+// Lock-step trace for one column: records for every iteration j whether |f(new_j)| > tol.
+// Exits early when every later midpoint is provably within tol (f is monotone on the bracket) or when
+// the bracket is stationary in floating point (then new, and the bit, never change again).
+template <typename TC, int KP>
+__device__ __forceinline__ void simplex_trace(const TC (&num)[KP], const TC (&den)[KP], int k, TC ls, TC tol,
+                                              int maxit, Mask128& bits, uint32_t& err) {
+    TC a, b;
+    simplex_bracket<TC, KP>(num, den, k, a, b);
+    TC fa = simplex_f<TC, KP>(num, den, a, k, ls);
+    TC fb = simplex_f<TC, KP>(num, den, b, k, ls);
+    // dicotomy.py:141-144 preconditions
+    if (!(fa > TC(0)) || !(fb < TC(0))) err |= ESPM_DEV_BRACKET;
+    TC nw = (a + b) / TC(2);
+    TC fn = simplex_f<TC, KP>(num, den, nw, k, ls);
+    for (int j = 0; j < maxit; ++j) {
+        const bool bad = Num<TC>::vabs(fn) > tol;
+        if (bad) bits.set(j);
+        if (fa <= tol && -fb <= tol) break;
+        if (nw == a || nw == b) {
+            if (bad) bits.set_from(j + 1, maxit);
+            break;
+        }
+        if (fa * fn <= TC(0)) {
+            b = nw;
+            fb = fn;
+        } else {
+            a = nw;
+            fa = fn;
+        }
+        nw = (a + b) / TC(2);
+        fn = simplex_f<TC, KP>(num, den, nw, k, ls);
+    }
+}
+
+// Replays exactly `its` updates of dicotomy.py:152-168 and returns new.
+template <typename TC, int KP>
+__device__ __forceinline__ TC simplex_replay(const TC (&num)[KP], const TC (&den)[KP], int k, TC ls, int its) {
+    TC a, b;
+    simplex_bracket<TC, KP>(num, den, k, a, b);
+    TC fa = simplex_f<TC, KP>(num, den, a, k, ls);
+    TC nw = (a + b) / TC(2);
+    TC fn = simplex_f<TC, KP>(num, den, nw, k, ls);
+    for (int j = 0; j < its; ++j) {
+        if (nw == a || nw == b) break;  // stationary: new no longer changes
+        if (fa * fn <= TC(0)) {
+            b = nw;
+        } else {
+            a = nw;
+            fa = fn;
+        }
+        nw = (a + b) / TC(2);
+        fn = simplex_f<TC, KP>(num, den, nw, k, ls);
+    }
+    return nw;
+}
+
+// OR-reduce a per-thread mask over the block and merge it into the global mask / error word.
+__device__ __forceinline__ void merge_mask(const Mask128& bits, uint32_t err, uint32_t* gmask, uint32_t* gflags) {
+    __shared__ uint32_t sm_mask[5];
+    if (threadIdx.x < 5) sm_mask[threadIdx.x] = 0u;
+    __syncthreads();
+    uint32_t v[5] = {bits.w[0], bits.w[1], bits.w[2], bits.w[3], err};
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const uint32_t r = __reduce_or_sync(0xffffffffu, v[i]);
+        if ((threadIdx.x & 31) == 0 && r) atomicOr(&sm_mask[i], r);
+    }
+    __syncthreads();
+    if (threadIdx.x < 4 && sm_mask[threadIdx.x] && gmask) atomicOr(&gmask[threadIdx.x], sm_mask[threadIdx.x]);
+    if (threadIdx.x == 4 && sm_mask[4]) atomicOr(&gflags[0], sm_mask[4]);
+}
+
+// Block reduction of NV per-thread doubles (sum for i < n_sum, max afterwards) into out[NV].
+// Fixed order (lane butterfly, then warps 0..7) => run-to-run deterministic.
+template <int NV>
+__device__ __forceinline__ void block_reduce_vals(const double (&vals)[NV], int n_sum, double* out) {
+    __shared__ double sm_vals[PX_WARPS][NV];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const double r = (i < n_sum) ? warp_sum(vals[i]) : warp_max(vals[i]);
+        if (lane == 0) sm_vals[warp][i] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double r = sm_vals[0][threadIdx.x];
+        for (int w = 1; w < PX_WARPS; ++w) {
+            const double u = sm_vals[w][threadIdx.x];
+            r = ((int)threadIdx.x < n_sum) ? r + u : (u > r ? u : r);
+        }
+        out[threadIdx.x] = r;
+    }
+}
+
+template <typename TC, int KP>
+__device__ __forceinline__ void store_h_next(const espm_state& st, int j, int k, const TC (&hn)[KP],
+                                             double (&vals)[3 + 3 * KP]) {
+    TC* Hn = reinterpret_cast<TC*>(st.H_next);
+    const TC* fx = reinterpret_cast<const TC*>(st.fixed_H);
+    const TC ls = (TC)st.log_shift;
+#pragma unroll
+    for (int kk = 0; kk < KP; ++kk)
+        if (kk < k) {
+            TC v = hn[kk];
+            if (st.flags & ESPM_FLAG_FIXED_H) {  // updates.py:154-155
+                const TC f = fx[(size_t)kk * st.ldh + j];
+                if (f >= TC(0)) v = f;
+            }
+            Hn[(size_t)kk * st.ldh + j] = v;
+            vals[2 + kk] = (double)v;
+            vals[2 + KP + kk] = (double)Num<TC>::vmax(v, ls);
+            vals[3 + 2 * KP + kk] = (double)v;
+        }
+}
+
+// ------------------------------------------------------------------------------------------------
+// h_finish: per-pixel assembly (updates.py:132-152) + loss regularisers + rel_H + bisection trace
+// ------------------------------------------------------------------------------------------------
+template <typename TC, int KP>
+__global__ void __launch_bounds__(PX_THREADS) h_finish_kernel(const espm_state st) {
+    const int j = blockIdx.x * PX_THREADS + threadIdx.x;
+    const bool active = j < st.p_loc;
+    const int k = st.k;
+    const TC ls = (TC)st.log_shift;
+    const TC* Hc = reinterpret_cast<const TC*>(st.H_cur);
+    const TC* Hp = reinterpret_cast<const TC*>(st.H_prev);
+    const double* hstats = reinterpret_cast<const double*>(st.hstats_cur);
+    const TC* gwstats = reinterpret_cast<const TC*>(st.gwstats_cur);
+    const bool lap = st.flags & ESPM_FLAG_LAPLACIAN;
+    const bool use_mu = st.flags & ESPM_FLAG_MU;
+    const bool simplex = st.flags & ESPM_FLAG_SIMPLEX_H;
+
+    constexpr int NV = 3 + 3 * KP;
+    double vals[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) vals[i] = 0.0;
+#pragma unroll
+    for (int kk = 0; kk < KP; ++kk) vals[3 + 2 * KP + kk] = -1e300;
+
+    Mask128 bits;
+    bits.clear();
+    uint32_t err = 0u;
+
+    if (active) {
+        TC h[KP], HL[KP], num[KP], den[KP];
+        double meanH = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < KP; ++kk)
+            if (kk < k) meanH += hstats[kk];
+        meanH /= ((double)k * (double)st.p_total);
+
+        int deg = 0;
+        bool up = false, down = false, left = false, right = false;
+        if (st.ny > 0) {
+            const int il = j / st.ny, col = j - il * st.ny;
+            const int ig = st.row0 + il;
+            left = col > 0;
+            right = col < st.ny - 1;
+            up = ig > 0;
+            down = ig < st.nx - 1;
+            deg = (int)left + (int)right + (int)up + (int)down;
+        }
+        double logreg = 0.0, lapl = 0.0, relh = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < KP; ++kk) {
+            if (kk < k) {
+                const TC* row = Hc + (size_t)kk * st.ldh;
+                h[kk] = row[j];
+                // ---- Laplacian stencil (utils.py:39-76; identity when shape_2d is None) ----
+                if (st.ny > 0) {
+                    TC nb = TC(0);
+                    if (up) nb += row[j - st.ny];
+                    if (left) nb += row[j - 1];
+                    if (right) nb += row[j + 1];
+                    if (down) nb += row[j + st.ny];
+                    HL[kk] = (TC)deg * h[kk] - nb;
+                } else {
+                    HL[kk] = h[kk];
+                }
+                // ---- ratio sums of the H pass (sum of channel splits in fixed order) ----
+                const TC* nr = reinterpret_cast<const TC*>(st.numraw) + (size_t)kk * st.p_pad + j;
+                TC s = nr[0];
+                for (int sp = 1; sp < st.h_nsplit; ++sp) s += nr[(size_t)sp * KP * st.p_pad];
+                if (!(Num<TC>::vabs(s) < Num<TC>::inf())) err |= ESPM_DEV_NONFINITE;
+                // ---- loss terms of the CURRENT iterate (measures.py:548, 577) ----
+                if (use_mu) logreg += st.mu[kk] * (double)Num<TC>::vlog(h[kk] + (TC)st.eps_reg);
+                if (lap) lapl += (double)(h[kk] * HL[kk]);
+                if (st.flags & ESPM_FLAG_HAVE_HPREV) {  // base.py:324
+                    const TC hp = Hp[(size_t)kk * st.ldh + j];
+                    const double rr = (double)Num<TC>::vabs(h[kk] - hp) / ((double)h[kk] + st.tol * meanH);
+                    relh = rr > relh ? rr : relh;
+                }
+                // ---- updates.py:132-142 ----
+                TC nm = s;
+                TC dn = gwstats[kk];
+                if (use_mu) dn = dn + (TC)st.mu[kk] / (h[kk] + (TC)st.eps_reg);
+                if (lap) {
+                    const TC lam = (TC)st.lambda_L;
+                    const TC ls_max = lam * (TC)st.sigma * (TC)hstats[2 * KP + kk];
+                    nm = nm + ls_max;
+                    dn = dn + ls_max + lam * HL[kk];
+                }
+                num[kk] = h[kk] * nm;
+                den[kk] = dn;
+                if (num[kk] < TC(0) || den[kk] < TC(0)) err |= ESPM_DEV_NEGATIVE;
+            } else {
+                h[kk] = HL[kk] = num[kk] = TC(0);
+                den[kk] = TC(1);
+            }
+        }
+        vals[0] = logreg;
+        vals[1] = lapl;
+        vals[2 + 2 * KP] = relh;
+
+        if (simplex) {
+            TC* num_o = reinterpret_cast<TC*>(st.num);
+            TC* den_o = reinterpret_cast<TC*>(st.den);
+#pragma unroll
+            for (int kk = 0; kk < KP; ++kk)
+                if (kk < k) {
+                    num_o[(size_t)kk * st.p_pad + j] = num[kk];
+                    den_o[(size_t)kk * st.p_pad + j] = den[kk];
+                }
+            simplex_trace<TC, KP>(num, den, k, ls, (TC)st.dicotomy_tol, st.maxit, bits, err);
+        } else {
+            TC hn[KP];  // updates.py:152 with nu = 0
+#pragma unroll
+            for (int kk = 0; kk < KP; ++kk) hn[kk] = (kk < k) ? Num<TC>::vmax(num[kk] / den[kk], ls) : TC(0);
+            store_h_next<TC, KP>(st, j, k, hn, vals);
+        }
+    }
+    block_reduce_vals<NV>(vals, px_part_nsum(KP), st.px_part + (size_t)blockIdx.x * NV);
+    merge_mask(bits, err, simplex ? st.bisect_mask : nullptr, st.dev_flags);
+}
+
+// ------------------------------------------------------------------------------------------------
+// h_apply: replay it* iterations, H_next = max(num/(den+nu), ls)  (updates.py:152-155)
+// ------------------------------------------------------------------------------------------------
+template <typename TC, int KP>
+__global__ void __launch_bounds__(PX_THREADS) h_apply_kernel(const espm_state st) {
+    const int j = blockIdx.x * PX_THREADS + threadIdx.x;
+    const int k = st.k;
+    const TC ls = (TC)st.log_shift;
+    constexpr int NV = 3 + 3 * KP;
+    double vals[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) vals[i] = 0.0;
+#pragma unroll
+    for (int kk = 0; kk < KP; ++kk) vals[3 + 2 * KP + kk] = -1e300;
+    const int its = first_clear_bit(st.bisect_mask, st.maxit);
+    if (j < st.p_loc) {
+        TC num[KP], den[KP], hn[KP];
+        const TC* num_i = reinterpret_cast<const TC*>(st.num);
+        const TC* den_i = reinterpret_cast<const TC*>(st.den);
+#pragma unroll
+        for (int kk = 0; kk < KP; ++kk) {
+            num[kk] = (kk < k) ? num_i[(size_t)kk * st.p_pad + j] : TC(0);
+            den[kk] = (kk < k) ? den_i[(size_t)kk * st.p_pad + j] : TC(1);
+        }
+        const TC nu = simplex_replay<TC, KP>(num, den, k, ls, its);
+#pragma unroll
+        for (int kk = 0; kk < KP; ++kk) hn[kk] = (kk < k) ? Num<TC>::vmax(num[kk] / (den[kk] + nu), ls) : TC(0);
+        store_h_next<TC, KP>(st, j, k, hn, vals);
+    }
+    // only the H_next statistics are produced here; keep the loss partials written by h_finish
+    __shared__ double tmp[NV];
+    block_reduce_vals<NV>(vals, px_part_nsum(KP), tmp);
+    __syncthreads();
+    double* out = st.px_part + (size_t)blockIdx.x * NV;
+    if (threadIdx.x < NV && threadIdx.x >= 2 && threadIdx.x != 2 + 2 * KP) out[threadIdx.x] = tmp[threadIdx.x];
+}
+
+// h_stats: statistics of H_next only (initialisation, operator-level API).
+template <typename TC, int KP>
+__global__ void __launch_bounds__(PX_THREADS) h_stats_kernel(const espm_state st) {
+    const int j = blockIdx.x * PX_THREADS + threadIdx.x;
+    const int k = st.k;
+    const TC ls = (TC)st.log_shift;
+    constexpr int NV = 3 + 3 * KP;
+    double vals[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) vals[i] = 0.0;
+#pragma unroll
+    for (int kk = 0; kk < KP; ++kk) vals[3 + 2 * KP + kk] = -1e300;
+    if (j < st.p_loc) {
+        const TC* Hn = reinterpret_cast<const TC*>(st.H_next);
+#pragma unroll
+        for (int kk = 0; kk < KP; ++kk)
+            if (kk < k) {
+                const TC v = Hn[(size_t)kk * st.ldh + j];
+                vals[2 + kk] = (double)v;
+                vals[2 + KP + kk] = (double)Num<TC>::vmax(v, ls);
+                vals[3 + 2 * KP + kk] = (double)v;
+            }
+    }
+    block_reduce_vals<NV>(vals, px_part_nsum(KP), st.px_part + (size_t)blockIdx.x * NV);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Reduce the px_part rows into hstats_next = {rowsum[kp], rowsumc[kp], rowmax[kp]} (one CTA).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void reduce_hstats_block(const espm_state& st, double* hstats_out) {
+    const int kp = st.kp, stride = px_part_stride(kp);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int v = warp; v < 3 * kp; v += nwarps) {
+        const bool is_max = v >= 2 * kp;
+        const int col = is_max ? (3 + 2 * kp + (v - 2 * kp)) : (2 + v);
+        double r = is_max ? -1e300 : 0.0;
+        for (int b = lane; b < st.px_blocks; b += 32) {
+            const double u = st.px_part[(size_t)b * stride + col];
+            r = is_max ? (u > r ? u : r) : r + u;
+        }
+        r = is_max ? warp_max(r) : warp_sum(r);
+        if (lane == 0) hstats_out[v] = r;
+    }
+}
+
+template <typename TC>
+__global__ void __launch_bounds__(256) hstats_reduce_kernel(const espm_state st) {
+    reduce_hstats_block(st, reinterpret_cast<double*>(st.hstats_next));
+}
+
+// ------------------------------------------------------------------------------------------------
+// h_scalars: loss parts of the current iterate + rel_H + bisection count into the scalar record
+// ------------------------------------------------------------------------------------------------
+template <typename TC>
+__global__ void __launch_bounds__(256) h_scalars_kernel(const espm_state st) {
+    __shared__ double sm[8][4];
+    const int kp = st.kp, stride = px_part_stride(kp);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double xl = 0.0, lr = 0.0, lp = 0.0, rh = 0.0;
+    for (int i = threadIdx.x; i < st.h_grid; i += blockDim.x) xl += st.xlogy_part[i];
+    for (int b = threadIdx.x; b < st.px_blocks; b += blockDim.x) {
+        const double* row = st.px_part + (size_t)b * stride;
+        lr += row[0];
+        lp += row[1];
+        rh = row[2 + 2 * kp] > rh ? row[2 + 2 * kp] : rh;
+    }
+    xl = warp_sum(xl);
+    lr = warp_sum(lr);
+    lp = warp_sum(lp);
+    rh = warp_max(rh);
+    if (lane == 0) {
+        sm[warp][0] = xl;
+        sm[warp][1] = lr;
+        sm[warp][2] = lp;
+        sm[warp][3] = rh;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) {
+            xl += sm[w][0];
+            lr += sm[w][1];
+            lp += sm[w][2];
+            rh = sm[w][3] > rh ? sm[w][3] : rh;
+        }
+        const double* hstats = reinterpret_cast<const double*>(st.hstats_cur);
+        const TC* gwstats = reinterpret_cast<const TC*>(st.gwstats_cur);
+        double sumy = 0.0, meanh = 0.0;
+        for (int kk = 0; kk < st.k; ++kk) {
+            sumy += (double)gwstats[kp + kk] * hstats[kp + kk];  // measures.py:502, analytic
+            meanh += hstats[kk];
+        }
+        double* rec = st.scalars;
+        rec[ESPM_S_XLOGY] = xl;
+        rec[ESPM_S_SUMY] = sumy;
+        rec[ESPM_S_LOGREG] = lr;
+        rec[ESPM_S_LAPL] = lp;
+        rec[ESPM_S_REL_H] = rh;
+        rec[ESPM_S_BISECT_ITS_H] =
+            (st.flags & ESPM_FLAG_SIMPLEX_H) ? (double)first_clear_bit(st.bisect_mask, st.maxit) : 0.0;
+        rec[ESPM_S_DEV_FLAGS] = (double)st.dev_flags[0];
+        rec[ESPM_S_MEAN_H] = meanh / ((double)st.k * (double)st.p_total);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// w_reduce: s_sum[c][k] = sum_r s_part[r][c][k]; the last block reduces the H_next statistics.
+// ------------------------------------------------------------------------------------------------
+template <typename TC>
+__global__ void __launch_bounds__(256) w_reduce_kernel(const espm_state st) {
+    if (blockIdx.x == gridDim.x - 1) {
+        reduce_hstats_block(st, reinterpret_cast<double*>(st.hstats_next));
+        return;
+    }
+    const size_t total = (size_t)st.n_pad * st.kp;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const TC* part = reinterpret_cast<const TC*>(st.s_part);
+    TC s = part[i];
+    for (int r = 1; r < st.w_nr; ++r) s += part[(size_t)r * total + i];
+    reinterpret_cast<TC*>(st.s_sum)[i] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GW = G.W (+ pad rows), clamped copy, column sums and flags.  Runs inside one CTA.
+// ------------------------------------------------------------------------------------------------
+template <typename TC>
+__device__ void gw_prepare_block(const espm_state& st, const TC* W, double* sm /* >= 2*kp + 64 doubles */) {
+    const int kp = st.kp, k = st.k, n = st.n, m = st.m;
+    const TC ls = (TC)st.log_shift;
+    const bool ident = st.flags & ESPM_FLAG_G_IDENTITY;
+    const TC* G = reinterpret_cast<const TC*>(st.G);
+    TC* GW = reinterpret_cast<TC*>(st.GW_next);
+    TC* GWc = reinterpret_cast<TC*>(st.GWc_next);
+    double cs[ESPM_MAX_K], csc[ESPM_MAX_K];
+    for (int kk = 0; kk < ESPM_MAX_K; ++kk) cs[kk] = csc[kk] = 0.0;
+    uint32_t flags = 0u;
+    if (threadIdx.x == 0) st.dev_flags[1] = 0u;
+    __syncthreads();
+    for (int c = threadIdx.x; c < st.n_pad; c += blockDim.x) {
+        bool all_zero = true;
+        for (int kk = 0; kk < kp; ++kk) {
+            TC v;
+            if (c >= n) {
+                v = (kk == 0) ? TC(1) : TC(0);  // pad channel: y = H[0] > 0, contributes nothing
+            } else if (kk >= k) {
+                v = TC(0);
+            } else if (ident) {
+                v = W[(size_t)c * k + kk];
+            } else {
+                TC acc = TC(0);
+                for (int mm = 0; mm < m; ++mm) acc = fma(G[(size_t)c * m + mm], W[(size_t)mm * k + kk], acc);
+                v = acc;
+            }
+            GW[(size_t)c * kp + kk] = v;
+            const TC vc = (c < n && kk < k) ? Num<TC>::vmax(v, ls) : v;
+            GWc[(size_t)c * kp + kk] = vc;
+            if (c < n && kk < k) {
+                cs[kk] += (double)v;
+                csc[kk] += (double)vc;
+                if (v < ls) flags |= ESPM_DEV_GW_BELOW_LS;
+                if (v > TC(0)) all_zero = false;
+            }
+        }
+        if (c < n && all_zero) flags |= ESPM_DEV_GW_ZERO_ROW;
+    }
+    // block reduction of the column sums (fixed order)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    double* red = sm;  // [nwarps][2*kp]
+    for (int kk = 0; kk < k; ++kk) {
+        const double a = warp_sum(cs[kk]), b = warp_sum(csc[kk]);
+        if (lane == 0) {
+            red[(size_t)warp * 2 * kp + kk] = a;
+            red[(size_t)warp * 2 * kp + kp + kk] = b;
+        }
+    }
+    const uint32_t f = __reduce_or_sync(0xffffffffu, flags);
+    if (lane == 0 && f) atomicOr(&st.dev_flags[1], f);
+    __syncthreads();
+    TC* gwstats = reinterpret_cast<TC*>(st.gwstats_next);
+    if ((int)threadIdx.x < 2 * kp) {
+        const int kk = threadIdx.x % kp;
+        double s = 0.0;
+        if (kk < k)
+            for (int w = 0; w < nwarps; ++w) s += red[(size_t)w * 2 * kp + threadIdx.x];
+        gwstats[threadIdx.x] = (TC)s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) st.scalars[ESPM_S_GW_FLAGS] = (double)st.dev_flags[1];
+}
+
+template <typename TC>
+__global__ void __launch_bounds__(1024) gw_prepare_kernel(const espm_state st) {
+    __shared__ double sm[32 * 2 * ESPM_MAX_K];
+    gw_prepare_block<TC>(st, reinterpret_cast<const TC*>(st.W_next), sm);
+}
+
+// colsum_G[m] = sum_c G[c][m]  (updates.py:60); one warp per column, Gt is m x n row-major.
+template <typename TC>
+__global__ void __launch_bounds__(256) colsum_g_kernel(const TC* Gt, int n, int m, TC* out) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= m) return;
+    double s = 0.0;
+    for (int c = lane; c < n; c += 32) s += (double)Gt[(size_t)warp * n + c];
+    s = warp_sum(s);
+    if (lane == 0) out[warp] = (TC)s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// w_finish: W update (updates.py:58-76) in a single CTA of 1024 threads.
+// ------------------------------------------------------------------------------------------------
+template <typename TC>
+__global__ void __launch_bounds__(1024) w_finish_kernel(const espm_state st) {
+    __shared__ double sm[32 * 2 * ESPM_MAX_K];
+    __shared__ double col_a[ESPM_MAX_K], col_b[ESPM_MAX_K], col_fa[ESPM_MAX_K], col_new[ESPM_MAX_K],
+        col_fn[ESPM_MAX_K];
+    __shared__ int s_its;
+    __shared__ uint32_t s_err;
+    const int k = st.k, kp = st.kp, m = st.m, n = st.n;
+    const TC ls = (TC)st.log_shift;
+    const bool ident = st.flags & ESPM_FLAG_G_IDENTITY;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const TC* S = reinterpret_cast<const TC*>(st.s_sum);
+    const TC* Gt = reinterpret_cast<const TC*>(st.Gt);
+    const TC* W = reinterpret_cast<const TC*>(st.W_cur);
+    const TC* colsumG = reinterpret_cast<const TC*>(st.colsum_G);
+    const double* hstats = reinterpret_cast<const double*>(st.hstats_next);
+    TC* wnum = reinterpret_cast<TC*>(st.w_num);
+    TC* wden = reinterpret_cast<TC*>(st.w_den);
+    TC* Wn = reinterpret_cast<TC*>(st.W_next);
+    if (threadIdx.x == 0) {
+        s_its = 0;
+        s_err = 0u;
+    }
+
+    // ---- num = W * (G^T S), den = colsum(G) (x) rowsum(H')   (updates.py:58-60) ----
+    if (ident) {
+        for (int i = threadIdx.x; i < m * k; i += blockDim.x) {
+            const int mm = i / k, kk = i - mm * k;
+            wnum[i] = W[i] * S[(size_t)mm * kp + kk];
+            wden[i] = (TC)hstats[kk];
+        }
+    } else {
+        for (int o = warp; o < m * k; o += nwarps) {
+            const int mm = o / k, kk = o - mm * k;
+            TC acc = TC(0);
+            for (int c = lane; c < n; c += 32) acc = fma(Gt[(size_t)mm * n + c], S[(size_t)c * kp + kk], acc);
+            acc = warp_sum(acc);
+            if (lane == 0) {
+                wnum[o] = W[o] * acc;
+                wden[o] = colsumG[mm] * (TC)hstats[kk];
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- simplex_W: lock-step bisection over the k columns (updates.py:61-68, dicotomy.py) ----
+    if (st.flags & ESPM_FLAG_SIMPLEX_W) {
+        const bool sub = st.flags & ESPM_FLAG_SIMPLEX_ROWS;
+        const int nrows = sub ? st.n_simplex_rows : m;
+        const TC tol = (TC)st.dicotomy_tol_w;
+        auto row_of = [&](int i) { return sub ? st.simplex_rows[i] : i; };
+        auto feval = [&](int kk, TC x) {  // warp-collective: sum_rows max(num/(x+den), ls) - 1
+            TC s = TC(0);
+            for (int i = lane; i < nrows; i += 32) {
+                const int o = row_of(i) * k + kk;
+                s += Num<TC>::vmax(wnum[o] / (x + wden[o]), ls);
+            }
+            return warp_sum(s) - TC(1);
+        };
+        if (warp < k) {
+            const int kk = warp;
+            TC amax = -Num<TC>::inf(), nmax = -Num<TC>::inf(), dmin = Num<TC>::inf(), nsum = TC(0);
+            bool neg = false;
+            for (int i = lane; i < nrows; i += 32) {
+                const int o = row_of(i) * k + kk;
+                const TC nv = wnum[o], dv = wden[o];
+                if (nv > TC(0)) amax = Num<TC>::vmax(amax, nv / TC(2) - dv);
+                nmax = Num<TC>::vmax(nmax, nv);
+                dmin = Num<TC>::vmin(dmin, dv);
+                nsum += nv;
+                neg |= (nv < TC(0)) || (dv < TC(0));
+            }
+            amax = warp_max(amax);
+            nmax = warp_max(nmax);
+            dmin = -warp_max(-dmin);
+            nsum = warp_sum(nsum);
+            neg = __any_sync(0xffffffffu, neg);
+            const TC a = amax, b = (TC)nrows * nmax / TC(0.5) - dmin;
+            const TC fa = feval(kk, a), fb = feval(kk, b);
+            const TC nw = (a + b) / TC(2);
+            const TC fn = feval(kk, nw);
+            if (lane == 0) {
+                uint32_t e = 0u;
+                if (!(fa > TC(0)) || !(fb < TC(0))) e |= ESPM_DEV_BRACKET;
+                if (neg || !(nsum > TC(0))) e |= ESPM_DEV_NEGATIVE;
+                if (e) atomicOr(&s_err, e);
+                col_a[kk] = (double)a;
+                col_b[kk] = (double)b;
+                col_fa[kk] = (double)fa;
+                col_new[kk] = (double)nw;
+                col_fn[kk] = (double)fn;
+            }
+        }
+        __syncthreads();
+        int it = 0;
+        while (true) {
+            double worst = 0.0;
+            for (int kk = 0; kk < k; ++kk) {
+                const double v = fabs(col_fn[kk]);
+                worst = v > worst ? v : worst;
+            }
+            if (!(worst > (double)tol)) break;  // dicotomy.py:152
+            it += 1;
+            __syncthreads();
+            if (warp < k) {
+                const int kk = warp;
+                TC a = (TC)col_a[kk], b = (TC)col_b[kk], fa = (TC)col_fa[kk], nw = (TC)col_new[kk],
+                   fn = (TC)col_fn[kk];
+                if (fa * fn <= TC(0)) {
+                    b = nw;
+                } else {
+                    a = nw;
+                    fa = fn;
+                }
+                nw = (a + b) / TC(2);
+                fn = feval(kk, nw);
+                if (lane == 0) {
+                    col_a[kk] = (double)a;
+                    col_b[kk] = (double)b;
+                    col_fa[kk] = (double)fa;
+                    col_new[kk] = (double)nw;
+                    col_fn[kk] = (double)fn;
+                }
+            }
+            __syncthreads();
+            if (it >= st.maxit) break;  // dicotomy.py:169-171
+        }
+        if (threadIdx.x == 0) s_its = it;
+        // denum[rows] += nu (updates.py:65,68)
+        for (int i = threadIdx.x; i < nrows * k; i += blockDim.x) {
+            const int r = row_of(i / k), kk = i % k;
+            wden[r * k + kk] += (TC)col_new[kk];
+        }
+        __syncthreads();
+    }
+
+    // ---- W' = max(num/den, ls), fixed_W (updates.py:70-76); rel_W (base.py:323) ----
+    const TC* fw = reinterpret_cast<const TC*>(st.fixed_W);
+    double wsum = 0.0;
+    for (int i = threadIdx.x; i < m * k; i += blockDim.x) {
+        TC v = Num<TC>::vmax(wnum[i] / wden[i], ls);
+        if (st.flags & ESPM_FLAG_FIXED_W) {
+            const TC f = fw[i];
+            if (f >= TC(0)) v = f;
+        }
+        Wn[i] = v;
+        wsum += (double)v;
+    }
+    wsum = warp_sum(wsum);
+    if (lane == 0) sm[warp] = wsum;
+    __syncthreads();
+    double meanW = 0.0;
+    for (int w = 0; w < nwarps; ++w) meanW += sm[w];
+    meanW /= (double)(m * k);
+    __syncthreads();
+    double rel = 0.0;
+    for (int i = threadIdx.x; i < m * k; i += blockDim.x) {
+        const double wn = (double)Wn[i], wo = (double)W[i];
+        const double r = fabs(wn - wo) / (wn + st.tol * meanW);
+        rel = r > rel ? r : rel;
+    }
+    rel = warp_max(rel);
+    if (lane == 0) sm[warp] = rel;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double r = sm[0];
+        for (int w = 1; w < nwarps; ++w) r = sm[w] > r ? sm[w] : r;
+        st.scalars[ESPM_S_REL_W] = r;
+        st.scalars[ESPM_S_BISECT_ITS_W] = (double)s_its;
+        st.scalars[ESPM_S_MEAN_W] = meanW;
+        if (s_err) atomicOr(&st.dev_flags[0], s_err);
+    }
+    __syncthreads();
+    // ---- GW' for the next H pass (updates.py:107) ----
+    gw_prepare_block<TC>(st, Wn, sm);
+}
+
+// ------------------------------------------------------------------------------------------------
+// retile: X (any strides) -> tile-major Xt, zero padded.  grid = (n_tiles, n_pad/32), 256 threads.
+// ------------------------------------------------------------------------------------------------
+template <typename TS, typename TX>
+__global__ void __launch_bounds__(256) retile_kernel(const TS* __restrict__ src, long long stride_c,
+                                                     long long stride_p, long long j0, int n, int n_pad, int p_loc,
+                                                     double scale, TX* __restrict__ Xt) {
+    __shared__ TX sm[32][TILE_PX + 1];
+    const int tile = blockIdx.x, cb = blockIdx.y * 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (stride_p == 1 || stride_c != 1) {
+        // pixels contiguous (or generic): read rows of 128 pixels
+        for (int ci = warp; ci < 32; ci += 8) {
+            const int c = cb + ci;
+            for (int q = lane; q < TILE_PX; q += 32) {
+                const long long j = (long long)tile * TILE_PX + q;
+                TX v = TX(0);
+                if (c < n && j < p_loc) v = (TX)((double)src[(long long)c * stride_c + (j0 + j) * stride_p] * scale);
+                sm[ci][q] = v;
+            }
+        }
+    } else {
+        // channels contiguous (hyperspy layout): read 32 channels of one pixel per warp access
+        for (int q = warp; q < TILE_PX; q += 8) {
+            const long long j = (long long)tile * TILE_PX + q;
+            const int c = cb + lane;
+            TX v = TX(0);
+            if (c < n && j < p_loc) v = (TX)((double)src[(long long)c * stride_c + (j0 + j) * stride_p] * scale);
+            sm[lane][q] = v;
+        }
+    }
+    __syncthreads();
+    TX* dst = Xt + ((size_t)tile * n_pad + cb) * TILE_PX;
+    for (int i = threadIdx.x; i < 32 * TILE_PX; i += 256) dst[i] = sm[i / TILE_PX][i % TILE_PX];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Standalone dichotomy_simplex(num, den) -> nu  (dicotomy.py:4-55), two kernels: trace, replay.
+// ------------------------------------------------------------------------------------------------
+template <typename TC, int KP>
+__global__ void __launch_bounds__(PX_THREADS) dicho_trace_kernel(const TC* num_i, const TC* den_i, long long p, int k,
+                                                                 double ls_d, double tol_d, int maxit,
+                                                                 uint32_t* gmask, uint32_t* gflags) {
+    const long long j = (long long)blockIdx.x * PX_THREADS + threadIdx.x;
+    Mask128 bits;
+    bits.clear();
+    uint32_t err = 0u;
+    if (j < p) {
+        TC num[KP], den[KP];
+        TC nsum = TC(0);
+#pragma unroll
+        for (int kk = 0; kk < KP; ++kk) {
+            num[kk] = (kk < k) ? num_i[(size_t)kk * p + j] : TC(0);
+            den[kk] = (kk < k) ? den_i[(size_t)kk * p + j] : TC(1);
+            if (kk < k) {
+                nsum += num[kk];
+                if (num[kk] < TC(0) || den[kk] < TC(0)) err |= ESPM_DEV_NEGATIVE;
+            }
+        }
+        if (!(nsum > TC(0))) err |= ESPM_DEV_NEGATIVE;  // dicotomy.py:19
+        simplex_trace<TC, KP>(num, den, k, (TC)ls_d, (TC)tol_d, maxit, bits, err);
+    }
+    merge_mask(bits, err, gmask, gflags);
+}
+
+template <typename TC, int KP>
+__global__ void __launch_bounds__(PX_THREADS) dicho_apply_kernel(const TC* num_i, const TC* den_i, long long p, int k,
+                                                                 double ls_d, int maxit, const uint32_t* gmask,
+                                                                 TC* nu_out, int* its_out) {
+    const long long j = (long long)blockIdx.x * PX_THREADS + threadIdx.x;
+    const int its = first_clear_bit(gmask, maxit);
+    if (j == 0 && its_out) *its_out = its;
+    if (j < p) {
+        TC num[KP], den[KP];
+#pragma unroll
+        for (int kk = 0; kk < KP; ++kk) {
+            num[kk] = (kk < k) ? num_i[(size_t)kk * p + j] : TC(0);
+            den[kk] = (kk < k) ? den_i[(size_t)kk * p + j] : TC(1);
+        }
+        nu_out[j] = simplex_replay<TC, KP>(num, den, k, (TC)ls_d, its);
+    }
+}
+
+}  // namespace espm

@@ -1,0 +1,125 @@
+// Launch helpers for the k x p / m x k kernels, instantiated once per arithmetic type.
+#pragma once
+#include "small.cuh"
+
+namespace espm {
+
+enum SmallOp {
+    OP_H_FINISH = 0,
+    OP_H_APPLY,
+    OP_H_STATS,
+    OP_H_SCALARS,
+    OP_W_REDUCE,
+    OP_W_FINISH,
+    OP_GW_PREPARE,
+};
+
+struct DichoArgs {
+    int k, kp, maxit;
+    long long p;
+    const void* num;
+    const void* den;
+    double log_shift, tol;
+    void* nu_out;
+    uint32_t* mask4;
+    uint32_t* dev_flags;
+    int* its_out;
+};
+
+#define ESPM_KP_SWITCH(kp, STMT)                                         \
+    switch (kp) {                                                        \
+        case 2: { constexpr int KP = 2; STMT; break; }                   \
+        case 3: { constexpr int KP = 3; STMT; break; }                   \
+        case 4: { constexpr int KP = 4; STMT; break; }                   \
+        case 5: { constexpr int KP = 5; STMT; break; }                   \
+        case 6: { constexpr int KP = 6; STMT; break; }                   \
+        case 8: { constexpr int KP = 8; STMT; break; }                   \
+        case 12: { constexpr int KP = 12; STMT; break; }                 \
+        case 16: { constexpr int KP = 16; STMT; break; }                 \
+        default:                                                         \
+            set_error("unsupported padded component count kp=%d", kp);   \
+            return ESPM_ERR_BAD_ARG;                                     \
+    }
+
+template <typename TC>
+static int small_launch_t(int op, const espm_state* st, cudaStream_t s) {
+    const int kp = st->kp;
+    switch (op) {
+        case OP_H_FINISH:
+            ESPM_KP_SWITCH(kp, (h_finish_kernel<TC, KP><<<st->px_blocks, PX_THREADS, 0, s>>>(*st)));
+            break;
+        case OP_H_APPLY:
+            ESPM_KP_SWITCH(kp, (h_apply_kernel<TC, KP><<<st->px_blocks, PX_THREADS, 0, s>>>(*st)));
+            break;
+        case OP_H_STATS:
+            ESPM_KP_SWITCH(kp, (h_stats_kernel<TC, KP><<<st->px_blocks, PX_THREADS, 0, s>>>(*st)));
+            hstats_reduce_kernel<TC><<<1, 256, 0, s>>>(*st);
+            break;
+        case OP_H_SCALARS:
+            h_scalars_kernel<TC><<<1, 256, 0, s>>>(*st);
+            break;
+        case OP_W_REDUCE: {
+            const size_t total = (size_t)st->n_pad * st->kp;
+            const int blocks = (int)((total + 255) / 256) + 1;
+            w_reduce_kernel<TC><<<blocks, 256, 0, s>>>(*st);
+            break;
+        }
+        case OP_W_FINISH:
+            w_finish_kernel<TC><<<1, 1024, 0, s>>>(*st);
+            break;
+        case OP_GW_PREPARE:
+            gw_prepare_kernel<TC><<<1, 1024, 0, s>>>(*st);
+            break;
+        default:
+            set_error("unknown small op %d", op);
+            return ESPM_ERR_BAD_ARG;
+    }
+    ESPM_CUDA_CHECK(cudaGetLastError());
+    return ESPM_OK;
+}
+
+template <typename TC>
+static int dicho_launch_t(const DichoArgs& d, cudaStream_t s) {
+    const int blocks = (int)((d.p + PX_THREADS - 1) / PX_THREADS);
+    ESPM_CUDA_CHECK(cudaMemsetAsync(d.mask4, 0, 4 * sizeof(uint32_t), s));
+    ESPM_KP_SWITCH(d.kp, (dicho_trace_kernel<TC, KP><<<blocks, PX_THREADS, 0, s>>>(
+                             (const TC*)d.num, (const TC*)d.den, d.p, d.k, d.log_shift, d.tol, d.maxit, d.mask4,
+                             d.dev_flags)));
+    ESPM_CUDA_CHECK(cudaGetLastError());
+    ESPM_KP_SWITCH(d.kp, (dicho_apply_kernel<TC, KP><<<blocks, PX_THREADS, 0, s>>>(
+                             (const TC*)d.num, (const TC*)d.den, d.p, d.k, d.log_shift, d.maxit, d.mask4,
+                             (TC*)d.nu_out, d.its_out)));
+    ESPM_CUDA_CHECK(cudaGetLastError());
+    return ESPM_OK;
+}
+
+template <typename TC>
+static int colsum_launch_t(const espm_state* st, void* out, cudaStream_t s) {
+    const int warps_per_block = 8;
+    const int blocks = (st->m + warps_per_block - 1) / warps_per_block;
+    colsum_g_kernel<TC><<<blocks, 256, 0, s>>>((const TC*)st->Gt, st->n, st->m, (TC*)out);
+    ESPM_CUDA_CHECK(cudaGetLastError());
+    return ESPM_OK;
+}
+
+template <typename TS, typename TX>
+static int retile_launch_t(const espm_state* st, const void* src, long long stride_c, long long stride_p,
+                           long long j0, double scale, cudaStream_t s) {
+    dim3 grid(st->n_tiles, st->n_pad / 32);
+    retile_kernel<TS, TX><<<grid, 256, 0, s>>>((const TS*)src, stride_c, stride_p, j0, st->n, st->n_pad, st->p_loc,
+                                              scale, (TX*)st->Xt);
+    ESPM_CUDA_CHECK(cudaGetLastError());
+    return ESPM_OK;
+}
+
+// defined in small_f32.cu / small_f64.cu
+int small_launch_f32(int op, const espm_state* st, cudaStream_t s);
+int small_launch_f64(int op, const espm_state* st, cudaStream_t s);
+int dicho_launch_f32(const DichoArgs& d, cudaStream_t s);
+int dicho_launch_f64(const DichoArgs& d, cudaStream_t s);
+int colsum_launch_f32(const espm_state* st, void* out, cudaStream_t s);
+int colsum_launch_f64(const espm_state* st, void* out, cudaStream_t s);
+int retile_launch(const espm_state* st, const void* src, int src_dtype, long long stride_c, long long stride_p,
+                  long long j0, double scale, cudaStream_t s);
+
+}  // namespace espm

@@ -1,0 +1,451 @@
+"""Device-side state of one SmoothNMF fit and the kernel sequencing of one iteration.
+
+The arithmetic lives in libespm_b200.so (hand-written sm_100a CUDA, see csrc/); this module only
+allocates device buffers through torch, fills the ``espm_state`` struct the C ABI takes, launches the
+kernels in order on torch's current stream and rotates the W / H / GW buffers between iterations.
+
+One iteration of the reference (base.py:316-324) maps to two phases here:
+
+  phase A ``evaluate(slot)``   h_pass -> h_finish -> h_scalars
+        streams X once with (GW_cur, H_cur): ratio sums for the next H update AND every loss term of
+        the current iterate (KL, log-reg, Laplacian), rel_H, written to the scalar record ``slot``.
+  phase B ``advance(slot)``    [h_apply] -> w_pass -> w_reduce -> w_finish, then buffer rotation
+        H_next from the lock-step bisection, streams X once more with (GW_cur, H_next), W_next,
+        GW_next; rel_W goes to record ``slot`` (the record of the iterate being produced).
+
+So X is read exactly twice per iteration; the loss of iterate t rides the H pass
+of iteration t+1.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+def _round_up(a, b):
+    return (a + b - 1) // b * b
+
+
+def _np_dtype(code):
+    return np.float64 if code == L.F64 else np.float32
+
+
+def _torch_dtype(code):
+    return torch.float64 if code == L.F64 else torch.float32
+
+
+def _code_of(dtype):
+    dtype = np.dtype(dtype)
+    if dtype == np.float64:
+        return L.F64
+    if dtype == np.float32:
+        return L.F32
+    raise TypeError("espm_b200 supports float32 and float64 data, got %s" % dtype)
+
+
+class FitEngine:
+    """Owns the device buffers of one fit on ONE GPU (one pixel shard when running on several)."""
+
+    def __init__(self, X, G, W0, H0, *, shape_2d=None, lambda_L=0.0, mu=0, epsilon_reg=1.0,
+                 log_shift=1e-14, dicotomy_tol=1e-5, dicotomy_tol_w=1e-5, tol=1e-4, sigma=8.0,
+                 simplex_H=False, simplex_W=True, simplex_rows=None, fixed_H=None, fixed_W=None,
+                 x_scale=1.0, max_records=512, device=None, shard=None, c_dtype=None, clamp_init=True):
+        """
+        X : (n, p) array-like view (any strides; C order or the transposed hyperspy layout are
+            uploaded without a host copy).  G : (n, m) array or None (identity).  W0 : (m, k), H0 : (k, p).
+        shard : None, or (rank, world, comm) for pixel-sharded multi-GPU runs (see dist.py).
+        """
+        self.lib = L.load()
+        self.clamp_init = clamp_init
+        if not torch.cuda.is_available():
+            raise L.EspmError("espm_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        torch.cuda.set_device(self.device)
+        self.shard = shard
+        n, p = X.shape
+        k = W0.shape[1]
+        self.n, self.p, self.k = n, p, k
+        self.identity_G = G is None
+        self.m = n if G is None else G.shape[1]
+        if W0.shape != (self.m, k) or H0.shape != (k, p):
+            raise ValueError("inconsistent shapes: X %s G %s W %s H %s" % (
+                X.shape, None if G is None else G.shape, W0.shape, H0.shape))
+        x_code = _code_of(X.dtype)
+        if c_dtype is None:
+            # NumPy promotion of the reference: any float64 operand makes the update float64
+            parts = [np.dtype(X.dtype), np.dtype(W0.dtype), np.dtype(H0.dtype)]
+            if G is not None:
+                parts.append(np.dtype(G.dtype))
+            c_dtype = np.result_type(*parts)
+        c_code = _code_of(c_dtype)
+        if x_code == L.F64:
+            c_code = L.F64
+        self.x_code, self.c_code = x_code, c_code
+        self.cdt = _torch_dtype(c_code)
+        self.cnp = _np_dtype(c_code)
+
+        # ---- pixel shard (contiguous image rows) ----
+        if shape_2d is not None:
+            nx, ny = int(shape_2d[0]), int(shape_2d[1])
+            if nx * ny != p:
+                raise ValueError("shape_2d %s does not match p=%d" % (shape_2d, p))
+        else:
+            nx, ny = 0, 0
+        self.nx, self.ny = nx, ny
+        if shard is None:
+            self.rank, self.world = 0, 1
+            j0, j1, row0 = 0, p, 0
+        else:
+            from .dist import shard_bounds
+            self.rank, self.world = shard.rank, shard.world
+            j0, j1, row0 = shard_bounds(p, nx, ny, self.rank, self.world)
+        self.j0, self.j1, self.row0 = j0, j1, row0
+        p_loc = j1 - j0
+        self.p_loc = p_loc
+
+        st = L.EspmState()
+        self.st = st
+        st.n, st.m, st.k = n, self.m, k
+        st.p_loc, st.p_total = p_loc, p
+        st.nx, st.ny, st.row0 = nx, ny, row0
+        st.x_dtype, st.c_dtype = x_code, c_code
+        st.maxit = L.MAXIT_DICHOTOMY
+        flags = 0
+        if simplex_H:
+            flags |= L.FLAG_SIMPLEX_H
+        if simplex_W:
+            flags |= L.FLAG_SIMPLEX_W
+        if self.identity_G:
+            flags |= L.FLAG_G_IDENTITY
+        mu_arr = np.zeros(L.MAX_K)
+        if np.isscalar(mu):
+            mu_arr[:k] = float(mu)
+        else:
+            mu_v = np.asarray(mu, dtype=np.float64).reshape(-1)
+            if mu_v.shape[0] != k:
+                raise ValueError("mu must be a scalar or a vector of length n_components")
+            mu_arr[:k] = mu_v
+        if np.any(mu_arr != 0):
+            flags |= L.FLAG_MU
+        if lambda_L != 0:
+            flags |= L.FLAG_LAPLACIAN
+        for i in range(L.MAX_K):
+            st.mu[i] = mu_arr[i]
+        st.lambda_L, st.sigma, st.eps_reg = float(lambda_L), float(sigma), float(epsilon_reg)
+        st.log_shift, st.dicotomy_tol, st.dicotomy_tol_w, st.tol = (
+            float(log_shift), float(dicotomy_tol), float(dicotomy_tol_w), float(tol))
+        st.flags = flags
+        L.check(self.lib.espm_plan(ctypes.byref(st)))
+
+        dev, cdt = self.device, self.cdt
+        kp, n_pad, p_pad = st.kp, st.n_pad, st.p_pad
+        halo = _round_up(ny, 32) if ny > 0 else 0
+        ldh = _round_up(halo + p_pad + halo, 32)
+        st.halo, st.ldh = halo, ldh
+        self.halo, self.ldh = halo, ldh
+
+        def zeros(*shape, dtype=cdt):
+            return torch.zeros(*shape, dtype=dtype, device=dev)
+
+        # ---- state buffers (rotated by pointer) ----
+        # H pad pixels hold 1 so that padded pixels give y > 0 (their X is 0: they contribute nothing)
+        self.Hbuf = [torch.ones(k, ldh, dtype=cdt, device=dev) for _ in range(3)]
+        self.Wbuf = [zeros(self.m, k) for _ in range(2)]
+        self.GWbuf = [zeros(n_pad, kp) for _ in range(2)]
+        self.GWcbuf = [zeros(n_pad, kp) for _ in range(2)]
+        self.gwstats = [zeros(2 * kp) for _ in range(2)]
+        self.hstats = [zeros(3 * kp, dtype=torch.float64) for _ in range(2)]
+        self.ih = [0, 1, 2]      # indices of (prev, cur, next) H buffers
+        self.iw = [0, 1]         # (cur, next) for W / GW / gwstats
+        self.ihs = [0, 1]        # (cur, next) for hstats
+        self.have_prev = False
+        # ---- scratch ----
+        self.numraw = zeros(st.h_nsplit, kp, p_pad)
+        self.num = zeros(kp, p_pad)
+        self.den = zeros(kp, p_pad)
+        self.s_part = zeros(st.w_nr, n_pad, kp)
+        self.s_sum = zeros(n_pad, kp)
+        self.w_num = zeros(self.m, k)
+        self.w_den = zeros(self.m, k)
+        self.xlogy_part = zeros(max(st.h_grid, 1), dtype=torch.float64)
+        self.px_part = zeros(st.px_blocks, 3 + 3 * kp, dtype=torch.float64)
+        self.mask = torch.zeros(4 * max(self.world, 1), dtype=torch.int32, device=dev)
+        self.dev_flags = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.max_records = int(max_records)
+        self.records = zeros(self.max_records, L.NSCALARS, dtype=torch.float64)
+        st.numraw, st.num, st.den = self.numraw.data_ptr(), self.num.data_ptr(), self.den.data_ptr()
+        st.s_part, st.s_sum = self.s_part.data_ptr(), self.s_sum.data_ptr()
+        st.t_mk = 0
+        st.w_num, st.w_den = self.w_num.data_ptr(), self.w_den.data_ptr()
+        st.xlogy_part, st.px_part = self.xlogy_part.data_ptr(), self.px_part.data_ptr()
+        st.bisect_mask, st.dev_flags = self.mask.data_ptr(), self.dev_flags.data_ptr()
+
+        # ---- constant inputs ----
+        self.fixed_H = None
+        if fixed_H is not None:
+            fh = torch.full((k, ldh), -1.0, dtype=cdt, device=dev)
+            fh[:, halo:halo + p_loc] = torch.as_tensor(np.ascontiguousarray(fixed_H[:, j0:j1]), dtype=cdt).to(dev)
+            self.fixed_H = fh
+            st.fixed_H = fh.data_ptr() + halo * fh.element_size()
+            st.flags |= L.FLAG_FIXED_H
+            if np.any((fixed_H >= 0) & (fixed_H < log_shift)):
+                st.flags |= L.FLAG_LOSS_DUAL      # H may drop below log_shift: loss clamps, update does not
+        self.fixed_W = None
+        if fixed_W is not None:
+            self.fixed_W = torch.as_tensor(np.ascontiguousarray(fixed_W), dtype=cdt).to(dev)
+            st.fixed_W = self.fixed_W.data_ptr()
+            st.flags |= L.FLAG_FIXED_W
+        self.simplex_rows = None
+        if simplex_rows is not None:
+            rows = np.asarray(simplex_rows, dtype=np.int32).reshape(-1)
+            self.simplex_rows = torch.as_tensor(rows).to(dev)
+            st.simplex_rows = self.simplex_rows.data_ptr()
+            st.n_simplex_rows = int(rows.shape[0])
+            st.flags |= L.FLAG_SIMPLEX_ROWS
+        self.G = self.Gt = self.colsum_G = None
+        self._bind()
+        self._upload_x(X, x_scale)
+        self.set_G(G, prepare=False)
+        self._init_WH(W0, H0)
+
+    # ------------------------------------------------------------------ helpers
+    @property
+    def stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _hptr(self, i):
+        t = self.Hbuf[i]
+        return t.data_ptr() + self.halo * t.element_size()
+
+    def _bind(self):
+        """Write the rotating buffer pointers into the C struct."""
+        st = self.st
+        hp, hc, hn = self.ih
+        wc, wn = self.iw
+        sc, sn = self.ihs
+        st.H_prev, st.H_cur, st.H_next = self._hptr(hp), self._hptr(hc), self._hptr(hn)
+        st.W_cur, st.W_next = self.Wbuf[wc].data_ptr(), self.Wbuf[wn].data_ptr()
+        st.GW_cur, st.GW_next = self.GWbuf[wc].data_ptr(), self.GWbuf[wn].data_ptr()
+        st.GWc_cur, st.GWc_next = self.GWcbuf[wc].data_ptr(), self.GWcbuf[wn].data_ptr()
+        st.gwstats_cur, st.gwstats_next = self.gwstats[wc].data_ptr(), self.gwstats[wn].data_ptr()
+        st.hstats_cur, st.hstats_next = self.hstats[sc].data_ptr(), self.hstats[sn].data_ptr()
+        if self.have_prev:
+            st.flags |= L.FLAG_HAVE_HPREV
+        else:
+            st.flags &= ~L.FLAG_HAVE_HPREV
+
+    def _set_record(self, slot):
+        if not 0 <= slot < self.max_records:
+            raise IndexError("scalar record slot %d out of range" % slot)
+        self.st.scalars = self.records.data_ptr() + slot * L.NSCALARS * 8
+
+    def _call(self, fn):
+        L.check(fn(ctypes.byref(self.st), self.stream))
+
+    # ------------------------------------------------------------------ uploads
+    def _upload_x(self, X, scale):
+        """H2D copy of this rank's pixel slab and re-tiling into the tile-major layout (base.py:262)."""
+        st = self.st
+        xdt = _torch_dtype(self.x_code)
+        self.Xt = torch.empty(st.n_tiles * st.n_pad * L.TILE_PX, dtype=xdt, device=self.device)
+        st.Xt = self.Xt.data_ptr()
+        j0, j1 = self.j0, self.j1
+        if isinstance(X, torch.Tensor):
+            Xv = X
+            if Xv.stride(1) == 1 or Xv.stride(0) != 1:
+                slab = Xv[:, j0:j1]
+                if not slab.is_contiguous():
+                    slab = slab.contiguous()
+                d = slab.to(self.device, non_blocking=True)
+                sc, sp = d.stride(0), 1
+            else:
+                slab = Xv.t()[j0:j1, :]
+                d = slab.to(self.device, non_blocking=True)
+                sc, sp = 1, d.stride(0)
+        else:
+            Xv = np.asarray(X)
+            if Xv.T.flags.c_contiguous and not Xv.flags.c_contiguous:
+                slab = Xv.T[j0:j1, :]                      # hyperspy layout (p, n): channels contiguous
+                d = torch.from_numpy(slab).to(self.device)
+                sc, sp = 1, self.n
+            else:
+                slab = Xv[:, j0:j1]
+                if not slab.flags.c_contiguous:
+                    slab = np.ascontiguousarray(slab)
+                d = torch.from_numpy(slab).to(self.device)
+                sc, sp = slab.shape[1], 1
+        L.check(self.lib.espm_retile_x(ctypes.byref(st), ctypes.c_void_p(d.data_ptr()), self.x_code,
+                                       sc, sp, 0, float(scale), self.stream))
+        torch.cuda.current_stream(self.device).synchronize()
+        del d
+
+    def set_G(self, G, prepare=True):
+        """(Re)load G (base.py:269-274, 388-389).  ``prepare`` also recomputes GW for W_cur."""
+        st = self.st
+        if G is None:
+            if not self.identity_G:
+                raise ValueError("G cannot switch to identity mid-fit")
+            st.G = st.Gt = st.colsum_G = 0
+        else:
+            Gn = np.ascontiguousarray(np.asarray(G), dtype=self.cnp)
+            if Gn.shape != (self.n, self.m):
+                raise ValueError("G has shape %s, expected %s" % (Gn.shape, (self.n, self.m)))
+            self.G = torch.from_numpy(Gn).to(self.device)
+            self.Gt = self.G.t().contiguous()
+            if self.colsum_G is None:
+                self.colsum_G = torch.zeros(self.m, dtype=self.cdt, device=self.device)
+            st.G, st.Gt, st.colsum_G = self.G.data_ptr(), self.Gt.data_ptr(), self.colsum_G.data_ptr()
+            L.check(self.lib.espm_colsum_g(ctypes.byref(st), ctypes.c_void_p(self.colsum_G.data_ptr()), self.stream))
+        if prepare:
+            # GW for the CURRENT W under the new G: write into the `next` slot, then swap GW only
+            wc, wn = self.iw
+            self.Wbuf[wn].copy_(self.Wbuf[wc])
+            self._set_record(self.max_records - 1)
+            self._call(self.lib.espm_gw_prepare)
+            self.iw = [wn, wc]
+            self._bind()
+
+    def _init_WH(self, W0, H0):
+        """updates.py:220-221: clamp the initial factors to log_shift; then GW and the H statistics."""
+        ls = self.st.log_shift
+        wc, wn = self.iw
+        W = torch.as_tensor(np.ascontiguousarray(W0), dtype=self.cdt).to(self.device)
+        Hs = torch.as_tensor(np.ascontiguousarray(H0[:, self.j0:self.j1]), dtype=self.cdt).to(self.device)
+        if self.clamp_init:
+            W, Hs = W.clamp_min(ls), Hs.clamp_min(ls)
+        self.Wbuf[wn].copy_(W)
+        hp, hc, hn = self.ih
+        self.Hbuf[hn][:, self.halo:self.halo + self.p_loc] = Hs
+        self._bind()
+        self._set_record(self.max_records - 1)
+        self._call(self.lib.espm_gw_prepare)
+        self._call(self.lib.espm_h_stats)
+        self._sync_hstats()
+        self._exchange_halo(self.ih[2])
+        # rotate: next -> cur
+        self.iw = [wn, wc]
+        self.ih = [hp, hn, hc]
+        self.ihs = [self.ihs[1], self.ihs[0]]
+        self.have_prev = False
+        self._bind()
+
+    # ------------------------------------------------------------------ multi-GPU hooks (dist.py)
+    def _sync_hstats(self):
+        if self.shard is not None:
+            self.shard.allreduce_hstats(self.hstats[self.ihs[1]], self.st.kp)
+
+    def _exchange_halo(self, ibuf):
+        if self.shard is not None and self.ny > 0:
+            self.shard.exchange_halo(self.Hbuf[ibuf], self.halo, self.p_loc, self.ny)
+
+    # ------------------------------------------------------------------ the two phases
+    def evaluate(self, slot):
+        """Phase A on (W_cur, H_cur): fills scalar record ``slot`` (loss parts, rel_H, flags)."""
+        self._set_record(slot)
+        self._call(self.lib.espm_h_pass)
+        self._call(self.lib.espm_h_finish)
+        self._call(self.lib.espm_h_scalars)
+        self._evaluated = True
+
+    def advance(self, slot):
+        """Phase B: (W_cur, H_cur) -> (W_next, H_next), rotate.  rel_W etc. go to record ``slot``."""
+        st = self.st
+        self._set_record(slot)
+        if st.flags & L.FLAG_SIMPLEX_H:
+            if self.shard is not None:
+                self.shard.gather_masks(self.mask)
+            self._call(self.lib.espm_h_apply)
+        self._exchange_halo(self.ih[2])
+        self._call(self.lib.espm_w_pass)
+        self._call(self.lib.espm_w_reduce)
+        if self.shard is not None:
+            self.shard.allreduce_sum(self.s_sum)
+            self._sync_hstats()
+        self._call(self.lib.espm_w_finish)
+        hp, hc, hn = self.ih
+        self.ih = [hc, hn, hp]
+        self.iw = [self.iw[1], self.iw[0]]
+        self.ihs = [self.ihs[1], self.ihs[0]]
+        self.have_prev = True
+        self._bind()
+
+    # ------------------------------------------------------------------ single steps (operator API)
+    def step_h_only(self):
+        """One H update from (W_cur, H_cur): returns (H_next local, scalar record)."""
+        self.evaluate(0)
+        if self.st.flags & L.FLAG_SIMPLEX_H:
+            if self.shard is not None:
+                self.shard.gather_masks(self.mask)
+            self._call(self.lib.espm_h_apply)
+        rec = self.read_records(0, 1)[0]
+        Hn = self.Hbuf[self.ih[2]][:, self.halo:self.halo + self.p_loc].cpu().numpy()
+        return Hn, rec
+
+    def step_w_only(self):
+        """One W update from (W_cur, H_cur) (the H given by the caller plays the role of H')."""
+        st = self.st
+        st.H_next = st.H_cur
+        st.hstats_next = st.hstats_cur
+        self._set_record(0)
+        self._call(self.lib.espm_w_pass)
+        self._call(self.lib.espm_w_reduce)
+        if self.shard is not None:
+            self.shard.allreduce_sum(self.s_sum)
+        self._call(self.lib.espm_w_finish)
+        rec = self.read_records(0, 1)[0]
+        rec[L.S_DEV_FLAGS] = float(int(self.dev_flags[0].item()) & 0xffffffff)
+        Wn = self.Wbuf[self.iw[1]].cpu().numpy()
+        self._bind()
+        return Wn, rec
+
+    def rollback(self):
+        """Undo the last ``advance`` (used when a stop test fires one step late): the previous
+        iterate's buffers are intact because every kernel writes only the `next` set."""
+        hp, hc, hn = self.ih
+        self.ih = [hn, hp, hc]
+        self.iw = [self.iw[1], self.iw[0]]
+        self.ihs = [self.ihs[1], self.ihs[0]]
+        self.have_prev = False
+        self._bind()
+
+    # ------------------------------------------------------------------ read-back
+    def read_records(self, lo, hi):
+        """Synchronous D2H read of scalar records [lo, hi) -> float64 array (hi-lo, NSCALARS)."""
+        rec = self.records[lo:hi].cpu().numpy()
+        if self.shard is not None:
+            rec = self.shard.combine_records(rec)
+        return rec
+
+    def loss_parts(self, rec, const_KL, numel):
+        """(kl, log_reg, lapl) of base.py:203-205 + smooth_nmf.py:461-469 from one scalar record."""
+        kl = (rec[L.S_SUMY] - rec[L.S_XLOGY] + const_KL) / numel
+        reg = rec[L.S_LOGREG] / numel
+        lap = 0.5 * self.st.lambda_L * rec[L.S_LAPL] / numel
+        return kl, reg, lap
+
+    def get_W(self):
+        return self.Wbuf[self.iw[0]].cpu().numpy()
+
+    def get_H_local(self):
+        return self.Hbuf[self.ih[1]][:, self.halo:self.halo + self.p_loc].cpu().numpy()
+
+    def get_H(self):
+        Hl = self.get_H_local()
+        if self.shard is not None:
+            return self.shard.gather_H(Hl, self.p)
+        return Hl
+
+    def get_GW(self):
+        return self.GWbuf[self.iw[0]][:self.n, :self.k].cpu().numpy()
+
+    def set_WH(self, W, H):
+        """Overwrite the current iterate (e.g. after rescaled_DH) and refresh the derived buffers."""
+        self._init_WH(W, H)
+
+    def set_flag(self, flag, on=True):
+        if on:
+            self.st.flags |= flag
+        else:
+            self.st.flags &= ~flag

@@ -1,0 +1,355 @@
+"""``SmoothNMF`` -- drop-in for ``espm.estimators.SmoothNMF`` whose fit loop runs on a B200.
+
+Same constructor arguments, ``fit`` / ``fit_transform`` / ``inverse_transform`` / ``loss`` /
+``get_losses``, fitted attributes and printed messages as the reference
+(espm/estimators/smooth_nmf.py:84-113, base.py:126-152, 209-517).  The host code below only validates,
+initialises and runs the stop tests; every pass over X happens in the CUDA kernels behind
+``espm_b200.engine.FitEngine``.  There is no CPU fallback: without a CUDA device ``fit`` raises.
+
+Supported on the device: ``algo="log_surrogate"`` (the default) with the KL loss, ``simplex_H`` /
+``simplex_W``, ``mu`` (scalar or per phase), ``lambda_L`` with ``shape_2d`` (5-point Laplacian) or
+without (identity), ``fixed_H`` / ``fixed_W``, ``normalize``, ``G`` as ``None`` / ndarray / physical
+model, ``hspy_comp``.  Other ``algo`` values, ``l2=True`` and ``linesearch=True`` raise
+``NotImplementedError`` (SURVEY.md section 8f lists them as "next").
+"""
+import time
+
+import numpy as np
+from sklearn.base import BaseEstimator, TransformerMixin
+from sklearn.utils.validation import check_is_fitted, validate_data
+
+from . import _lib as L
+from .conf import dicotomy_tol as _DICOTOMY_TOL
+from .conf import log_shift as _LOG_SHIFT
+from .conf import sigmaL as _SIGMA_L
+from .host import (initialize_factors, is_physical_model, normalization_factor, remove_zeros_lines,
+                   rescaled_DH)
+
+
+class SmoothNMF(TransformerMixin, BaseEstimator):
+    """NMF ``X ~ G W H`` with KL loss, simplex constraints, Laplacian and log regularisation."""
+
+    loss_names_ = ["KL_div_loss", "log_reg_loss", "Lapl_reg_loss", "gamma"]
+    const_KL_ = None
+
+    def __init__(self, lambda_L=0.0, linesearch=False, mu=0, epsilon_reg=1, algo="log_surrogate",
+                 dicotomy_tol=_DICOTOMY_TOL, gamma=None, n_components=2, init=None, tol=1e-4, max_iter=200,
+                 random_state=None, verbose=1, debug=False, l2=False, G=None, shape_2d=None, normalize=False,
+                 log_shift=_LOG_SHIFT, eval_print=10, true_D=None, true_H=None, fixed_H=None, fixed_W=None,
+                 hspy_comp=False, no_stop_criterion=False, simplex_H=False, simplex_W=True):
+        self.n_components = n_components
+        self.init = init
+        self.tol = tol
+        self.max_iter = max_iter
+        self.random_state = random_state
+        self.verbose = verbose
+        self.log_shift = log_shift
+        self.debug = debug
+        self.l2 = l2
+        self.G = G
+        self.shape_2d = shape_2d
+        self.eval_print = eval_print
+        self.true_D = true_D
+        self.true_H = true_H
+        self.fixed_H = fixed_H
+        self.fixed_W = fixed_W
+        self.hspy_comp = hspy_comp
+        self.normalize = normalize
+        self.no_stop_criterion = no_stop_criterion
+        self.simplex_H = simplex_H
+        self.simplex_W = simplex_W
+        self.lambda_L = lambda_L
+        self.linesearch = linesearch
+        self.mu = mu
+        self.epsilon_reg = epsilon_reg
+        self.dicotomy_tol = dicotomy_tol
+        self.algo = algo
+        self.gamma = gamma
+        self.check_params()
+
+    # ------------------------------------------------------------------ sklearn plumbing
+    def __sklearn_tags__(self):
+        tags = super().__sklearn_tags__()
+        tags.input_tags.positive_only = True
+        return tags
+
+    def _more_tags(self):
+        return {"requires_positive_X": True}
+
+    def check_params(self):
+        """Soft validation: bad values are reported and reset, never raised (smooth_nmf.py:145-237)."""
+        def reset(name, value, why):
+            print(why)
+            print("The %s parameter is set to %r" % (name, value))
+            setattr(self, name, value)
+
+        if not isinstance(self.lambda_L, (int, float)):
+            reset("lambda_L", 0.0, "The regularization parameter lambda_L must be a float or int")
+        if not isinstance(self.linesearch, bool):
+            reset("linesearch", False, "The linesearch parameter must be a boolean")
+        if not isinstance(self.mu, (int, float, np.ndarray)):
+            reset("mu", 0, "The regularization parameter mu must be a float, int or np.ndarray")
+        if not isinstance(self.epsilon_reg, (int, float)):
+            reset("epsilon_reg", 1, "The regularization parameter epsilon_reg must be a float or int")
+        if not isinstance(self.algo, str):
+            reset("algo", "log_surrogate", "The algorithm parameter must be a string")
+        if not isinstance(self.simplex_H, bool):
+            reset("simplex_H", False, "The simplex_H parameter must be a boolean")
+        if not isinstance(self.simplex_W, bool):
+            reset("simplex_W", True, "The simplex_W parameter must be a boolean")
+        if not isinstance(self.dicotomy_tol, (int, float)):
+            reset("dicotomy_tol", 1e-3, "The dicotomy_tol parameter must be a float or int")
+        if self.gamma is not None and not isinstance(self.gamma, (int, float, list)):
+            reset("gamma", None, "The gamma parameter must be a float, int, or list")
+        if not isinstance(self.verbose, (bool, int)):
+            reset("verbose", 1, "The verbose parameter must be a boolean or int")
+        if not isinstance(self.debug, bool):
+            reset("debug", False, "The debug parameter must be a boolean")
+        if not isinstance(self.l2, bool):
+            reset("l2", False, "The l2 parameter must be a boolean")
+        if not isinstance(self.n_components, int):
+            reset("n_components", 2, "The n_components parameter must be an int")
+        if self.algo not in ("l2_surrogate", "log_surrogate", "projected_gradient", "bmd"):
+            reset("algo", "log_surrogate",
+                  "The algorithm must be 'l2_surrogate', 'log_surrogate', 'bmd' or 'projected_gradient'")
+        if not (self.lambda_L >= 0):
+            reset("lambda_L", 0, "The regularization parameter lambda_L must be non-negative")
+        if not (self.epsilon_reg > 0.0):
+            reset("epsilon_reg", 1.0, "The regularization parameter epsilon_reg must be positive")
+        if not np.all(np.array(self.mu) >= 0):
+            reset("mu", 0, "The regularization parameter mu must be non-negative")
+        if self.simplex_H and self.simplex_W:
+            print("The simplex constraint must be applied to either W or H or none of them")
+            print("The simplex constraint is applied to W and not to H")
+            self.simplex_W = True
+            self.simplex_H = False
+        if self.linesearch:
+            if self.l2:
+                reset("l2", False, "The l2 parameter must be False when using linesearch")
+            if not (self.lambda_L > 0):
+                reset("lambda_L", 1, "The regularization parameter lambda_L must be non-zero when using linesearch")
+        if self.algo != "l2_surrogate" and self.l2:
+            reset("l2", False, "The l2 parameter must be False when using the algorithm " + self.algo)
+
+    def _require_supported(self):
+        if self.algo != "log_surrogate":
+            raise NotImplementedError(
+                "espm_b200 runs algo='log_surrogate' on the device; algo=%r is not available yet" % self.algo)
+        if self.l2:
+            raise NotImplementedError("espm_b200: the Frobenius loss (l2=True) is not available yet")
+        if self.linesearch:
+            raise NotImplementedError("espm_b200: linesearch=True is not available yet")
+        if self.true_D is not None and self.true_H is not None:
+            raise NotImplementedError("espm_b200: ground-truth tracking (true_D/true_H) is not available yet")
+
+    # ------------------------------------------------------------------ loss
+    def _loss_from_record(self, rec):
+        kl, reg, lap = self._engine.loss_parts(rec, self.const_KL_, self.GWH_numel_)
+        self.detailed_loss_ = [kl, reg, lap, self.gamma_]
+        return kl + reg + lap
+
+    def loss(self, W, H, average=True, X=None):
+        """Regularised loss of (W, H) (smooth_nmf.py:457-475, base.py:167-207), evaluated on the device."""
+        from .ops import full_loss
+        check_is_fitted(self, "G_")
+        Xe = self.X_ if X is None else X
+        const = self.const_KL_
+        if X is not None or const is None:
+            # base.py:201 (the constant mixes X and self.X_ exactly like the reference)
+            const = float(np.sum(Xe * np.log(np.maximum(self.X_, self.log_shift))) - np.sum(Xe))
+            if self.const_KL_ is None:
+                self.const_KL_ = const
+        val, det = full_loss(Xe, self.G_ if not self._identity_G else None, W, H, mu=self.mu,
+                             epsilon_reg=self.epsilon_reg, lambda_L=self.lambda_L, shape_2d=self.shape_2d,
+                             log_shift=self.log_shift, const=const, average=average)
+        self.GWH_numel_ = Xe.shape[0] * H.shape[1]
+        self.detailed_loss_ = det + [self.gamma_ if not isinstance(self.gamma_, list) else self.gamma_[0]]
+        return val
+
+    # ------------------------------------------------------------------ fit
+    def fit_transform(self, X, y=None, W=None, H=None):
+        """Learn the model on a B200 and return ``G W`` (or ``H.T`` with ``hspy_comp``), base.py:209-420."""
+        from .engine import FitEngine
+        self._require_supported()
+        self.gamma_ = None                                             # smooth_nmf.py:280
+        if self.hspy_comp:                                             # base.py:243-247
+            self.X_ = validate_data(self, X.T, dtype=[np.float64, np.float32])
+        else:
+            self.X_ = validate_data(self, X, dtype=[np.float64, np.float32])
+            try:                                                       # base.py:249-259
+                import inspect
+                calframe = inspect.getouterframes(inspect.currentframe(), 2)
+                if calframe[1][3] == "decomposition" and "hyperspy" in calframe[1][1]:
+                    print("Are you calling the function decomposition from Hyperspy?\n"
+                          "If so, please set the compatibility argument 'hspy_comp' to True.\n\n"
+                          "If this argument is not set correctly, the function will not work properly!!!")
+            except Exception:
+                pass
+        self.X_ = remove_zeros_lines(self.X_, self.log_shift)          # base.py:262
+        self.const_KL_ = None
+        if self.normalize:                                             # base.py:264-267
+            self.norm_factor_ = normalization_factor(self.X_, self.n_components)
+            self.X_ = self.norm_factor_ * self.X_
+        if is_physical_model(self.G):                                  # base.py:269-274
+            self.physics_model_ = self.G
+            G = self.physics_model_.NMF_update()
+        else:
+            self.physics_model_ = None
+            G = self.G
+        self._identity_G = G is None
+        G_full, W0, H0 = initialize_factors(self.X_, G, W, H, self.n_components, self.init, self.random_state,
+                                            self.simplex_H, self.simplex_W, self.log_shift, self.physics_model_)
+        n, p = self.X_.shape
+        self.GWH_numel_ = n * p
+        # base.py:200-201
+        self.const_KL_ = float(np.sum(self.X_ * np.log(np.maximum(self.X_, self.log_shift))) - np.sum(self.X_))
+        self.gamma_ = _SIGMA_L if self.gamma is None else self.gamma   # smooth_nmf.py:290-306
+        simplex_rows = None
+        if self.physics_model_ is not None and self.simplex_W:
+            simplex_rows = self.physics_model_.NMF_simplex()           # updates.py:62-65
+        if self.lambda_L != 0 and self.shape_2d is not None:
+            from .ops import check_shape_2d
+            check_shape_2d(self.shape_2d, p)
+        max_iter = int(self.max_iter)
+        eng = FitEngine(self.X_, None if self._identity_G else G, W0, H0,
+                        shape_2d=self.shape_2d, lambda_L=self.lambda_L, mu=self.mu, epsilon_reg=self.epsilon_reg,
+                        log_shift=self.log_shift, dicotomy_tol=self.dicotomy_tol, dicotomy_tol_w=_DICOTOMY_TOL,
+                        tol=self.tol, sigma=float(self.gamma_), simplex_H=self.simplex_H, simplex_W=self.simplex_W,
+                        simplex_rows=simplex_rows, fixed_H=self.fixed_H, fixed_W=self.fixed_W,
+                        max_records=max(max_iter, 1) + 8)
+        self._engine = eng
+        self.G_ = G_full
+        self.L_ = None  # the Laplacian is a stencil inside the kernels (utils.py:39-76 is never materialised)
+
+        algo_start = time.time()
+        self.n_iter_ = 0
+        self.losses_, self.rel_, self.detailed_losses_ = [], [], []
+        batch = (self.no_stop_criterion and self.physics_model_ is None
+                 and not (self.verbose > 0 and self.eval_print > 0))
+        try:
+            if batch:
+                self._run_batch(eng, max_iter)
+            else:
+                self._run_checked(eng, max_iter, algo_start)
+        except KeyboardInterrupt:                                      # base.py:393-394
+            pass
+
+        self.W_ = eng.get_W()
+        self.H_ = eng.get_H()
+        if not self.simplex_H and not self.simplex_W:                  # base.py:399-400
+            self.W_, self.H_ = rescaled_DH(self.W_, self.H_)
+            eng.set_WH(self.W_, self.H_)
+            eng.evaluate(eng.max_records - 2)
+            self._final_rec = eng.read_records(eng.max_records - 2, eng.max_records - 1)[0]
+        algo_time = time.time() - algo_start
+        print(f"Stopped after {self.n_iter_} iterations in {algo_time // 60} minutes "
+              f"and {np.round(algo_time) % 60} seconds.")
+        self.reconstruction_err_ = self._loss_from_record(self._final_rec)   # base.py:407
+        self._check_flags(self._final_rec)
+        if self.normalize:                                             # base.py:409-410
+            self.W_ = self.W_ / self.norm_factor_
+        GW = self.G_ @ self.W_ if not self._identity_G else self.W_.copy()
+        self.n_components_ = self.H_.shape[0]
+        if self.hspy_comp:                                             # base.py:415-420
+            self.components_ = GW.T
+            return self.H_.T
+        self.components_ = self.H_
+        return GW
+
+    # ---- loop variants -----------------------------------------------------------------------
+    def _append(self, rec):
+        loss = self._loss_from_record(rec)
+        self.losses_.append(loss)
+        self.detailed_losses_.append(self.detailed_loss_)
+        self.rel_.append([rec[L.S_REL_W], rec[L.S_REL_H]])
+        return loss
+
+    def _check_flags(self, rec):
+        flags = int(rec[L.S_DEV_FLAGS])
+        if flags & L.DEV_NONFINITE:
+            raise FloatingPointError("espm_b200: non-finite values in the H update (zero row in G W?)")
+        if flags & (L.DEV_BRACKET | L.DEV_NEGATIVE):
+            raise AssertionError("espm_b200: simplex bisection preconditions violated "
+                                 "(dicotomy.py:17-19,141-144), device flags=%#x" % flags)
+
+    def _run_batch(self, eng, max_iter):
+        """no_stop_criterion and nothing to print: enqueue every iteration, read the scalars once."""
+        eng.evaluate(0)
+        for it in range(1, max_iter + 1):
+            eng.advance(it)
+            eng.evaluate(it)
+        recs = eng.read_records(0, max_iter + 1)
+        self._eval_init = self._loss_from_record(recs[0])
+        for it in range(1, max_iter + 1):
+            self._append(recs[it])
+        self.n_iter_ = max_iter
+        self._final_rec = recs[max_iter]
+        print("exits because max_iteration was reached")
+
+    def _run_checked(self, eng, max_iter, algo_start):
+        """The reference's while-loop with its ordered stop tests (base.py:313-393)."""
+        eng.evaluate(0)
+        rec = eng.read_records(0, 1)[0]
+        self._check_flags(rec)
+        eval_init = self._loss_from_record(rec)                        # base.py:295
+        self._eval_init = eval_init
+        self._final_rec = rec
+        eval_before = np.inf
+        while True:
+            it = self.n_iter_ + 1
+            eng.advance(it)
+            eng.evaluate(it)
+            rec = eng.read_records(it, it + 1)[0]
+            self._check_flags(rec)
+            eval_after = self._append(rec)                             # base.py:320-351
+            self.n_iter_ = it
+            self._final_rec = rec
+            rel_W, rel_H = rec[L.S_REL_W], rec[L.S_REL_H]
+            if self.n_iter_ >= max_iter:                               # base.py:354-378
+                print("exits because max_iteration was reached")
+                break
+            if not self.no_stop_criterion:
+                if max(rel_H, rel_W) < self.tol:
+                    print("exits because of relative change rel_A {} and rel_P {} < tol ".format(rel_H, rel_W))
+                    break
+                elif abs((eval_before - eval_after) / eval_init) < self.tol:
+                    print("exits because of relative change < tol: {}".format((eval_before - eval_after) / eval_init))
+                    break
+                elif np.isnan(eval_after):
+                    print("exit because of the presence of NaN")
+                    break
+                elif (eval_before - eval_after) < 0:
+                    print("exit because of negative decrease {}: {}, {}".format(
+                        (eval_before - eval_after), eval_before, eval_after))
+                    break
+            if self.verbose > 0 and np.mod(self.n_iter_, self.eval_print) == 0:
+                print(f"It {self.n_iter_} / {max_iter}: loss {eval_after:3e},  "
+                      f"{self.n_iter_ / (time.time() - algo_start + _LOG_SHIFT):0.3f} it/s")
+            if self.physics_model_ is not None and self.n_iter_ % 3 == 0:   # base.py:388-392
+                self.G_ = self.physics_model_.NMF_update(eng.get_W())
+                eng.set_G(self.G_)
+                slot = eng.max_records - 3
+                eng.evaluate(slot)
+                rec2 = eng.read_records(slot, slot + 1)[0]
+                eval_before = self._loss_from_record(rec2)
+                self._final_rec = rec2
+            else:
+                eval_before = eval_after
+
+    def fit(self, X, y=None, **params):
+        """Learn the model (base.py:422-441)."""
+        self.fit_transform(X, **params)
+        return self
+
+    def inverse_transform(self, W):
+        """G W H (base.py:461-477)."""
+        check_is_fitted(self)
+        return self.G_ @ W @ self.H_
+
+    def get_losses(self):
+        """Structured array of the loss history (base.py:479-517)."""
+        names = ["full_loss"] + self.loss_names_ + ["rel_W", "rel_H"]
+        dt = np.dtype([(name, "float64") for name in names])
+        rows = [(self.losses_[i],) + tuple(self.detailed_losses_[i]) + tuple(self.rel_[i])
+                for i in range(len(self.losses_))]
+        return np.array(rows, dtype=dt)

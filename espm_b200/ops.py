@@ -1,0 +1,241 @@
+"""Operator-level API: the functions of the reference that sit on the fit-loop path, with the same
+names and argument meaning, executed by the CUDA kernels.
+
+    multiplicative_step_h / multiplicative_step_w   espm/estimators/updates.py:83 / :6
+    dichotomy_simplex                                espm/estimators/dicotomy.py:4
+    KLdiv_loss / log_reg / trace_xtLx                espm/measures.py:456 / :524 / :560
+    create_laplacian_matrix                          espm/utils.py:39 (returns the image shape: the
+                                                     Laplacian is a stencil inside the kernels)
+
+Inputs and outputs are NumPy arrays on the host (like the reference); each call uploads, runs the
+kernels once and downloads -- these entry points exist for parity tests and small problems, the
+estimator keeps everything resident instead.  No CPU fallback.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .conf import dicotomy_tol as _TOL
+from .conf import log_shift as _LS
+from .conf import maxit_dichotomy as _MAXIT
+from .conf import sigmaL as _SIGMA
+from .engine import FitEngine
+
+
+class GridLaplacian:
+    """Stand-in for the scipy.sparse matrix of ``create_laplacian_matrix``: remembers (nx, ny)."""
+
+    def __init__(self, nx, ny):
+        self.shape_2d = (int(nx), int(ny))
+        self.shape = (nx * ny, nx * ny)
+
+
+def create_laplacian_matrix(nx, ny=None):
+    """utils.py:39-76.  The 5-point Neumann Laplacian is applied as a stencil by the kernels, so this
+    only records the image shape."""
+    if ny is None:
+        ny = nx
+    assert nx > 1
+    assert ny > 1
+    return GridLaplacian(nx, ny)
+
+
+def check_shape_2d(shape_2d, p):
+    if shape_2d is None:
+        return None
+    nx, ny = int(shape_2d[0]), int(shape_2d[1])
+    if nx * ny != p:
+        raise ValueError("shape_2d %s does not match the number of pixels %d" % (shape_2d, p))
+    return nx, ny
+
+
+def _shape_from_L(Lm, p):
+    """Accept what the reference accepts for ``L``: our GridLaplacian, a (nx, ny) tuple, None, or the
+    reference's own matrix (scipy.sparse / dense) -- identity or grid Laplacian -- whose shape is inferred."""
+    if Lm is None:
+        return None, False
+    if isinstance(Lm, GridLaplacian):
+        return Lm.shape_2d, True
+    if isinstance(Lm, tuple):
+        return (int(Lm[0]), int(Lm[1])), True
+    try:
+        import scipy.sparse as sp
+        M = sp.csr_matrix(Lm)
+    except Exception as exc:  # pragma: no cover
+        raise TypeError("unsupported Laplacian object %r" % type(Lm)) from exc
+    if M.shape != (p, p):
+        raise ValueError("Laplacian has shape %s, expected %s" % (M.shape, (p, p)))
+    if M.nnz == p and np.all(M.diagonal() == 1):
+        return None, True                       # identity (base.py:289-291)
+    row0 = M.getrow(0).indices
+    ny = int(row0.max())
+    if ny < 1 or p % ny != 0:
+        raise ValueError("cannot infer the image shape from the Laplacian matrix")
+    nx = p // ny
+    if p <= 4096:
+        from scipy.sparse import lil_matrix
+        ref = lil_matrix((p, p), dtype=np.float64)
+        for i in range(nx):
+            for j in range(ny):
+                a = i * ny + j
+                for di, dj in ((-1, 0), (1, 0), (0, -1), (0, 1)):
+                    ii, jj = i + di, j + dj
+                    if 0 <= ii < nx and 0 <= jj < ny:
+                        ref[a, a] += 1
+                        ref[a, ii * ny + jj] = -1
+        if abs(ref.tocsr() - M.astype(np.float64)).sum() != 0:
+            raise ValueError("L is neither the identity nor the grid Laplacian of utils.py:39-76")
+    return (nx, ny), True
+
+
+def _engine(X, G, W, H, **kw):
+    X = np.asarray(X)
+    if X.dtype not in (np.float32, np.float64):
+        X = X.astype(np.float64)
+    return FitEngine(X, None if G is None else np.asarray(G), np.asarray(W), np.asarray(H), **kw)
+
+
+def _is_identity(G):
+    return G is not None and G.shape[0] == G.shape[1] and np.array_equal(G, np.eye(G.shape[0], dtype=G.dtype))
+
+
+def _raise_flags(rec):
+    flags = int(rec[L.S_DEV_FLAGS])
+    if flags & L.DEV_NONFINITE:
+        raise FloatingPointError("espm_b200: non-finite ratio sums (zero row in G W?)")
+    if flags & (L.DEV_BRACKET | L.DEV_NEGATIVE):
+        raise AssertionError("espm_b200: bisection preconditions violated (dicotomy.py:17-19,141-144)")
+
+
+def multiplicative_step_h(X, G, W, H, simplex_H=False, mu=0, log_shift=_LS, epsilon_reg=1, safe=True,
+                          dicotomy_tol=_TOL, lambda_L=0, L=None, l2=False, sigmaL=_SIGMA, fixed_H=None,
+                          use_bregman=False, return_its=False):
+    """updates.py:83-156 (KL branch)."""
+    if l2 or use_bregman:
+        raise NotImplementedError("espm_b200: only the KL multiplicative update is implemented on the device")
+    p = np.shape(H)[1]
+    shape_2d = None
+    if lambda_L != 0:
+        if L is None:
+            raise ValueError("Please provide the laplacian")          # updates.py:94-95
+        shape_2d, _ = _shape_from_L(L, p)
+    if simplex_H and log_shift > 0 and np.shape(H)[0] * log_shift >= 1:
+        raise ValueError("No solution exists!")                       # dicotomy.py:22-23
+    Ge = None if (G is None or _is_identity(np.asarray(G))) else G
+    eng = _engine(X, Ge, W, H, shape_2d=shape_2d, lambda_L=lambda_L, mu=mu, epsilon_reg=epsilon_reg,
+                  log_shift=log_shift, dicotomy_tol=dicotomy_tol, sigma=sigmaL, simplex_H=simplex_H,
+                  simplex_W=False, fixed_H=fixed_H, max_records=8)
+    Hn, rec = eng.step_h_only()
+    _raise_flags(rec)
+    if return_its:
+        return Hn, int(rec[L.S_BISECT_ITS_H])
+    return Hn
+
+
+def multiplicative_step_w(X, G, W, H, simplex_W=False, log_shift=_LS, safe=True, l2=False, fixed_W=None,
+                          physics_model=None, use_bregman=False):
+    """updates.py:6-78 (KL branch)."""
+    if l2 or use_bregman:
+        raise NotImplementedError("espm_b200: only the KL multiplicative update is implemented on the device")
+    rows = None
+    if simplex_W and physics_model is not None:
+        rows = physics_model.NMF_simplex()
+    nrows = len(rows) if rows is not None else np.shape(W)[0]
+    if simplex_W and log_shift > 0 and nrows * log_shift >= 1:
+        raise ValueError("No solution exists!")
+    Ge = None if (G is None or _is_identity(np.asarray(G))) else G
+    eng = _engine(X, Ge, W, H, log_shift=log_shift, simplex_H=False, simplex_W=simplex_W, simplex_rows=rows,
+                  fixed_W=fixed_W, max_records=8)
+    Wn, rec = eng.step_w_only()
+    _raise_flags(rec)
+    return Wn
+
+
+def dichotomy_simplex(num, denum, log_shift=_LS, tol=_TOL, maxit=_MAXIT, return_its=False):
+    """dicotomy.py:4-55: per-column root of sum_i max(num_i/(x+den_i), log_shift) - 1 with the
+    reference's bracket and its GLOBAL (lock-step) stop test."""
+    lib = L.load()
+    num = np.asarray(num)
+    denum = np.asarray(denum)
+    if num.ndim == 1:
+        num, denum = num[:, None], denum[:, None]
+    k, p = num.shape
+    if log_shift > 0 and k * log_shift >= 1:
+        raise ValueError("No solution exists!")
+    dt = np.result_type(num.dtype, denum.dtype, np.float32)
+    code = L.F64 if dt == np.float64 else L.F32
+    tdt = torch.float64 if code == L.F64 else torch.float32
+    dev = torch.device("cuda", torch.cuda.current_device())
+    d_num = torch.as_tensor(np.ascontiguousarray(num), dtype=tdt).to(dev)
+    d_den = torch.as_tensor(np.ascontiguousarray(denum), dtype=tdt).to(dev)
+    nu = torch.empty(p, dtype=tdt, device=dev)
+    mask = torch.zeros(4, dtype=torch.int32, device=dev)
+    flags = torch.zeros(4, dtype=torch.int32, device=dev)
+    its = torch.zeros(1, dtype=torch.int32, device=dev)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    L.check(lib.espm_dichotomy_simplex(code, k, p, d_num.data_ptr(), d_den.data_ptr(), float(log_shift), float(tol),
+                                       int(maxit), nu.data_ptr(), mask.data_ptr(), flags.data_ptr(),
+                                       its.data_ptr(), stream))
+    f = int(flags[0].item())
+    if f & (L.DEV_BRACKET | L.DEV_NEGATIVE):
+        raise AssertionError("dichotomy_simplex: preconditions violated (dicotomy.py:17-19,141-144)")
+    out = nu.cpu().numpy()
+    n_it = int(its.item())
+    if n_it >= maxit:
+        print("Dicotomy stopped for maximum number of iterations")
+    if return_its:
+        return out, n_it
+    return out
+
+
+def full_loss(X, G, W, H, mu=0, epsilon_reg=1, lambda_L=0, shape_2d=None, log_shift=_LS, const=0.0,
+              average=True):
+    """KL + log-reg + Laplacian loss of (W, H) (base.py:167-207, smooth_nmf.py:457-475).
+    Returns (loss, [kl, log_reg, lapl])."""
+    eng = _engine(X, G, W, H, shape_2d=shape_2d, lambda_L=lambda_L, mu=mu, epsilon_reg=epsilon_reg,
+                  log_shift=log_shift, simplex_H=False, simplex_W=False, max_records=8)
+    eng.evaluate(0)
+    rec = eng.read_records(0, 1)[0]
+    numel = X.shape[0] * np.shape(H)[1] if average else 1
+    kl, reg, lap = eng.loss_parts(rec, const, numel)
+    return kl + reg + lap, [kl, reg, lap]
+
+
+def KLdiv_loss(X, W, H, log_shift=_LS, average=False):
+    """measures.py:456-504 with ``W`` playing the role of G W (n x k)."""
+    X = np.asarray(X)
+    # the engine clamps W, H to log_shift on upload, which is exactly measures.py:493-494
+    eng = _engine(X, None, W, H, log_shift=log_shift, simplex_H=False, simplex_W=False, max_records=8)
+    eng.evaluate(0)
+    rec = eng.read_records(0, 1)[0]
+    val = rec[L.S_SUMY] - rec[L.S_XLOGY]
+    return val / X.size if average else val
+
+
+def log_reg(H, mu, epsilon=1, average=False):
+    """measures.py:524-548, evaluated by the h_finish kernel."""
+    H = np.asarray(H)
+    k, p = H.shape
+    X = np.ones((1, p), dtype=H.dtype if H.dtype in (np.float32, np.float64) else np.float64)
+    eng = _engine(X, None, np.ones((1, k), dtype=X.dtype), H, mu=mu, epsilon_reg=epsilon, log_shift=0.0,
+                  simplex_H=False, simplex_W=False, max_records=8, clamp_init=False)
+    eng.evaluate(0)
+    val = eng.read_records(0, 1)[0][L.S_LOGREG]
+    return val / H.size if average else val
+
+
+def trace_xtLx(Lm, x, average=False):
+    """measures.py:560-577 for the grid (or identity) Laplacian; ``x`` is H.T (p x k) as in
+    smooth_nmf.py:466."""
+    x = np.asarray(x)
+    H = np.ascontiguousarray(x.T)
+    k, p = H.shape
+    shape_2d, _ = _shape_from_L(Lm, p)
+    X = np.ones((1, p), dtype=H.dtype if H.dtype in (np.float32, np.float64) else np.float64)
+    eng = _engine(X, None, np.ones((1, k), dtype=X.dtype), H, lambda_L=1.0, shape_2d=shape_2d, log_shift=0.0,
+                  simplex_H=False, simplex_W=False, max_records=8, clamp_init=False)
+    eng.evaluate(0)
+    val = eng.read_records(0, 1)[0][L.S_LAPL]
+    return val / x.size if average else val

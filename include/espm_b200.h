@@ -1,0 +1,238 @@
+/*
+ * espm_b200.h -- C ABI of the B200-native SmoothNMF fit loop (libespm_b200.so).
+ *
+ * This is the drop-in boundary for ONE path of adriente/espm v1.1.3: the SmoothNMF fit loop
+ * (espm/estimators/base.py:209-420, smooth_nmf.py:284-475, updates.py:6-156, dicotomy.py:4-173,
+ * measures.py:456-577, utils.py:39-76).  The reference has no FFI of its own (it is pure Python);
+ * the entry points below are what a ctypes binding inside espm.estimators would call -- see
+ * INTEGRATION.md for that binding.  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *   - every entry point returns 0 on success, a negative espm_status otherwise;
+ *     espm_last_error() returns a thread-local human-readable message.
+ *   - all device pointers are allocated by the caller (the Python host uses torch for that);
+ *     `stream` is a cudaStream_t passed as void*.  Launches are asynchronous on that stream.
+ *   - X: n energy channels x p pixels, G: n x m, W: m x k, H: k x p, GW = G.W: n x k  (base.py:58-63).
+ *   - "x dtype" is the storage type of X, "c dtype" the arithmetic type (ESPM_F32 / ESPM_F64).
+ *
+ * Device layouts (all chosen for streaming from HBM3e)
+ *   Xt   tile-major copy of X: Xt[tile][channel 0..n_pad)[pixel 0..128), zero padded.
+ *        pixel j of the local shard lives in tile j/128, lane j%128.  One (tile, 16 KiB channel
+ *        chunk) is contiguous, so a stage of the pipeline is ONE cp.async.bulk (TMA) copy.
+ *   GW   [n_pad][kp] row-major (c dtype); pad rows are (1,0,..,0) so that padded channels give y>0.
+ *   H    k rows of `ldh` elements; the pointer addresses local pixel 0, and `halo` elements before
+ *        and after the p_loc owned pixels hold the neighbouring ranks' image rows (Laplacian stencil).
+ */
+#ifndef ESPM_B200_H
+#define ESPM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ESPM_F32 0
+#define ESPM_F64 1
+
+#define ESPM_TILE_PX 128          /* pixels per tile of Xt */
+#define ESPM_STAGE_BYTES 16384    /* bytes of X per pipeline stage (one bulk copy) */
+#define ESPM_MAX_K 16             /* largest supported n_components */
+#define ESPM_NSCALARS 24          /* doubles per slot of the per-iteration scalar record */
+#define ESPM_MAXIT_DICHOTOMY 100  /* espm/conf.py:59 */
+
+typedef enum espm_status {
+    ESPM_OK = 0,
+    ESPM_ERR_CUDA = -1,        /* a CUDA runtime call failed (message has the CUDA error string) */
+    ESPM_ERR_BAD_ARG = -2,     /* inconsistent sizes / unsupported k / null pointer */
+    ESPM_ERR_NO_DEVICE = -3,   /* no sm_100 device: the product path has NO CPU fallback */
+    ESPM_ERR_UNSUPPORTED = -4
+} espm_status;
+
+/* flag bits of espm_state.flags */
+#define ESPM_FLAG_SIMPLEX_H   (1u << 0)  /* updates.py:143-144 */
+#define ESPM_FLAG_SIMPLEX_W   (1u << 1)  /* updates.py:61-68 */
+#define ESPM_FLAG_G_IDENTITY  (1u << 2)  /* G=None: G is the identity, m == n (updates.py:163-166) */
+#define ESPM_FLAG_CLAMP_Y     (1u << 3)  /* GWH = max(GWH, log_shift) fallback (updates.py:129-131, 54-56) */
+#define ESPM_FLAG_LOSS_DUAL   (1u << 4)  /* loss needs max(GW,ls).max(H,ls) != GW.H (measures.py:493-497) */
+#define ESPM_FLAG_FIXED_H     (1u << 5)  /* updates.py:154-155 */
+#define ESPM_FLAG_FIXED_W     (1u << 6)  /* updates.py:75-76 */
+#define ESPM_FLAG_MU          (1u << 7)  /* log regulariser active (updates.py:134-137) */
+#define ESPM_FLAG_LAPLACIAN   (1u << 8)  /* lambda_L != 0 (updates.py:93-96, 138-141) */
+#define ESPM_FLAG_HAVE_HPREV  (1u << 9)  /* H_prev is valid: h_finish also emits rel_H of the current iterate */
+#define ESPM_FLAG_SIMPLEX_ROWS (1u << 10) /* simplex_W restricted to simplex_rows (updates.py:62-65) */
+#define ESPM_FLAG_HQ          (1u << 11) /* algo="l2_surrogate": quadratic surrogate H step (updates.py:263-301) */
+
+/* bits of the device-side error word (espm_state.dev_flags[0]) */
+#define ESPM_DEV_NONFINITE    (1u << 0)  /* non-finite ratio sums (x/0): caller must redo with CLAMP_Y */
+#define ESPM_DEV_BRACKET      (1u << 1)  /* bisection bracket precondition failed (dicotomy.py:141-144) */
+#define ESPM_DEV_NEGATIVE     (1u << 2)  /* negative num/denum (updates.py:148-149, dicotomy.py:17-19) */
+#define ESPM_DEV_GW_BELOW_LS  (1u << 3)  /* some GW entry < log_shift: loss needs ESPM_FLAG_LOSS_DUAL */
+#define ESPM_DEV_GW_ZERO_ROW  (1u << 4)  /* some row of GW is all zero: updates need ESPM_FLAG_CLAMP_Y */
+
+/* layout of one scalar record (doubles), written by espm_h_scalars / espm_w_finish */
+enum {
+    ESPM_S_XLOGY = 0,     /* sum max(X,ls)*log(Y) of the iterate fed to the H pass (measures.py:503) */
+    ESPM_S_SUMY = 1,      /* sum Y = colsum(max(GW,ls)) . rowsum(max(H,ls)) (measures.py:502) */
+    ESPM_S_LOGREG = 2,    /* sum mu_k log(H+eps) (measures.py:548) */
+    ESPM_S_LAPL = 3,      /* sum H*(HL) (measures.py:577) */
+    ESPM_S_REL_H = 4,     /* base.py:324 for (H_cur, H_prev) */
+    ESPM_S_REL_W = 5,     /* base.py:323, written by espm_w_finish for (W_next, W_cur) */
+    ESPM_S_BISECT_ITS_H = 6, /* lock-step iteration count of the H bisection (dicotomy.py:152-171) */
+    ESPM_S_BISECT_ITS_W = 7,
+    ESPM_S_DEV_FLAGS = 8, /* copy of the device error word */
+    ESPM_S_MEAN_H = 9,
+    ESPM_S_MEAN_W = 10,
+    ESPM_S_GW_FLAGS = 11  /* ESPM_DEV_GW_* bits of the GW produced for the NEXT H pass */
+};
+
+/*
+ * One fit's device state.  Plain data; the Python host mirrors it with ctypes.Structure and rotates
+ * the W/H/GW buffer pointers between iterations.  All pointers are device pointers unless noted.
+ */
+typedef struct espm_state {
+    /* ---- sizes ---- */
+    int32_t n;          /* energy channels */
+    int32_t n_pad;      /* n rounded up to a whole number of pipeline stages */
+    int32_t m;          /* columns of G (== n when G is the identity) */
+    int32_t k;          /* phases (n_components) */
+    int32_t kp;         /* k padded to an instantiated kernel width (2,3,4,5,6,8,12,16) */
+    int32_t p_loc;      /* pixels owned by this rank */
+    int32_t p_pad;      /* n_tiles * 128: row stride of numraw / num / den */
+    int32_t n_tiles;    /* ceil(p_loc / 128) */
+    int32_t nx;         /* global image height (rows); 0 when shape_2d is None */
+    int32_t ny;         /* image width; 0 when shape_2d is None (identity Laplacian, base.py:289-291) */
+    int32_t row0;       /* first global image row owned by this rank */
+    int32_t halo;       /* elements available before/after the owned pixels in every H row (>= ny) */
+    int32_t ldh;        /* row stride of the H buffers, in elements */
+    int32_t x_dtype;    /* ESPM_F32 / ESPM_F64: storage of Xt */
+    int32_t c_dtype;    /* ESPM_F32 / ESPM_F64: arithmetic, and storage of every other array */
+    uint32_t flags;     /* ESPM_FLAG_* */
+    int32_t n_simplex_rows;
+    int32_t maxit;      /* maxit_dichotomy (conf.py:59) */
+    /* ---- launch plan (filled by espm_plan) ---- */
+    int32_t n_sms;
+    int32_t h_grid;     /* CTAs of the H pass */
+    int32_t h_nsplit;   /* channel splits of a tile in the H pass (partial ratio sums are added in h_finish) */
+    int32_t w_nb;       /* channel blocks of the W pass */
+    int32_t w_nr;       /* tile ranges of the W pass (grid = w_nb * w_nr) */
+    int32_t px_blocks;  /* CTAs of the per-pixel kernels (h_finish / h_apply) */
+    int32_t h_depth;    /* pipeline stages of the H pass */
+    int32_t w_depth;    /* pipeline stages of the W pass */
+    int32_t w_sacc_rows; /* channel rows of the W pass shared-memory accumulator */
+    int32_t h_smem;     /* dynamic shared memory bytes of the H pass */
+    int32_t w_smem;     /* dynamic shared memory bytes of the W pass */
+    int32_t reserved0;
+    int64_t p_total;    /* pixels of the whole image (all ranks), for mean(H) in rel_H (base.py:324) */
+    /* ---- hyper-parameters ---- */
+    double lambda_L;    /* smooth_nmf.py:58 */
+    double sigma;       /* gamma_ = sigmaL (smooth_nmf.py:293-294) */
+    double eps_reg;     /* epsilon_reg */
+    double log_shift;
+    double dicotomy_tol;
+    double dicotomy_tol_w; /* the W bisection uses the module constant (updates.py:64,67) */
+    double tol;         /* for rel_W / rel_H (base.py:323-324) */
+    double mu[ESPM_MAX_K];
+    /* ---- data ---- */
+    const void* Xt;         /* tile-major X (x dtype) */
+    const void* G;          /* n x m row-major (c dtype) or NULL when identity */
+    const void* Gt;         /* m x n row-major (G transposed) or NULL when identity */
+    const void* colsum_G;   /* m (c dtype) */
+    const void* W_cur;      /* m x k row-major */
+    void* W_next;
+    const void* GW_cur;     /* n_pad x kp */
+    const void* GWc_cur;    /* max(GW, ls), n_pad x kp (only read when ESPM_FLAG_LOSS_DUAL) */
+    void* GW_next;
+    void* GWc_next;
+    void* gwstats_cur;      /* 2*kp (c dtype): colsum(GW), colsum(max(GW,ls)) over the n real rows */
+    void* gwstats_next;
+    const void* H_prev;     /* k x ldh */
+    const void* H_cur;
+    void* H_next;
+    void* hstats_cur;       /* 3*kp doubles: rowsum(H), rowsum(max(H,ls)), rowmax(H)  (global) */
+    void* hstats_next;
+    const void* fixed_H;    /* k x ldh (negative = free) or NULL */
+    const void* fixed_W;    /* m x k or NULL */
+    const int32_t* simplex_rows; /* n_simplex_rows row indices of W or NULL */
+    /* ---- scratch ---- */
+    void* numraw;           /* h_nsplit x kp x p_loc */
+    void* num;              /* kp x p_loc */
+    void* den;              /* kp x p_loc */
+    void* s_part;           /* w_nr x n_pad x kp */
+    void* s_sum;            /* n_pad x kp: sum over tile ranges; all-reduced across ranks by the host */
+    void* t_mk;             /* m x k: G^T S (identity G: aliases s_sum semantics) */
+    void* w_num;            /* m x k scratch */
+    void* w_den;            /* m x k scratch */
+    double* xlogy_part;     /* h_grid */
+    double* px_part;        /* px_blocks x (4 + 3*kp) partials of the per-pixel kernels */
+    uint32_t* bisect_mask;  /* 4 words: bit j set <=> max|f_j| > tol somewhere (lock-step trace) */
+    uint32_t* dev_flags;    /* 4 words: [0] sticky ESPM_DEV_* error bits, [1] ESPM_DEV_GW_* of GW_next */
+    double* scalars;        /* ESPM_NSCALARS doubles: the record being filled */
+} espm_state;
+
+/* library / device */
+const char* espm_last_error(void);
+int espm_version(void);
+/* ABI self-check for bindings: out8 = {sizeof(espm_state), offsetof p_total, lambda_L, mu, Xt, H_prev,
+ * numraw, scalars}. */
+int espm_state_layout(int64_t* out8);
+/* number of usable CUDA devices; ESPM_ERR_NO_DEVICE if none (there is no CPU fallback). */
+int espm_device_count(void);
+/* fills n_pad, kp, n_tiles and the launch plan of `st` for the current device. */
+int espm_plan(espm_state* st);
+/* bytes of dynamic shared memory / CTAs per SM the H and W pass kernels will use (diagnostics). */
+int espm_plan_info(const espm_state* st, int32_t* info8);
+
+/*
+ * Upload helper: re-tile a device copy of X into Xt (replaces the host-side copy of base.py:262).
+ *   src: device pointer, element (c, j) at src[c*stride_c + j*stride_p] (so both the (n,p) layout of
+ *   base.py:246-247 and the transposed hyperspy layout of base.py:243-244 are accepted in place).
+ *   j0: first source pixel of this rank's shard.  `scale` multiplies every entry (normalize, base.py:267).
+ */
+int espm_retile_x(const espm_state* st, const void* src, int32_t src_dtype, int64_t stride_c,
+                  int64_t stride_p, int64_t j0, double scale, void* stream);
+
+/* GW_next = G.W_next (+pad rows), gwstats_next, ESPM_DEV_GW_* flags.  base.py:189, updates.py:107. */
+int espm_gw_prepare(const espm_state* st, void* stream);
+/* colsum_G[m] = sum_c G[c][m]  (updates.py:60). */
+int espm_colsum_g(const espm_state* st, void* colsum_out, void* stream);
+/* hstats_next = {rowsum, rowsum(max(.,ls)), rowmax} of H_next over the local pixels (updates.py:139). */
+int espm_h_stats(const espm_state* st, void* stream);
+
+/*
+ * H pass (updates.py:127-128 + measures.py:497-503): streams Xt once.
+ *   numraw[s][k][j] = sum_{c in split s} GW[c][k] * X[c][j] / (GW.H)[c][j]
+ *   xlogy_part[cta] = partial of sum max(X,ls)*log(Y) for (GW_cur, H_cur)
+ */
+int espm_h_pass(const espm_state* st, void* stream);
+/*
+ * Per-pixel assembly (updates.py:132-142): num, den with the log and Laplacian surrogates, the loss
+ * regularisers of the CURRENT iterate (measures.py:548,577), rel_H (base.py:324), and either
+ *   simplex_H: the bisection bracket and the lock-step trace mask (dicotomy.py:29-49, 138-171), or
+ *   otherwise: H_next = max(num/den, ls) (+fixed_H) directly (updates.py:152-155).
+ */
+int espm_h_finish(const espm_state* st, void* stream);
+/* Replays exactly it* bisection iterations (first clear bit of bisect_mask) and writes H_next. */
+int espm_h_apply(const espm_state* st, void* stream);
+/* Reduces the H-side partials into st->scalars (loss parts of the current iterate, rel_H, flags). */
+int espm_h_scalars(const espm_state* st, void* stream);
+
+/* W pass (updates.py:38-59, re-associated as G^T (R H^T)): streams Xt once with H_next.
+ *   s_part[r][c][k] = sum_{j in tile range r} X[c][j]/(GW.H_next)[c][j] * H_next[k][j]            */
+int espm_w_pass(const espm_state* st, void* stream);
+/* s_sum = sum_r s_part[r]  (fixed order => deterministic). */
+int espm_w_reduce(const espm_state* st, void* stream);
+/* hstats_next from the per-pixel partials; W_next (updates.py:59-76, incl. simplex_W bisection and
+ * fixed_W), rel_W, then GW_next / gwstats_next for the next H pass.  Single CTA. */
+int espm_w_finish(const espm_state* st, void* stream);
+
+/* Standalone operator used by the unit-level API: nu = dichotomy_simplex(num, den) (dicotomy.py:4-55).
+ * num/den: k x p (c dtype, row stride p), nu_out: p.  its_out (device int32) receives it*. */
+int espm_dichotomy_simplex(int32_t c_dtype, int32_t k, int64_t p, const void* num, const void* den,
+                           double log_shift, double tol, int32_t maxit, void* nu_out,
+                           uint32_t* mask4, uint32_t* dev_flags, int32_t* its_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ESPM_B200_H */

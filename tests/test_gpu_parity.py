@@ -1,0 +1,359 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the golden vectors produced by the
+unmodified reference and against the oracle on seeded inputs.
+
+Tolerances (BASELINE.json north_star): one update step within 1e-10 relative in fp64 and 1e-5 in fp32;
+loss trajectory and final W/H within 1e-4 relative after max_iter.
+"""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+STEP_TOL_F64 = 1e-10
+STEP_TOL_F32 = 1e-5
+TRAJ_TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from espm_b200 import ops as _ops
+    return _ops
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import smooth_nmf_oracle
+    return smooth_nmf_oracle
+
+
+# ---------------------------------------------------------------------------------- single steps
+def test_step_h_golden(ops, golden_steps):
+    g = golden_steps
+    X, G, W, H = g["X"], g["G"], g["W0"], g["H0"]
+    nx, ny = int(g["nx"]), int(g["ny"])
+    Lg = ops.create_laplacian_matrix(nx, ny)
+    assert rel_err(ops.multiplicative_step_h(X, G, W, H, simplex_H=True), g["h_simplex"]) < STEP_TOL_F64
+    assert rel_err(ops.multiplicative_step_h(X, G, W, H, simplex_H=False), g["h_plain"]) < STEP_TOL_F64
+    assert rel_err(ops.multiplicative_step_h(X, G, W, H, simplex_H=False, log_shift=0), g["h_plain_ls0"]) < STEP_TOL_F64
+    out = ops.multiplicative_step_h(X, G, W, H, simplex_H=True, mu=g["mu_vec"], lambda_L=2.0, L=Lg)
+    assert rel_err(out, g["h_simplex_mu_lap"]) < STEP_TOL_F64
+    out = ops.multiplicative_step_h(X, G, W, H, simplex_H=False, mu=0.07, lambda_L=0.5, L=Lg, epsilon_reg=0.5,
+                                    sigmaL=6.0)
+    assert rel_err(out, g["h_plain_mu_scalar_lap"]) < STEP_TOL_F64
+    out = ops.multiplicative_step_h(X, G, W, H, simplex_H=True, fixed_H=g["fixed_H"])
+    assert rel_err(out, g["h_simplex_fixed"]) < STEP_TOL_F64
+    out = ops.multiplicative_step_h(X, G, W, H, simplex_H=True, dicotomy_tol=1e-8)
+    assert rel_err(out, g["h_simplex_tol1e-8"]) < STEP_TOL_F64
+    # identity "Laplacian" given as the reference's own sparse matrix
+    from scipy.sparse import identity
+    out = ops.multiplicative_step_h(X, G, W, H, simplex_H=True, lambda_L=2.0, L=identity(nx * ny, format="csr"))
+    assert rel_err(out, g["h_simplex_lap_identity"]) < STEP_TOL_F64
+    with pytest.raises(ValueError):
+        ops.multiplicative_step_h(X, G, W, H, lambda_L=1.0, L=None)
+
+
+def test_step_h_accepts_reference_sparse_laplacian(ops, golden_steps):
+    g = golden_steps
+    from scipy.sparse import csr_matrix
+    Lref = csr_matrix(g["L_dense"])
+    out = ops.multiplicative_step_h(g["X"], g["G"], g["W0"], g["H0"], simplex_H=True, mu=g["mu_vec"], lambda_L=2.0,
+                                    L=Lref)
+    assert rel_err(out, g["h_simplex_mu_lap"]) < STEP_TOL_F64
+
+
+def test_step_w_golden(ops, golden_steps):
+    g = golden_steps
+    X, G, W, H1 = g["X"], g["G"], g["W0"], g["h_simplex"]
+    assert rel_err(ops.multiplicative_step_w(X, G, W, H1, simplex_W=False), g["w_plain"]) < STEP_TOL_F64
+    assert rel_err(ops.multiplicative_step_w(X, G, W, H1, simplex_W=True), g["w_simplex"]) < STEP_TOL_F64
+    assert rel_err(ops.multiplicative_step_w(X, G, W, H1, simplex_W=False, fixed_W=g["fixed_W"]),
+                   g["w_fixed"]) < STEP_TOL_F64
+
+    class Rows:
+        def NMF_simplex(self):
+            return [int(v) for v in g["simplex_rows"]]
+
+    out = ops.multiplicative_step_w(X, G, W, H1, simplex_W=True, physics_model=Rows())
+    assert rel_err(out, g["w_simplex_rows"]) < STEP_TOL_F64
+
+
+def test_identity_G_steps(ops, golden_identity):
+    g = golden_identity
+    X, W, H = g["X"], g["W0"], g["H0"]
+    h = ops.multiplicative_step_h(X, None, W, H, simplex_H=False)
+    assert rel_err(h, g["h_plain"]) < STEP_TOL_F64
+    # a dense identity is recognised and takes the same fast path
+    h2 = ops.multiplicative_step_h(X, np.eye(X.shape[0]), W, H, simplex_H=False)
+    assert np.array_equal(h, h2)
+    assert rel_err(ops.multiplicative_step_w(X, None, W, g["h_plain"], simplex_W=True), g["w_simplex"]) < STEP_TOL_F64
+
+
+def test_losses_golden(ops, golden_steps):
+    g = golden_steps
+    GW = g["G"] @ g["W0"]
+    nx, ny = int(g["nx"]), int(g["ny"])
+    assert rel_err(ops.KLdiv_loss(g["X"], GW, g["H0"]), g["kl_loss"]) < 1e-12
+    assert rel_err(ops.KLdiv_loss(g["X"], GW, g["H0"], average=True), g["kl_loss_avg"]) < 1e-12
+    assert rel_err(ops.log_reg(g["H0"], g["mu_vec"], 1.0), g["log_reg"]) < 1e-12
+    assert rel_err(ops.log_reg(g["H0"], 0.3, 0.5), g["log_reg_scalar"]) < 1e-12
+    assert rel_err(ops.trace_xtLx(ops.create_laplacian_matrix(nx, ny), g["H0"].T), g["trace_xtLx"]) < 1e-12
+    # known answers of the reference's test_measures.py:212-221
+    Lg = ops.create_laplacian_matrix(4, 5)
+    assert abs(ops.trace_xtLx(Lg, np.ones((20, 1)))) < 1e-14
+    bump = np.zeros((20, 1))
+    bump[6] = 1.0   # interior pixel (row 1, col 1): 4 neighbours
+    assert abs(ops.trace_xtLx(Lg, bump) - 4.0) < 1e-14
+
+
+def test_bisection_golden(ops, golden_bisect):
+    g = golden_bisect
+    nu, its = ops.dichotomy_simplex(g["num"], g["den"], 1e-14, 1e-5, return_its=True)
+    # same bracket, same lock-step iteration count, IEEE arithmetic -> identical to the reference
+    assert rel_err(nu, g["nu"]) < 1e-13
+    assert rel_err(ops.dichotomy_simplex(g["num"], g["den"], 1e-14, 1e-9), g["nu_tol1e-9"]) < 1e-13
+    assert rel_err(ops.dichotomy_simplex(g["num"], g["den"], 0, 1e-6), g["nu_ls0"]) < 1e-13
+    f = np.sum(np.maximum(g["num"] / (g["den"] + nu), 1e-14), axis=0) - 1
+    assert np.max(np.abs(f)) <= 1e-5
+    with pytest.raises(ValueError):
+        ops.dichotomy_simplex(np.ones((4, 2)), np.ones((4, 2)), log_shift=0.3)
+
+
+def test_bisection_lockstep_count_matches_oracle(ops, orc):
+    rng = np.random.default_rng(11)
+    for k, p in ((3, 1000), (5, 4097), (8, 300), (1, 17)):
+        num = rng.uniform(size=(k, p)) * (rng.uniform(size=(k, p)) > 0.2)
+        num[0] += 1e-3
+        den = rng.uniform(size=(k, p)) + 0.01
+        ref, its_ref = orc.dichotomy_simplex(num.copy(), den.copy(), 1e-14, 1e-5, return_its=True)
+        nu, its = ops.dichotomy_simplex(num, den, 1e-14, 1e-5, return_its=True)
+        assert its == its_ref
+        assert rel_err(nu, ref) < 1e-12
+
+
+def test_bisection_properties_from_reference_tests(ops):
+    # reference test_updates.py:93-100: 1x1 closed form
+    rng = np.random.default_rng(3)
+    num = rng.uniform(size=(1, 1)) + 1
+    den = rng.uniform(size=(1, 1))
+    sol = ops.dichotomy_simplex(num, den, 0, tol=1e-8)
+    assert abs((num - den)[0, 0] - sol[0]) < 2e-8
+    # zero entries stress (test_updates.py:200-249 style)
+    num = rng.uniform(size=(6, 500))
+    num[rng.uniform(size=num.shape) < 0.6] = 0
+    num[0] += 0.5
+    den = rng.uniform(size=(6, 500))
+    nu = ops.dichotomy_simplex(num, den, 1e-14, tol=1e-6)
+    f = np.sum(np.maximum(num / (den + nu), 1e-14), axis=0) - 1
+    assert np.max(np.abs(f)) <= 1e-6
+
+
+# ---------------------------------------------------------------------------------- seeded vs oracle
+def _problem(rng, n, nx, ny, k, m, counts=20.0, dtype=np.float64):
+    p = nx * ny
+    x = np.linspace(0, 1, n)
+    G = np.zeros((n, m))
+    for j in range(m - 2):
+        c, s = rng.uniform(0.05, 0.95), rng.uniform(0.01, 0.04)
+        G[:, j] = np.exp(-0.5 * ((x - c) / s) ** 2)
+    G[:, m - 2] = np.exp(-3 * x) + 0.05
+    G[:, m - 1] = (1 - x) * 0.5 + 0.05
+    Wt = rng.uniform(size=(m, k))
+    Ht = rng.uniform(size=(k, p)) ** 2
+    Ht /= Ht.sum(0, keepdims=True)
+    lam = G @ Wt @ Ht
+    X = rng.poisson(lam / lam.sum(0, keepdims=True) * counts).astype(dtype)
+    W0 = rng.uniform(0.05, 1.0, size=(m, k))
+    H0 = rng.uniform(0.05, 1.0, size=(k, p))
+    H0 /= H0.sum(0, keepdims=True)
+    return X, G, W0, H0
+
+
+@pytest.mark.parametrize("n,nx,ny,k,m", [(1980, 80, 80, 3, 11), (517, 33, 19, 5, 7), (64, 3, 130, 2, 4),
+                                         (300, 16, 16, 8, 12), (40, 1, 1, 3, 5)])
+def test_one_iteration_vs_oracle_fp64(ops, orc, n, nx, ny, k, m):
+    rng = np.random.default_rng(n + k)
+    X, G, W0, H0 = _problem(rng, n, nx, ny, k, m)
+    shape = (nx, ny) if nx > 1 and ny > 1 else None
+    Lg = ops.create_laplacian_matrix(nx, ny) if shape else None
+    lam = 2.0 if shape else 0.0
+    ref_h, its_ref = orc.multiplicative_step_h(X, G, W0, H0, simplex_H=True, mu=0.05, lambda_L=lam, shape_2d=shape,
+                                               return_its=True)
+    h, its = ops.multiplicative_step_h(X, G, W0, H0, simplex_H=True, mu=0.05, lambda_L=lam, L=Lg, return_its=True)
+    assert its == its_ref
+    assert rel_err(h, ref_h) < STEP_TOL_F64
+    assert np.max(np.abs(h.sum(0) - 1)) <= 1e-5 * 1.0001
+    ref_w = orc.multiplicative_step_w(X, G, W0, ref_h, simplex_W=False)
+    assert rel_err(ops.multiplicative_step_w(X, G, W0, ref_h, simplex_W=False), ref_w) < STEP_TOL_F64
+    # loss of the initial iterate
+    val, det = ops.full_loss(X, G, W0, H0, mu=0.05, lambda_L=lam, shape_2d=shape, const=orc.const_KL(X))
+    ref_val, ref_det = orc.full_loss(X, G, W0, H0, mu=0.05, lambda_L=lam, shape_2d=shape)
+    assert rel_err(val, ref_val) < 1e-11
+    assert rel_err(det, ref_det[:3]) < 1e-10
+
+
+@pytest.mark.parametrize("n,nx,ny,k,m", [(1980, 80, 80, 3, 11), (300, 16, 16, 8, 12)])
+def test_one_iteration_vs_oracle_fp32(ops, orc, n, nx, ny, k, m):
+    """fp32 mode: X, G, W, H all float32 -> fp32 kernels; compared with the fp64 oracle on the same
+    fp32-rounded inputs."""
+    rng = np.random.default_rng(n + k + 1)
+    X, G, W0, H0 = [a.astype(np.float32) for a in _problem(rng, n, nx, ny, k, m)]
+    Lg = ops.create_laplacian_matrix(nx, ny)
+    args64 = [a.astype(np.float64) for a in (X, G, W0, H0)]
+    ref_h = orc.multiplicative_step_h(*args64, simplex_H=True, mu=0.05, lambda_L=2.0, shape_2d=(nx, ny))
+    h = ops.multiplicative_step_h(X, G, W0, H0, simplex_H=True, mu=0.05, lambda_L=2.0, L=Lg)
+    assert h.dtype == np.float32
+    # the fp32 lock-step count may differ by rounding from the fp64 one: nu moves by <= tol-level amounts
+    assert rel_err(h, ref_h) < 2e-4
+    ref_plain = orc.multiplicative_step_h(*args64, simplex_H=False, mu=0.05, lambda_L=2.0, shape_2d=(nx, ny))
+    h_plain = ops.multiplicative_step_h(X, G, W0, H0, simplex_H=False, mu=0.05, lambda_L=2.0, L=Lg)
+    assert rel_err(h_plain, ref_plain) < STEP_TOL_F32
+    ref_w = orc.multiplicative_step_w(args64[0], args64[1], args64[2], ref_plain, simplex_W=False)
+    w = ops.multiplicative_step_w(X, G, W0, ref_plain.astype(np.float32), simplex_W=False)
+    assert rel_err(w, ref_w) < STEP_TOL_F32
+    val, _ = ops.full_loss(X, G, W0, H0, mu=0.05, lambda_L=2.0, shape_2d=(nx, ny), const=orc.const_KL(args64[0]))
+    ref_val, _ = orc.full_loss(*args64, mu=0.05, lambda_L=2.0, shape_2d=(nx, ny))
+    assert rel_err(val, ref_val) < STEP_TOL_F32
+
+
+def test_mixed_mode_fp32_storage_fp64_math(ops, orc):
+    """X float32 with G float64: the reference computes in float64 on the fp32 data."""
+    rng = np.random.default_rng(5)
+    X, G, W0, H0 = _problem(rng, 200, 12, 11, 4, 6)
+    X32 = X.astype(np.float32)
+    ref = orc.multiplicative_step_h(X32.astype(np.float64), G, W0, H0, simplex_H=True)
+    h = ops.multiplicative_step_h(X32, G, W0, H0, simplex_H=True)
+    assert h.dtype == np.float64
+    assert rel_err(h, ref) < STEP_TOL_F64
+
+
+# ---------------------------------------------------------------------------------- full fits
+FIT_CASES = {
+    "c1": dict(simplex_H=True, simplex_W=False),
+    "c2": dict(simplex_H=True, simplex_W=False, lambda_L=2.0, mu=0.05),
+    "c2b": dict(simplex_H=True, simplex_W=False, lambda_L=1.0, mu=np.array([0.0, 0.1, 0.3]), shape_2d=None),
+    "sw": dict(simplex_H=False, simplex_W=True, lambda_L=0.5),
+    "none": dict(simplex_H=False, simplex_W=False),
+    "norm": dict(simplex_H=True, simplex_W=False, normalize=True, mu=0.02),
+    "stop": dict(simplex_H=True, simplex_W=False, tol=2e-3, max_iter=200, no_stop_criterion=False),
+}
+
+
+def _fit(tag_kwargs, g, prefix="A__", verbose=0, **extra):
+    from espm_b200 import SmoothNMF
+    kw = dict(tol=0, no_stop_criterion=True, max_iter=12, verbose=verbose,
+              shape_2d=tuple(int(v) for v in g["A__shape"]))
+    kw.update(tag_kwargs)
+    kw.update(extra)
+    W0 = g[prefix + "W0"]
+    est = SmoothNMF(n_components=W0.shape[1], G=g["A__G"] if prefix == "A__" else None, **kw)
+    out = est.fit_transform(g[prefix + "X"], W=W0.copy(), H=g[prefix + "H0"].copy())
+    return est, out
+
+
+@pytest.mark.parametrize("tag", sorted(FIT_CASES))
+@pytest.mark.parametrize("verbose", [0, 1])
+def test_fit_trajectory_golden(golden_fits, tag, verbose, capsys):
+    """Both loop variants (batched scalars for verbose=0 + no_stop_criterion, checked otherwise)."""
+    g = golden_fits
+    est, out = _fit(FIT_CASES[tag], g, verbose=verbose)
+    assert est.n_iter_ == int(g[tag + "__n_iter"])
+    assert rel_err(est.losses_, g[tag + "__losses"]) < TRAJ_TOL
+    assert rel_err(est.losses_, g[tag + "__losses"]) < 1e-9      # what we actually get in fp64
+    assert rel_err(np.array(est.rel_), g[tag + "__rel"]) < 1e-6
+    assert rel_err(est.W_, g[tag + "__W"]) < 1e-8
+    assert rel_err(est.H_, g[tag + "__H"]) < 1e-8
+    assert rel_err(out, g[tag + "__out"]) < 1e-8
+    assert rel_err(est.reconstruction_err_, g[tag + "__rec"]) < 1e-9
+    det = np.array(est.detailed_losses_, dtype=float)
+    np.testing.assert_allclose(det[:, :3], g[tag + "__detailed"][:, :3], rtol=1e-8, atol=1e-16)
+    names = est.get_losses().dtype.names
+    assert names == ("full_loss", "KL_div_loss", "log_reg_loss", "Lapl_reg_loss", "gamma", "rel_W", "rel_H")
+
+
+def test_fit_fixed_entries(golden_fits):
+    g = golden_fits
+    est, _ = _fit(dict(simplex_H=True, simplex_W=False, fixed_H=g["A__fixed_H"], fixed_W=g["A__fixed_W"]), g)
+    assert rel_err(est.losses_, g["fixed__losses"]) < 1e-9
+    assert rel_err(est.H_, g["fixed__H"]) < 1e-8
+    fh, fw = g["A__fixed_H"], g["A__fixed_W"]
+    assert np.array_equal(est.H_[fh >= 0], fh[fh >= 0])       # honoured exactly (test_estimators.py:155-166)
+    assert np.array_equal(est.W_[fw >= 0], fw[fw >= 0])
+
+
+def test_fit_identity_G_fp64_and_fp32(golden_fits):
+    g = golden_fits
+    est, _ = _fit(dict(simplex_H=False, simplex_W=True, shape_2d=(6, 7)), g, prefix="I__")
+    assert rel_err(est.losses_, g["c5__losses"]) < 1e-9
+    assert rel_err(est.W_, g["c5__W"]) < 1e-8
+    assert rel_err(est.H_, g["c5__H"]) < 1e-8
+    from espm_b200 import SmoothNMF
+    est32 = SmoothNMF(n_components=4, G=None, simplex_H=False, simplex_W=True, shape_2d=(6, 7), tol=0,
+                      no_stop_criterion=True, max_iter=12, verbose=0)
+    est32.fit_transform(g["I__X"].astype(np.float32), W=g["I__W0"].astype(np.float32),
+                        H=g["I__H0"].astype(np.float32))
+    assert est32.W_.dtype == np.float32
+    # vs the fp64 trajectory (tolerance of the north star) and vs the reference's own fp32 run
+    assert rel_err(est32.losses_, g["c5__losses"]) < TRAJ_TOL
+    assert rel_err(est32.W_, g["c5__W"]) < TRAJ_TOL * 10
+    assert rel_err(est32.losses_, g["c5f32__losses"]) < 1e-3
+
+
+def test_fit_hyperspy_layout(golden_fits):
+    g = golden_fits
+    from espm_b200 import SmoothNMF
+    est = SmoothNMF(n_components=3, G=g["A__G"], simplex_H=True, simplex_W=False, hspy_comp=True, lambda_L=1.0,
+                    shape_2d=tuple(int(v) for v in g["A__shape"]), tol=0, no_stop_criterion=True, max_iter=12,
+                    verbose=0)
+    out = est.fit_transform(np.ascontiguousarray(g["A__X"].T), W=g["A__W0"].copy(), H=g["A__H0"].copy())
+    assert rel_err(est.losses_, g["hspy__losses"]) < 1e-9
+    assert rel_err(out, g["hspy__out"]) < 1e-8                 # returns H.T (base.py:415-417)
+    assert rel_err(est.components_, g["hspy__components"]) < 1e-8
+
+
+def test_fit_physical_model_refresh(golden_fits):
+    """G refresh every 3rd iteration through the PhysicalModel callbacks (base.py:388-392)."""
+    g = golden_fits
+    G0 = g["A__G"].copy()
+
+    class FakeModel:
+        def __init__(self):
+            self.G = G0.copy()
+
+        def NMF_initialize_W(self, D):
+            return np.abs(np.linalg.lstsq(self.G, D, rcond=None)[0])
+
+        def NMF_simplex(self):
+            return list(range(G0.shape[1] - 2))
+
+        def NMF_update(self, W=None):
+            if W is None:
+                return self.G
+            s = np.mean(W[self.NMF_simplex(), :])
+            newG = self.G.copy()
+            newG[:, -2] = G0[:, -2] * (1.0 + 0.3 * np.tanh(5 * s))
+            newG[:, -1] = G0[:, -1] * (1.0 - 0.2 * np.tanh(3 * s))
+            self.G = newG
+            return self.G
+
+    from espm_b200 import SmoothNMF
+    est = SmoothNMF(n_components=3, G=FakeModel(), simplex_H=False, simplex_W=True, lambda_L=0.3,
+                    shape_2d=tuple(int(v) for v in g["A__shape"]), tol=0, no_stop_criterion=True, max_iter=12,
+                    verbose=0)
+    est.fit_transform(g["A__X"], W=g["A__W0"].copy(), H=g["A__H0"].copy())
+    assert rel_err(est.losses_, g["pm__losses"]) < 1e-9
+    assert rel_err(est.W_, g["pm__W"]) < 1e-8
+    assert rel_err(est.G_, g["pm__G"]) < 1e-12
+
+
+def test_unsupported_variants_fail_loudly():
+    from espm_b200 import SmoothNMF
+    X = np.random.default_rng(0).poisson(3.0, size=(20, 12)).astype(float)
+    for kw in (dict(algo="bmd"), dict(algo="projected_gradient"), dict(algo="l2_surrogate", l2=True)):
+        with pytest.raises(NotImplementedError):
+            SmoothNMF(n_components=2, max_iter=2, verbose=0, **kw).fit_transform(X)
+    with pytest.raises(ValueError):
+        SmoothNMF(n_components=2, max_iter=2, verbose=0).fit_transform(-X)
