@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""Benchmark of the SmoothNMF fit loop (BASELINE.json metric): iterations/s and fraction of the HBM
+roofline on a synthetic EDXS spectrum image.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C3] [--dtype f32|f64]
+    python bench.py --impl reference ...        # the reference algorithm (oracle port) on the host CPU
+
+One "step" = one full SmoothNMF iteration (H update incl. lock-step bisection, W update, loss, rel-change)
+on X resident in HBM.  Prints ONE JSON line on rank 0.  For N > 1 launch with torch.distributed.run; the
+image rows are sharded over the ranks (strong scaling: the image is fixed).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: nx, ny, n, k, n_elements, estimator kwargs            (BASELINE.json configs[0..2])
+    "C1": dict(nx=80, ny=80, n=1980, k=3, n_elements=9, kw=dict(simplex_H=True, simplex_W=False)),
+    "C2": dict(nx=256, ny=256, n=2048, k=3, n_elements=9,
+               kw=dict(simplex_H=True, simplex_W=False, lambda_L=2.0, mu=0.05)),
+    "C3": dict(nx=512, ny=512, n=2048, k=4, n_elements=25,
+               kw=dict(simplex_H=True, simplex_W=False, lambda_L=2.0, mu=0.05)),
+}
+KERNELS_PER_ITER = 7   # h_pass, h_finish, h_scalars, h_apply, w_pass, w_reduce, w_finish
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                if out.returncode == 0 and out.stdout.strip():
+                    self.samples.append([v.strip() for v in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=5)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for i, nm in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_baseline(prob, wl, X_crop, rows_crop, steps, seed):
+    """The reference algorithm (oracle port, NumPy + BLAS threads) on a crop of the same image.
+    Every operation of the reference is linear in the pixel count, so it/s scales as p_crop / p."""
+    from oracle import smooth_nmf_oracle as orc
+    from espm_b200 import synth
+    nx, ny, k = wl["nx"], wl["ny"], wl["k"]
+    p_crop = rows_crop * ny
+    W0, H0 = synth.init_factors(prob["G_full"].shape[1], k, nx * ny, seed)
+    kw = dict(wl["kw"])
+    kw.update(tol=0, no_stop_criterion=True, shape_2d=(rows_crop, ny))
+    orc.fit(X_crop, prob["G_full"], W0, H0[:, :p_crop], max_iter=1, **kw)       # warm-up (BLAS threads, pages)
+    t0 = time.perf_counter()
+    orc.fit(X_crop, prob["G_full"], W0, H0[:, :p_crop], max_iter=steps, **kw)
+    dt = time.perf_counter() - t0
+    its_crop = steps / dt
+    return its_crop * p_crop / (nx * ny), its_crop, dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--seed", type=int, default=93)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-rows", type=int, default=8, help="image rows of the CPU-baseline crop")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    nx, ny, n, k = wl["nx"], wl["ny"], wl["n"], wl["k"]
+    p = nx * ny
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    W = max(args.warmup, 3)
+    K = max(args.steps, 1)
+    from espm_b200 import synth
+    prob = synth.make_problem(nx, ny, n, k, wl["n_elements"], seed=args.seed)
+    np_dtype = np.float32 if args.dtype == "f32" else np.float64
+    config = {"workload": "%s: %dx%d px x %d ch synthetic EDXS, %d phases, G %dx%d, %s" % (
+        args.workload, nx, ny, n, k, n, prob["G_full"].shape[1],
+        ", ".join("%s=%s" % kv for kv in sorted(wl["kw"].items()))),
+        "x_dtype": args.dtype, "sharding": "image rows over %d rank(s)" % world,
+        "l2": "inputs (%.2f GB of X per pass) are larger than L2; no flush needed" % (n * p * np_dtype().itemsize / 1e9)}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        rows = min(args.cpu_rows, nx)
+        X_crop = synth.poisson_X_numpy(prob, 0, rows * ny, args.seed, dtype=np_dtype)
+        steps = max(1, min(K, 20))
+        val, its_crop, dt = cpu_baseline(prob, wl, X_crop, rows, steps, args.seed)
+        cores = os.cpu_count()
+        line = {"impl": "reference", "metric": "smoothnmf_iterations_per_s", "value": val, "unit": "it/s",
+                "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": 1e3 / val,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": "it/s", "cores": cores, "kind": "port",
+                                 "sample": "oracle port of the reference (NumPy/OpenBLAS, all host threads) on the first "
+                                           "%d of %d image rows (%d px x %d ch), %d iterations in %.1f s = %.3f it/s on the "
+                                           "crop, scaled by p_crop/p (every reference op is linear in p)" % (
+                                               rows, nx, rows * ny, n, steps, dt, its_crop)},
+                "e2e": {"value": val, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm (GPU)
+    import torch
+    import torch.distributed as dist
+    from espm_b200 import _lib as L
+    from espm_b200.engine import FitEngine
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    shard = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        from espm_b200.dist import Shard, shard_bounds
+        shard = Shard()
+        j0, j1, _ = shard_bounds(p, nx, ny, rank, world)
+    else:
+        j0, j1 = 0, p
+    tdt = torch.float32 if args.dtype == "f32" else torch.float64
+    X_loc = synth.poisson_X_torch(prob, j0, j1, args.seed, dev, tdt)
+    W0, H0 = synth.init_factors(prob["G_full"].shape[1], k, p, args.seed, dtype=np_dtype)
+    G = prob["G_full"].astype(np_dtype)
+    eng = FitEngine(X_loc, G, W0, H0, shape_2d=(nx, ny), max_records=W + K + 8, shard=shard, x_local=True,
+                    tol=0.0, **wl["kw"])
+    x_bytes_total = n * p * np_dtype().itemsize
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    eng.evaluate(0)
+    for i in range(1, W + 1):
+        eng.advance(i)
+        eng.evaluate(i)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    eng.profile = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(W + 1, W + K + 1):
+        eng.advance(i)
+        eng.evaluate(i)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ms = e0.elapsed_time(e1)
+    prof = eng.profile
+    eng.profile = None
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms = float(t_ms.item())
+    value = K / (ms * 1e-3)
+
+    # per-kernel durations of the two X passes inside the timed region
+    def mean_ms(name):
+        ev = prof.get(name, [])
+        return float(np.mean([a.elapsed_time(b) for a, b in ev])) if ev else float("nan")
+
+    h_ms, w_ms = mean_ms("h_pass"), mean_ms("w_pass")
+    peak, peak_src = load_peaks()
+    bytes_launch = x_bytes_total / world          # algorithmic bytes one launch streams on this rank
+    dom = "h_pass" if h_ms >= w_ms else "w_pass"
+    dom_ms = max(h_ms, w_ms)
+    achieved = bytes_launch / (dom_ms * 1e-3) / 1e9
+    recs = eng.read_records(W + K, W + K + 1)[0]
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "bytes_per_launch": bytes_launch,
+                "h_pass_ms": h_ms, "w_pass_ms": w_ms,
+                "h_pass_gbs": bytes_launch / (h_ms * 1e-3) / 1e9, "w_pass_gbs": bytes_launch / (w_ms * 1e-3) / 1e9,
+                "iteration_frac": (2 * bytes_launch / (ms / K * 1e-3) / 1e9) / peak}
+
+    # ------------------------------------------------------------------ end to end through the public API
+    e2e = None
+    if not args.no_e2e:
+        import espm_b200
+        from espm_b200 import SmoothNMF
+        del eng
+        torch.cuda.empty_cache()
+        # the user's host buffer: the whole image in pinned host memory (every rank reads its own rows)
+        X_host = torch.empty((n, p), dtype=tdt, pin_memory=True)
+        X_host[:, j0:j1].copy_(X_loc)
+        if world > 1:
+            # assemble the full image on every rank, as a user would hold it
+            parts = [torch.empty((n, b - a), dtype=tdt, device=dev) for a, b in
+                     [shard_bounds(p, nx, ny, r, world)[:2] for r in range(world)]]
+            dist.all_gather(parts, X_loc)
+            for r, part in enumerate(parts):
+                a, b, _ = shard_bounds(p, nx, ny, r, world)
+                X_host[:, a:b].copy_(part)
+            del parts
+        del X_loc
+        torch.cuda.synchronize()
+        espm_b200.config.distributed = world > 1
+        est = SmoothNMF(n_components=k, G=G, shape_2d=(nx, ny), tol=0.0, no_stop_criterion=True, max_iter=K,
+                        verbose=0, **wl["kw"])
+        import contextlib
+        import io
+        barrier()
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            est.fit_transform(X_host.numpy(), W=W0.copy(), H=H0.copy())
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        dt = float(t_e.item())
+        e2e = {"value": K / dt, "unit": "it/s",
+               "h2d_bytes_per_step": (x_bytes_total + (W0.nbytes + H0.nbytes + G.nbytes) * world) / K,
+               "d2h_bytes_per_step": (est.W_.nbytes + est.H_.nbytes + (K + 1) * L.NSCALARS * 8 * world) / K,
+               "what": "SmoothNMF.fit_transform(X in pinned host memory, max_iter=%d): H2D of X + re-tiling + %d "
+                       "iterations + D2H of W, H and the loss history; wall time %.3f s" % (K, K, dt),
+               "final_loss": float(est.losses_[-1])}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        rows = min(args.cpu_rows, nx)
+        X_crop = synth.poisson_X_numpy(prob, 0, rows * ny, args.seed, dtype=np_dtype)
+        val, its_crop, dtc = cpu_baseline(prob, wl, X_crop, rows, 6, args.seed)
+        cpu = {"value": val, "unit": "it/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": "oracle port of the reference (NumPy/OpenBLAS, all host threads) on the first %d of %d image "
+                         "rows (%d px x %d ch), 6 iterations in %.1f s = %.3f it/s on the crop, scaled by p_crop/p" % (
+                             rows, nx, rows * ny, n, dtc, its_crop)}
+
+    line = {"metric": "smoothnmf_iterations_per_s", "value": value, "unit": "it/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic", "config": config, "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": e2e, "gpu_launches": KERNELS_PER_ITER * K, "clocks": clocks,
+            "check": {"loss_kl_sumY": float(recs[L.S_SUMY]), "bisect_its_H": float(recs[L.S_BISECT_ITS_H]),
+                      "dev_flags": float(recs[L.S_DEV_FLAGS])}}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

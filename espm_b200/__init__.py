@@ -5,8 +5,9 @@ Drop-in for ``espm.estimators.SmoothNMF`` and for the update / bisection / loss 
 All arithmetic runs in hand-written CUDA kernels (``espm_b200/csrc``) behind the C ABI declared in
 ``include/espm_b200.h``; there is no CPU fallback.
 """
+from . import config  # noqa: F401
 from .estimators import SmoothNMF  # noqa: F401
 from . import ops  # noqa: F401
 
-__all__ = ["SmoothNMF", "ops"]
+__all__ = ["SmoothNMF", "ops", "config"]
 __version__ = "0.1.0"

@@ -293,7 +293,15 @@ __global__ void __launch_bounds__(PX_THREADS) h_finish_kernel(const espm_state s
                     num_o[(size_t)kk * st.p_pad + j] = num[kk];
                     den_o[(size_t)kk * st.p_pad + j] = den[kk];
                 }
-            simplex_trace<TC, KP>(num, den, k, ls, (TC)st.dicotomy_tol, st.maxit, bits, err);
+            // The bisection itself always runs in fp64 (k x p data, negligible cost): in fp32 mode this
+            // keeps the lock-step iteration count and nu aligned with the fp64 reference.
+            double numd[KP], dend[KP];
+#pragma unroll
+            for (int kk = 0; kk < KP; ++kk) {
+                numd[kk] = (double)num[kk];
+                dend[kk] = (double)den[kk];
+            }
+            simplex_trace<double, KP>(numd, dend, k, st.log_shift, st.dicotomy_tol, st.maxit, bits, err);
         } else {
             TC hn[KP];  // updates.py:152 with nu = 0
 #pragma unroll
@@ -321,17 +329,19 @@ __global__ void __launch_bounds__(PX_THREADS) h_apply_kernel(const espm_state st
     for (int kk = 0; kk < KP; ++kk) vals[3 + 2 * KP + kk] = -1e300;
     const int its = first_clear_bit(st.bisect_mask, st.maxit);
     if (j < st.p_loc) {
-        TC num[KP], den[KP], hn[KP];
+        double num[KP], den[KP];
+        TC hn[KP];
         const TC* num_i = reinterpret_cast<const TC*>(st.num);
         const TC* den_i = reinterpret_cast<const TC*>(st.den);
 #pragma unroll
         for (int kk = 0; kk < KP; ++kk) {
-            num[kk] = (kk < k) ? num_i[(size_t)kk * st.p_pad + j] : TC(0);
-            den[kk] = (kk < k) ? den_i[(size_t)kk * st.p_pad + j] : TC(1);
+            num[kk] = (kk < k) ? (double)num_i[(size_t)kk * st.p_pad + j] : 0.0;
+            den[kk] = (kk < k) ? (double)den_i[(size_t)kk * st.p_pad + j] : 1.0;
         }
-        const TC nu = simplex_replay<TC, KP>(num, den, k, ls, its);
+        const double nu = simplex_replay<double, KP>(num, den, k, st.log_shift, its);
 #pragma unroll
-        for (int kk = 0; kk < KP; ++kk) hn[kk] = (kk < k) ? Num<TC>::vmax(num[kk] / (den[kk] + nu), ls) : TC(0);
+        for (int kk = 0; kk < KP; ++kk)
+            hn[kk] = (kk < k) ? (TC)fmax(num[kk] / (den[kk] + nu), st.log_shift) : TC(0);
         store_h_next<TC, KP>(st, j, k, hn, vals);
     }
     // only the H_next statistics are produced here; keep the loss partials written by h_finish
@@ -601,48 +611,50 @@ __global__ void __launch_bounds__(1024) w_finish_kernel(const espm_state st) {
     if (st.flags & ESPM_FLAG_SIMPLEX_W) {
         const bool sub = st.flags & ESPM_FLAG_SIMPLEX_ROWS;
         const int nrows = sub ? st.n_simplex_rows : m;
-        const TC tol = (TC)st.dicotomy_tol_w;
+        typedef double TB;  // the bisection runs in fp64 in every mode (m x k data)
+        const TB tol = st.dicotomy_tol_w;
+        const TB lsb = st.log_shift;
         auto row_of = [&](int i) { return sub ? st.simplex_rows[i] : i; };
-        auto feval = [&](int kk, TC x) {  // warp-collective: sum_rows max(num/(x+den), ls) - 1
-            TC s = TC(0);
+        auto feval = [&](int kk, TB x) {  // warp-collective: sum_rows max(num/(x+den), ls) - 1
+            TB s = 0.0;
             for (int i = lane; i < nrows; i += 32) {
                 const int o = row_of(i) * k + kk;
-                s += Num<TC>::vmax(wnum[o] / (x + wden[o]), ls);
+                s += fmax((TB)wnum[o] / (x + (TB)wden[o]), lsb);
             }
-            return warp_sum(s) - TC(1);
+            return warp_sum(s) - 1.0;
         };
         if (warp < k) {
             const int kk = warp;
-            TC amax = -Num<TC>::inf(), nmax = -Num<TC>::inf(), dmin = Num<TC>::inf(), nsum = TC(0);
+            TB amax = -Num<TB>::inf(), nmax = -Num<TB>::inf(), dmin = Num<TB>::inf(), nsum = 0.0;
             bool neg = false;
             for (int i = lane; i < nrows; i += 32) {
                 const int o = row_of(i) * k + kk;
-                const TC nv = wnum[o], dv = wden[o];
-                if (nv > TC(0)) amax = Num<TC>::vmax(amax, nv / TC(2) - dv);
-                nmax = Num<TC>::vmax(nmax, nv);
-                dmin = Num<TC>::vmin(dmin, dv);
+                const TB nv = (TB)wnum[o], dv = (TB)wden[o];
+                if (nv > 0.0) amax = fmax(amax, nv / 2.0 - dv);
+                nmax = fmax(nmax, nv);
+                dmin = fmin(dmin, dv);
                 nsum += nv;
-                neg |= (nv < TC(0)) || (dv < TC(0));
+                neg |= (nv < 0.0) || (dv < 0.0);
             }
             amax = warp_max(amax);
             nmax = warp_max(nmax);
             dmin = -warp_max(-dmin);
             nsum = warp_sum(nsum);
             neg = __any_sync(0xffffffffu, neg);
-            const TC a = amax, b = (TC)nrows * nmax / TC(0.5) - dmin;
-            const TC fa = feval(kk, a), fb = feval(kk, b);
-            const TC nw = (a + b) / TC(2);
-            const TC fn = feval(kk, nw);
+            const TB a = amax, b = (TB)nrows * nmax / 0.5 - dmin;
+            const TB fa = feval(kk, a), fb = feval(kk, b);
+            const TB nw = (a + b) / 2.0;
+            const TB fn = feval(kk, nw);
             if (lane == 0) {
                 uint32_t e = 0u;
-                if (!(fa > TC(0)) || !(fb < TC(0))) e |= ESPM_DEV_BRACKET;
-                if (neg || !(nsum > TC(0))) e |= ESPM_DEV_NEGATIVE;
+                if (!(fa > 0.0) || !(fb < 0.0)) e |= ESPM_DEV_BRACKET;
+                if (neg || !(nsum > 0.0)) e |= ESPM_DEV_NEGATIVE;
                 if (e) atomicOr(&s_err, e);
-                col_a[kk] = (double)a;
-                col_b[kk] = (double)b;
-                col_fa[kk] = (double)fa;
-                col_new[kk] = (double)nw;
-                col_fn[kk] = (double)fn;
+                col_a[kk] = a;
+                col_b[kk] = b;
+                col_fa[kk] = fa;
+                col_new[kk] = nw;
+                col_fn[kk] = fn;
             }
         }
         __syncthreads();
@@ -658,15 +670,14 @@ __global__ void __launch_bounds__(1024) w_finish_kernel(const espm_state st) {
             __syncthreads();
             if (warp < k) {
                 const int kk = warp;
-                TC a = (TC)col_a[kk], b = (TC)col_b[kk], fa = (TC)col_fa[kk], nw = (TC)col_new[kk],
-                   fn = (TC)col_fn[kk];
-                if (fa * fn <= TC(0)) {
+                TB a = col_a[kk], b = col_b[kk], fa = col_fa[kk], nw = col_new[kk], fn = col_fn[kk];
+                if (fa * fn <= 0.0) {
                     b = nw;
                 } else {
                     a = nw;
                     fa = fn;
                 }
-                nw = (a + b) / TC(2);
+                nw = (a + b) / 2.0;
                 fn = feval(kk, nw);
                 if (lane == 0) {
                     col_a[kk] = (double)a;

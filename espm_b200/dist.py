@@ -1,0 +1,130 @@
+"""Pixel sharding over the GPUs of one box (one process per GPU, torch.distributed).
+
+The path shards over pixels: rank r owns a contiguous block of image rows, keeps
+its X slab and H columns local, and exchanges per iteration only
+  * one image row of H with each neighbour (Laplacian halo),
+  * the 128-bit lock-step trace mask of the H bisection (OR),
+  * the n x k ratio sums S of the W update and the k row statistics of H (sum / max),
+  * the handful of loss scalars (sum / max), off the critical path.
+All messages are < 128 KiB, i.e. latency bound; NCCL is used for them through torch.distributed.
+The same class runs on CPU tensors with the gloo backend (used by the CPU tests of the host logic).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+
+
+def shard_bounds(p, nx, ny, rank, world):
+    """Pixel range [j0, j1) and first image row of ``rank``: contiguous image rows (pixel = i*ny + j)."""
+    if nx > 0 and ny > 0:
+        if world > nx:
+            raise ValueError("more ranks (%d) than image rows (%d)" % (world, nx))
+        base, rem = divmod(nx, world)
+        r0 = rank * base + min(rank, rem)
+        r1 = r0 + base + (1 if rank < rem else 0)
+        return r0 * ny, r1 * ny, r0
+    if world > p:
+        raise ValueError("more ranks (%d) than pixels (%d)" % (world, p))
+    base, rem = divmod(p, world)
+    j0 = rank * base + min(rank, rem)
+    j1 = j0 + base + (1 if rank < rem else 0)
+    return j0, j1, 0
+
+
+class Shard:
+    """Collectives of the sharded fit.  ``group`` is a torch.distributed process group (None = world)."""
+
+    def __init__(self, rank=None, world=None, group=None):
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        self._mask_all = None
+
+    # ---- W update inputs -------------------------------------------------------------------------
+    def allreduce_sum(self, t):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    def allreduce_hstats(self, hstats, kp):
+        """hstats = {rowsum[kp], rowsum(max(.,ls))[kp], rowmax[kp]} (float64)."""
+        dist.all_reduce(hstats[:2 * kp], op=dist.ReduceOp.SUM, group=self.group)
+        dist.all_reduce(hstats[2 * kp:3 * kp], op=dist.ReduceOp.MAX, group=self.group)
+
+    # ---- lock-step bisection ---------------------------------------------------------------------
+    def gather_masks(self, mask):
+        """mask[:4] <- OR over ranks of the 128-bit trace masks (NCCL has no bitwise OR: gather + fold)."""
+        if self._mask_all is None or self._mask_all.device != mask.device:
+            self._mask_all = torch.zeros(self.world * 4, dtype=mask.dtype, device=mask.device)
+        dist.all_gather_into_tensor(self._mask_all, mask[:4].contiguous(), group=self.group)
+        folded = self._mask_all.view(self.world, 4)
+        acc = folded[0].clone()
+        for r in range(1, self.world):
+            acc = torch.bitwise_or(acc, folded[r])
+        mask[:4].copy_(acc)
+
+    # ---- Laplacian halo --------------------------------------------------------------------------
+    def exchange_halo(self, Hbuf, halo, p_loc, ny):
+        """Hbuf: (k, ldh).  Sends the first / last owned image row to the previous / next rank and
+        receives theirs into the ny elements just before / after the owned pixels."""
+        ops = []
+        first = Hbuf[:, halo:halo + ny].contiguous()
+        last = Hbuf[:, halo + p_loc - ny:halo + p_loc].contiguous()
+        recv_lo = torch.empty_like(first)
+        recv_hi = torch.empty_like(last)
+        if self.rank > 0:
+            ops.append(dist.P2POp(dist.isend, first, self._peer(self.rank - 1), group=self.group))
+            ops.append(dist.P2POp(dist.irecv, recv_lo, self._peer(self.rank - 1), group=self.group))
+        if self.rank < self.world - 1:
+            ops.append(dist.P2POp(dist.isend, last, self._peer(self.rank + 1), group=self.group))
+            ops.append(dist.P2POp(dist.irecv, recv_hi, self._peer(self.rank + 1), group=self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        if self.rank > 0:
+            Hbuf[:, halo - ny:halo] = recv_lo
+        if self.rank < self.world - 1:
+            Hbuf[:, halo + p_loc:halo + p_loc + ny] = recv_hi
+
+    def _peer(self, r):
+        return r if self.group is None else dist.get_global_rank(self.group, r)
+
+    # ---- scalars / results -----------------------------------------------------------------------
+    def combine_records(self, rec):
+        """rec: (m, NSCALARS) local records (NumPy) -> global records, identical on every rank."""
+        t = torch.from_numpy(np.ascontiguousarray(rec))
+        backend = dist.get_backend(self.group)
+        if backend == "nccl":
+            t = t.cuda()
+        gathered = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(gathered, t, group=self.group)
+        allr = np.stack([g.cpu().numpy() for g in gathered])          # (world, m, NSCALARS)
+        return combine_record_arrays(allr)
+
+    def gather_H(self, H_local, p):
+        """Concatenate the H shards along pixels (rank order)."""
+        k = H_local.shape[0]
+        t = torch.from_numpy(np.ascontiguousarray(H_local))
+        backend = dist.get_backend(self.group)
+        sizes = [None] * self.world
+        dist.all_gather_object(sizes, H_local.shape[1], group=self.group)
+        mx = max(sizes)
+        pad = torch.zeros(k, mx, dtype=t.dtype)
+        pad[:, :t.shape[1]] = t
+        if backend == "nccl":
+            pad = pad.cuda()
+        out = [torch.empty_like(pad) for _ in range(self.world)]
+        dist.all_gather(out, pad, group=self.group)
+        return np.concatenate([o.cpu().numpy()[:, :s] for o, s in zip(out, sizes)], axis=1)
+
+
+def combine_record_arrays(allr):
+    """(world, m, NSCALARS) -> (m, NSCALARS): sums for the additive loss parts, max for rel_H, OR for
+    flags; everything else is replicated and taken from rank 0."""
+    out = allr[0].copy()
+    for s in (L.S_XLOGY, L.S_LOGREG, L.S_LAPL):
+        out[:, s] = allr[:, :, s].sum(axis=0)
+    out[:, L.S_REL_H] = allr[:, :, L.S_REL_H].max(axis=0)
+    flags = allr[:, :, L.S_DEV_FLAGS].astype(np.int64)
+    out[:, L.S_DEV_FLAGS] = np.bitwise_or.reduce(flags, axis=0).astype(np.float64)
+    return out

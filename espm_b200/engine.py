@@ -51,7 +51,8 @@ class FitEngine:
     def __init__(self, X, G, W0, H0, *, shape_2d=None, lambda_L=0.0, mu=0, epsilon_reg=1.0,
                  log_shift=1e-14, dicotomy_tol=1e-5, dicotomy_tol_w=1e-5, tol=1e-4, sigma=8.0,
                  simplex_H=False, simplex_W=True, simplex_rows=None, fixed_H=None, fixed_W=None,
-                 x_scale=1.0, max_records=512, device=None, shard=None, c_dtype=None, clamp_init=True):
+                 x_scale=1.0, max_records=512, device=None, shard=None, c_dtype=None, clamp_init=True,
+                 x_local=False):
         """
         X : (n, p) array-like view (any strides; C order or the transposed hyperspy layout are
             uploaded without a host copy).  G : (n, m) array or None (identity).  W0 : (m, k), H0 : (k, p).
@@ -65,6 +66,10 @@ class FitEngine:
         torch.cuda.set_device(self.device)
         self.shard = shard
         n, p = X.shape
+        if x_local:
+            p = H0.shape[1]          # X is already this rank's pixel slab (n, p_loc); H0 is global
+        self.x_local = x_local
+        self.profile = None          # set to {} to record CUDA events around the two X passes
         k = W0.shape[1]
         self.n, self.p, self.k = n, p, k
         self.identity_G = G is None
@@ -244,6 +249,16 @@ class FitEngine:
     def _call(self, fn):
         L.check(fn(ctypes.byref(self.st), self.stream))
 
+    def _call_timed(self, fn, name):
+        if self.profile is None:
+            return self._call(fn)
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        self._call(fn)
+        e1.record()
+        self.profile.setdefault(name, []).append((e0, e1))
+
     # ------------------------------------------------------------------ uploads
     def _upload_x(self, X, scale):
         """H2D copy of this rank's pixel slab and re-tiling into the tile-major layout (base.py:262)."""
@@ -252,6 +267,10 @@ class FitEngine:
         self.Xt = torch.empty(st.n_tiles * st.n_pad * L.TILE_PX, dtype=xdt, device=self.device)
         st.Xt = self.Xt.data_ptr()
         j0, j1 = self.j0, self.j1
+        if self.x_local:
+            if X.shape[1] != j1 - j0:
+                raise ValueError("x_local: X has %d pixels, this rank owns %d" % (X.shape[1], j1 - j0))
+            j0, j1 = 0, X.shape[1]
         if isinstance(X, torch.Tensor):
             Xv = X
             if Xv.stride(1) == 1 or Xv.stride(0) != 1:
@@ -344,10 +363,9 @@ class FitEngine:
     def evaluate(self, slot):
         """Phase A on (W_cur, H_cur): fills scalar record ``slot`` (loss parts, rel_H, flags)."""
         self._set_record(slot)
-        self._call(self.lib.espm_h_pass)
+        self._call_timed(self.lib.espm_h_pass, "h_pass")
         self._call(self.lib.espm_h_finish)
         self._call(self.lib.espm_h_scalars)
-        self._evaluated = True
 
     def advance(self, slot):
         """Phase B: (W_cur, H_cur) -> (W_next, H_next), rotate.  rel_W etc. go to record ``slot``."""
@@ -358,7 +376,7 @@ class FitEngine:
                 self.shard.gather_masks(self.mask)
             self._call(self.lib.espm_h_apply)
         self._exchange_halo(self.ih[2])
-        self._call(self.lib.espm_w_pass)
+        self._call_timed(self.lib.espm_w_pass, "w_pass")
         self._call(self.lib.espm_w_reduce)
         if self.shard is not None:
             self.shard.allreduce_sum(self.s_sum)

@@ -211,12 +211,19 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
             from .ops import check_shape_2d
             check_shape_2d(self.shape_2d, p)
         max_iter = int(self.max_iter)
+        shard = None
+        from . import config
+        if config.distributed:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                from .dist import Shard
+                shard = Shard()
         eng = FitEngine(self.X_, None if self._identity_G else G, W0, H0,
                         shape_2d=self.shape_2d, lambda_L=self.lambda_L, mu=self.mu, epsilon_reg=self.epsilon_reg,
                         log_shift=self.log_shift, dicotomy_tol=self.dicotomy_tol, dicotomy_tol_w=_DICOTOMY_TOL,
                         tol=self.tol, sigma=float(self.gamma_), simplex_H=self.simplex_H, simplex_W=self.simplex_W,
                         simplex_rows=simplex_rows, fixed_H=self.fixed_H, fixed_W=self.fixed_W,
-                        max_records=max(max_iter, 1) + 8)
+                        max_records=max(max_iter, 1) + 8, shard=shard)
         self._engine = eng
         self.G_ = G_full
         self.L_ = None  # the Laplacian is a stencil inside the kernels (utils.py:39-76 is never materialised)

@@ -1,0 +1,94 @@
+"""Synthetic STEM-EDXS spectrum images of the BASELINE.json shapes (no network, no hyperspy/exspy):
+an EDXS-like G (Gaussian x-ray lines + two bremsstrahlung columns), sphere phase maps and Poisson counts,
+following the recipe of SURVEY.md section 8d (espm/datasets/base.py:13-68, models/edxs.py:163-254,
+weights/generate_weights.py:182-223).  Host-side NumPy for small cases, torch for device generation."""
+import numpy as np
+
+
+def edxs_G(n, n_elements, seed, e_offset=0.2, e_scale=0.01, E0=200.0):
+    """G (n x (n_elements+2)): per element 1-4 Gaussian lines with width (0.01 E + 0.065)/2.3548, times a
+    smooth detector efficiency, plus two Lifshin-type bremsstrahlung columns; columns scaled to max 1."""
+    rng = np.random.default_rng(seed)
+    x = np.linspace(e_offset, e_offset + n * e_scale, n)
+    det = 1.0 - np.exp(-x / 0.6) * 0.9            # low-energy roll-off of an SDD-like efficiency
+    G = np.zeros((n, n_elements + 2))
+    for e in range(n_elements):
+        for _ in range(rng.integers(1, 5)):
+            E = rng.uniform(x[0] + 0.3, x[-1] - 0.3)
+            w = (0.01 * E + 0.065) / 2.3548
+            cs = rng.uniform(0.2, 1.0)
+            G[:, e] += cs * np.exp(-0.5 * ((x - E) / w) ** 2) * np.interp(E, x, det)
+    G[:, -2] = (E0 - x) / x * det
+    G[:, -1] = (E0 - x) ** 2 / (E0 * x) * det
+    G /= G.max(axis=0, keepdims=True)
+    return G
+
+
+def true_W(m, k, seed):
+    rng = np.random.default_rng(seed + 1)
+    W = np.zeros((m, k))
+    for c in range(k):
+        idx = rng.choice(m - 2, size=int(rng.integers(3, 7)), replace=False)
+        W[idx, c] = rng.uniform(size=idx.size)
+        W[:m - 2, c] /= W[:m - 2, c].sum()
+        W[m - 2, c] = 1e-5 * rng.uniform(0.5, 1.0)
+        W[m - 1, c] = 1e-3 * rng.uniform(0.5, 1.0)
+    return W
+
+
+def sphere_maps(nx, ny, k, seed):
+    """H_true (k x p): k-1 spheres of radius ~nx/4 with concentration 1/(k-1); phase 0 is the complement."""
+    rng = np.random.default_rng(seed + 2)
+    ii, jj = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
+    H = np.zeros((k, nx, ny))
+    r = max(min(nx, ny) / 4.0, 1.0)
+    for c in range(1, k):
+        ci, cj = rng.uniform(0, nx), rng.uniform(0, ny)
+        d2 = (ii - ci) ** 2 + (jj - cj) ** 2
+        H[c] = np.clip(1.0 - d2 / r ** 2, 0.0, None) ** 0.5 / max(k - 1, 1)
+    H[0] = 1.0 - H[1:].sum(axis=0)
+    return H.reshape(k, nx * ny)
+
+
+def init_factors(m, k, p, seed, dtype=np.float64):
+    rng = np.random.default_rng(seed + 3)
+    W0 = rng.uniform(size=(m, k)) + 1e-3
+    H0 = rng.uniform(size=(k, p)) + 1e-3
+    H0 /= H0.sum(axis=0, keepdims=True)
+    return W0.astype(dtype), H0.astype(dtype)
+
+
+def make_problem(nx, ny, n, k, n_elements, seed=91, counts=500.0, identity_G=False):
+    """Returns dict(G, W_true, H_true, dens, D) -- everything but the (large) X."""
+    G = edxs_G(n, n_elements, seed, e_scale=0.01 if n <= 2048 else 0.005)
+    m = G.shape[1]
+    Wt = true_W(m, k, seed)
+    D = G @ Wt
+    D = D / D.sum(axis=0, keepdims=True)
+    Ht = sphere_maps(nx, ny, k, seed)
+    rng = np.random.default_rng(seed + 4)
+    dens = rng.uniform(0.6, 1.0, size=k)
+    return dict(G=None if identity_G else G, G_full=G, W_true=Wt, H_true=Ht, D=D, dens=dens, counts=counts,
+                m=(n if identity_G else m))
+
+
+def poisson_X_numpy(prob, j0, j1, seed, dtype=np.float32):
+    """Host generation of X[:, j0:j1] ~ Poisson(N * (D * dens) @ H_true)."""
+    rng = np.random.default_rng([seed, j0])
+    lam = prob["counts"] * (prob["D"] * prob["dens"][None, :]) @ prob["H_true"][:, j0:j1]
+    return rng.poisson(lam).astype(dtype)
+
+
+def poisson_X_torch(prob, j0, j1, seed, device, dtype, chunk=32768):
+    """Device generation of the same distribution (different random stream), (n, j1-j0) tensor."""
+    import torch
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed * 1000003 + j0)
+    Dd = torch.as_tensor(prob["counts"] * prob["D"] * prob["dens"][None, :], dtype=torch.float32, device=device)
+    n = Dd.shape[0]
+    X = torch.empty(n, j1 - j0, dtype=dtype, device=device)
+    for a in range(j0, j1, chunk):
+        b = min(a + chunk, j1)
+        Ht = torch.as_tensor(prob["H_true"][:, a:b], dtype=torch.float32, device=device)
+        X[:, a - j0:b - j0] = torch.poisson(Dd @ Ht, generator=gen).to(dtype)
+    return X
