@@ -37,6 +37,10 @@ def _torch_dtype(code):
 
 
 def _code_of(dtype):
+    if isinstance(dtype, torch.dtype):
+        dtype = {torch.float32: np.float32, torch.float64: np.float64}.get(dtype, None)
+        if dtype is None:
+            raise TypeError("espm_b200 supports float32 and float64 data")
     dtype = np.dtype(dtype)
     if dtype == np.float64:
         return L.F64
@@ -80,7 +84,7 @@ class FitEngine:
         x_code = _code_of(X.dtype)
         if c_dtype is None:
             # NumPy promotion of the reference: any float64 operand makes the update float64
-            parts = [np.dtype(X.dtype), np.dtype(W0.dtype), np.dtype(H0.dtype)]
+            parts = [np.dtype(_np_dtype(x_code)), np.dtype(W0.dtype), np.dtype(H0.dtype)]
             if G is not None:
                 parts.append(np.dtype(G.dtype))
             c_dtype = np.result_type(*parts)

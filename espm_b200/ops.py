@@ -16,7 +16,7 @@ import ctypes
 import numpy as np
 import torch
 
-from . import _lib as L
+from . import _lib as _L
 from .conf import dicotomy_tol as _TOL
 from .conf import log_shift as _LS
 from .conf import maxit_dichotomy as _MAXIT
@@ -102,10 +102,10 @@ def _is_identity(G):
 
 
 def _raise_flags(rec):
-    flags = int(rec[L.S_DEV_FLAGS])
-    if flags & L.DEV_NONFINITE:
+    flags = int(rec[_L.S_DEV_FLAGS])
+    if flags & _L.DEV_NONFINITE:
         raise FloatingPointError("espm_b200: non-finite ratio sums (zero row in G W?)")
-    if flags & (L.DEV_BRACKET | L.DEV_NEGATIVE):
+    if flags & (_L.DEV_BRACKET | _L.DEV_NEGATIVE):
         raise AssertionError("espm_b200: bisection preconditions violated (dicotomy.py:17-19,141-144)")
 
 
@@ -130,7 +130,7 @@ def multiplicative_step_h(X, G, W, H, simplex_H=False, mu=0, log_shift=_LS, epsi
     Hn, rec = eng.step_h_only()
     _raise_flags(rec)
     if return_its:
-        return Hn, int(rec[L.S_BISECT_ITS_H])
+        return Hn, int(rec[_L.S_BISECT_ITS_H])
     return Hn
 
 
@@ -156,7 +156,7 @@ def multiplicative_step_w(X, G, W, H, simplex_W=False, log_shift=_LS, safe=True,
 def dichotomy_simplex(num, denum, log_shift=_LS, tol=_TOL, maxit=_MAXIT, return_its=False):
     """dicotomy.py:4-55: per-column root of sum_i max(num_i/(x+den_i), log_shift) - 1 with the
     reference's bracket and its GLOBAL (lock-step) stop test."""
-    lib = L.load()
+    lib = _L.load()
     num = np.asarray(num)
     denum = np.asarray(denum)
     if num.ndim == 1:
@@ -165,8 +165,8 @@ def dichotomy_simplex(num, denum, log_shift=_LS, tol=_TOL, maxit=_MAXIT, return_
     if log_shift > 0 and k * log_shift >= 1:
         raise ValueError("No solution exists!")
     dt = np.result_type(num.dtype, denum.dtype, np.float32)
-    code = L.F64 if dt == np.float64 else L.F32
-    tdt = torch.float64 if code == L.F64 else torch.float32
+    code = _L.F64 if dt == np.float64 else _L.F32
+    tdt = torch.float64 if code == _L.F64 else torch.float32
     dev = torch.device("cuda", torch.cuda.current_device())
     d_num = torch.as_tensor(np.ascontiguousarray(num), dtype=tdt).to(dev)
     d_den = torch.as_tensor(np.ascontiguousarray(denum), dtype=tdt).to(dev)
@@ -175,11 +175,11 @@ def dichotomy_simplex(num, denum, log_shift=_LS, tol=_TOL, maxit=_MAXIT, return_
     flags = torch.zeros(4, dtype=torch.int32, device=dev)
     its = torch.zeros(1, dtype=torch.int32, device=dev)
     stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-    L.check(lib.espm_dichotomy_simplex(code, k, p, d_num.data_ptr(), d_den.data_ptr(), float(log_shift), float(tol),
+    _L.check(lib.espm_dichotomy_simplex(code, k, p, d_num.data_ptr(), d_den.data_ptr(), float(log_shift), float(tol),
                                        int(maxit), nu.data_ptr(), mask.data_ptr(), flags.data_ptr(),
                                        its.data_ptr(), stream))
     f = int(flags[0].item())
-    if f & (L.DEV_BRACKET | L.DEV_NEGATIVE):
+    if f & (_L.DEV_BRACKET | _L.DEV_NEGATIVE):
         raise AssertionError("dichotomy_simplex: preconditions violated (dicotomy.py:17-19,141-144)")
     out = nu.cpu().numpy()
     n_it = int(its.item())
@@ -210,7 +210,7 @@ def KLdiv_loss(X, W, H, log_shift=_LS, average=False):
     eng = _engine(X, None, W, H, log_shift=log_shift, simplex_H=False, simplex_W=False, max_records=8)
     eng.evaluate(0)
     rec = eng.read_records(0, 1)[0]
-    val = rec[L.S_SUMY] - rec[L.S_XLOGY]
+    val = rec[_L.S_SUMY] - rec[_L.S_XLOGY]
     return val / X.size if average else val
 
 
@@ -222,7 +222,7 @@ def log_reg(H, mu, epsilon=1, average=False):
     eng = _engine(X, None, np.ones((1, k), dtype=X.dtype), H, mu=mu, epsilon_reg=epsilon, log_shift=0.0,
                   simplex_H=False, simplex_W=False, max_records=8, clamp_init=False)
     eng.evaluate(0)
-    val = eng.read_records(0, 1)[0][L.S_LOGREG]
+    val = eng.read_records(0, 1)[0][_L.S_LOGREG]
     return val / H.size if average else val
 
 
@@ -237,5 +237,5 @@ def trace_xtLx(Lm, x, average=False):
     eng = _engine(X, None, np.ones((1, k), dtype=X.dtype), H, lambda_L=1.0, shape_2d=shape_2d, log_shift=0.0,
                   simplex_H=False, simplex_W=False, max_records=8, clamp_init=False)
     eng.evaluate(0)
-    val = eng.read_records(0, 1)[0][L.S_LAPL]
+    val = eng.read_records(0, 1)[0][_L.S_LAPL]
     return val / x.size if average else val
