@@ -50,9 +50,9 @@ class EspmState(ctypes.Structure):
         ("p_loc", _i32), ("p_pad", _i32), ("n_tiles", _i32), ("nx", _i32), ("ny", _i32),
         ("row0", _i32), ("halo", _i32), ("ldh", _i32), ("x_dtype", _i32), ("c_dtype", _i32),
         ("flags", _u32), ("n_simplex_rows", _i32), ("maxit", _i32),
-        ("n_sms", _i32), ("h_grid", _i32), ("h_nsplit", _i32), ("w_nb", _i32), ("w_nr", _i32),
-        ("px_blocks", _i32), ("h_depth", _i32), ("w_depth", _i32), ("w_sacc_rows", _i32),
-        ("h_smem", _i32), ("w_smem", _i32), ("reserved0", _i32),
+        ("n_sms", _i32), ("h_grid", _i32), ("h_nsplit", _i32), ("w_upc", _i32), ("w_nr", _i32),
+        ("px_blocks", _i32), ("h_depth", _i32), ("w_depth", _i32), ("cs", _i32),
+        ("h_smem", _i32), ("w_smem", _i32), ("w_grid", _i32),
         ("p_total", _i64),
         ("lambda_L", _f64), ("sigma", _f64), ("eps_reg", _f64), ("log_shift", _f64),
         ("dicotomy_tol", _f64), ("dicotomy_tol_w", _f64), ("tol", _f64),

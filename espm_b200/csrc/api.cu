@@ -35,13 +35,10 @@ static xpass_fn pick_xpass(const espm_state* st) {
     return nullptr;
 }
 
-static void sizes_of(const espm_state* st, int safe, int* stride, int* red, int* fixed, int* cs, int* halves) {
-    if (st->x_dtype == ESPM_F32 && st->c_dtype == ESPM_F32)
-        xpass_sizes<float, float>(st->kp, safe, stride, red, fixed, cs, halves);
-    else if (st->x_dtype == ESPM_F32 && st->c_dtype == ESPM_F64)
-        xpass_sizes<float, double>(st->kp, safe, stride, red, fixed, cs, halves);
-    else
-        xpass_sizes<double, double>(st->kp, safe, stride, red, fixed, cs, halves);
+static int sizes_of(const espm_state* st, int safe, XPassSizes* o) {
+    if (st->x_dtype == ESPM_F32 && st->c_dtype == ESPM_F32) return xpass_sizes<float, float>(st->kp, safe, o);
+    if (st->x_dtype == ESPM_F32 && st->c_dtype == ESPM_F64) return xpass_sizes<float, double>(st->kp, safe, o);
+    return xpass_sizes<double, double>(st->kp, safe, o);
 }
 
 static bool is_safe(const espm_state* st) { return (st->flags & (ESPM_FLAG_CLAMP_Y | ESPM_FLAG_LOSS_DUAL)) != 0; }
@@ -73,8 +70,6 @@ static int check_state(const espm_state* st) {
 static XPassArgs make_args(const espm_state* st, bool w_pass) {
     XPassArgs a;
     memset(&a, 0, sizeof(a));
-    int stride, red, fixed, cs, halves;
-    sizes_of(st, is_safe(st), &stride, &red, &fixed, &cs, &halves);
     a.Xt = st->Xt;
     a.GW = st->GW_cur;
     a.GWc = st->GWc_cur;
@@ -87,12 +82,10 @@ static XPassArgs make_args(const espm_state* st, bool w_pass) {
     a.n_tiles = st->n_tiles;
     a.ldh = st->ldh;
     a.p_pad = st->p_pad;
-    a.nstages_tile = st->n_pad / cs;
+    a.nstages_tile = st->n_pad / st->cs;
     a.nsplit = st->h_nsplit;
-    a.w_nb = st->w_nb;
-    a.w_nr = st->w_nr;
+    a.w_upc = st->w_upc;
     a.depth = w_pass ? st->w_depth : st->h_depth;
-    a.sacc_rows = st->w_sacc_rows;
     a.clamp_y = (st->flags & ESPM_FLAG_CLAMP_Y) ? 1 : 0;
     a.dual = (st->flags & ESPM_FLAG_LOSS_DUAL) ? 1 : 0;
     a.log_shift = st->log_shift;
@@ -150,7 +143,6 @@ int espm_plan(espm_state* st) {
         return ESPM_ERR_NO_DEVICE;
     }
     st->n_sms = prop.multiProcessorCount;
-    st->n_pad = (st->n + 31) / 32 * 32;
     st->n_tiles = (st->p_loc + TILE_PX - 1) / TILE_PX;
     st->p_pad = st->n_tiles * TILE_PX;
     st->px_blocks = (st->p_loc + PX_THREADS - 1) / PX_THREADS;
@@ -158,25 +150,28 @@ int espm_plan(espm_state* st) {
 
     // The plan is made for the SAFE variant's shared-memory footprint so that switching on the
     // clamp / dual-loss fallbacks mid-fit never needs a re-plan.
-    int stride, red, fixed, cs, halves;
-    sizes_of(st, 1, &stride, &red, &fixed, &cs, &halves);
-    const int NS = st->n_pad / cs;
-    const int tc_bytes = st->c_dtype == ESPM_F64 ? 8 : 4;
-    const int want_occ = (st->kp * tc_bytes <= 32) ? 2 : 1;
+    XPassSizes z;
+    rc = sizes_of(st, 1, &z);
+    if (rc) return rc;
+    st->cs = z.cs;
+    st->n_pad = (st->n + 31) / 32 * 32;   // whole stages for every storage type (CS is 32 or 16)
+    const int NS = st->n_pad / z.cs;
     const int smem_cap = (int)prop.sharedMemPerBlockOptin;                      // 227 KiB on B200
-    const int per_cta = (int)(prop.sharedMemPerMultiprocessor / want_occ) - 1024;  // 1 KiB reserved per CTA
-    const int budget = per_cta < smem_cap ? per_cta : smem_cap;
+    auto budget_for = [&](int want_occ) {
+        const int per_cta = (int)(prop.sharedMemPerMultiprocessor / want_occ) - 1024;  // 1 KiB reserved per CTA
+        return per_cta < smem_cap ? per_cta : smem_cap;
+    };
     xpass_fn fn = pick_xpass(st);
 
     // ---- H pass ----
-    int depth = (budget - fixed - red) / stride;
+    int depth = (budget_for(z.h_occ) - z.fixed - z.h_tail) / z.h_stride;
     if (depth > 8) depth = 8;
     if (depth < 2) {
         set_error("shared memory budget too small for the H pass (kp=%d)", st->kp);
         return ESPM_ERR_UNSUPPORTED;
     }
     st->h_depth = depth;
-    st->h_smem = fixed + depth * stride + red;
+    st->h_smem = z.fixed + depth * z.h_stride + z.h_tail;
     int occ = 0;
     {
         XPassLaunch l{XPASS_H, st->kp, 1, 1, st->h_smem};
@@ -211,26 +206,16 @@ int espm_plan(espm_state* st) {
         st->h_grid = (int)(items < cap_h ? items : cap_h);
     }
 
-    // ---- W pass ----
+    // ---- W pass: contiguous ranges of (channel block, tile) units, one per CTA ----
     {
-        int wdepth = depth;
-        // channel blocks: accumulator <= 32 KiB, and enough CTAs to fill the machine on small images
-        const int acc_cap = 32 * 1024;
-        int nb = 1;
-        while (nb < NS) {
-            const int rows = ((NS + nb - 1) / nb) * cs;
-            if (halves * rows * st->kp * tc_bytes <= acc_cap) break;
-            ++nb;
+        int wdepth = (budget_for(z.w_occ) - z.fixed - z.w_tail) / z.w_stride;
+        if (wdepth > 8) wdepth = 8;
+        if (wdepth < 2) {
+            set_error("shared memory budget too small for the W pass (kp=%d)", st->kp);
+            return ESPM_ERR_UNSUPPORTED;
         }
-        const int want = (cap_h + st->n_tiles - 1) / st->n_tiles;  // blocks needed to reach cap with few tiles
-        if (want > nb) nb = want < NS ? want : NS;
-        const int rows = ((NS + nb - 1) / nb) * cs;
-        const int acc = halves * rows * st->kp * tc_bytes;
-        while (wdepth > 2 && fixed + wdepth * stride + acc > budget) --wdepth;
-        st->w_nb = nb;
-        st->w_sacc_rows = rows;
         st->w_depth = wdepth;
-        st->w_smem = fixed + wdepth * stride + acc;
+        st->w_smem = z.fixed + wdepth * z.w_stride + z.w_tail;
         int wocc = 0;
         XPassLaunch l{XPASS_W, st->kp, 1, 1, st->w_smem};
         rc = fn(l, nullptr, &wocc, 0);
@@ -239,9 +224,16 @@ int espm_plan(espm_state* st) {
             set_error("W pass kernel does not fit on an SM (smem=%d)", st->w_smem);
             return ESPM_ERR_UNSUPPORTED;
         }
-        int nr = (st->n_sms * wocc) / nb;
-        if (nr < 1) nr = 1;
-        if (nr > st->n_tiles) nr = st->n_tiles;
+        const long long total = (long long)NS * st->n_tiles;
+        const long long cap_w = (long long)st->n_sms * wocc;
+        const long long upc = (total + cap_w - 1) / cap_w;
+        st->w_upc = (int)upc;
+        st->w_grid = (int)((total + upc - 1) / upc);
+        int nr = 1;
+        for (int cb = 0; cb < NS; ++cb) {
+            const int c = w_last_cta(cb, st->n_tiles, st->w_upc) - w_first_cta(cb, st->n_tiles, st->w_upc) + 1;
+            if (c > nr) nr = c;
+        }
         st->w_nr = nr;
     }
     return ESPM_OK;
@@ -249,16 +241,17 @@ int espm_plan(espm_state* st) {
 
 int espm_plan_info(const espm_state* st, int32_t* info8) {
     if (!st || !info8) return ESPM_ERR_BAD_ARG;
-    int stride, red, fixed, cs, halves;
-    sizes_of(st, 1, &stride, &red, &fixed, &cs, &halves);
-    info8[0] = stride;
-    info8[1] = red;
-    info8[2] = cs;
-    info8[3] = halves;
+    XPassSizes z;
+    int rc = sizes_of(st, 1, &z);
+    if (rc) return rc;
+    info8[0] = z.h_stride;
+    info8[1] = z.w_stride;
+    info8[2] = z.cs;
+    info8[3] = z.halves;
     info8[4] = st->h_smem;
     info8[5] = st->w_smem;
     info8[6] = st->h_grid;
-    info8[7] = st->w_nb * st->w_nr;
+    info8[7] = st->w_grid;
     return ESPM_OK;
 }
 
@@ -309,7 +302,7 @@ int espm_w_pass(const espm_state* st, void* stream) {
     int rc = check_state(st);
     if (rc) return rc;
     XPassArgs a = make_args(st, true);
-    XPassLaunch l{XPASS_W, st->kp, is_safe(st) ? 1 : 0, st->w_nb * st->w_nr, st->w_smem};
+    XPassLaunch l{XPASS_W, st->kp, is_safe(st) ? 1 : 0, st->w_grid, st->w_smem};
     return pick_xpass(st)(l, &a, nullptr, (cudaStream_t)stream);
 }
 

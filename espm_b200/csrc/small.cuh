@@ -468,9 +468,13 @@ __global__ void __launch_bounds__(256) w_reduce_kernel(const espm_state st) {
     const size_t total = (size_t)st.n_pad * st.kp;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
+    // slots of this channel block that a CTA of the W pass actually wrote (see w_pass_kernel)
+    const int cb = (int)(i / ((size_t)st.cs * st.kp));
+    const int first = (int)(((long long)cb * st.n_tiles) / st.w_upc);
+    const int last = (int)((((long long)cb + 1) * st.n_tiles - 1) / st.w_upc);
     const TC* part = reinterpret_cast<const TC*>(st.s_part);
     TC s = part[i];
-    for (int r = 1; r < st.w_nr; ++r) s += part[(size_t)r * total + i];
+    for (int r = 1; r <= last - first; ++r) s += part[(size_t)r * total + i];
     reinterpret_cast<TC*>(st.s_sum)[i] = s;
 }
 

@@ -1,13 +1,16 @@
 // The two kernels that stream X from HBM: the H pass and the W pass.
 //
 // Both are warp-specialised persistent kernels: one producer warp issues TMA bulk copies
-// (cp.async.bulk, SASS UBLKCP) of 16 KiB X chunks + the matching GW rows into a ring of shared-memory
-// stages guarded by mbarriers; eight consumer warps read the stages with 128-bit LDS, rebuild
-// y = GW.H in registers (never materialised), form x/y and contract it on the fly.
+// (cp.async.bulk, SASS UBLKCP) of 16 KiB X chunks + the matching GW rows (+ the H tile in the W pass)
+// into a ring of shared-memory stages guarded by mbarriers; eight consumer warps read the stages with
+// 128-bit LDS, rebuild y = GW.H in registers (never materialised), form x/y and contract it on the fly.
 //
 //   h_pass : numraw[k][j] = sum_c GW[c][k] * X[c][j] / y[c][j]      (updates.py:127-128)
 //            + partial sums of max(X,ls)*log(y)                      (measures.py:497-503)
 //   w_pass : S[c][k]      = sum_j X[c][j] / y'[c][j] * H'[k][j]      (updates.py:53-59, G^T(R H^T))
+//
+// The fp32 fast path (TX = TC = float, !SAFE) uses the packed f32x2 FMAs of sm_100 (FFMA2/FMUL2: two
+// pixels per issue slot) and single-instruction .ftz MUFU.RCP / MUFU.LG2.
 #pragma once
 #include "common.cuh"
 
@@ -24,9 +27,8 @@ struct XPassArgs {
     int n_pad, k, n_tiles, ldh, p_pad;
     int nstages_tile;    // n_pad / CS
     int nsplit;          // H pass
-    int w_nb, w_nr;      // W pass
+    int w_upc;           // W pass: (channel block, tile) units per CTA
     int depth;           // pipeline stages
-    int sacc_rows;       // W pass: channel rows reserved per half in the smem accumulator
     int clamp_y, dual;   // SAFE variants only
     double log_shift;
 };
@@ -37,14 +39,22 @@ struct XPassSmem {
     static constexpr int X_BYTES = STAGE_BYTES;
     static constexpr int GW_BYTES = G::CS * KP * (int)sizeof(TC);
     static constexpr int GW_BYTES_AL = (GW_BYTES + 127) / 128 * 128;
-    static constexpr int STAGE_STRIDE = X_BYTES + GW_BYTES_AL * (SAFE ? 2 : 1);
+    static constexpr int HROW_BYTES = TILE_PX * (int)sizeof(TC);
+    static constexpr int H_STRIDE = X_BYTES + GW_BYTES_AL * (SAFE ? 2 : 1);   // stage of the H pass
+    static constexpr int W_STRIDE = X_BYTES + GW_BYTES_AL + KP * HROW_BYTES;  // stage of the W pass (+ H tile)
     static constexpr int BAR_BYTES = 256;  // up to 16 full + 16 empty barriers
-    static constexpr int RED_BYTES = G::NSLOT * KP * TILE_PX * (int)sizeof(TC);
     static constexpr int MISC_BYTES = 128;
-    static __host__ __device__ int h_bytes(int depth) { return BAR_BYTES + MISC_BYTES + depth * STAGE_STRIDE + RED_BYTES; }
-    static __host__ __device__ int w_bytes(int depth, int sacc_rows) {
-        return BAR_BYTES + MISC_BYTES + depth * STAGE_STRIDE + G::HALVES * sacc_rows * KP * (int)sizeof(TC);
-    }
+    static constexpr int RED_BYTES = G::NSLOT * KP * TILE_PX * (int)sizeof(TC);          // H pass epilogue
+    static constexpr int WTAIL_BYTES = G::HALVES * G::CS * KP * (int)sizeof(TC);          // W pass flush / accumulator
+    // the W pass keeps CPW x KP ratio sums per lane in registers when they fit, else in shared memory
+    static constexpr bool FAST32 = !SAFE && sizeof(TX) == 4 && sizeof(TC) == 4;
+    static constexpr int ACC_WORDS = G::CPW * KP * (FAST32 ? 2 : (int)sizeof(TC) / 4);
+    static constexpr bool ACC_REG = ACC_WORDS <= 64;
+    // CTAs per SM the kernels are compiled for (register budget: 96 regs/thread at 2, 168 at 1)
+    static constexpr int H_OCC = (KP * (int)sizeof(TC) <= 32) ? 2 : 1;
+    static constexpr int W_REGS_EST = (ACC_REG ? ACC_WORDS : KP * (int)sizeof(TC) / 4 * (FAST32 ? 2 : 1)) +
+                                      KP * G::PPL * (int)sizeof(TC) / 4 + 36;
+    static constexpr int W_OCC = (H_OCC == 2 && W_REGS_EST <= 110) ? 2 : 1;
 };
 
 template <typename T, int N>
@@ -85,8 +95,8 @@ __device__ __forceinline__ void lds_gw(TC (&gw)[KP], const void* row) {
     }
 }
 
-// Loads the PPL consecutive H values of KP rows for this lane's pixels (H pad pixels hold 1, pad
-// rows are treated as 0).
+// Loads the PPL consecutive H values of KP rows for this lane's pixels (H pad pixels hold a positive
+// value, pad rows are treated as 0).  `H` may be global or shared memory.
 template <typename TC, int KP, int PPL>
 __device__ __forceinline__ void load_h(TC (&h)[KP][PPL], const TC* H, int ldh, int k, int px0) {
 #pragma unroll
@@ -100,21 +110,32 @@ __device__ __forceinline__ void load_h(TC (&h)[KP][PPL], const TC* H, int ldh, i
     }
 }
 
+// single-instruction MUFU forms (no denormal fix-up code around them)
+__device__ __forceinline__ float rcp_ftz(float y) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y));
+    return r;
+}
+__device__ __forceinline__ float lg2_ftz(float y) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y));
+    return r;
+}
+__device__ __forceinline__ float2 dup2(float v) { return make_float2(v, v); }
+
 // ------------------------------------------------------------------------------------------------
-// Producer: one elected lane streams (tile, stage) chunks into the ring.
+// Ring of pipeline stages: one elected producer lane fills it, the consumer warps drain it.
 // ------------------------------------------------------------------------------------------------
-template <typename TX, typename TC, int KP, bool SAFE>
+template <int STRIDE>
 struct Ring {
-    using S = XPassSmem<TX, TC, KP, SAFE>;
-    using G = PassGeom<TX, TC>;
     uint64_t* full;
     uint64_t* empty;
     unsigned char* stages;
     int depth;
-    __device__ __forceinline__ Ring(unsigned char* smem, int depth_) : depth(depth_) {
+    __device__ __forceinline__ Ring(unsigned char* smem, int depth_, int head_bytes) : depth(depth_) {
         full = reinterpret_cast<uint64_t*>(smem);
         empty = full + 16;
-        stages = smem + S::BAR_BYTES + S::MISC_BYTES;
+        stages = smem + head_bytes;
     }
     __device__ __forceinline__ void init() {
         for (int i = 0; i < depth; ++i) {
@@ -123,25 +144,12 @@ struct Ring {
         }
         mbar_fence_init();
     }
-    __device__ __forceinline__ unsigned char* x_ptr(int slot) { return stages + (size_t)slot * S::STAGE_STRIDE; }
-    __device__ __forceinline__ unsigned char* gw_ptr(int slot) { return x_ptr(slot) + S::X_BYTES; }
-    __device__ __forceinline__ unsigned char* gwc_ptr(int slot) { return gw_ptr(slot) + S::GW_BYTES_AL; }
-
-    __device__ __forceinline__ void produce(const XPassArgs& a, int tile, int st, uint32_t cnt, uint64_t pol_x,
-                                            uint64_t pol_gw) {
+    __device__ __forceinline__ unsigned char* stage(int slot) { return stages + (size_t)slot * STRIDE; }
+    // producer: wait until the slot of fill number `cnt` is free; returns the slot
+    __device__ __forceinline__ int acquire(uint32_t cnt) {
         const int slot = cnt % depth;
-        const uint32_t phase = (cnt / depth) & 1u;
-        mbar_wait(&empty[slot], phase ^ 1u);
-        const bool dual = SAFE && a.dual;
-        mbar_expect_tx(&full[slot], S::X_BYTES + S::GW_BYTES * (dual ? 2 : 1));
-        const TX* xsrc = reinterpret_cast<const TX*>(a.Xt) + ((size_t)tile * a.n_pad + (size_t)st * G::CS) * TILE_PX;
-        tma_bulk_g2s(x_ptr(slot), xsrc, S::X_BYTES, &full[slot], pol_x);
-        const TC* gsrc = reinterpret_cast<const TC*>(a.GW) + (size_t)st * G::CS * KP;
-        tma_bulk_g2s(gw_ptr(slot), gsrc, S::GW_BYTES, &full[slot], pol_gw);
-        if (dual) {
-            const TC* csrc = reinterpret_cast<const TC*>(a.GWc) + (size_t)st * G::CS * KP;
-            tma_bulk_g2s(gwc_ptr(slot), csrc, S::GW_BYTES, &full[slot], pol_gw);
-        }
+        mbar_wait(&empty[slot], ((cnt / depth) & 1u) ^ 1u);
+        return slot;
     }
     __device__ __forceinline__ void consumer_wait(uint32_t cnt) {
         mbar_wait(&full[cnt % depth], (cnt / depth) & 1u);
@@ -156,15 +164,16 @@ struct Ring {
 // H pass
 // ------------------------------------------------------------------------------------------------
 template <typename TX, typename TC, int KP, bool SAFE>
-__global__ void __launch_bounds__(XPASS_THREADS, (KP * sizeof(TC) <= 32) ? 2 : 1)
+__global__ void __launch_bounds__(XPASS_THREADS, (XPassSmem<TX, TC, KP, SAFE>::H_OCC))
 h_pass_kernel(const XPassArgs a) {
     using G = PassGeom<TX, TC>;
     using S = XPassSmem<TX, TC, KP, SAFE>;
     constexpr int PPL = G::PPL;
+    constexpr bool FAST32 = !SAFE && sizeof(TX) == 4 && sizeof(TC) == 4;
     extern __shared__ __align__(128) unsigned char smem[];
-    Ring<TX, TC, KP, SAFE> ring(smem, a.depth);
+    Ring<S::H_STRIDE> ring(smem, a.depth, S::BAR_BYTES + S::MISC_BYTES);
     double* misc = reinterpret_cast<double*>(smem + S::BAR_BYTES);
-    TC* red = reinterpret_cast<TC*>(smem + S::BAR_BYTES + S::MISC_BYTES + (size_t)a.depth * S::STAGE_STRIDE);
+    TC* red = reinterpret_cast<TC*>(smem + S::BAR_BYTES + S::MISC_BYTES + (size_t)a.depth * S::H_STRIDE);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) ring.init();
@@ -178,11 +187,24 @@ h_pass_kernel(const XPassArgs a) {
         if (lane == 0) {
             const uint64_t pol_x = l2_policy_evict_first();
             const uint64_t pol_gw = l2_policy_evict_last();
+            const bool dual = SAFE && a.dual;
             uint32_t cnt = 0;
             for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
                 const int tile = it / a.nsplit, split = it - tile * a.nsplit;
                 const int s0 = (int)((long long)split * NS / a.nsplit), s1 = (int)((long long)(split + 1) * NS / a.nsplit);
-                for (int st = s0; st < s1; ++st, ++cnt) ring.produce(a, tile, st, cnt, pol_x, pol_gw);
+                for (int st = s0; st < s1; ++st, ++cnt) {
+                    const int slot = ring.acquire(cnt);
+                    unsigned char* sp = ring.stage(slot);
+                    mbar_expect_tx(&ring.full[slot], S::X_BYTES + S::GW_BYTES * (dual ? 2 : 1));
+                    const TX* xsrc = reinterpret_cast<const TX*>(a.Xt) + ((size_t)tile * a.n_pad + (size_t)st * G::CS) * TILE_PX;
+                    tma_bulk_g2s(sp, xsrc, S::X_BYTES, &ring.full[slot], pol_x);
+                    const TC* gsrc = reinterpret_cast<const TC*>(a.GW) + (size_t)st * G::CS * KP;
+                    tma_bulk_g2s(sp + S::X_BYTES, gsrc, S::GW_BYTES, &ring.full[slot], pol_gw);
+                    if (dual) {
+                        const TC* csrc = reinterpret_cast<const TC*>(a.GWc) + (size_t)st * G::CS * KP;
+                        tma_bulk_g2s(sp + S::X_BYTES + S::GW_BYTES_AL, csrc, S::GW_BYTES, &ring.full[slot], pol_gw);
+                    }
+                }
             }
         }
         return;
@@ -194,81 +216,122 @@ h_pass_kernel(const XPassArgs a) {
     const TC ls = (TC)a.log_shift;
     const TC* Hc = reinterpret_cast<const TC*>(a.H);
     double xl_total = 0.0;   // sum x*log2(y) over x>0
-    double zl_total = 0.0;   // sum log2(y) over x==0 (fp64 only; weighted by log_shift at the end)
+    double zl_total = 0.0;   // sum log2(y) over x==0 (weighted by log_shift at the end)
     uint32_t cnt = 0;
 
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const int tile = it / a.nsplit, split = it - tile * a.nsplit;
         const int s0 = (int)((long long)split * NS / a.nsplit), s1 = (int)((long long)(split + 1) * NS / a.nsplit);
-        TC h[KP][PPL], hc[SAFE ? KP : 1][PPL], num[KP][PPL];
+        TC h[KP][PPL], num[KP][PPL];
         load_h<TC, KP, PPL>(h, Hc, a.ldh, a.k, tile * TILE_PX + lane_px);
-#pragma unroll
-        for (int kk = 0; kk < KP; ++kk)
-#pragma unroll
-            for (int q = 0; q < PPL; ++q) {
-                num[kk][q] = TC(0);
-                if constexpr (SAFE) hc[kk][q] = (kk < a.k) ? Num<TC>::vmax(h[kk][q], ls) : TC(0);
-            }
 
-        for (int st = s0; st < s1; ++st, ++cnt) {
-            ring.consumer_wait(cnt);
-            const unsigned char* xs = ring.x_ptr(cnt % a.depth);
-            const unsigned char* gs = ring.gw_ptr(cnt % a.depth);
-            const unsigned char* gcs = ring.gwc_ptr(cnt % a.depth);
-            TC xl = TC(0);
-            float zl = 0.f;
+        if constexpr (FAST32) {
+            // ---- fp32 fast path: pixel pairs in packed f32x2 registers ----
+            float2 h2[KP][2], num2[KP][2];
 #pragma unroll
-            for (int ci = 0; ci < G::CPW; ++ci) {
-                const int c = slot + ci * G::NSLOT;
-                TX xv[PPL];
-                TC gw[KP];
-                lds_vec<TX, PPL>(xv, xs + ((size_t)c * TILE_PX + lane_px) * sizeof(TX));
-                lds_gw<TC, KP>(gw, gs + (size_t)c * KP * sizeof(TC));
-                TC y[PPL], r[PPL];
+            for (int kk = 0; kk < KP; ++kk)
 #pragma unroll
-                for (int q = 0; q < PPL; ++q) {
-                    y[q] = gw[0] * h[0][q];
-#pragma unroll
-                    for (int kk = 1; kk < KP; ++kk) y[q] = fma(gw[kk], h[kk][q], y[q]);
+                for (int j = 0; j < 2; ++j) {
+                    h2[kk][j] = make_float2(h[kk][2 * j], h[kk][2 * j + 1]);
+                    num2[kk][j] = make_float2(0.f, 0.f);
                 }
-                if constexpr (SAFE) {
-                    if (a.clamp_y) {
+            for (int st = s0; st < s1; ++st, ++cnt) {
+                ring.consumer_wait(cnt);
+                const unsigned char* xs = ring.stage(cnt % a.depth);
+                const unsigned char* gs = xs + S::X_BYTES;
+                float2 xl2 = make_float2(0.f, 0.f);
 #pragma unroll
-                        for (int q = 0; q < PPL; ++q) y[q] = Num<TC>::vmax(y[q], ls);
+                for (int ci = 0; ci < G::CPW; ++ci) {
+                    const int c = slot + ci * G::NSLOT;
+                    const float4 xv = *reinterpret_cast<const float4*>(xs + ((size_t)c * TILE_PX + lane_px) * sizeof(float));
+                    float gw[KP];
+                    lds_gw<float, KP>(gw, gs + (size_t)c * KP * sizeof(float));
+                    const float2 x2[2] = {make_float2(xv.x, xv.y), make_float2(xv.z, xv.w)};
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        float2 y = __fmul2_rn(dup2(gw[0]), h2[0][j]);
+#pragma unroll
+                        for (int kk = 1; kk < KP; ++kk) y = __ffma2_rn(dup2(gw[kk]), h2[kk][j], y);
+                        const float2 r = __fmul2_rn(x2[j], make_float2(rcp_ftz(y.x), rcp_ftz(y.y)));
+#pragma unroll
+                        for (int kk = 0; kk < KP; ++kk) num2[kk][j] = __ffma2_rn(dup2(gw[kk]), r, num2[kk][j]);
+                        // 0*log2(y) == 0 because y > 0 is guaranteed on this path; the reference's
+                        // ls*log(Y) terms of zero entries are below fp32 rounding of the sum.
+                        xl2 = __ffma2_rn(x2[j], make_float2(lg2_ftz(y.x), lg2_ftz(y.y)), xl2);
                     }
                 }
+                ring.consumer_release(cnt, lane);
+                xl_total += (double)(xl2.x + xl2.y);
+            }
 #pragma unroll
-                for (int q = 0; q < PPL; ++q) r[q] = Num<TC>::ratio((TC)xv[q], y[q]);
+            for (int kk = 0; kk < KP; ++kk)
 #pragma unroll
-                for (int kk = 0; kk < KP; ++kk)
+                for (int j = 0; j < 2; ++j) {
+                    num[kk][2 * j] = num2[kk][j].x;
+                    num[kk][2 * j + 1] = num2[kk][j].y;
+                }
+        } else {
+            TC hc[SAFE ? KP : 1][PPL];
 #pragma unroll
-                    for (int q = 0; q < PPL; ++q) num[kk][q] = fma(gw[kk], r[q], num[kk][q]);
-                // ---- loss of the current iterate: sum max(x,ls)*log(Y), Y from clamped GW, H ----
-                TC yl[PPL];
-                if constexpr (SAFE) {
-                    if (a.dual) {
-                        TC gwc[KP];
-                        lds_gw<TC, KP>(gwc, gcs + (size_t)c * KP * sizeof(TC));
+            for (int kk = 0; kk < KP; ++kk)
 #pragma unroll
-                        for (int q = 0; q < PPL; ++q) {
-                            yl[q] = gwc[0] * hc[0][q];
+                for (int q = 0; q < PPL; ++q) {
+                    num[kk][q] = TC(0);
+                    if constexpr (SAFE) hc[kk][q] = (kk < a.k) ? Num<TC>::vmax(h[kk][q], ls) : TC(0);
+                }
+            for (int st = s0; st < s1; ++st, ++cnt) {
+                ring.consumer_wait(cnt);
+                const unsigned char* xs = ring.stage(cnt % a.depth);
+                const unsigned char* gs = xs + S::X_BYTES;
+                const unsigned char* gcs = gs + S::GW_BYTES_AL;
+                TC xl = TC(0);
+                float zl = 0.f;
 #pragma unroll
-                            for (int kk = 1; kk < KP; ++kk) yl[q] = fma(gwc[kk], hc[kk][q], yl[q]);
+                for (int ci = 0; ci < G::CPW; ++ci) {
+                    const int c = slot + ci * G::NSLOT;
+                    TX xv[PPL];
+                    TC gw[KP];
+                    lds_vec<TX, PPL>(xv, xs + ((size_t)c * TILE_PX + lane_px) * sizeof(TX));
+                    lds_gw<TC, KP>(gw, gs + (size_t)c * KP * sizeof(TC));
+                    TC y[PPL], r[PPL];
+#pragma unroll
+                    for (int q = 0; q < PPL; ++q) {
+                        y[q] = gw[0] * h[0][q];
+#pragma unroll
+                        for (int kk = 1; kk < KP; ++kk) y[q] = fma(gw[kk], h[kk][q], y[q]);
+                    }
+                    if constexpr (SAFE) {
+                        if (a.clamp_y) {
+#pragma unroll
+                            for (int q = 0; q < PPL; ++q) y[q] = Num<TC>::vmax(y[q], ls);
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < PPL; ++q) r[q] = Num<TC>::ratio((TC)xv[q], y[q]);
+#pragma unroll
+                    for (int kk = 0; kk < KP; ++kk)
+#pragma unroll
+                        for (int q = 0; q < PPL; ++q) num[kk][q] = fma(gw[kk], r[q], num[kk][q]);
+                    // ---- loss of the current iterate: sum max(x,ls)*log(Y), Y from clamped GW, H ----
+                    TC yl[PPL];
+                    if constexpr (SAFE) {
+                        if (a.dual) {
+                            TC gwc[KP];
+                            lds_gw<TC, KP>(gwc, gcs + (size_t)c * KP * sizeof(TC));
+#pragma unroll
+                            for (int q = 0; q < PPL; ++q) {
+                                yl[q] = gwc[0] * hc[0][q];
+#pragma unroll
+                                for (int kk = 1; kk < KP; ++kk) yl[q] = fma(gwc[kk], hc[kk][q], yl[q]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < PPL; ++q) yl[q] = y[q];
                         }
                     } else {
 #pragma unroll
                         for (int q = 0; q < PPL; ++q) yl[q] = y[q];
                     }
-                } else {
-#pragma unroll
-                    for (int q = 0; q < PPL; ++q) yl[q] = y[q];
-                }
-                if constexpr (sizeof(TC) == 4 && !SAFE) {
-                    // fp32 fast path: 0*log2(y) == 0 because y > 0 is guaranteed here; the reference's
-                    // ls*log(Y) terms of zero entries are below fp32 rounding of the sum.
-#pragma unroll
-                    for (int q = 0; q < PPL; ++q) xl = fma((TC)xv[q], Num<TC>::log2_fast(yl[q]), xl);
-                } else {
 #pragma unroll
                     for (int q = 0; q < PPL; ++q) {
                         const TC x = (TC)xv[q];
@@ -279,10 +342,10 @@ h_pass_kernel(const XPassArgs a) {
                         }
                     }
                 }
+                ring.consumer_release(cnt, lane);
+                xl_total += (double)xl;
+                zl_total += (double)zl;
             }
-            ring.consumer_release(cnt, lane);
-            xl_total += (double)xl;
-            zl_total += (double)zl;
         }
 
         // ---- cross-warp reduction of the ratio sums of this item (fixed order => deterministic) ----
@@ -317,35 +380,64 @@ h_pass_kernel(const XPassArgs a) {
 
 // ------------------------------------------------------------------------------------------------
 // W pass
+//
+// Work unit = (channel block of CS channels, pixel tile) = one pipeline stage.  Units are ordered
+// channel-block major and CTA i owns the contiguous range [i*upc, (i+1)*upc).  Every consumer lane keeps
+// the ratio sums of ITS channels and pixels in registers across all tiles of a channel block; the
+// cross-lane reduction happens once per (CTA, channel block), when the block changes ("flush").
+// Partial slot of a flush = CTA index - first CTA that touches the block, so w_reduce can add the slots
+// of a block in a fixed order without zero-filling.
 // ------------------------------------------------------------------------------------------------
+__host__ __device__ inline int w_first_cta(int cb, int n_tiles, int upc) {
+    return (int)(((long long)cb * n_tiles) / upc);
+}
+__host__ __device__ inline int w_last_cta(int cb, int n_tiles, int upc) {
+    return (int)((((long long)cb + 1) * n_tiles - 1) / upc);
+}
+
 template <typename TX, typename TC, int KP, bool SAFE>
-__global__ void __launch_bounds__(XPASS_THREADS, (KP * sizeof(TC) <= 32) ? 2 : 1)
+__global__ void __launch_bounds__(XPASS_THREADS, (XPassSmem<TX, TC, KP, SAFE>::W_OCC))
 w_pass_kernel(const XPassArgs a) {
     using G = PassGeom<TX, TC>;
     using S = XPassSmem<TX, TC, KP, SAFE>;
     constexpr int PPL = G::PPL;
+    constexpr int CPW = G::CPW;
+    constexpr bool FAST32 = S::FAST32;
+    constexpr bool ACC_REG = S::ACC_REG;
     extern __shared__ __align__(128) unsigned char smem[];
-    Ring<TX, TC, KP, SAFE> ring(smem, a.depth);
-    TC* sacc = reinterpret_cast<TC*>(smem + S::BAR_BYTES + S::MISC_BYTES + (size_t)a.depth * S::STAGE_STRIDE);
+    Ring<S::W_STRIDE> ring(smem, a.depth, S::BAR_BYTES + S::MISC_BYTES);
+    // tail: [HALVES][CS][KP] -- flush staging (ACC_REG) or the running accumulator (!ACC_REG)
+    TC* tail = reinterpret_cast<TC*>(smem + S::BAR_BYTES + S::MISC_BYTES + (size_t)a.depth * S::W_STRIDE);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int NS = a.nstages_tile;
-    const int b = blockIdx.x % a.w_nb, r = blockIdx.x / a.w_nb;
-    const int sb0 = (int)((long long)b * NS / a.w_nb), sb1 = (int)((long long)(b + 1) * NS / a.w_nb);
-    const int t0 = (int)((long long)r * a.n_tiles / a.w_nr), t1 = (int)((long long)(r + 1) * a.n_tiles / a.w_nr);
-    const int rows = (sb1 - sb0) * G::CS;
+    const long long total = (long long)a.nstages_tile * a.n_tiles;
+    const long long u0 = (long long)blockIdx.x * a.w_upc;
+    const long long u1 = (u0 + a.w_upc < total) ? u0 + a.w_upc : total;
 
     if (threadIdx.x == 0) ring.init();
-    for (int i = threadIdx.x; i < G::HALVES * a.sacc_rows * KP; i += blockDim.x) sacc[i] = TC(0);
+    for (int i = threadIdx.x; i < G::HALVES * G::CS * KP; i += blockDim.x) tail[i] = TC(0);
     __syncthreads();
 
     if (warp == N_CONSUMER_WARPS) {
         if (lane == 0) {
             const uint64_t pol_x = l2_policy_evict_first();
             const uint64_t pol_gw = l2_policy_evict_last();
+            const TC* Hn = reinterpret_cast<const TC*>(a.H);
             uint32_t cnt = 0;
-            for (int tile = t0; tile < t1; ++tile)
-                for (int st = sb0; st < sb1; ++st, ++cnt) ring.produce(a, tile, st, cnt, pol_x, pol_gw);
+            for (long long u = u0; u < u1; ++u, ++cnt) {
+                const int cb = (int)(u / a.n_tiles), tile = (int)(u - (long long)cb * a.n_tiles);
+                const int slot = ring.acquire(cnt);
+                unsigned char* sp = ring.stage(slot);
+                mbar_expect_tx(&ring.full[slot], S::X_BYTES + S::GW_BYTES + a.k * S::HROW_BYTES);
+                const TX* xsrc = reinterpret_cast<const TX*>(a.Xt) + ((size_t)tile * a.n_pad + (size_t)cb * G::CS) * TILE_PX;
+                tma_bulk_g2s(sp, xsrc, S::X_BYTES, &ring.full[slot], pol_x);
+                const TC* gsrc = reinterpret_cast<const TC*>(a.GW) + (size_t)cb * G::CS * KP;
+                tma_bulk_g2s(sp + S::X_BYTES, gsrc, S::GW_BYTES, &ring.full[slot], pol_gw);
+                unsigned char* hp = sp + S::X_BYTES + S::GW_BYTES_AL;
+                for (int kk = 0; kk < a.k; ++kk)
+                    tma_bulk_g2s(hp + kk * S::HROW_BYTES, Hn + (size_t)kk * a.ldh + (size_t)tile * TILE_PX,
+                                 S::HROW_BYTES, &ring.full[slot], pol_gw);
+            }
         }
         return;
     }
@@ -353,27 +445,122 @@ w_pass_kernel(const XPassArgs a) {
     const int half = warp % G::HALVES, slot = warp / G::HALVES;
     const int lane_px = half * (32 * PPL) + lane * PPL;
     const TC ls = (TC)a.log_shift;
-    const TC* Hn = reinterpret_cast<const TC*>(a.H);
-    TC* my_acc = sacc + (size_t)half * a.sacc_rows * KP;
-    uint32_t cnt = 0;
+    (void)ls;
 
-    for (int tile = t0; tile < t1; ++tile) {
-        TC h[KP][PPL];
-        load_h<TC, KP, PPL>(h, Hn, a.ldh, a.k, tile * TILE_PX + lane_px);
-        for (int st = sb0; st < sb1; ++st, ++cnt) {
-            ring.consumer_wait(cnt);
-            const unsigned char* xs = ring.x_ptr(cnt % a.depth);
-            const unsigned char* gs = ring.gw_ptr(cnt % a.depth);
+    // per-lane accumulators: CPW channels x KP phases (x 2 pixel parities on the packed path)
+    constexpr int NACC = ACC_REG ? CPW : 1;
+    TC acc[FAST32 ? 1 : NACC][FAST32 ? 1 : KP];
+    float2 acc2[FAST32 ? NACC : 1][FAST32 ? KP : 1];
 #pragma unroll
-            for (int ci = 0; ci < G::CPW; ++ci) {
+    for (int ci = 0; ci < NACC; ++ci)
+#pragma unroll
+        for (int kk = 0; kk < KP; ++kk) {
+            if constexpr (FAST32) acc2[ci][kk] = make_float2(0.f, 0.f);
+            else acc[ci][kk] = TC(0);
+        }
+
+    // Ends the channel block `cb` of this CTA: s_part[slot of this CTA in cb][channels of cb][KP].
+    auto flush = [&](int cb) {
+        const int ps = blockIdx.x - w_first_cta(cb, a.n_tiles, a.w_upc);
+        TC* out = reinterpret_cast<TC*>(a.s_part) + ((size_t)ps * a.n_pad + (size_t)cb * G::CS) * KP;
+        if constexpr (ACC_REG) {
+#pragma unroll
+            for (int ci = 0; ci < CPW; ++ci)
+#pragma unroll
+                for (int kk = 0; kk < KP; ++kk) {
+                    TC v;
+                    if constexpr (FAST32) {
+                        v = acc2[ci][kk].x + acc2[ci][kk].y;
+                        acc2[ci][kk] = make_float2(0.f, 0.f);
+                    } else {
+                        v = acc[ci][kk];
+                        acc[ci][kk] = TC(0);
+                    }
+                    v = warp_sum(v);
+                    if (lane == 0) tail[((size_t)half * G::CS + slot + ci * G::NSLOT) * KP + kk] = v;
+                }
+        }
+        named_bar_sync(1, N_CONSUMER_THREADS);
+        for (int i = threadIdx.x; i < G::CS * KP; i += N_CONSUMER_THREADS) {
+            TC v = tail[i];
+            if constexpr (G::HALVES == 2) v += tail[(size_t)G::CS * KP + i];
+            out[i] = v;
+        }
+        named_bar_sync(1, N_CONSUMER_THREADS);
+        if constexpr (!ACC_REG) {
+            for (int i = threadIdx.x; i < G::HALVES * G::CS * KP; i += N_CONSUMER_THREADS) tail[i] = TC(0);
+            named_bar_sync(1, N_CONSUMER_THREADS);
+        }
+    };
+
+    uint32_t cnt = 0;
+    int cb_cur = (u0 < u1) ? (int)(u0 / a.n_tiles) : -1;
+    for (long long u = u0; u < u1; ++u, ++cnt) {
+        const int cb = (int)(u / a.n_tiles);
+        if (cb != cb_cur) {
+            flush(cb_cur);
+            cb_cur = cb;
+        }
+        ring.consumer_wait(cnt);
+        const unsigned char* xs = ring.stage(cnt % a.depth);
+        const unsigned char* gs = xs + S::X_BYTES;
+        const TC* hs = reinterpret_cast<const TC*>(gs + S::GW_BYTES_AL);
+        TC h[KP][PPL];
+        load_h<TC, KP, PPL>(h, hs, TILE_PX, a.k, lane_px);
+
+        if constexpr (FAST32) {
+            float2 h2[KP][2];
+#pragma unroll
+            for (int kk = 0; kk < KP; ++kk) {
+                h2[kk][0] = make_float2(h[kk][0], h[kk][1]);
+                h2[kk][1] = make_float2(h[kk][2], h[kk][3]);
+            }
+#pragma unroll
+            for (int ci = 0; ci < CPW; ++ci) {
+                const int c = slot + ci * G::NSLOT;
+                const float4 xv = *reinterpret_cast<const float4*>(xs + ((size_t)c * TILE_PX + lane_px) * sizeof(float));
+                float gw[KP];
+                lds_gw<float, KP>(gw, gs + (size_t)c * KP * sizeof(float));
+                const float2 x2[2] = {make_float2(xv.x, xv.y), make_float2(xv.z, xv.w)};
+                float2 tloc[KP];
+                float2 (&t2)[KP] = ACC_REG ? acc2[ACC_REG ? ci : 0] : tloc;
+                if constexpr (!ACC_REG) {
+#pragma unroll
+                    for (int kk = 0; kk < KP; ++kk) tloc[kk] = make_float2(0.f, 0.f);
+                }
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    float2 y = __fmul2_rn(dup2(gw[0]), h2[0][j]);
+#pragma unroll
+                    for (int kk = 1; kk < KP; ++kk) y = __ffma2_rn(dup2(gw[kk]), h2[kk][j], y);
+                    const float2 r = __fmul2_rn(x2[j], make_float2(rcp_ftz(y.x), rcp_ftz(y.y)));
+#pragma unroll
+                    for (int kk = 0; kk < KP; ++kk) t2[kk] = __ffma2_rn(r, h2[kk][j], t2[kk]);
+                }
+                if constexpr (!ACC_REG) {
+                    float mine = 0.f;
+#pragma unroll
+                    for (int kk = 0; kk < KP; ++kk) {
+                        const float sv = warp_sum(tloc[kk].x + tloc[kk].y);
+                        if (lane == kk) mine = sv;
+                    }
+                    if (lane < KP) tail[((size_t)half * G::CS + c) * KP + lane] += mine;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int ci = 0; ci < CPW; ++ci) {
                 const int c = slot + ci * G::NSLOT;
                 TX xv[PPL];
                 TC gw[KP];
                 lds_vec<TX, PPL>(xv, xs + ((size_t)c * TILE_PX + lane_px) * sizeof(TX));
                 lds_gw<TC, KP>(gw, gs + (size_t)c * KP * sizeof(TC));
-                TC t[KP];
+                TC tloc[KP];
+                TC (&t)[KP] = ACC_REG ? acc[ACC_REG ? ci : 0] : tloc;
+                if constexpr (!ACC_REG) {
 #pragma unroll
-                for (int kk = 0; kk < KP; ++kk) t[kk] = TC(0);
+                    for (int kk = 0; kk < KP; ++kk) tloc[kk] = TC(0);
+                }
 #pragma unroll
                 for (int q = 0; q < PPL; ++q) {
                     TC y = gw[0] * h[0][q];
@@ -386,28 +573,20 @@ w_pass_kernel(const XPassArgs a) {
 #pragma unroll
                     for (int kk = 0; kk < KP; ++kk) t[kk] = fma(rq, h[kk][q], t[kk]);
                 }
-                // reduce over the 32 lanes (pixels) and accumulate into this warp's private rows
-                TC mine = TC(0);
+                if constexpr (!ACC_REG) {
+                    TC mine = TC(0);
 #pragma unroll
-                for (int kk = 0; kk < KP; ++kk) {
-                    const TC s = warp_sum(t[kk]);
-                    if (lane == kk) mine = s;
-                }
-                if (lane < KP) {
-                    TC* dst = my_acc + ((size_t)(st - sb0) * G::CS + c) * KP + lane;
-                    *dst += mine;
+                    for (int kk = 0; kk < KP; ++kk) {
+                        const TC sv = warp_sum(tloc[kk]);
+                        if (lane == kk) mine = sv;
+                    }
+                    if (lane < KP) tail[((size_t)half * G::CS + c) * KP + lane] += mine;
                 }
             }
-            ring.consumer_release(cnt, lane);
         }
+        ring.consumer_release(cnt, lane);
     }
-    named_bar_sync(1, N_CONSUMER_THREADS);
-    TC* out = reinterpret_cast<TC*>(a.s_part) + ((size_t)r * a.n_pad + (size_t)sb0 * G::CS) * KP;
-    for (int idx = threadIdx.x; idx < rows * KP; idx += N_CONSUMER_THREADS) {
-        TC s = sacc[idx];
-        if constexpr (G::HALVES == 2) s += sacc[(size_t)a.sacc_rows * KP + idx];
-        out[idx] = s;
-    }
+    if (cb_cur >= 0) flush(cb_cur);
 }
 
 }  // namespace espm

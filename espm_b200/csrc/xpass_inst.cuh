@@ -51,16 +51,42 @@ static int xpass_entry(const XPassLaunch& l, const XPassArgs* a, int* occ_out, c
 }
 
 // sizes needed by the planner (host)
+struct XPassSizes {
+    int h_stride, w_stride;  // bytes per pipeline stage
+    int h_tail, w_tail;      // bytes after the ring (epilogue staging)
+    int fixed;               // barriers + misc
+    int cs, halves;
+    int h_occ, w_occ;        // CTAs per SM the kernels are compiled for
+};
+
+template <typename TX, typename TC, int KP>
+static void xpass_sizes_kp(int safe, XPassSizes* o) {
+    using S0 = XPassSmem<TX, TC, KP, false>;
+    using S1 = XPassSmem<TX, TC, KP, true>;
+    o->h_stride = safe ? S1::H_STRIDE : S0::H_STRIDE;
+    o->w_stride = S0::W_STRIDE;
+    o->h_tail = S0::RED_BYTES;
+    o->w_tail = S0::WTAIL_BYTES;
+    o->fixed = S0::BAR_BYTES + S0::MISC_BYTES;
+    o->cs = S0::G::CS;
+    o->halves = S0::G::HALVES;
+    o->h_occ = S0::H_OCC < S1::H_OCC ? S0::H_OCC : S1::H_OCC;
+    o->w_occ = S0::W_OCC < S1::W_OCC ? S0::W_OCC : S1::W_OCC;
+}
+
 template <typename TX, typename TC>
-static void xpass_sizes(int kp, int safe, int* stage_stride, int* red_bytes, int* fixed_bytes, int* cs, int* halves) {
-    using G = PassGeom<TX, TC>;
-    const int gw_bytes = G::CS * kp * (int)sizeof(TC);
-    const int gw_al = (gw_bytes + 127) / 128 * 128;
-    *stage_stride = STAGE_BYTES + gw_al * (safe ? 2 : 1);
-    *red_bytes = G::NSLOT * kp * TILE_PX * (int)sizeof(TC);
-    *fixed_bytes = 256 + 128;
-    *cs = G::CS;
-    *halves = G::HALVES;
+static int xpass_sizes(int kp, int safe, XPassSizes* o) {
+    switch (kp) {
+        case 2: xpass_sizes_kp<TX, TC, 2>(safe, o); return ESPM_OK;
+        case 3: xpass_sizes_kp<TX, TC, 3>(safe, o); return ESPM_OK;
+        case 4: xpass_sizes_kp<TX, TC, 4>(safe, o); return ESPM_OK;
+        case 5: xpass_sizes_kp<TX, TC, 5>(safe, o); return ESPM_OK;
+        case 6: xpass_sizes_kp<TX, TC, 6>(safe, o); return ESPM_OK;
+        case 8: xpass_sizes_kp<TX, TC, 8>(safe, o); return ESPM_OK;
+        case 12: xpass_sizes_kp<TX, TC, 12>(safe, o); return ESPM_OK;
+        case 16: xpass_sizes_kp<TX, TC, 16>(safe, o); return ESPM_OK;
+        default: set_error("unsupported padded component count kp=%d", kp); return ESPM_ERR_BAD_ARG;
+    }
 }
 
 // defined in xpass_f32f32.cu / xpass_f32f64.cu / xpass_f64f64.cu

@@ -114,15 +114,15 @@ typedef struct espm_state {
     int32_t n_sms;
     int32_t h_grid;     /* CTAs of the H pass */
     int32_t h_nsplit;   /* channel splits of a tile in the H pass (partial ratio sums are added in h_finish) */
-    int32_t w_nb;       /* channel blocks of the W pass */
-    int32_t w_nr;       /* tile ranges of the W pass (grid = w_nb * w_nr) */
+    int32_t w_upc;      /* W pass: (channel block, pixel tile) work units per CTA */
+    int32_t w_nr;       /* W pass: partial-sum slots per channel block (max CTAs touching one block) */
     int32_t px_blocks;  /* CTAs of the per-pixel kernels (h_finish / h_apply) */
     int32_t h_depth;    /* pipeline stages of the H pass */
     int32_t w_depth;    /* pipeline stages of the W pass */
-    int32_t w_sacc_rows; /* channel rows of the W pass shared-memory accumulator */
+    int32_t cs;         /* channels per pipeline stage = channels per W-pass channel block */
     int32_t h_smem;     /* dynamic shared memory bytes of the H pass */
     int32_t w_smem;     /* dynamic shared memory bytes of the W pass */
-    int32_t reserved0;
+    int32_t w_grid;     /* CTAs of the W pass */
     int64_t p_total;    /* pixels of the whole image (all ranks), for mean(H) in rel_H (base.py:324) */
     /* ---- hyper-parameters ---- */
     double lambda_L;    /* smooth_nmf.py:58 */
@@ -218,9 +218,9 @@ int espm_h_apply(const espm_state* st, void* stream);
 int espm_h_scalars(const espm_state* st, void* stream);
 
 /* W pass (updates.py:38-59, re-associated as G^T (R H^T)): streams Xt once with H_next.
- *   s_part[r][c][k] = sum_{j in tile range r} X[c][j]/(GW.H_next)[c][j] * H_next[k][j]            */
+ *   s_part[s][c][k] = sum_{j in the tiles CTA (first_cta(c/cs)+s) owns} X[c][j]/(GW.H_next)[c][j] * H_next[k][j] */
 int espm_w_pass(const espm_state* st, void* stream);
-/* s_sum = sum_r s_part[r]  (fixed order => deterministic). */
+/* s_sum = sum over the slots of each channel block of s_part (fixed order => deterministic). */
 int espm_w_reduce(const espm_state* st, void* stream);
 /* hstats_next from the per-pixel partials; W_next (updates.py:59-76, incl. simplex_W bisection and
  * fixed_W), rel_W, then GW_next / gwstats_next for the next H pass.  Single CTA. */
