@@ -65,7 +65,7 @@ class EspmState(ctypes.Structure):
         ("hstats_cur", _vp), ("hstats_next", _vp),
         ("fixed_H", _vp), ("fixed_W", _vp), ("simplex_rows", _vp),
         ("numraw", _vp), ("num", _vp), ("den", _vp),
-        ("s_part", _vp), ("s_sum", _vp), ("t_mk", _vp), ("w_num", _vp), ("w_den", _vp),
+        ("s_part", _vp), ("s_sum", _vp), ("Ht", _vp), ("w_num", _vp), ("w_den", _vp),
         ("xlogy_part", _vp), ("px_part", _vp), ("bisect_mask", _vp), ("dev_flags", _vp), ("scalars", _vp),
     ]
 

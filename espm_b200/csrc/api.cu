@@ -73,7 +73,8 @@ static XPassArgs make_args(const espm_state* st, bool w_pass) {
     a.Xt = st->Xt;
     a.GW = st->GW_cur;
     a.GWc = st->GWc_cur;
-    a.H = w_pass ? st->H_next : st->H_cur;
+    a.H = st->H_cur;
+    a.Ht = st->Ht;
     a.numraw = st->numraw;
     a.xlogy_part = st->xlogy_part;
     a.s_part = st->s_part;

@@ -168,6 +168,7 @@ template <typename TC, int KP>
 __device__ __forceinline__ void store_h_next(const espm_state& st, int j, int k, const TC (&hn)[KP],
                                              double (&vals)[3 + 3 * KP]) {
     TC* Hn = reinterpret_cast<TC*>(st.H_next);
+    TC* Ht = reinterpret_cast<TC*>(st.Ht);
     const TC* fx = reinterpret_cast<const TC*>(st.fixed_H);
     const TC ls = (TC)st.log_shift;
 #pragma unroll
@@ -179,6 +180,7 @@ __device__ __forceinline__ void store_h_next(const espm_state& st, int j, int k,
                 if (f >= TC(0)) v = f;
             }
             Hn[(size_t)kk * st.ldh + j] = v;
+            Ht[((size_t)(j / TILE_PX) * KP + kk) * TILE_PX + (j % TILE_PX)] = v;   // tile-major copy for the W pass
             vals[2 + kk] = (double)v;
             vals[2 + KP + kk] = (double)Num<TC>::vmax(v, ls);
             vals[3 + 2 * KP + kk] = (double)v;
@@ -370,6 +372,7 @@ __global__ void __launch_bounds__(PX_THREADS) h_stats_kernel(const espm_state st
         for (int kk = 0; kk < KP; ++kk)
             if (kk < k) {
                 const TC v = Hn[(size_t)kk * st.ldh + j];
+                reinterpret_cast<TC*>(st.Ht)[((size_t)(j / TILE_PX) * KP + kk) * TILE_PX + (j % TILE_PX)] = v;
                 vals[2 + kk] = (double)v;
                 vals[2 + KP + kk] = (double)Num<TC>::vmax(v, ls);
                 vals[3 + 2 * KP + kk] = (double)v;

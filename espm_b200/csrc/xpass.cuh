@@ -20,7 +20,8 @@ struct XPassArgs {
     const void* Xt;
     const void* GW;
     const void* GWc;
-    const void* H;       // H_cur for the H pass, H_next for the W pass (points at local pixel 0)
+    const void* H;       // H pass: H_cur [k][ldh] (points at local pixel 0)
+    const void* Ht;      // W pass: tile-major copy of H_next, [tile][KP][128]
     void* numraw;        // [nsplit][KP][P_pad]
     double* xlogy_part;  // [grid]
     void* s_part;        // [w_nr][n_pad][KP]
@@ -41,11 +42,12 @@ struct XPassSmem {
     static constexpr int GW_BYTES_AL = (GW_BYTES + 127) / 128 * 128;
     static constexpr int HROW_BYTES = TILE_PX * (int)sizeof(TC);
     static constexpr int H_STRIDE = X_BYTES + GW_BYTES_AL * (SAFE ? 2 : 1);   // stage of the H pass
-    static constexpr int W_STRIDE = X_BYTES + GW_BYTES_AL + KP * HROW_BYTES;  // stage of the W pass (+ H tile)
+    static constexpr int W_STRIDE = X_BYTES + KP * HROW_BYTES;                // stage of the W pass: X + H tile
     static constexpr int BAR_BYTES = 256;  // up to 16 full + 16 empty barriers
     static constexpr int MISC_BYTES = 128;
     static constexpr int RED_BYTES = G::NSLOT * KP * TILE_PX * (int)sizeof(TC);          // H pass epilogue
-    static constexpr int WTAIL_BYTES = G::HALVES * G::CS * KP * (int)sizeof(TC);          // W pass flush / accumulator
+    static constexpr int WACC_BYTES = G::HALVES * G::CS * KP * (int)sizeof(TC);           // W pass flush / accumulator
+    static constexpr int WTAIL_BYTES = GW_BYTES_AL + WACC_BYTES;                          // + GW rows of the channel block
     // the W pass keeps CPW x KP ratio sums per lane in registers when they fit, else in shared memory
     static constexpr bool FAST32 = !SAFE && sizeof(TX) == 4 && sizeof(TC) == 4;
     static constexpr int ACC_WORDS = G::CPW * KP * (FAST32 ? 2 : (int)sizeof(TC) / 4);
@@ -145,18 +147,23 @@ struct Ring {
         mbar_fence_init();
     }
     __device__ __forceinline__ unsigned char* stage(int slot) { return stages + (size_t)slot * STRIDE; }
-    // producer: wait until the slot of fill number `cnt` is free; returns the slot
-    __device__ __forceinline__ int acquire(uint32_t cnt) {
-        const int slot = cnt % depth;
-        mbar_wait(&empty[slot], ((cnt / depth) & 1u) ^ 1u);
-        return slot;
+    // position in the ring: slot index + phase parity (no integer division in the loops)
+    struct Pos {
+        int slot;
+        uint32_t phase;
+    };
+    __device__ __forceinline__ void next(Pos& p) const {
+        if (++p.slot == depth) {
+            p.slot = 0;
+            p.phase ^= 1u;
+        }
     }
-    __device__ __forceinline__ void consumer_wait(uint32_t cnt) {
-        mbar_wait(&full[cnt % depth], (cnt / depth) & 1u);
-    }
-    __device__ __forceinline__ void consumer_release(uint32_t cnt, int lane) {
+    // producer: wait until the slot is free
+    __device__ __forceinline__ void acquire(const Pos& p) { mbar_wait(&empty[p.slot], p.phase ^ 1u); }
+    __device__ __forceinline__ void consumer_wait(const Pos& p) { mbar_wait(&full[p.slot], p.phase); }
+    __device__ __forceinline__ void consumer_release(const Pos& p, int lane) {
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[cnt % depth]);
+        if (lane == 0) mbar_arrive(&empty[p.slot]);
     }
 };
 
@@ -188,12 +195,13 @@ h_pass_kernel(const XPassArgs a) {
             const uint64_t pol_x = l2_policy_evict_first();
             const uint64_t pol_gw = l2_policy_evict_last();
             const bool dual = SAFE && a.dual;
-            uint32_t cnt = 0;
+            typename Ring<S::H_STRIDE>::Pos pos{0, 0u};
             for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
                 const int tile = it / a.nsplit, split = it - tile * a.nsplit;
                 const int s0 = (int)((long long)split * NS / a.nsplit), s1 = (int)((long long)(split + 1) * NS / a.nsplit);
-                for (int st = s0; st < s1; ++st, ++cnt) {
-                    const int slot = ring.acquire(cnt);
+                for (int st = s0; st < s1; ++st, ring.next(pos)) {
+                    ring.acquire(pos);
+                    const int slot = pos.slot;
                     unsigned char* sp = ring.stage(slot);
                     mbar_expect_tx(&ring.full[slot], S::X_BYTES + S::GW_BYTES * (dual ? 2 : 1));
                     const TX* xsrc = reinterpret_cast<const TX*>(a.Xt) + ((size_t)tile * a.n_pad + (size_t)st * G::CS) * TILE_PX;
@@ -217,7 +225,7 @@ h_pass_kernel(const XPassArgs a) {
     const TC* Hc = reinterpret_cast<const TC*>(a.H);
     double xl_total = 0.0;   // sum x*log2(y) over x>0
     double zl_total = 0.0;   // sum log2(y) over x==0 (weighted by log_shift at the end)
-    uint32_t cnt = 0;
+    typename Ring<S::H_STRIDE>::Pos pos{0, 0u};
 
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const int tile = it / a.nsplit, split = it - tile * a.nsplit;
@@ -235,9 +243,9 @@ h_pass_kernel(const XPassArgs a) {
                     h2[kk][j] = make_float2(h[kk][2 * j], h[kk][2 * j + 1]);
                     num2[kk][j] = make_float2(0.f, 0.f);
                 }
-            for (int st = s0; st < s1; ++st, ++cnt) {
-                ring.consumer_wait(cnt);
-                const unsigned char* xs = ring.stage(cnt % a.depth);
+            for (int st = s0; st < s1; ++st, ring.next(pos)) {
+                ring.consumer_wait(pos);
+                const unsigned char* xs = ring.stage(pos.slot);
                 const unsigned char* gs = xs + S::X_BYTES;
                 float2 xl2 = make_float2(0.f, 0.f);
 #pragma unroll
@@ -260,7 +268,7 @@ h_pass_kernel(const XPassArgs a) {
                         xl2 = __ffma2_rn(x2[j], make_float2(lg2_ftz(y.x), lg2_ftz(y.y)), xl2);
                     }
                 }
-                ring.consumer_release(cnt, lane);
+                ring.consumer_release(pos, lane);
                 xl_total += (double)(xl2.x + xl2.y);
             }
 #pragma unroll
@@ -279,9 +287,9 @@ h_pass_kernel(const XPassArgs a) {
                     num[kk][q] = TC(0);
                     if constexpr (SAFE) hc[kk][q] = (kk < a.k) ? Num<TC>::vmax(h[kk][q], ls) : TC(0);
                 }
-            for (int st = s0; st < s1; ++st, ++cnt) {
-                ring.consumer_wait(cnt);
-                const unsigned char* xs = ring.stage(cnt % a.depth);
+            for (int st = s0; st < s1; ++st, ring.next(pos)) {
+                ring.consumer_wait(pos);
+                const unsigned char* xs = ring.stage(pos.slot);
                 const unsigned char* gs = xs + S::X_BYTES;
                 const unsigned char* gcs = gs + S::GW_BYTES_AL;
                 TC xl = TC(0);
@@ -342,7 +350,7 @@ h_pass_kernel(const XPassArgs a) {
                         }
                     }
                 }
-                ring.consumer_release(cnt, lane);
+                ring.consumer_release(pos, lane);
                 xl_total += (double)xl;
                 zl_total += (double)zl;
             }
@@ -406,13 +414,18 @@ w_pass_kernel(const XPassArgs a) {
     constexpr bool ACC_REG = S::ACC_REG;
     extern __shared__ __align__(128) unsigned char smem[];
     Ring<S::W_STRIDE> ring(smem, a.depth, S::BAR_BYTES + S::MISC_BYTES);
-    // tail: [HALVES][CS][KP] -- flush staging (ACC_REG) or the running accumulator (!ACC_REG)
-    TC* tail = reinterpret_cast<TC*>(smem + S::BAR_BYTES + S::MISC_BYTES + (size_t)a.depth * S::W_STRIDE);
+    // tail: GW rows of the current channel block, then [HALVES][CS][KP] flush staging (ACC_REG) or the
+    // running accumulator (!ACC_REG)
+    unsigned char* tail0 = smem + S::BAR_BYTES + S::MISC_BYTES + (size_t)a.depth * S::W_STRIDE;
+    TC* gwbuf = reinterpret_cast<TC*>(tail0);
+    TC* tail = reinterpret_cast<TC*>(tail0 + S::GW_BYTES_AL);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long total = (long long)a.nstages_tile * a.n_tiles;
     const long long u0 = (long long)blockIdx.x * a.w_upc;
     const long long u1 = (u0 + a.w_upc < total) ? u0 + a.w_upc : total;
+    const int n_units = (u1 > u0) ? (int)(u1 - u0) : 0;
+    const int cb0 = (int)(u0 / a.n_tiles), tile0 = (int)(u0 - (long long)cb0 * a.n_tiles);
 
     if (threadIdx.x == 0) ring.init();
     for (int i = threadIdx.x; i < G::HALVES * G::CS * KP; i += blockDim.x) tail[i] = TC(0);
@@ -421,22 +434,22 @@ w_pass_kernel(const XPassArgs a) {
     if (warp == N_CONSUMER_WARPS) {
         if (lane == 0) {
             const uint64_t pol_x = l2_policy_evict_first();
-            const uint64_t pol_gw = l2_policy_evict_last();
-            const TC* Hn = reinterpret_cast<const TC*>(a.H);
-            uint32_t cnt = 0;
-            for (long long u = u0; u < u1; ++u, ++cnt) {
-                const int cb = (int)(u / a.n_tiles), tile = (int)(u - (long long)cb * a.n_tiles);
-                const int slot = ring.acquire(cnt);
-                unsigned char* sp = ring.stage(slot);
-                mbar_expect_tx(&ring.full[slot], S::X_BYTES + S::GW_BYTES + a.k * S::HROW_BYTES);
+            const uint64_t pol_h = l2_policy_evict_last();
+            const TC* Ht = reinterpret_cast<const TC*>(a.Ht);
+            typename Ring<S::W_STRIDE>::Pos pos{0, 0u};
+            int cb = cb0, tile = tile0;
+            for (int i = 0; i < n_units; ++i, ring.next(pos)) {
+                ring.acquire(pos);
+                unsigned char* sp = ring.stage(pos.slot);
+                mbar_expect_tx(&ring.full[pos.slot], S::X_BYTES + KP * S::HROW_BYTES);
                 const TX* xsrc = reinterpret_cast<const TX*>(a.Xt) + ((size_t)tile * a.n_pad + (size_t)cb * G::CS) * TILE_PX;
-                tma_bulk_g2s(sp, xsrc, S::X_BYTES, &ring.full[slot], pol_x);
-                const TC* gsrc = reinterpret_cast<const TC*>(a.GW) + (size_t)cb * G::CS * KP;
-                tma_bulk_g2s(sp + S::X_BYTES, gsrc, S::GW_BYTES, &ring.full[slot], pol_gw);
-                unsigned char* hp = sp + S::X_BYTES + S::GW_BYTES_AL;
-                for (int kk = 0; kk < a.k; ++kk)
-                    tma_bulk_g2s(hp + kk * S::HROW_BYTES, Hn + (size_t)kk * a.ldh + (size_t)tile * TILE_PX,
-                                 S::HROW_BYTES, &ring.full[slot], pol_gw);
+                tma_bulk_g2s(sp, xsrc, S::X_BYTES, &ring.full[pos.slot], pol_x);
+                tma_bulk_g2s(sp + S::X_BYTES, Ht + (size_t)tile * KP * TILE_PX, KP * S::HROW_BYTES, &ring.full[pos.slot],
+                             pol_h);
+                if (++tile == a.n_tiles) {
+                    tile = 0;
+                    ++cb;
+                }
             }
         }
         return;
@@ -493,18 +506,21 @@ w_pass_kernel(const XPassArgs a) {
         }
     };
 
-    uint32_t cnt = 0;
-    int cb_cur = (u0 < u1) ? (int)(u0 / a.n_tiles) : -1;
-    for (long long u = u0; u < u1; ++u, ++cnt) {
-        const int cb = (int)(u / a.n_tiles);
-        if (cb != cb_cur) {
-            flush(cb_cur);
-            cb_cur = cb;
-        }
-        ring.consumer_wait(cnt);
-        const unsigned char* xs = ring.stage(cnt % a.depth);
-        const unsigned char* gs = xs + S::X_BYTES;
-        const TC* hs = reinterpret_cast<const TC*>(gs + S::GW_BYTES_AL);
+    // GW rows of a channel block: CS x KP values, kept in shared memory while the block is processed
+    auto load_gw = [&](int cb) {
+        const TC* src = reinterpret_cast<const TC*>(a.GW) + (size_t)cb * G::CS * KP;
+        for (int i = threadIdx.x; i < G::CS * KP; i += N_CONSUMER_THREADS) gwbuf[i] = src[i];
+        named_bar_sync(1, N_CONSUMER_THREADS);
+    };
+
+    typename Ring<S::W_STRIDE>::Pos pos{0, 0u};
+    int cb = cb0, tile = tile0;
+    if (n_units > 0) load_gw(cb);
+    for (int i = 0; i < n_units; ++i, ring.next(pos)) {
+        ring.consumer_wait(pos);
+        const unsigned char* xs = ring.stage(pos.slot);
+        const unsigned char* gs = reinterpret_cast<const unsigned char*>(gwbuf);
+        const TC* hs = reinterpret_cast<const TC*>(xs + S::X_BYTES);
         TC h[KP][PPL];
         load_h<TC, KP, PPL>(h, hs, TILE_PX, a.k, lane_px);
 
@@ -584,9 +600,15 @@ w_pass_kernel(const XPassArgs a) {
                 }
             }
         }
-        ring.consumer_release(cnt, lane);
+        ring.consumer_release(pos, lane);
+        if (++tile == a.n_tiles && i + 1 < n_units) {
+            flush(cb);   // ends with a barrier: every warp is done with gwbuf
+            tile = 0;
+            ++cb;
+            load_gw(cb);
+        }
     }
-    if (cb_cur >= 0) flush(cb_cur);
+    if (n_units > 0) flush(cb);
 }
 
 }  // namespace espm

@@ -186,7 +186,9 @@ class FitEngine:
         self.records = zeros(self.max_records, L.NSCALARS, dtype=torch.float64)
         st.numraw, st.num, st.den = self.numraw.data_ptr(), self.num.data_ptr(), self.den.data_ptr()
         st.s_part, st.s_sum = self.s_part.data_ptr(), self.s_sum.data_ptr()
-        st.t_mk = 0
+        # tile-major copy of H_next read by the W pass; pad pixels stay 1 (y > 0), pad rows are never read
+        self.Ht = torch.ones(st.n_tiles * kp * L.TILE_PX, dtype=cdt, device=dev)
+        st.Ht = self.Ht.data_ptr()
         st.w_num, st.w_den = self.w_num.data_ptr(), self.w_den.data_ptr()
         st.xlogy_part, st.px_part = self.xlogy_part.data_ptr(), self.px_part.data_ptr()
         st.bisect_mask, st.dev_flags = self.mask.data_ptr(), self.dev_flags.data_ptr()
@@ -409,6 +411,7 @@ class FitEngine:
         """One W update from (W_cur, H_cur) (the H given by the caller plays the role of H')."""
         st = self.st
         st.H_next = st.H_cur
+        self._call(self.lib.espm_h_stats)      # rebuilds Ht from H_next (= H_cur); hstats go to the `next` slot
         st.hstats_next = st.hstats_cur
         self._set_record(0)
         self._call(self.lib.espm_w_pass)

@@ -160,7 +160,7 @@ typedef struct espm_state {
     void* den;              /* kp x p_loc */
     void* s_part;           /* w_nr x n_pad x kp */
     void* s_sum;            /* n_pad x kp: sum over tile ranges; all-reduced across ranks by the host */
-    void* t_mk;             /* m x k: G^T S (identity G: aliases s_sum semantics) */
+    void* Ht;               /* tile-major copy of H_next for the W pass: [n_tiles][kp][128] (pad pixels > 0) */
     void* w_num;            /* m x k scratch */
     void* w_den;            /* m x k scratch */
     double* xlogy_part;     /* h_grid */
@@ -196,7 +196,8 @@ int espm_retile_x(const espm_state* st, const void* src, int32_t src_dtype, int6
 int espm_gw_prepare(const espm_state* st, void* stream);
 /* colsum_G[m] = sum_c G[c][m]  (updates.py:60). */
 int espm_colsum_g(const espm_state* st, void* colsum_out, void* stream);
-/* hstats_next = {rowsum, rowsum(max(.,ls)), rowmax} of H_next over the local pixels (updates.py:139). */
+/* hstats_next = {rowsum, rowsum(max(.,ls)), rowmax} of H_next over the local pixels (updates.py:139);
+ * also rebuilds Ht from H_next (used when H_next was written by the host rather than by a kernel). */
 int espm_h_stats(const espm_state* st, void* stream);
 
 /*
@@ -212,7 +213,7 @@ int espm_h_pass(const espm_state* st, void* stream);
  *   otherwise: H_next = max(num/den, ls) (+fixed_H) directly (updates.py:152-155).
  */
 int espm_h_finish(const espm_state* st, void* stream);
-/* Replays exactly it* bisection iterations (first clear bit of bisect_mask) and writes H_next. */
+/* Replays exactly it* bisection iterations (first clear bit of bisect_mask) and writes H_next (and Ht). */
 int espm_h_apply(const espm_state* st, void* stream);
 /* Reduces the H-side partials into st->scalars (loss parts of the current iterate, rel_H, flags). */
 int espm_h_scalars(const espm_state* st, void* stream);
