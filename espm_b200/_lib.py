@@ -28,6 +28,8 @@ FLAG_LAPLACIAN = 1 << 8
 FLAG_HAVE_HPREV = 1 << 9
 FLAG_SIMPLEX_ROWS = 1 << 10
 FLAG_HQ = 1 << 11
+FLAG_FUSED_WREDUCE = 1 << 12
+COOP_BLOCKS = 32
 
 # device error word
 DEV_NONFINITE = 1 << 0
@@ -66,7 +68,7 @@ class EspmState(ctypes.Structure):
         ("fixed_H", _vp), ("fixed_W", _vp), ("simplex_rows", _vp),
         ("numraw", _vp), ("num", _vp), ("den", _vp),
         ("s_part", _vp), ("s_sum", _vp), ("Ht", _vp), ("w_num", _vp), ("w_den", _vp),
-        ("xlogy_part", _vp), ("px_part", _vp), ("bisect_mask", _vp), ("dev_flags", _vp), ("scalars", _vp),
+        ("xlogy_part", _vp), ("px_part", _vp), ("bisect_mask", _vp), ("dev_flags", _vp), ("scalars", _vp), ("coop_part", _vp),
     ]
 
 

@@ -77,6 +77,7 @@ static XPassArgs make_args(const espm_state* st, bool w_pass) {
     a.Ht = st->Ht;
     a.numraw = st->numraw;
     a.xlogy_part = st->xlogy_part;
+    a.bisect_mask = st->bisect_mask;
     a.s_part = st->s_part;
     a.n_pad = st->n_pad;
     a.k = st->k;
@@ -292,8 +293,7 @@ int espm_colsum_g(const espm_state* st, void* colsum_out, void* stream) {
 int espm_h_pass(const espm_state* st, void* stream) {
     int rc = check_state(st);
     if (rc) return rc;
-    // the trace mask of the coming h_finish is cleared here, ahead of it on the same stream
-    ESPM_CUDA_CHECK(cudaMemsetAsync(st->bisect_mask, 0, 4 * sizeof(uint32_t), (cudaStream_t)stream));
+    // (the kernel also clears the trace mask of the coming h_finish)
     XPassArgs a = make_args(st, false);
     XPassLaunch l{XPASS_H, st->kp, is_safe(st) ? 1 : 0, st->h_grid, st->h_smem};
     return pick_xpass(st)(l, &a, nullptr, (cudaStream_t)stream);

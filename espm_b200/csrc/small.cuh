@@ -6,6 +6,22 @@
 namespace espm {
 
 constexpr int PX_THREADS = 256;
+
+// KP consecutive values of one row (16-byte vector loads when the row size allows it)
+template <typename T, int N>
+__device__ __forceinline__ void lds_row(T (&dst)[N], const T* src) {
+    constexpr int BYTES = N * (int)sizeof(T);
+    if constexpr (BYTES % 16 == 0) {
+        const uint4* s4 = reinterpret_cast<const uint4*>(src);
+        uint4 tmp[BYTES / 16];
+#pragma unroll
+        for (int i = 0; i < BYTES / 16; ++i) tmp[i] = s4[i];
+        memcpy(dst, tmp, BYTES);
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) dst[i] = src[i];
+    }
+}
 constexpr int PX_WARPS = PX_THREADS / 32;
 
 // px_part row layout (doubles), sums first, maxima last:
@@ -16,14 +32,22 @@ __host__ __device__ inline int px_part_nsum(int kp) { return 2 + 2 * kp; }
 
 // ------------------------------------------------------------------------------------------------
 // simplex function  f(x) = sum_k max(num_k / (x + den_k), ls) - 1   (dicotomy.py:51-53)
-// Sequential sum over k, IEEE division: the same arithmetic as the NumPy reference.
+// Sequential sum over k like the NumPy reference.  The bisection only consumes the SIGN of f and the
+// test |f| <= tol, and the midpoints (a+b)/2 are exact either way, so the fp64 quotient may be the
+// <= 1 ulp Newton reciprocal (Num<double>::ratio) instead of the ~3x more expensive IEEE division: nu is
+// bit-identical to the reference unless some |f| lands within 1e-16 of 0 or of tol.
 // ------------------------------------------------------------------------------------------------
+template <typename TC>
+__device__ __forceinline__ TC simplex_quot(TC a, TC b) {
+    if constexpr (sizeof(TC) == 8) return Num<TC>::ratio(a, b);
+    else return a / b;
+}
 template <typename TC, int KP>
 __device__ __forceinline__ TC simplex_f(const TC (&num)[KP], const TC (&den)[KP], TC x, int k, TC ls) {
-    TC s = Num<TC>::vmax(num[0] / (x + den[0]), ls);
+    TC s = Num<TC>::vmax(simplex_quot<TC>(num[0], x + den[0]), ls);
 #pragma unroll
     for (int kk = 1; kk < KP; ++kk)
-        if (kk < k) s += Num<TC>::vmax(num[kk] / (x + den[kk]), ls);
+        if (kk < k) s += Num<TC>::vmax(simplex_quot<TC>(num[kk], x + den[kk]), ls);
     return s - TC(1);
 }
 
@@ -187,6 +211,9 @@ __device__ __forceinline__ void store_h_next(const espm_state& st, int j, int k,
         }
 }
 
+template <typename TC>
+__device__ __forceinline__ void h_scalars_block(const espm_state& st);
+
 // ------------------------------------------------------------------------------------------------
 // h_finish: per-pixel assembly (updates.py:132-152) + loss regularisers + rel_H + bisection trace
 // ------------------------------------------------------------------------------------------------
@@ -313,6 +340,18 @@ __global__ void __launch_bounds__(PX_THREADS) h_finish_kernel(const espm_state s
     }
     block_reduce_vals<NV>(vals, px_part_nsum(KP), st.px_part + (size_t)blockIdx.x * NV);
     merge_mask(bits, err, simplex ? st.bisect_mask : nullptr, st.dev_flags);
+    // The last CTA to finish folds every partial into the scalar record (what espm_h_scalars does),
+    // in a fixed order that does not depend on which CTA that is.
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(&st.dev_flags[2], 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        h_scalars_block<TC>(st);
+        if (threadIdx.x == 0) st.dev_flags[2] = 0u;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -409,7 +448,7 @@ __global__ void __launch_bounds__(256) hstats_reduce_kernel(const espm_state st)
 // h_scalars: loss parts of the current iterate + rel_H + bisection count into the scalar record
 // ------------------------------------------------------------------------------------------------
 template <typename TC>
-__global__ void __launch_bounds__(256) h_scalars_kernel(const espm_state st) {
+__device__ __forceinline__ void h_scalars_block(const espm_state& st) {
     __shared__ double sm[8][4];
     const int kp = st.kp, stride = px_part_stride(kp);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -457,6 +496,11 @@ __global__ void __launch_bounds__(256) h_scalars_kernel(const espm_state st) {
         rec[ESPM_S_DEV_FLAGS] = (double)st.dev_flags[0];
         rec[ESPM_S_MEAN_H] = meanh / ((double)st.k * (double)st.p_total);
     }
+}
+
+template <typename TC>
+__global__ void __launch_bounds__(256) h_scalars_kernel(const espm_state st) {
+    h_scalars_block<TC>(st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -567,184 +611,320 @@ __global__ void __launch_bounds__(256) colsum_g_kernel(const TC* Gt, int n, int 
 }
 
 // ------------------------------------------------------------------------------------------------
-// w_finish: W update (updates.py:58-76) in a single CTA of 1024 threads.
+// w_finish: the W update (updates.py:58-76) + GW' for the next H pass, as ONE cooperative kernel of
+// W_COOP_BLOCKS CTAs separated by grid barriers:
+//   phase 0 (all CTAs, optional)  s_sum = sum of the W-pass partial slots; H' row statistics
+//   phase A (all CTAs)            num = W * (G^T S),  den = colsum(G) (x) rowsum(H')
+//   phase B (CTA 0)               simplex_W lock-step bisection, W' = max(num/den, ls), fixed_W, rel_W
+//   phase C (all CTAs)            GW' = G W' (+ pad rows, clamped copy), per-CTA column sums / flags
+//   phase D (CTA 0)               column sums in CTA order (deterministic), flags
 // ------------------------------------------------------------------------------------------------
-template <typename TC>
-__global__ void __launch_bounds__(1024) w_finish_kernel(const espm_state st) {
-    __shared__ double sm[32 * 2 * ESPM_MAX_K];
+constexpr int W_COOP_BLOCKS = 32;
+constexpr int W_COOP_THREADS = 256;
+
+// Grid barrier for a cooperative launch: monotonically increasing arrival counter, every CTA arrives
+// exactly once per barrier, so the target of an arrival is the next multiple of the grid size.
+__device__ __forceinline__ void grid_barrier(uint32_t* ctr, uint32_t nblocks) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const uint32_t t = atomicAdd(ctr, 1u);
+        const uint32_t target = (t / nblocks + 1u) * nblocks;
+        while (*reinterpret_cast<volatile uint32_t*>(ctr) < target) {
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+template <typename TC, int KP>
+__global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_state st) {
+    __shared__ double sm[8 * 2 * ESPM_MAX_K + 8];
     __shared__ double col_a[ESPM_MAX_K], col_b[ESPM_MAX_K], col_fa[ESPM_MAX_K], col_new[ESPM_MAX_K],
         col_fn[ESPM_MAX_K];
     __shared__ int s_its;
     __shared__ uint32_t s_err;
-    const int k = st.k, kp = st.kp, m = st.m, n = st.n;
+    const int k = st.k, m = st.m, n = st.n;
     const TC ls = (TC)st.log_shift;
     const bool ident = st.flags & ESPM_FLAG_G_IDENTITY;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    const TC* S = reinterpret_cast<const TC*>(st.s_sum);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int NWARPS = W_COOP_THREADS / 32;
+    const int gthread = blockIdx.x * W_COOP_THREADS + threadIdx.x;
+    const int gthreads = gridDim.x * W_COOP_THREADS;
+    uint32_t* bar = st.dev_flags + 3;
+    TC* S = reinterpret_cast<TC*>(st.s_sum);
     const TC* Gt = reinterpret_cast<const TC*>(st.Gt);
     const TC* W = reinterpret_cast<const TC*>(st.W_cur);
     const TC* colsumG = reinterpret_cast<const TC*>(st.colsum_G);
-    const double* hstats = reinterpret_cast<const double*>(st.hstats_next);
+    double* hstats = reinterpret_cast<double*>(st.hstats_next);
     TC* wnum = reinterpret_cast<TC*>(st.w_num);
     TC* wden = reinterpret_cast<TC*>(st.w_den);
     TC* Wn = reinterpret_cast<TC*>(st.W_next);
-    if (threadIdx.x == 0) {
-        s_its = 0;
-        s_err = 0u;
+
+    // ---- phase 0: fold the W-pass partial slots and the per-pixel statistics ----
+    if (st.flags & ESPM_FLAG_FUSED_WREDUCE) {
+        const size_t total = (size_t)st.n_pad * KP;
+        const TC* part = reinterpret_cast<const TC*>(st.s_part);
+        for (size_t i = gthread; i < total; i += gthreads) {
+            const int cb = (int)(i / ((size_t)st.cs * KP));
+            const int first = (int)(((long long)cb * st.n_tiles) / st.w_upc);
+            const int last = (int)((((long long)cb + 1) * st.n_tiles - 1) / st.w_upc);
+            TC v = part[i];
+            for (int r = 1; r <= last - first; ++r) v += part[(size_t)r * total + i];
+            S[i] = v;
+        }
+        if (blockIdx.x == gridDim.x - 1) reduce_hstats_block(st, hstats);
+        grid_barrier(bar, gridDim.x);
     }
 
-    // ---- num = W * (G^T S), den = colsum(G) (x) rowsum(H')   (updates.py:58-60) ----
+    // ---- phase A: num = W * (G^T S), den = colsum(G) (x) rowsum(H')   (updates.py:58-60) ----
     if (ident) {
-        for (int i = threadIdx.x; i < m * k; i += blockDim.x) {
+        for (int i = gthread; i < m * k; i += gthreads) {
             const int mm = i / k, kk = i - mm * k;
-            wnum[i] = W[i] * S[(size_t)mm * kp + kk];
+            wnum[i] = W[i] * S[(size_t)mm * KP + kk];
             wden[i] = (TC)hstats[kk];
         }
     } else {
-        for (int o = warp; o < m * k; o += nwarps) {
-            const int mm = o / k, kk = o - mm * k;
-            TC acc = TC(0);
-            for (int c = lane; c < n; c += 32) acc = fma(Gt[(size_t)mm * n + c], S[(size_t)c * kp + kk], acc);
-            acc = warp_sum(acc);
-            if (lane == 0) {
-                wnum[o] = W[o] * acc;
-                wden[o] = colsumG[mm] * (TC)hstats[kk];
+        for (int mm = blockIdx.x * NWARPS + warp; mm < m; mm += gridDim.x * NWARPS) {
+            TC acc[KP];
+#pragma unroll
+            for (int kk = 0; kk < KP; ++kk) acc[kk] = TC(0);
+            for (int c = lane; c < n; c += 32) {
+                const TC g = Gt[(size_t)mm * n + c];
+                TC srow[KP];
+                lds_row<TC, KP>(srow, S + (size_t)c * KP);
+#pragma unroll
+                for (int kk = 0; kk < KP; ++kk) acc[kk] = fma(g, srow[kk], acc[kk]);
+            }
+#pragma unroll
+            for (int kk = 0; kk < KP; ++kk) {
+                const TC v = warp_sum(acc[kk]);
+                if (lane == 0 && kk < k) {
+                    wnum[mm * k + kk] = W[mm * k + kk] * v;
+                    wden[mm * k + kk] = colsumG[mm] * (TC)hstats[kk];
+                }
             }
         }
     }
-    __syncthreads();
+    grid_barrier(bar, gridDim.x);
 
-    // ---- simplex_W: lock-step bisection over the k columns (updates.py:61-68, dicotomy.py) ----
-    if (st.flags & ESPM_FLAG_SIMPLEX_W) {
-        const bool sub = st.flags & ESPM_FLAG_SIMPLEX_ROWS;
-        const int nrows = sub ? st.n_simplex_rows : m;
-        typedef double TB;  // the bisection runs in fp64 in every mode (m x k data)
-        const TB tol = st.dicotomy_tol_w;
-        const TB lsb = st.log_shift;
-        auto row_of = [&](int i) { return sub ? st.simplex_rows[i] : i; };
-        auto feval = [&](int kk, TB x) {  // warp-collective: sum_rows max(num/(x+den), ls) - 1
-            TB s = 0.0;
-            for (int i = lane; i < nrows; i += 32) {
-                const int o = row_of(i) * k + kk;
-                s += fmax((TB)wnum[o] / (x + (TB)wden[o]), lsb);
-            }
-            return warp_sum(s) - 1.0;
-        };
-        if (warp < k) {
-            const int kk = warp;
-            TB amax = -Num<TB>::inf(), nmax = -Num<TB>::inf(), dmin = Num<TB>::inf(), nsum = 0.0;
-            bool neg = false;
-            for (int i = lane; i < nrows; i += 32) {
-                const int o = row_of(i) * k + kk;
-                const TB nv = (TB)wnum[o], dv = (TB)wden[o];
-                if (nv > 0.0) amax = fmax(amax, nv / 2.0 - dv);
-                nmax = fmax(nmax, nv);
-                dmin = fmin(dmin, dv);
-                nsum += nv;
-                neg |= (nv < 0.0) || (dv < 0.0);
-            }
-            amax = warp_max(amax);
-            nmax = warp_max(nmax);
-            dmin = -warp_max(-dmin);
-            nsum = warp_sum(nsum);
-            neg = __any_sync(0xffffffffu, neg);
-            const TB a = amax, b = (TB)nrows * nmax / 0.5 - dmin;
-            const TB fa = feval(kk, a), fb = feval(kk, b);
-            const TB nw = (a + b) / 2.0;
-            const TB fn = feval(kk, nw);
-            if (lane == 0) {
-                uint32_t e = 0u;
-                if (!(fa > 0.0) || !(fb < 0.0)) e |= ESPM_DEV_BRACKET;
-                if (neg || !(nsum > 0.0)) e |= ESPM_DEV_NEGATIVE;
-                if (e) atomicOr(&s_err, e);
-                col_a[kk] = a;
-                col_b[kk] = b;
-                col_fa[kk] = fa;
-                col_new[kk] = nw;
-                col_fn[kk] = fn;
-            }
+    // ---- phase B (CTA 0): simplex_W, W', rel_W ----
+    if (blockIdx.x == 0) {
+        if (threadIdx.x == 0) {
+            s_its = 0;
+            s_err = 0u;
         }
         __syncthreads();
-        int it = 0;
-        while (true) {
-            double worst = 0.0;
-            for (int kk = 0; kk < k; ++kk) {
-                const double v = fabs(col_fn[kk]);
-                worst = v > worst ? v : worst;
-            }
-            if (!(worst > (double)tol)) break;  // dicotomy.py:152
-            it += 1;
-            __syncthreads();
-            if (warp < k) {
-                const int kk = warp;
-                TB a = col_a[kk], b = col_b[kk], fa = col_fa[kk], nw = col_new[kk], fn = col_fn[kk];
-                if (fa * fn <= 0.0) {
-                    b = nw;
-                } else {
-                    a = nw;
-                    fa = fn;
+        // simplex_W: lock-step bisection over the k columns (updates.py:61-68, dicotomy.py)
+        if (st.flags & ESPM_FLAG_SIMPLEX_W) {
+            const bool sub = st.flags & ESPM_FLAG_SIMPLEX_ROWS;
+            const int nrows = sub ? st.n_simplex_rows : m;
+            typedef double TB;  // the bisection runs in fp64 in every mode (m x k data)
+            const TB tol = st.dicotomy_tol_w;
+            const TB lsb = st.log_shift;
+            auto row_of = [&](int i) { return sub ? st.simplex_rows[i] : i; };
+            auto feval = [&](int kk, TB x) {  // warp-collective: sum_rows max(num/(x+den), ls) - 1
+                TB sacc = 0.0;
+                for (int i = lane; i < nrows; i += 32) {
+                    const int o = row_of(i) * k + kk;
+                    sacc += fmax((TB)wnum[o] / (x + (TB)wden[o]), lsb);
                 }
-                nw = (a + b) / 2.0;
-                fn = feval(kk, nw);
+                return warp_sum(sacc) - 1.0;
+            };
+            for (int kk = warp; kk < k; kk += NWARPS) {
+                TB amax = -Num<TB>::inf(), nmax = -Num<TB>::inf(), dmin = Num<TB>::inf(), nsum = 0.0;
+                bool neg = false;
+                for (int i = lane; i < nrows; i += 32) {
+                    const int o = row_of(i) * k + kk;
+                    const TB nv = (TB)wnum[o], dv = (TB)wden[o];
+                    if (nv > 0.0) amax = fmax(amax, nv / 2.0 - dv);
+                    nmax = fmax(nmax, nv);
+                    dmin = fmin(dmin, dv);
+                    nsum += nv;
+                    neg |= (nv < 0.0) || (dv < 0.0);
+                }
+                amax = warp_max(amax);
+                nmax = warp_max(nmax);
+                dmin = -warp_max(-dmin);
+                nsum = warp_sum(nsum);
+                neg = __any_sync(0xffffffffu, neg);
+                const TB a = amax, b = (TB)nrows * nmax / 0.5 - dmin;
+                const TB fa = feval(kk, a), fb = feval(kk, b);
+                const TB nw = (a + b) / 2.0;
+                const TB fn = feval(kk, nw);
                 if (lane == 0) {
-                    col_a[kk] = (double)a;
-                    col_b[kk] = (double)b;
-                    col_fa[kk] = (double)fa;
-                    col_new[kk] = (double)nw;
-                    col_fn[kk] = (double)fn;
+                    uint32_t e = 0u;
+                    if (!(fa > 0.0) || !(fb < 0.0)) e |= ESPM_DEV_BRACKET;
+                    if (neg || !(nsum > 0.0)) e |= ESPM_DEV_NEGATIVE;
+                    if (e) atomicOr(&s_err, e);
+                    col_a[kk] = a;
+                    col_b[kk] = b;
+                    col_fa[kk] = fa;
+                    col_new[kk] = nw;
+                    col_fn[kk] = fn;
                 }
             }
             __syncthreads();
-            if (it >= st.maxit) break;  // dicotomy.py:169-171
+            int it = 0;
+            while (true) {
+                double worst = 0.0;
+                for (int kk = 0; kk < k; ++kk) {
+                    const double v = fabs(col_fn[kk]);
+                    worst = v > worst ? v : worst;
+                }
+                if (!(worst > (double)tol)) break;  // dicotomy.py:152
+                it += 1;
+                __syncthreads();
+                for (int kk = warp; kk < k; kk += NWARPS) {
+                    TB a = col_a[kk], b = col_b[kk], fa = col_fa[kk], nw = col_new[kk], fn = col_fn[kk];
+                    if (fa * fn <= 0.0) {
+                        b = nw;
+                    } else {
+                        a = nw;
+                        fa = fn;
+                    }
+                    nw = (a + b) / 2.0;
+                    fn = feval(kk, nw);
+                    if (lane == 0) {
+                        col_a[kk] = a;
+                        col_b[kk] = b;
+                        col_fa[kk] = fa;
+                        col_new[kk] = nw;
+                        col_fn[kk] = fn;
+                    }
+                }
+                __syncthreads();
+                if (it >= st.maxit) break;  // dicotomy.py:169-171
+            }
+            if (threadIdx.x == 0) s_its = it;
+            // denum[rows] += nu (updates.py:65,68)
+            for (int i = threadIdx.x; i < nrows * k; i += W_COOP_THREADS) {
+                const int r = row_of(i / k), kk = i % k;
+                wden[r * k + kk] += (TC)col_new[kk];
+            }
+            __syncthreads();
         }
-        if (threadIdx.x == 0) s_its = it;
-        // denum[rows] += nu (updates.py:65,68)
-        for (int i = threadIdx.x; i < nrows * k; i += blockDim.x) {
-            const int r = row_of(i / k), kk = i % k;
-            wden[r * k + kk] += (TC)col_new[kk];
-        }
-        __syncthreads();
-    }
 
-    // ---- W' = max(num/den, ls), fixed_W (updates.py:70-76); rel_W (base.py:323) ----
-    const TC* fw = reinterpret_cast<const TC*>(st.fixed_W);
-    double wsum = 0.0;
-    for (int i = threadIdx.x; i < m * k; i += blockDim.x) {
-        TC v = Num<TC>::vmax(wnum[i] / wden[i], ls);
-        if (st.flags & ESPM_FLAG_FIXED_W) {
-            const TC f = fw[i];
-            if (f >= TC(0)) v = f;
+        // W' = max(num/den, ls), fixed_W (updates.py:70-76); rel_W (base.py:323)
+        const TC* fw = reinterpret_cast<const TC*>(st.fixed_W);
+        double wsum = 0.0;
+        for (int i = threadIdx.x; i < m * k; i += W_COOP_THREADS) {
+            TC v = Num<TC>::vmax(wnum[i] / wden[i], ls);
+            if (st.flags & ESPM_FLAG_FIXED_W) {
+                const TC f = fw[i];
+                if (f >= TC(0)) v = f;
+            }
+            Wn[i] = v;
+            wsum += (double)v;
         }
-        Wn[i] = v;
-        wsum += (double)v;
+        wsum = warp_sum(wsum);
+        if (lane == 0) sm[warp] = wsum;
+        __syncthreads();
+        double meanW = 0.0;
+        for (int w = 0; w < NWARPS; ++w) meanW += sm[w];
+        meanW /= (double)(m * k);
+        __syncthreads();
+        double rel = 0.0;
+        for (int i = threadIdx.x; i < m * k; i += W_COOP_THREADS) {
+            const double wn = (double)Wn[i], wo = (double)W[i];
+            const double r = fabs(wn - wo) / (wn + st.tol * meanW);
+            rel = r > rel ? r : rel;
+        }
+        rel = warp_max(rel);
+        if (lane == 0) sm[warp] = rel;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double r = sm[0];
+            for (int w = 1; w < NWARPS; ++w) r = sm[w] > r ? sm[w] : r;
+            st.scalars[ESPM_S_REL_W] = r;
+            st.scalars[ESPM_S_BISECT_ITS_W] = (double)s_its;
+            st.scalars[ESPM_S_MEAN_W] = meanW;
+            if (s_err) atomicOr(&st.dev_flags[0], s_err);
+        }
     }
-    wsum = warp_sum(wsum);
-    if (lane == 0) sm[warp] = wsum;
-    __syncthreads();
-    double meanW = 0.0;
-    for (int w = 0; w < nwarps; ++w) meanW += sm[w];
-    meanW /= (double)(m * k);
-    __syncthreads();
-    double rel = 0.0;
-    for (int i = threadIdx.x; i < m * k; i += blockDim.x) {
-        const double wn = (double)Wn[i], wo = (double)W[i];
-        const double r = fabs(wn - wo) / (wn + st.tol * meanW);
-        rel = r > rel ? r : rel;
+    grid_barrier(bar, gridDim.x);
+
+    // ---- phase C: GW' = G W' for the next H pass (updates.py:107), one channel per thread ----
+    {
+        TC* GW = reinterpret_cast<TC*>(st.GW_next);
+        TC* GWc = reinterpret_cast<TC*>(st.GWc_next);
+        double cs[KP], csc[KP];
+#pragma unroll
+        for (int kk = 0; kk < KP; ++kk) cs[kk] = csc[kk] = 0.0;
+        uint32_t flags = 0u;
+        for (int c = gthread; c < st.n_pad; c += gthreads) {
+            TC v[KP];
+#pragma unroll
+            for (int kk = 0; kk < KP; ++kk) v[kk] = TC(0);
+            if (c >= n) {
+                v[0] = TC(1);  // pad channel: y = H[0] > 0, contributes nothing
+            } else if (ident) {
+#pragma unroll
+                for (int kk = 0; kk < KP; ++kk)
+                    if (kk < k) v[kk] = Wn[(size_t)c * k + kk];
+            } else {
+                for (int mm = 0; mm < m; ++mm) {
+                    const TC g = Gt[(size_t)mm * n + c];   // coalesced over the channels of a warp
+#pragma unroll
+                    for (int kk = 0; kk < KP; ++kk)
+                        if (kk < k) v[kk] = fma(g, Wn[(size_t)mm * k + kk], v[kk]);
+                }
+            }
+            bool all_zero = true;
+#pragma unroll
+            for (int kk = 0; kk < KP; ++kk) {
+                const bool real = c < n && kk < k;
+                const TC vc = real ? Num<TC>::vmax(v[kk], ls) : v[kk];
+                GW[(size_t)c * KP + kk] = v[kk];
+                GWc[(size_t)c * KP + kk] = vc;
+                if (real) {
+                    cs[kk] += (double)v[kk];
+                    csc[kk] += (double)vc;
+                    if (v[kk] < ls) flags |= ESPM_DEV_GW_BELOW_LS;
+                    if (v[kk] > TC(0)) all_zero = false;
+                }
+            }
+            if (c < n && all_zero) flags |= ESPM_DEV_GW_ZERO_ROW;
+        }
+        // per-CTA column sums (fixed order) -> coop_part[block][2*KP + 1]
+#pragma unroll
+        for (int kk = 0; kk < KP; ++kk) {
+            const double a = warp_sum(cs[kk]), b = warp_sum(csc[kk]);
+            if (lane == 0) {
+                sm[warp * 2 * KP + kk] = a;
+                sm[warp * 2 * KP + KP + kk] = b;
+            }
+        }
+        const uint32_t f = __reduce_or_sync(0xffffffffu, flags);
+        if (threadIdx.x == 0) s_err = 0u;
+        __syncthreads();
+        if (lane == 0 && f) atomicOr(&s_err, f);
+        __syncthreads();
+        double* part = st.coop_part + (size_t)blockIdx.x * (2 * ESPM_MAX_K + 1);
+        if (threadIdx.x < 2 * KP) {
+            double a = 0.0;
+            for (int w = 0; w < NWARPS; ++w) a += sm[w * 2 * KP + threadIdx.x];
+            part[threadIdx.x] = a;
+        }
+        if (threadIdx.x == 0) part[2 * ESPM_MAX_K] = (double)s_err;
     }
-    rel = warp_max(rel);
-    if (lane == 0) sm[warp] = rel;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double r = sm[0];
-        for (int w = 1; w < nwarps; ++w) r = sm[w] > r ? sm[w] : r;
-        st.scalars[ESPM_S_REL_W] = r;
-        st.scalars[ESPM_S_BISECT_ITS_W] = (double)s_its;
-        st.scalars[ESPM_S_MEAN_W] = meanW;
-        if (s_err) atomicOr(&st.dev_flags[0], s_err);
+    grid_barrier(bar, gridDim.x);
+
+    // ---- phase D (CTA 0): column sums over the CTAs in index order ----
+    if (blockIdx.x == 0) {
+        TC* gwstats = reinterpret_cast<TC*>(st.gwstats_next);
+        if (threadIdx.x < 2 * KP) {
+            double a = 0.0;
+            for (int b = 0; b < (int)gridDim.x; ++b) a += st.coop_part[(size_t)b * (2 * ESPM_MAX_K + 1) + threadIdx.x];
+            gwstats[threadIdx.x] = (TC)a;
+        }
+        if (threadIdx.x == 0) {
+            uint32_t f = 0u;
+            for (int b = 0; b < (int)gridDim.x; ++b) f |= (uint32_t)st.coop_part[(size_t)b * (2 * ESPM_MAX_K + 1) + 2 * ESPM_MAX_K];
+            st.dev_flags[1] = f;
+            st.scalars[ESPM_S_GW_FLAGS] = (double)f;
+        }
     }
-    __syncthreads();
-    // ---- GW' for the next H pass (updates.py:107) ----
-    gw_prepare_block<TC>(st, Wn, sm);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -64,9 +64,15 @@ static int small_launch_t(int op, const espm_state* st, cudaStream_t s) {
             w_reduce_kernel<TC><<<blocks, 256, 0, s>>>(*st);
             break;
         }
-        case OP_W_FINISH:
-            w_finish_kernel<TC><<<1, 1024, 0, s>>>(*st);
+        case OP_W_FINISH: {
+            // cooperative launch: the kernel separates its phases with grid barriers
+            espm_state copy = *st;
+            void* args[] = {&copy};
+            const void* fn = nullptr;
+            ESPM_KP_SWITCH(kp, (fn = (const void*)w_finish_kernel<TC, KP>));
+            ESPM_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(W_COOP_BLOCKS), dim3(W_COOP_THREADS), args, 0, s));
             break;
+        }
         case OP_GW_PREPARE:
             gw_prepare_kernel<TC><<<1, 1024, 0, s>>>(*st);
             break;

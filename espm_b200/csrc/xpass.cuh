@@ -24,6 +24,7 @@ struct XPassArgs {
     const void* Ht;      // W pass: tile-major copy of H_next, [tile][KP][128]
     void* numraw;        // [nsplit][KP][P_pad]
     double* xlogy_part;  // [grid]
+    uint32_t* bisect_mask;  // H pass: cleared for the h_finish that follows
     void* s_part;        // [w_nr][n_pad][KP]
     int n_pad, k, n_tiles, ldh, p_pad;
     int nstages_tile;    // n_pad / CS
@@ -184,6 +185,7 @@ h_pass_kernel(const XPassArgs a) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) ring.init();
+    if (blockIdx.x == 0 && threadIdx.x < 4 && a.bisect_mask) a.bisect_mask[threadIdx.x] = 0u;
     __syncthreads();
 
     const int n_items = a.n_tiles * a.nsplit;

@@ -73,7 +73,8 @@ class FitEngine:
         if x_local:
             p = H0.shape[1]          # X is already this rank's pixel slab (n, p_loc); H0 is global
         self.x_local = x_local
-        self.profile = None          # set to {} to record CUDA events around the two X passes
+        self.profile = None          # set to {} to record CUDA events around kernel launches
+        self.profile_names = ("h_pass", "w_pass")
         k = W0.shape[1]
         self.n, self.p, self.k = n, p, k
         self.identity_G = G is None
@@ -181,7 +182,8 @@ class FitEngine:
         self.xlogy_part = zeros(max(st.h_grid, 1), dtype=torch.float64)
         self.px_part = zeros(st.px_blocks, 3 + 3 * kp, dtype=torch.float64)
         self.mask = torch.zeros(4 * max(self.world, 1), dtype=torch.int32, device=dev)
-        self.dev_flags = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.dev_flags = torch.zeros(8, dtype=torch.int32, device=dev)
+        self.coop_part = zeros(L.COOP_BLOCKS * (2 * L.MAX_K + 1), dtype=torch.float64)
         self.max_records = int(max_records)
         self.records = zeros(self.max_records, L.NSCALARS, dtype=torch.float64)
         st.numraw, st.num, st.den = self.numraw.data_ptr(), self.num.data_ptr(), self.den.data_ptr()
@@ -192,6 +194,9 @@ class FitEngine:
         st.w_num, st.w_den = self.w_num.data_ptr(), self.w_den.data_ptr()
         st.xlogy_part, st.px_part = self.xlogy_part.data_ptr(), self.px_part.data_ptr()
         st.bisect_mask, st.dev_flags = self.mask.data_ptr(), self.dev_flags.data_ptr()
+        st.coop_part = self.coop_part.data_ptr()
+        if shard is None:
+            st.flags |= L.FLAG_FUSED_WREDUCE      # w_finish folds the W-pass partials itself
 
         # ---- constant inputs ----
         self.fixed_H = None
@@ -252,16 +257,18 @@ class FitEngine:
             raise IndexError("scalar record slot %d out of range" % slot)
         self.st.scalars = self.records.data_ptr() + slot * L.NSCALARS * 8
 
-    def _call(self, fn):
-        L.check(fn(ctypes.byref(self.st), self.stream))
-
-    def _call_timed(self, fn, name):
-        if self.profile is None:
-            return self._call(fn)
+    def _call(self, fn, name=None):
+        """Launch one C-ABI entry point on the current stream.  With ``self.profile`` set to a dict,
+        calls whose name is in ``self.profile_names`` (or every named call when that is None) are
+        bracketed by CUDA events."""
+        if self.profile is None or name is None or (self.profile_names is not None
+                                                    and name not in self.profile_names):
+            L.check(fn(ctypes.byref(self.st), self.stream))
+            return
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
-        self._call(fn)
+        L.check(fn(ctypes.byref(self.st), self.stream))
         e1.record()
         self.profile.setdefault(name, []).append((e0, e1))
 
@@ -369,9 +376,8 @@ class FitEngine:
     def evaluate(self, slot):
         """Phase A on (W_cur, H_cur): fills scalar record ``slot`` (loss parts, rel_H, flags)."""
         self._set_record(slot)
-        self._call_timed(self.lib.espm_h_pass, "h_pass")
-        self._call(self.lib.espm_h_finish)
-        self._call(self.lib.espm_h_scalars)
+        self._call(self.lib.espm_h_pass, "h_pass")
+        self._call(self.lib.espm_h_finish, "h_finish")      # its last CTA also writes the scalar record
 
     def advance(self, slot):
         """Phase B: (W_cur, H_cur) -> (W_next, H_next), rotate.  rel_W etc. go to record ``slot``."""
@@ -380,14 +386,14 @@ class FitEngine:
         if st.flags & L.FLAG_SIMPLEX_H:
             if self.shard is not None:
                 self.shard.gather_masks(self.mask)
-            self._call(self.lib.espm_h_apply)
+            self._call(self.lib.espm_h_apply, "h_apply")
         self._exchange_halo(self.ih[2])
-        self._call_timed(self.lib.espm_w_pass, "w_pass")
-        self._call(self.lib.espm_w_reduce)
+        self._call(self.lib.espm_w_pass, "w_pass")
         if self.shard is not None:
+            self._call(self.lib.espm_w_reduce, "w_reduce")
             self.shard.allreduce_sum(self.s_sum)
             self._sync_hstats()
-        self._call(self.lib.espm_w_finish)
+        self._call(self.lib.espm_w_finish, "w_finish")
         hp, hc, hn = self.ih
         self.ih = [hc, hn, hp]
         self.iw = [self.iw[1], self.iw[0]]
@@ -415,8 +421,8 @@ class FitEngine:
         st.hstats_next = st.hstats_cur
         self._set_record(0)
         self._call(self.lib.espm_w_pass)
-        self._call(self.lib.espm_w_reduce)
         if self.shard is not None:
+            self._call(self.lib.espm_w_reduce)
             self.shard.allreduce_sum(self.s_sum)
         self._call(self.lib.espm_w_finish)
         rec = self.read_records(0, 1)[0]

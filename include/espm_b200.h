@@ -38,6 +38,7 @@ extern "C" {
 #define ESPM_TILE_PX 128          /* pixels per tile of Xt */
 #define ESPM_STAGE_BYTES 16384    /* bytes of X per pipeline stage (one bulk copy) */
 #define ESPM_MAX_K 16             /* largest supported n_components */
+#define ESPM_COOP_BLOCKS 32        /* CTAs of the cooperative w_finish kernel */
 #define ESPM_NSCALARS 24          /* doubles per slot of the per-iteration scalar record */
 #define ESPM_MAXIT_DICHOTOMY 100  /* espm/conf.py:59 */
 
@@ -62,6 +63,7 @@ typedef enum espm_status {
 #define ESPM_FLAG_HAVE_HPREV  (1u << 9)  /* H_prev is valid: h_finish also emits rel_H of the current iterate */
 #define ESPM_FLAG_SIMPLEX_ROWS (1u << 10) /* simplex_W restricted to simplex_rows (updates.py:62-65) */
 #define ESPM_FLAG_HQ          (1u << 11) /* algo="l2_surrogate": quadratic surrogate H step (updates.py:263-301) */
+#define ESPM_FLAG_FUSED_WREDUCE (1u << 12) /* espm_w_finish also does the work of espm_w_reduce (single-GPU fits) */
 
 /* bits of the device-side error word (espm_state.dev_flags[0]) */
 #define ESPM_DEV_NONFINITE    (1u << 0)  /* non-finite ratio sums (x/0): caller must redo with CLAMP_Y */
@@ -166,8 +168,10 @@ typedef struct espm_state {
     double* xlogy_part;     /* h_grid */
     double* px_part;        /* px_blocks x (4 + 3*kp) partials of the per-pixel kernels */
     uint32_t* bisect_mask;  /* 4 words: bit j set <=> max|f_j| > tol somewhere (lock-step trace) */
-    uint32_t* dev_flags;    /* 4 words: [0] sticky ESPM_DEV_* error bits, [1] ESPM_DEV_GW_* of GW_next */
+    uint32_t* dev_flags;    /* 8 words: [0] sticky ESPM_DEV_* error bits, [1] ESPM_DEV_GW_* of GW_next,
+                             * [2] h_finish completion ticket, [3] grid-barrier counter of w_finish (start at 0) */
     double* scalars;        /* ESPM_NSCALARS doubles: the record being filled */
+    double* coop_part;      /* ESPM_COOP_BLOCKS x (2*ESPM_MAX_K + 1) doubles: per-CTA partials of w_finish */
 } espm_state;
 
 /* library / device */
@@ -215,7 +219,9 @@ int espm_h_pass(const espm_state* st, void* stream);
 int espm_h_finish(const espm_state* st, void* stream);
 /* Replays exactly it* bisection iterations (first clear bit of bisect_mask) and writes H_next (and Ht). */
 int espm_h_apply(const espm_state* st, void* stream);
-/* Reduces the H-side partials into st->scalars (loss parts of the current iterate, rel_H, flags). */
+/* Reduces the H-side partials into st->scalars (loss parts of the current iterate, rel_H, flags).
+ * espm_h_finish already does this in its last CTA; the entry point remains for callers that changed
+ * st->scalars in between. */
 int espm_h_scalars(const espm_state* st, void* stream);
 
 /* W pass (updates.py:38-59, re-associated as G^T (R H^T)): streams Xt once with H_next.
@@ -223,8 +229,9 @@ int espm_h_scalars(const espm_state* st, void* stream);
 int espm_w_pass(const espm_state* st, void* stream);
 /* s_sum = sum over the slots of each channel block of s_part (fixed order => deterministic). */
 int espm_w_reduce(const espm_state* st, void* stream);
-/* hstats_next from the per-pixel partials; W_next (updates.py:59-76, incl. simplex_W bisection and
- * fixed_W), rel_W, then GW_next / gwstats_next for the next H pass.  Single CTA. */
+/* W_next (updates.py:59-76, incl. simplex_W bisection and fixed_W), rel_W, then GW_next / gwstats_next for
+ * the next H pass; with ESPM_FLAG_FUSED_WREDUCE also s_sum and hstats_next (espm_w_reduce).  One
+ * cooperative kernel of ESPM_COOP_BLOCKS CTAs. */
 int espm_w_finish(const espm_state* st, void* stream);
 
 /* Standalone operator used by the unit-level API: nu = dichotomy_simplex(num, den) (dicotomy.py:4-55).
