@@ -104,20 +104,19 @@ struct Num<float> {
 };
 template <>
 struct Num<double> {
-    // fp64 ratio: fp32 MUFU.RCP seed + two Newton steps in fp64 (full double accuracy, ~1 ulp),
-    // falls back to IEEE division when y is outside the fp32 range.
-    static __device__ __forceinline__ double ratio(double x, double y) {
-        float yf = __double2float_rn(y);
-        if (yf > 1e-30f && yf < 1e30f) {
-            double r = (double)__frcp_rn(yf);
-            double e = fma(-y, r, 1.0);
-            r = fma(r, e, r);
-            e = fma(-y, r, 1.0);
-            r = fma(r, e, r);
-            return x * r;
-        }
-        return x / y;
+    // fp64 reciprocal: MUFU.RCP64H seed (rcp.approx.ftz.f64, ~20 good bits, full exponent range) + two
+    // Newton steps in fp64 => <= 1 ulp.  y == 0 gives NaN/inf like the division would (callers flag
+    // non-finite results); 7 instructions instead of the ~25 of an IEEE fp64 division.
+    static __device__ __forceinline__ double rcp(double y) {
+        double r;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));
+        double e = fma(-y, r, 1.0);
+        r = fma(r, e, r);
+        e = fma(-y, r, 1.0);
+        r = fma(r, e, r);
+        return r;
     }
+    static __device__ __forceinline__ double ratio(double x, double y) { return x * rcp(y); }
     static __device__ __forceinline__ double log2_fast(double y) { return log2(y); }
     static __device__ __forceinline__ double vmax(double a, double b) { return fmax(a, b); }
     static __device__ __forceinline__ double vmin(double a, double b) { return fmin(a, b); }
