@@ -72,6 +72,14 @@ class EspmState(ctypes.Structure):
     ]
 
 
+class EspmIngest(ctypes.Structure):
+    """Mirror of ``struct espm_ingest``."""
+    _fields_ = [("row_nz", _vp), ("col_nz", _vp), ("flags", _vp), ("sum_part", _vp)]
+
+
+X_NAN, X_INF, X_NEGATIVE = 1, 2, 4
+
+
 class EspmError(RuntimeError):
     pass
 
@@ -84,7 +92,11 @@ _EXPORTS = {
     "espm_device_count": (ctypes.c_int, []),
     "espm_plan": (ctypes.c_int, [ctypes.POINTER(EspmState)]),
     "espm_plan_info": (ctypes.c_int, [ctypes.POINTER(EspmState), ctypes.POINTER(_i32)]),
-    "espm_retile_x": (ctypes.c_int, [ctypes.POINTER(EspmState), _vp, _i32, _i64, _i64, _i64, _f64, _vp]),
+    "espm_retile_x": (ctypes.c_int, [ctypes.POINTER(EspmState), _vp, _i32, _i64, _i64, _i64, _f64,
+                                     ctypes.POINTER(EspmIngest), _vp]),
+    "espm_xt_fixup": (ctypes.c_int, [ctypes.POINTER(EspmState), _vp, _vp, _f64, _f64, _vp]),
+    "espm_xt_const": (ctypes.c_int, [ctypes.POINTER(EspmState), _vp, _vp]),
+    "espm_reduce_sum": (ctypes.c_int, [_vp, _i64, _vp, _vp]),
     "espm_gw_prepare": (ctypes.c_int, [ctypes.POINTER(EspmState), _vp]),
     "espm_colsum_g": (ctypes.c_int, [ctypes.POINTER(EspmState), _vp, _vp]),
     "espm_h_stats": (ctypes.c_int, [ctypes.POINTER(EspmState), _vp]),

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 
+#include "ingest_decl.h"
 #include "small_inst.cuh"
 #include "xpass_inst.cuh"
 
@@ -258,10 +259,43 @@ int espm_plan_info(const espm_state* st, int32_t* info8) {
 }
 
 int espm_retile_x(const espm_state* st, const void* src, int32_t src_dtype, int64_t stride_c, int64_t stride_p,
-                  int64_t j0, double scale, void* stream) {
+                  int64_t j0, double scale, const espm_ingest* stats, void* stream) {
     int rc = check_state(st);
     if (rc) return rc;
-    return retile_launch(st, src, src_dtype, stride_c, stride_p, j0, scale, (cudaStream_t)stream);
+    IngestOut io{nullptr, nullptr, nullptr, nullptr};
+    if (stats) {
+        if (!stats->row_nz || !stats->col_nz || !stats->flags || !stats->sum_part) {
+            set_error("espm_retile_x: incomplete espm_ingest");
+            return ESPM_ERR_BAD_ARG;
+        }
+        io = IngestOut{stats->row_nz, stats->col_nz, stats->flags, stats->sum_part};
+    }
+    return retile_launch(st, src, src_dtype, stride_c, stride_p, j0, scale, io, (cudaStream_t)stream);
+}
+
+int espm_xt_fixup(const espm_state* st, const int32_t* row_zero, const int32_t* col_zero, double eps, double scale,
+                  void* stream) {
+    int rc = check_state(st);
+    if (rc) return rc;
+    return xt_fixup_launch(st, row_zero, col_zero, eps, scale, (cudaStream_t)stream);
+}
+
+int espm_xt_const(const espm_state* st, double* part_out, void* stream) {
+    int rc = check_state(st);
+    if (rc) return rc;
+    if (!part_out) {
+        set_error("espm_xt_const: null output");
+        return ESPM_ERR_BAD_ARG;
+    }
+    return xt_const_launch(st, part_out, (cudaStream_t)stream);
+}
+
+int espm_reduce_sum(const double* in, int64_t n, double* out, void* stream) {
+    if (!in || !out || n < 0) {
+        set_error("espm_reduce_sum: bad arguments");
+        return ESPM_ERR_BAD_ARG;
+    }
+    return reduce_sum_launch(in, (long long)n, out, (cudaStream_t)stream);
 }
 
 static int small(int op, const espm_state* st, void* stream) {

@@ -1,0 +1,60 @@
+// X ingest kernels (see ingest.cuh) and their launchers.
+#include "ingest.cuh"
+
+namespace espm {
+
+template <typename TS, typename TX>
+static int retile_launch_t(const espm_state* st, const void* src, long long stride_c, long long stride_p,
+                           long long j0, double scale, const IngestOut& io, cudaStream_t s) {
+    dim3 grid(st->n_tiles, st->n_pad / 32);
+    retile_kernel<TS, TX><<<grid, 256, 0, s>>>((const TS*)src, stride_c, stride_p, j0, st->n, st->n_pad, st->p_loc,
+                                              scale, (TX*)st->Xt, io);
+    ESPM_CUDA_CHECK(cudaGetLastError());
+    return ESPM_OK;
+}
+
+int retile_launch(const espm_state* st, const void* src, int src_dtype, long long stride_c, long long stride_p,
+                  long long j0, double scale, const IngestOut& io, cudaStream_t s) {
+    if (src_dtype == ESPM_F32 && st->x_dtype == ESPM_F32)
+        return retile_launch_t<float, float>(st, src, stride_c, stride_p, j0, scale, io, s);
+    if (src_dtype == ESPM_F64 && st->x_dtype == ESPM_F64)
+        return retile_launch_t<double, double>(st, src, stride_c, stride_p, j0, scale, io, s);
+    if (src_dtype == ESPM_F64 && st->x_dtype == ESPM_F32)
+        return retile_launch_t<double, float>(st, src, stride_c, stride_p, j0, scale, io, s);
+    if (src_dtype == ESPM_F32 && st->x_dtype == ESPM_F64)
+        return retile_launch_t<float, double>(st, src, stride_c, stride_p, j0, scale, io, s);
+    set_error("retile: unsupported dtype combination %d -> %d", src_dtype, st->x_dtype);
+    return ESPM_ERR_BAD_ARG;
+}
+
+int xt_fixup_launch(const espm_state* st, const int32_t* row_zero, const int32_t* col_zero, double eps, double scale,
+                    cudaStream_t s) {
+    dim3 grid(st->n_tiles, st->n_pad / 32);
+    if (st->x_dtype == ESPM_F32)
+        xt_fixup_kernel<float><<<grid, 256, 0, s>>>((float*)st->Xt, row_zero, col_zero, st->n, st->n_pad, st->p_loc, eps,
+                                                   scale);
+    else
+        xt_fixup_kernel<double><<<grid, 256, 0, s>>>((double*)st->Xt, row_zero, col_zero, st->n, st->n_pad, st->p_loc,
+                                                    eps, scale);
+    ESPM_CUDA_CHECK(cudaGetLastError());
+    return ESPM_OK;
+}
+
+int xt_const_launch(const espm_state* st, double* part, cudaStream_t s) {
+    if (st->x_dtype == ESPM_F32)
+        xt_const_kernel<float><<<st->n_tiles, 256, 0, s>>>((const float*)st->Xt, st->n, st->n_pad, st->p_loc,
+                                                          st->log_shift, part);
+    else
+        xt_const_kernel<double><<<st->n_tiles, 256, 0, s>>>((const double*)st->Xt, st->n, st->n_pad, st->p_loc,
+                                                           st->log_shift, part);
+    ESPM_CUDA_CHECK(cudaGetLastError());
+    return ESPM_OK;
+}
+
+int reduce_sum_launch(const double* in, long long n, double* out, cudaStream_t s) {
+    reduce_sum_kernel<<<1, 1024, 0, s>>>(in, n, out);
+    ESPM_CUDA_CHECK(cudaGetLastError());
+    return ESPM_OK;
+}
+
+}  // namespace espm

@@ -928,42 +928,6 @@ __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_sta
 }
 
 // ------------------------------------------------------------------------------------------------
-// retile: X (any strides) -> tile-major Xt, zero padded.  grid = (n_tiles, n_pad/32), 256 threads.
-// ------------------------------------------------------------------------------------------------
-template <typename TS, typename TX>
-__global__ void __launch_bounds__(256) retile_kernel(const TS* __restrict__ src, long long stride_c,
-                                                     long long stride_p, long long j0, int n, int n_pad, int p_loc,
-                                                     double scale, TX* __restrict__ Xt) {
-    __shared__ TX sm[32][TILE_PX + 1];
-    const int tile = blockIdx.x, cb = blockIdx.y * 32;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (stride_p == 1 || stride_c != 1) {
-        // pixels contiguous (or generic): read rows of 128 pixels
-        for (int ci = warp; ci < 32; ci += 8) {
-            const int c = cb + ci;
-            for (int q = lane; q < TILE_PX; q += 32) {
-                const long long j = (long long)tile * TILE_PX + q;
-                TX v = TX(0);
-                if (c < n && j < p_loc) v = (TX)((double)src[(long long)c * stride_c + (j0 + j) * stride_p] * scale);
-                sm[ci][q] = v;
-            }
-        }
-    } else {
-        // channels contiguous (hyperspy layout): read 32 channels of one pixel per warp access
-        for (int q = warp; q < TILE_PX; q += 8) {
-            const long long j = (long long)tile * TILE_PX + q;
-            const int c = cb + lane;
-            TX v = TX(0);
-            if (c < n && j < p_loc) v = (TX)((double)src[(long long)c * stride_c + (j0 + j) * stride_p] * scale);
-            sm[lane][q] = v;
-        }
-    }
-    __syncthreads();
-    TX* dst = Xt + ((size_t)tile * n_pad + cb) * TILE_PX;
-    for (int i = threadIdx.x; i < 32 * TILE_PX; i += 256) dst[i] = sm[i / TILE_PX][i % TILE_PX];
-}
-
-// ------------------------------------------------------------------------------------------------
 // Standalone dichotomy_simplex(num, den) -> nu  (dicotomy.py:4-55), two kernels: trace, replay.
 // ------------------------------------------------------------------------------------------------
 template <typename TC, int KP>

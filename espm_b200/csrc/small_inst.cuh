@@ -108,16 +108,6 @@ static int colsum_launch_t(const espm_state* st, void* out, cudaStream_t s) {
     return ESPM_OK;
 }
 
-template <typename TS, typename TX>
-static int retile_launch_t(const espm_state* st, const void* src, long long stride_c, long long stride_p,
-                           long long j0, double scale, cudaStream_t s) {
-    dim3 grid(st->n_tiles, st->n_pad / 32);
-    retile_kernel<TS, TX><<<grid, 256, 0, s>>>((const TS*)src, stride_c, stride_p, j0, st->n, st->n_pad, st->p_loc,
-                                              scale, (TX*)st->Xt);
-    ESPM_CUDA_CHECK(cudaGetLastError());
-    return ESPM_OK;
-}
-
 // defined in small_f32.cu / small_f64.cu
 int small_launch_f32(int op, const espm_state* st, cudaStream_t s);
 int small_launch_f64(int op, const espm_state* st, cudaStream_t s);
@@ -125,7 +115,5 @@ int dicho_launch_f32(const DichoArgs& d, cudaStream_t s);
 int dicho_launch_f64(const DichoArgs& d, cudaStream_t s);
 int colsum_launch_f32(const espm_state* st, void* out, cudaStream_t s);
 int colsum_launch_f64(const espm_state* st, void* out, cudaStream_t s);
-int retile_launch(const espm_state* st, const void* src, int src_dtype, long long stride_c, long long stride_p,
-                  long long j0, double scale, cudaStream_t s);
 
 }  // namespace espm

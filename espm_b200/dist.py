@@ -51,6 +51,23 @@ class Shard:
         dist.all_reduce(hstats[:2 * kp], op=dist.ReduceOp.SUM, group=self.group)
         dist.all_reduce(hstats[2 * kp:3 * kp], op=dist.ReduceOp.MAX, group=self.group)
 
+    # ---- X ingest (once per fit) -----------------------------------------------------------------
+    def combine_ingest(self, info, row_nz):
+        """info = [ESPM_X_* flags, sum of X, number of all-zero pixels] of this rank's slab (float64),
+        row_nz = per-channel "has a non-zero" marks (int32).  Returns the global versions: flags OR-ed,
+        sums added, marks OR-ed (a channel is an all-zero row only if it is zero on every rank)."""
+        gathered = [torch.empty_like(info) for _ in range(self.world)]
+        dist.all_gather(gathered, info.contiguous(), group=self.group)
+        allr = torch.stack(gathered)
+        flags = 0
+        for v in allr[:, 0].cpu().tolist():
+            flags |= int(v)
+        out = torch.stack([torch.tensor(float(flags), dtype=info.dtype, device=info.device),
+                           allr[:, 1].sum(), allr[:, 2].sum()])
+        row = row_nz.clone()
+        dist.all_reduce(row, op=dist.ReduceOp.MAX, group=self.group)
+        return out, row
+
     # ---- lock-step bisection ---------------------------------------------------------------------
     def gather_masks(self, mask):
         """mask[:4] <- OR over ranks of the 128-bit trace masks (NCCL has no bitwise OR: gather + fold)."""

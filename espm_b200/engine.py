@@ -56,11 +56,16 @@ class FitEngine:
                  log_shift=1e-14, dicotomy_tol=1e-5, dicotomy_tol_w=1e-5, tol=1e-4, sigma=8.0,
                  simplex_H=False, simplex_W=True, simplex_rows=None, fixed_H=None, fixed_W=None,
                  x_scale=1.0, max_records=512, device=None, shard=None, c_dtype=None, clamp_init=True,
-                 x_local=False):
+                 x_local=False, ingest=None):
         """
         X : (n, p) array-like view (any strides; C order or the transposed hyperspy layout are
             uploaded without a host copy).  G : (n, m) array or None (identity).  W0 : (m, k), H0 : (k, p).
         shard : None, or (rank, world, comm) for pixel-sharded multi-GPU runs (see dist.py).
+        ingest : None (X is used as given, times ``x_scale``), or dict(eps=..., normalize=None | n_components):
+            the prologue of the reference's fit runs on the device instead of the host -- NaN / inf /
+            negative checks, remove_zeros_lines (base.py:519-528), normalize (base.py:264-267) and
+            const_KL_ (base.py:200-201).  Results: ``self.const_KL``, ``self.norm_factor``,
+            ``self.n_zero_rows`` / ``self.n_zero_cols``.
         """
         self.lib = L.load()
         self.clamp_init = clamp_init
@@ -222,7 +227,10 @@ class FitEngine:
             st.flags |= L.FLAG_SIMPLEX_ROWS
         self.G = self.Gt = self.colsum_G = None
         self._bind()
-        self._upload_x(X, x_scale)
+        self.const_KL = None
+        self.norm_factor = None
+        self.n_zero_rows = self.n_zero_cols = 0
+        self._upload_x(X, x_scale, ingest)
         self.set_G(G, prepare=False)
         self._init_WH(W0, H0)
 
@@ -273,7 +281,7 @@ class FitEngine:
         self.profile.setdefault(name, []).append((e0, e1))
 
     # ------------------------------------------------------------------ uploads
-    def _upload_x(self, X, scale):
+    def _upload_x(self, X, scale, ingest=None):
         """H2D copy of this rank's pixel slab and re-tiling into the tile-major layout (base.py:262)."""
         st = self.st
         xdt = _torch_dtype(self.x_code)
@@ -308,10 +316,63 @@ class FitEngine:
                     slab = np.ascontiguousarray(slab)
                 d = torch.from_numpy(slab).to(self.device)
                 sc, sp = slab.shape[1], 1
-        L.check(self.lib.espm_retile_x(ctypes.byref(st), ctypes.c_void_p(d.data_ptr()), self.x_code,
-                                       sc, sp, 0, float(scale), self.stream))
-        torch.cuda.current_stream(self.device).synchronize()
-        del d
+        src = ctypes.c_void_p(d.data_ptr())
+        if ingest is None:
+            L.check(self.lib.espm_retile_x(ctypes.byref(st), src, self.x_code, sc, sp, 0, float(scale), None,
+                                           self.stream))
+            torch.cuda.current_stream(self.device).synchronize()
+            return
+        self._ingest(src, sc, sp, float(ingest.get("eps", st.log_shift)), ingest.get("normalize"))
+
+    def _ingest(self, src, sc, sp, eps, normalize_nc):
+        """Device-side prologue of the fit (see ``ingest`` in __init__)."""
+        st, dev = self.st, self.device
+        i32 = torch.int32
+        row_nz = torch.zeros(st.n_pad, dtype=i32, device=dev)
+        col_nz = torch.zeros(st.p_pad, dtype=i32, device=dev)
+        xflags = torch.zeros(1, dtype=i32, device=dev)
+        sum_part = torch.zeros(st.n_tiles * (st.n_pad // 32), dtype=torch.float64, device=dev)
+        io = L.EspmIngest(row_nz.data_ptr(), col_nz.data_ptr(), xflags.data_ptr(), sum_part.data_ptr())
+        L.check(self.lib.espm_retile_x(ctypes.byref(st), src, self.x_code, sc, sp, 0, 1.0, ctypes.byref(io),
+                                       self.stream))
+        scal = torch.zeros(2, dtype=torch.float64, device=dev)
+        L.check(self.lib.espm_reduce_sum(sum_part.data_ptr(), sum_part.numel(), scal.data_ptr(), self.stream))
+        n, p_loc, p = self.n, self.p_loc, self.p
+        info = torch.stack([xflags[0].to(torch.float64), scal[0],
+                            (p_loc - col_nz[:p_loc].sum()).to(torch.float64)])
+        if self.shard is not None:
+            info, row_nz = self.shard.combine_ingest(info, row_nz)
+        info = info.cpu().numpy()                                  # one small D2H (synchronises)
+        flags = int(info[0])
+        if flags & L.X_NAN:
+            raise ValueError("Input X contains NaN.")
+        if flags & L.X_INF:
+            raise ValueError("Input X contains infinity or a value too large for dtype('%s')."
+                             % np.dtype(_np_dtype(self.x_code)).name)
+        if flags & L.X_NEGATIVE:
+            raise ValueError("Negative values in data")            # base.py:528
+        total = float(info[1])
+        zc = int(round(info[2]))
+        zr = int(n - int(row_nz[:n].sum().item()))
+        self.n_zero_rows, self.n_zero_cols = zr, zc
+        scale = 1.0
+        if normalize_nc is not None:                               # base.py:16-18 on the repaired X
+            patched = total + eps * (zr * p + zc * n - zr * zc)
+            self.norm_factor = normalize_nc / ((patched / (n * p)) * n)
+            scale = self.norm_factor
+        if zr or zc or scale != 1.0:
+            row_zero = (1 - row_nz) if zr else None
+            col_zero = (1 - col_nz) if zc else None
+            L.check(self.lib.espm_xt_fixup(
+                ctypes.byref(st), ctypes.c_void_p(row_zero.data_ptr() if zr else None),
+                ctypes.c_void_p(col_zero.data_ptr() if zc else None), eps, scale, self.stream))
+        part = torch.zeros(st.n_tiles, dtype=torch.float64, device=dev)
+        L.check(self.lib.espm_xt_const(ctypes.byref(st), ctypes.c_void_p(part.data_ptr()), self.stream))
+        L.check(self.lib.espm_reduce_sum(part.data_ptr(), part.numel(), scal[1:].data_ptr(), self.stream))
+        c = scal[1:2].clone()
+        if self.shard is not None:
+            self.shard.allreduce_sum(c)
+        self.const_KL = float(c.item())
 
     def set_G(self, G, prepare=True):
         """(Re)load G (base.py:269-274, 388-389).  ``prepare`` also recomputes GW for W_cur."""

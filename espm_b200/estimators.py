@@ -12,6 +12,7 @@ without (identity), ``fixed_H`` / ``fixed_W``, ``normalize``, ``G`` as ``None`` 
 model, ``hspy_comp``.  Other ``algo`` values, ``l2=True`` and ``linesearch=True`` raise
 ``NotImplementedError`` (SURVEY.md section 8f lists them as "next").
 """
+import sys
 import time
 
 import numpy as np
@@ -142,6 +143,34 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
         if self.true_D is not None and self.true_H is not None:
             raise NotImplementedError("espm_b200: ground-truth tracking (true_D/true_H) is not available yet")
 
+    # ------------------------------------------------------------------ X_ (lazy)
+    def _host_X(self, Xv):
+        """The reference's processed data matrix (base.py:262-267) computed on the host."""
+        from sklearn.utils import assert_all_finite
+        assert_all_finite(Xv, input_name="X")
+        Xh = remove_zeros_lines(Xv, self.log_shift)
+        if self.normalize:
+            Xh = normalization_factor(Xh, self.n_components) * Xh
+        return Xh
+
+    def __getattr__(self, name):
+        # ``X_`` is a fitted attribute of the reference (a repaired / normalised COPY of the input).  The
+        # device never needs that copy, so it is only built if somebody asks for it.
+        if name == "X_" and "_X_in" in self.__dict__:
+            Xv = self.__dict__["_X_in"]
+            fix = self.__dict__.get("_x_fix")
+            if fix is None or fix[0]:
+                Xh = remove_zeros_lines(Xv, self.log_shift)
+            else:
+                Xh = Xv
+            if fix is not None and fix[1] is not None:
+                Xh = fix[1] * Xh
+            elif fix is None and self.normalize:
+                Xh = normalization_factor(Xh, self.n_components) * Xh
+            self.__dict__["X_"] = Xh
+            return Xh
+        raise AttributeError("%r object has no attribute %r" % (type(self).__name__, name))
+
     # ------------------------------------------------------------------ loss
     def _loss_from_record(self, rec):
         kl, reg, lap = self._engine.loss_parts(rec, self.const_KL_, self.GWH_numel_)
@@ -172,24 +201,23 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
         from .engine import FitEngine
         self._require_supported()
         self.gamma_ = None                                             # smooth_nmf.py:280
-        if self.hspy_comp:                                             # base.py:243-247
-            self.X_ = validate_data(self, X.T, dtype=[np.float64, np.float32])
+        self.__dict__.pop("X_", None)
+        # base.py:243-247.  NaN / inf are rejected by the device pass over X (FitEngine ingest) with
+        # sklearn's messages instead of a host pass here.
+        if self.hspy_comp:
+            Xv = validate_data(self, X.T, dtype=[np.float64, np.float32], ensure_all_finite=False)
         else:
-            self.X_ = validate_data(self, X, dtype=[np.float64, np.float32])
-            try:                                                       # base.py:249-259
-                import inspect
-                calframe = inspect.getouterframes(inspect.currentframe(), 2)
-                if calframe[1][3] == "decomposition" and "hyperspy" in calframe[1][1]:
-                    print("Are you calling the function decomposition from Hyperspy?\n"
-                          "If so, please set the compatibility argument 'hspy_comp' to True.\n\n"
-                          "If this argument is not set correctly, the function will not work properly!!!")
-            except Exception:
-                pass
-        self.X_ = remove_zeros_lines(self.X_, self.log_shift)          # base.py:262
+            Xv = validate_data(self, X, dtype=[np.float64, np.float32], ensure_all_finite=False)
+            f = sys._getframe(1)                                       # base.py:249-259
+            if f is not None and f.f_code.co_name == "fit":
+                f = f.f_back
+            if f is not None and f.f_code.co_name == "decomposition" and "hyperspy" in f.f_code.co_filename:
+                print("Are you calling the function decomposition from Hyperspy?\n"
+                      "If so, please set the compatibility argument 'hspy_comp' to True.\n\n"
+                      "If this argument is not set correctly, the function will not work properly!!!")
+        self._X_in = Xv          # X_ (base.py:262-267) is materialised on first access, see __getattr__
+        self._x_fix = None
         self.const_KL_ = None
-        if self.normalize:                                             # base.py:264-267
-            self.norm_factor_ = normalization_factor(self.X_, self.n_components)
-            self.X_ = self.norm_factor_ * self.X_
         if is_physical_model(self.G):                                  # base.py:269-274
             self.physics_model_ = self.G
             G = self.physics_model_.NMF_update()
@@ -197,12 +225,13 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
             self.physics_model_ = None
             G = self.G
         self._identity_G = G is None
-        G_full, W0, H0 = initialize_factors(self.X_, G, W, H, self.n_components, self.init, self.random_state,
+        n, p = Xv.shape
+        # initial factors (updates.py:160-223): only a missing factor needs the data on the host
+        X_init = Xv if (W is not None and H is not None) else self._host_X(Xv)
+        G_full, W0, H0 = initialize_factors(X_init, G, W, H, self.n_components, self.init, self.random_state,
                                             self.simplex_H, self.simplex_W, self.log_shift, self.physics_model_)
-        n, p = self.X_.shape
+        del X_init
         self.GWH_numel_ = n * p
-        # base.py:200-201
-        self.const_KL_ = float(np.sum(self.X_ * np.log(np.maximum(self.X_, self.log_shift))) - np.sum(self.X_))
         self.gamma_ = _SIGMA_L if self.gamma is None else self.gamma   # smooth_nmf.py:290-306
         simplex_rows = None
         if self.physics_model_ is not None and self.simplex_W:
@@ -218,13 +247,19 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
             if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
                 from .dist import Shard
                 shard = Shard()
-        eng = FitEngine(self.X_, None if self._identity_G else G, W0, H0,
+        eng = FitEngine(Xv, None if self._identity_G else G, W0, H0,
                         shape_2d=self.shape_2d, lambda_L=self.lambda_L, mu=self.mu, epsilon_reg=self.epsilon_reg,
                         log_shift=self.log_shift, dicotomy_tol=self.dicotomy_tol, dicotomy_tol_w=_DICOTOMY_TOL,
                         tol=self.tol, sigma=float(self.gamma_), simplex_H=self.simplex_H, simplex_W=self.simplex_W,
                         simplex_rows=simplex_rows, fixed_H=self.fixed_H, fixed_W=self.fixed_W,
-                        max_records=max(max_iter, 1) + 8, shard=shard)
+                        max_records=max(max_iter, 1) + 8, shard=shard,
+                        ingest=dict(eps=self.log_shift, normalize=self.n_components if self.normalize else None))
         self._engine = eng
+        # device-side prologue results: const_KL_ (base.py:200-201), norm_factor_ (base.py:264-267)
+        self.const_KL_ = eng.const_KL
+        if self.normalize:
+            self.norm_factor_ = eng.norm_factor
+        self._x_fix = (eng.n_zero_rows > 0 or eng.n_zero_cols > 0, self.norm_factor_ if self.normalize else None)
         self.G_ = G_full
         self.L_ = None  # the Laplacian is a stencil inside the kernels (utils.py:39-76 is never materialised)
 

@@ -188,13 +188,38 @@ int espm_plan(espm_state* st);
 int espm_plan_info(const espm_state* st, int32_t* info8);
 
 /*
- * Upload helper: re-tile a device copy of X into Xt (replaces the host-side copy of base.py:262).
+ * X ingest: what the reference does to X on the host before the loop (base.py:243-267, 519-528, 200-201)
+ * as device passes, so that a fit touches the host copy of X exactly once (the H2D copy).
+ *
+ * espm_retile_x: re-tile a device copy of X into Xt (replaces the host-side copy of base.py:262).
  *   src: device pointer, element (c, j) at src[c*stride_c + j*stride_p] (so both the (n,p) layout of
  *   base.py:246-247 and the transposed hyperspy layout of base.py:243-244 are accepted in place).
- *   j0: first source pixel of this rank's shard.  `scale` multiplies every entry (normalize, base.py:267).
+ *   j0: first source pixel of this rank's shard.  `scale` multiplies every entry.
+ *   stats (may be NULL): what remove_zeros_lines / validate_data / normalize need to know about the RAW
+ *   values -- the caller zero-fills the arrays first:
+ *     row_nz[n_pad], col_nz[p_pad]  set to 1 where a channel / pixel has a non-zero entry (base.py:522-526)
+ *     flags[1]                      ESPM_X_* bits (NaN / inf -> sklearn's check, negative -> base.py:528)
+ *     sum_part[n_tiles * n_pad/32]  block sums of the finite raw values (mean(X), base.py:16-18)
+ * espm_xt_fixup: Xt <- (row_zero[c] or col_zero[j] ? eps : Xt) * scale on the real entries (base.py:525-526,
+ *   267); either array may be NULL.
+ * espm_xt_const: part_out[tile] = sum X log max(X, log_shift) - sum X over the tile (const_KL_, base.py:200-201).
+ * espm_reduce_sum: out[0] = sum of n doubles with a fixed summation tree.
  */
+#define ESPM_X_NAN       (1u << 0)
+#define ESPM_X_INF       (1u << 1)
+#define ESPM_X_NEGATIVE  (1u << 2)
+typedef struct espm_ingest {
+    int32_t* row_nz;
+    int32_t* col_nz;
+    uint32_t* flags;
+    double* sum_part;
+} espm_ingest;
 int espm_retile_x(const espm_state* st, const void* src, int32_t src_dtype, int64_t stride_c,
-                  int64_t stride_p, int64_t j0, double scale, void* stream);
+                  int64_t stride_p, int64_t j0, double scale, const espm_ingest* stats, void* stream);
+int espm_xt_fixup(const espm_state* st, const int32_t* row_zero, const int32_t* col_zero, double eps,
+                  double scale, void* stream);
+int espm_xt_const(const espm_state* st, double* part_out, void* stream);
+int espm_reduce_sum(const double* in, int64_t n, double* out, void* stream);
 
 /* GW_next = G.W_next (+pad rows), gwstats_next, ESPM_DEV_GW_* flags.  base.py:189, updates.py:107. */
 int espm_gw_prepare(const espm_state* st, void* stream);
