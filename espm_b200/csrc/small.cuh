@@ -32,15 +32,22 @@ __host__ __device__ inline int px_part_nsum(int kp) { return 2 + 2 * kp; }
 
 // ------------------------------------------------------------------------------------------------
 // simplex function  f(x) = sum_k max(num_k / (x + den_k), ls) - 1   (dicotomy.py:51-53)
-// Sequential sum over k like the NumPy reference.  The bisection only consumes the SIGN of f and the
-// test |f| <= tol, and the midpoints (a+b)/2 are exact either way, so the fp64 quotient may be the
-// <= 1 ulp Newton reciprocal (Num<double>::ratio) instead of the ~3x more expensive IEEE division: nu is
-// bit-identical to the reference unless some |f| lands within 1e-16 of 0 or of tol.
+// Sequential sum over k like the NumPy reference.  The fp64 quotient is the Newton reciprocal plus one
+// residual correction (q' = q + (a - b q) r): correctly rounded like the IEEE division NumPy uses, except
+// for rare double-rounding cases, at a third of the cost.  Bit-level agreement matters: when a pixel has
+// no counts the root sits within a few ulps of -den and the bisection result is decided by the last bit
+// of f (it then runs to maxit, dicotomy.py:169-171).
 // ------------------------------------------------------------------------------------------------
 template <typename TC>
 __device__ __forceinline__ TC simplex_quot(TC a, TC b) {
-    if constexpr (sizeof(TC) == 8) return Num<TC>::ratio(a, b);
-    else return a / b;
+    if constexpr (sizeof(TC) == 8) {
+        const double r = Num<double>::rcp(b);
+        const double q = a * r;
+        const double rem = fma(-b, q, a);
+        return fma(rem, r, q);
+    } else {
+        return a / b;
+    }
 }
 template <typename TC, int KP>
 __device__ __forceinline__ TC simplex_f(const TC (&num)[KP], const TC (&den)[KP], TC x, int k, TC ls) {

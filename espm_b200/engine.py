@@ -283,6 +283,12 @@ class FitEngine:
     # ------------------------------------------------------------------ uploads
     def _upload_x(self, X, scale, ingest=None):
         """H2D copy of this rank's pixel slab and re-tiling into the tile-major layout (base.py:262)."""
+        if isinstance(X, np.ndarray) and not X.flags.writeable:
+            # read-only inputs (memmaps, sklearn's checks) are only ever read; silence torch's notice
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore", UserWarning)
+                X = torch.from_numpy(X)
         st = self.st
         xdt = _torch_dtype(self.x_code)
         self.Xt = torch.empty(st.n_tiles * st.n_pad * L.TILE_PX, dtype=xdt, device=self.device)

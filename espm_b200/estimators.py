@@ -173,9 +173,18 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
 
     # ------------------------------------------------------------------ loss
     def _loss_from_record(self, rec):
-        kl, reg, lap = self._engine.loss_parts(rec, self.const_KL_, self.GWH_numel_)
+        """base.py:203-205 + smooth_nmf.py:461-469 from one scalar record of the device."""
+        numel = self.GWH_numel_
+        kl = (rec[L.S_SUMY] - rec[L.S_XLOGY] + self.const_KL_) / numel
+        reg = rec[L.S_LOGREG] / numel
+        lap = 0.5 * self.lambda_L * rec[L.S_LAPL] / numel
         self.detailed_loss_ = [kl, reg, lap, self.gamma_]
         return kl + reg + lap
+
+    def __getstate__(self):
+        state = super().__getstate__()
+        state.pop("_engine", None)      # device buffers / ctypes handles never travel with a pickle
+        return state
 
     def loss(self, W, H, average=True, X=None):
         """Regularised loss of (W, H) (smooth_nmf.py:457-475, base.py:167-207), evaluated on the device."""
@@ -292,6 +301,7 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
             self.W_ = self.W_ / self.norm_factor_
         GW = self.G_ @ self.W_ if not self._identity_G else self.W_.copy()
         self.n_components_ = self.H_.shape[0]
+        self._engine = None            # release the device copy of X
         if self.hspy_comp:                                             # base.py:415-420
             self.components_ = GW.T
             return self.H_.T

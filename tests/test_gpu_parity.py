@@ -357,3 +357,65 @@ def test_unsupported_variants_fail_loudly():
             SmoothNMF(n_components=2, max_iter=2, verbose=0, **kw).fit_transform(X)
     with pytest.raises(ValueError):
         SmoothNMF(n_components=2, max_iter=2, verbose=0).fit_transform(-X)
+
+
+# ---------------------------------------------------------------------------------- device-side prologue
+def test_prologue_on_device_matches_reference_host_passes(orc):
+    """remove_zeros_lines / normalize / const_KL_ / input checks run as device passes over X
+    (base.py:243-267, 519-528, 200-201)."""
+    from espm_b200 import SmoothNMF
+    rng = np.random.default_rng(21)
+    X, G, W0, H0 = _problem(rng, 200, 9, 14, 3, 6)
+    X[:, 7] = 0.0          # all-zero pixel
+    X[:, 100] = 0.0
+    X[31, :] = 0.0         # all-zero channel
+    kw = dict(simplex_H=False, simplex_W=True, lambda_L=0.3, shape_2d=(9, 14), tol=0, no_stop_criterion=True,
+              max_iter=6)
+    for normalize in (False, True):
+        for layout in ("np", "hspy"):
+            est = SmoothNMF(n_components=3, G=G, verbose=0, normalize=normalize, hspy_comp=(layout == "hspy"), **kw)
+            Xin = X if layout == "np" else np.ascontiguousarray(X.T)
+            est.fit_transform(Xin, W=W0.copy(), H=H0.copy())
+            ref = orc.fit(X, G, W0, H0, normalize=normalize, **kw)
+            assert rel_err(est.losses_, ref["losses"]) < 1e-9
+            assert rel_err(est.W_, ref["W"]) < 1e-8
+            assert rel_err(est.H_, ref["H"]) < 1e-8
+            Xref = orc.remove_zeros_lines(X, 1e-14)
+            if normalize:
+                assert rel_err(est.norm_factor_, ref["norm_factor"]) < 1e-13
+                Xref = ref["norm_factor"] * Xref
+            assert rel_err(est.const_KL_, orc.const_KL(Xref)) < 1e-12
+            np.testing.assert_allclose(est.X_, Xref, rtol=1e-13, atol=0)     # lazily built host copy
+    for bad, msg in ((np.nan, "NaN"), (np.inf, "infinity"), (-1.0, "Negative values in data")):
+        Xb = X.copy()
+        Xb[3, 4] = bad
+        with pytest.raises(ValueError, match=msg):
+            SmoothNMF(n_components=3, G=G, verbose=0, **kw).fit_transform(Xb, W=W0.copy(), H=H0.copy())
+        with pytest.raises(ValueError):   # same checks on the host path used when a factor is missing
+            SmoothNMF(n_components=3, G=G, verbose=0, **kw).fit_transform(Xb)
+
+
+def test_fp32_prologue_and_float32_fit(orc):
+    from espm_b200 import SmoothNMF
+    rng = np.random.default_rng(22)
+    X, G, W0, H0 = [a.astype(np.float32) for a in _problem(rng, 256, 16, 8, 3, 5)]
+    X[:, 3] = 0.0
+    kw = dict(simplex_H=True, simplex_W=False, mu=0.05, lambda_L=1.0, shape_2d=(16, 8), tol=0,
+              no_stop_criterion=True, max_iter=6, normalize=True)
+    est = SmoothNMF(n_components=3, G=G, verbose=0, **kw)
+    est.fit_transform(X, W=W0.copy(), H=H0.copy())
+    ref = orc.fit(*[a.astype(np.float64) for a in (X, G, W0, H0)], **kw)
+    assert est.W_.dtype == np.float32
+    assert rel_err(est.losses_, ref["losses"]) < TRAJ_TOL
+    assert rel_err(est.norm_factor_, ref["norm_factor"]) < 1e-6
+
+
+def test_sklearn_check_estimator():
+    """The reference passes sklearn's estimator checks (test_estimators.py:100-104); so must the drop-in."""
+    from sklearn.utils.estimator_checks import check_estimator
+    from espm_b200 import SmoothNMF
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        check_estimator(SmoothNMF(n_components=3, max_iter=10, verbose=0))
+        check_estimator(SmoothNMF(n_components=3, max_iter=10, verbose=0, lambda_L=2, mu=0.1))
