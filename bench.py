@@ -105,7 +105,7 @@ def main():
     ap.add_argument("--seed", type=int, default=93)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-rows", type=int, default=8, help="image rows of the CPU-baseline crop")
+    ap.add_argument("--cpu-rows", type=int, default=48, help="image rows of the CPU-baseline crop")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     nx, ny, n, k = wl["nx"], wl["ny"], wl["n"], wl["k"]
@@ -282,10 +282,10 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         rows = min(args.cpu_rows, nx)
         X_crop = synth.poisson_X_numpy(prob, 0, rows * ny, args.seed, dtype=np_dtype)
-        val, its_crop, dtc = cpu_baseline(prob, wl, X_crop, rows, 6, args.seed)
+        val, its_crop, dtc = cpu_baseline(prob, wl, X_crop, rows, 12, args.seed)
         cpu = {"value": val, "unit": "it/s", "cores": os.cpu_count(), "kind": "port",
                "sample": "oracle port of the reference (NumPy/OpenBLAS, all host threads) on the first %d of %d image "
-                         "rows (%d px x %d ch), 6 iterations in %.1f s = %.3f it/s on the crop, scaled by p_crop/p" % (
+                         "rows (%d px x %d ch), 12 iterations in %.1f s = %.3f it/s on the crop, scaled by p_crop/p" % (
                              rows, nx, rows * ny, n, dtc, its_crop)}
 
     line = {"metric": "smoothnmf_iterations_per_s", "value": value, "unit": "it/s", "n_gpus": world, "steps": K,
