@@ -121,7 +121,10 @@ def main():
     config = {"workload": "%s: %dx%d px x %d ch synthetic EDXS, %d phases, G %dx%d, %s" % (
         args.workload, nx, ny, n, k, n, prob["G_full"].shape[1],
         ", ".join("%s=%s" % kv for kv in sorted(wl["kw"].items()))),
-        "x_dtype": args.dtype, "sharding": "image rows over %d rank(s)" % world,
+        "x_dtype": args.dtype,
+        "sharding": "image rows over %d rank(s)%s" % (world, "" if world == 1 else (
+            ", exchange through %s" % ("NCCL" if os.environ.get("ESPM_B200_PEER", "1") == "0"
+                                       else "CUDA-IPC peer memory inside the kernels"))),
         "l2": "inputs (%.2f GB of X per pass) are larger than L2; no flush needed" % (n * p * np_dtype().itemsize / 1e9)}
 
     # ------------------------------------------------------------------ reference arm (CPU)
@@ -157,8 +160,8 @@ def main():
     shard = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-        from espm_b200.dist import Shard, shard_bounds
-        shard = Shard()
+        from espm_b200.dist import make_shard, shard_bounds
+        shard = make_shard()
         j0, j1, _ = shard_bounds(p, nx, ny, rank, world)
     else:
         j0, j1 = 0, p
@@ -235,6 +238,7 @@ def main():
     if not args.no_e2e:
         import espm_b200
         from espm_b200 import SmoothNMF
+        eng.close()
         del eng
         torch.cuda.empty_cache()
         # the user's host buffer: the whole image in pinned host memory (every rank reads its own rows)
@@ -273,6 +277,8 @@ def main():
                        "iterations + D2H of W, H and the loss history; wall time %.3f s" % (K, K, dt),
                "final_loss": float(est.losses_[-1])}
 
+    if args.no_e2e:
+        eng.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -14,6 +14,8 @@ TILE_PX = 128
 MAX_K = 16
 NSCALARS = 24
 MAXIT_DICHOTOMY = 100
+MAX_RANKS = 16
+PF_SFLAG, PF_MFLAG, PF_MASK, PF_WORDS = 0, 16, 32, 128
 
 # espm_state.flags
 FLAG_SIMPLEX_H = 1 << 0
@@ -29,6 +31,7 @@ FLAG_HAVE_HPREV = 1 << 9
 FLAG_SIMPLEX_ROWS = 1 << 10
 FLAG_HQ = 1 << 11
 FLAG_FUSED_WREDUCE = 1 << 12
+FLAG_PEER = 1 << 13
 COOP_BLOCKS = 32
 
 # device error word
@@ -37,6 +40,7 @@ DEV_BRACKET = 1 << 1
 DEV_NEGATIVE = 1 << 2
 DEV_GW_BELOW_LS = 1 << 3
 DEV_GW_ZERO_ROW = 1 << 4
+DEV_PEER_TIMEOUT = 1 << 5
 
 # scalar record slots
 S_XLOGY, S_SUMY, S_LOGREG, S_LAPL, S_REL_H, S_REL_W, S_BISECT_ITS_H, S_BISECT_ITS_W, S_DEV_FLAGS, \
@@ -69,6 +73,9 @@ class EspmState(ctypes.Structure):
         ("numraw", _vp), ("num", _vp), ("den", _vp),
         ("s_part", _vp), ("s_sum", _vp), ("Ht", _vp), ("w_num", _vp), ("w_den", _vp),
         ("xlogy_part", _vp), ("px_part", _vp), ("bisect_mask", _vp), ("dev_flags", _vp), ("scalars", _vp), ("coop_part", _vp),
+        ("rank", _i32), ("world", _i32), ("seq_s", _u32), ("seq_m", _u32), ("nb_prev_ldh", _i32), ("nb_next_ldh", _i32),
+        ("xchg_stride", _i64), ("xchg_hs_off", _i64), ("nb_prev_halo", _vp), ("nb_next_halo", _vp),
+        ("peer_xchg", _vp * MAX_RANKS), ("peer_flags", _vp * MAX_RANKS),
     ]
 
 
@@ -107,6 +114,11 @@ _EXPORTS = {
     "espm_w_pass": (ctypes.c_int, [ctypes.POINTER(EspmState), _vp]),
     "espm_w_reduce": (ctypes.c_int, [ctypes.POINTER(EspmState), _vp]),
     "espm_w_finish": (ctypes.c_int, [ctypes.POINTER(EspmState), _vp]),
+    "espm_peer_alloc": (ctypes.c_int, [_i64, ctypes.POINTER(_vp)]),
+    "espm_peer_export": (ctypes.c_int, [_vp, ctypes.c_char_p]),
+    "espm_peer_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(_vp)]),
+    "espm_peer_close": (ctypes.c_int, [_vp]),
+    "espm_peer_free": (ctypes.c_int, [_vp]),
     "espm_dichotomy_simplex": (ctypes.c_int, [_i32, _i32, _i64, _vp, _vp, _f64, _f64, _i32, _vp, _vp, _vp, _vp, _vp]),
 }
 

@@ -61,6 +61,16 @@ static int check_state(const espm_state* st) {
         set_error("empty problem n=%d p_loc=%d m=%d", st->n, st->p_loc, st->m);
         return ESPM_ERR_BAD_ARG;
     }
+    if (st->flags & ESPM_FLAG_PEER) {
+        if (st->world < 1 || st->world > ESPM_MAX_RANKS || st->rank < 0 || st->rank >= st->world) {
+            set_error("peer exchange: bad rank %d / world %d", st->rank, st->world);
+            return ESPM_ERR_BAD_ARG;
+        }
+        if (!(st->flags & ESPM_FLAG_FUSED_WREDUCE)) {
+            set_error("ESPM_FLAG_PEER requires ESPM_FLAG_FUSED_WREDUCE");
+            return ESPM_ERR_BAD_ARG;
+        }
+    }
     if (st->flags & ESPM_FLAG_HQ) {
         set_error("algo=l2_surrogate is not implemented on the device yet");
         return ESPM_ERR_UNSUPPORTED;
@@ -339,6 +349,50 @@ int espm_w_pass(const espm_state* st, void* stream) {
     XPassArgs a = make_args(st, true);
     XPassLaunch l{XPASS_W, st->kp, is_safe(st) ? 1 : 0, st->w_grid, st->w_smem};
     return pick_xpass(st)(l, &a, nullptr, (cudaStream_t)stream);
+}
+
+int espm_peer_alloc(int64_t bytes, void** ptr_out) {
+    if (!ptr_out || bytes <= 0) {
+        set_error("espm_peer_alloc: bad arguments");
+        return ESPM_ERR_BAD_ARG;
+    }
+    void* p = nullptr;
+    ESPM_CUDA_CHECK(cudaMalloc(&p, (size_t)bytes));
+    ESPM_CUDA_CHECK(cudaMemset(p, 0, (size_t)bytes));
+    ESPM_CUDA_CHECK(cudaDeviceSynchronize());
+    *ptr_out = p;
+    return ESPM_OK;
+}
+
+int espm_peer_export(void* ptr, unsigned char* handle64) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    if (!ptr || !handle64) return ESPM_ERR_BAD_ARG;
+    cudaIpcMemHandle_t h;
+    ESPM_CUDA_CHECK(cudaIpcGetMemHandle(&h, ptr));
+    memcpy(handle64, &h, 64);
+    return ESPM_OK;
+}
+
+int espm_peer_open(const unsigned char* handle64, void** ptr_out) {
+    if (!handle64 || !ptr_out) return ESPM_ERR_BAD_ARG;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    ESPM_CUDA_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *ptr_out = p;
+    return ESPM_OK;
+}
+
+int espm_peer_close(void* ptr) {
+    if (!ptr) return ESPM_OK;
+    ESPM_CUDA_CHECK(cudaIpcCloseMemHandle(ptr));
+    return ESPM_OK;
+}
+
+int espm_peer_free(void* ptr) {
+    if (!ptr) return ESPM_OK;
+    ESPM_CUDA_CHECK(cudaFree(ptr));
+    return ESPM_OK;
 }
 
 int espm_dichotomy_simplex(int32_t c_dtype, int32_t k, int64_t p, const void* num, const void* den, double log_shift,

@@ -24,6 +24,33 @@ __device__ __forceinline__ void lds_row(T (&dst)[N], const T* src) {
 }
 constexpr int PX_WARPS = PX_THREADS / 32;
 
+// ------------------------------------------------------------------------------------------------
+// Peer exchange primitives (ESPM_FLAG_PEER): system-scope flags in CUDA-IPC memory over NVLink.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// Threads 0..world-1 of the CTA wait until flags[r] has reached `seq` for every rank r; bounded (~1 s) so
+// that a dead peer turns into ESPM_DEV_PEER_TIMEOUT instead of a hung GPU.  Ends with __syncthreads().
+__device__ __forceinline__ void wait_peer_flags(const uint32_t* flags, int world, uint32_t seq, uint32_t* dev_flags) {
+    if ((int)threadIdx.x < world) {
+        const long long t0 = clock64();
+        while ((int32_t)(ld_acquire_sys(flags + threadIdx.x) - seq) < 0) {
+            if (clock64() - t0 > (1ll << 31)) {
+                atomicOr(dev_flags, ESPM_DEV_PEER_TIMEOUT);
+                break;
+            }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+}
+
 // px_part row layout (doubles), sums first, maxima last:
 //   [0] log-reg  [1] laplacian trace  [2 + kk] rowsum(H_next)  [2 + kp + kk] rowsum(max(H_next, ls))
 //   [2 + 2kp] rel_H max   [3 + 2kp + kk] rowmax(H_next)
@@ -212,6 +239,13 @@ __device__ __forceinline__ void store_h_next(const espm_state& st, int j, int k,
             }
             Hn[(size_t)kk * st.ldh + j] = v;
             Ht[((size_t)(j / TILE_PX) * KP + kk) * TILE_PX + (j % TILE_PX)] = v;   // tile-major copy for the W pass
+            if (st.flags & ESPM_FLAG_PEER) {
+                // Laplacian halo: my first / last image row lands in the neighbours' H_next (peer stores)
+                if (st.nb_prev_halo && j < st.ny)
+                    reinterpret_cast<TC*>(st.nb_prev_halo)[(size_t)kk * st.nb_prev_ldh + j] = v;
+                if (st.nb_next_halo && j >= st.p_loc - st.ny)
+                    reinterpret_cast<TC*>(st.nb_next_halo)[(size_t)kk * st.nb_next_ldh + (j - (st.p_loc - st.ny))] = v;
+            }
             vals[2 + kk] = (double)v;
             vals[2 + KP + kk] = (double)Num<TC>::vmax(v, ls);
             vals[3 + 2 * KP + kk] = (double)v;
@@ -358,7 +392,16 @@ __global__ void __launch_bounds__(PX_THREADS) h_finish_kernel(const espm_state s
         __threadfence();
         h_scalars_block<TC>(st);
         if (threadIdx.x == 0) st.dev_flags[2] = 0u;
+        if ((st.flags & ESPM_FLAG_PEER) && simplex && (int)threadIdx.x < st.world) {
+            // publish this rank's complete trace mask on every rank (its own included), then raise the flag
+            uint32_t* pf = st.peer_flags[threadIdx.x];
+#pragma unroll
+            for (int w = 0; w < 4; ++w) pf[ESPM_PF_MASK + 4 * st.rank + w] = __ldcg(st.bisect_mask + w);
+            __threadfence_system();
+            st_release_sys(pf + ESPM_PF_MFLAG + st.rank, st.seq_m);
+        }
     }
+    if (st.flags & ESPM_FLAG_PEER) __threadfence_system();   // halo rows pushed by store_h_next (no simplex)
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -375,7 +418,22 @@ __global__ void __launch_bounds__(PX_THREADS) h_apply_kernel(const espm_state st
     for (int i = 0; i < NV; ++i) vals[i] = 0.0;
 #pragma unroll
     for (int kk = 0; kk < KP; ++kk) vals[3 + 2 * KP + kk] = -1e300;
-    const int its = first_clear_bit(st.bisect_mask, st.maxit);
+    int its;
+    if (st.flags & ESPM_FLAG_PEER) {
+        // lock-step count over ALL shards: wait for every rank's mask, OR them
+        __shared__ uint32_t gmask[4];
+        const uint32_t* pf = st.peer_flags[st.rank];
+        wait_peer_flags(pf + ESPM_PF_MFLAG, st.world, st.seq_m, st.dev_flags);
+        if (threadIdx.x < 4) {
+            uint32_t m = 0u;
+            for (int r = 0; r < st.world; ++r) m |= __ldcg(pf + ESPM_PF_MASK + 4 * r + threadIdx.x);
+            gmask[threadIdx.x] = m;
+        }
+        __syncthreads();
+        its = first_clear_bit(gmask, st.maxit);
+    } else {
+        its = first_clear_bit(st.bisect_mask, st.maxit);
+    }
     if (j < st.p_loc) {
         double num[KP], den[KP];
         TC hn[KP];
@@ -398,6 +456,7 @@ __global__ void __launch_bounds__(PX_THREADS) h_apply_kernel(const espm_state st
     __syncthreads();
     double* out = st.px_part + (size_t)blockIdx.x * NV;
     if (threadIdx.x < NV && threadIdx.x >= 2 && threadIdx.x != 2 + 2 * KP) out[threadIdx.x] = tmp[threadIdx.x];
+    if (st.flags & ESPM_FLAG_PEER) __threadfence_system();   // halo rows pushed by store_h_next
 }
 
 // h_stats: statistics of H_next only (initialisation, operator-level API).
@@ -670,18 +729,51 @@ __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_sta
 
     // ---- phase 0: fold the W-pass partial slots and the per-pixel statistics ----
     if (st.flags & ESPM_FLAG_FUSED_WREDUCE) {
+        const bool peer = st.flags & ESPM_FLAG_PEER;
         const size_t total = (size_t)st.n_pad * KP;
         const TC* part = reinterpret_cast<const TC*>(st.s_part);
+        // sharded: the local sums go to this rank's exchange buffer (parity = seq & 1), read by every rank
+        unsigned char* my_x = peer ? reinterpret_cast<unsigned char*>(st.peer_xchg[st.rank]) +
+                                         (size_t)(st.seq_s & 1u) * st.xchg_stride
+                                   : nullptr;
+        TC* Sloc = peer ? reinterpret_cast<TC*>(my_x) : S;
+        double* hsloc = peer ? reinterpret_cast<double*>(my_x + st.xchg_hs_off) : hstats;
         for (size_t i = gthread; i < total; i += gthreads) {
             const int cb = (int)(i / ((size_t)st.cs * KP));
             const int first = (int)(((long long)cb * st.n_tiles) / st.w_upc);
             const int last = (int)((((long long)cb + 1) * st.n_tiles - 1) / st.w_upc);
             TC v = part[i];
             for (int r = 1; r <= last - first; ++r) v += part[(size_t)r * total + i];
-            S[i] = v;
+            Sloc[i] = v;
         }
-        if (blockIdx.x == gridDim.x - 1) reduce_hstats_block(st, hstats);
+        if (blockIdx.x == gridDim.x - 1) reduce_hstats_block(st, hsloc);
         grid_barrier(bar, gridDim.x);
+        if (peer) {
+            if (blockIdx.x == 0 && (int)threadIdx.x < st.world) {
+                __threadfence_system();
+                st_release_sys(st.peer_flags[threadIdx.x] + ESPM_PF_SFLAG + st.rank, st.seq_s);
+            }
+            wait_peer_flags(st.peer_flags[st.rank] + ESPM_PF_SFLAG, st.world, st.seq_s, st.dev_flags);
+            // fold the ranks' buffers in rank order: every rank computes the identical sums (no broadcast)
+            const size_t poff = (size_t)(st.seq_s & 1u) * st.xchg_stride;
+            for (size_t i = gthread; i < total; i += gthreads) {
+                TC v = __ldcg(reinterpret_cast<const TC*>(reinterpret_cast<const unsigned char*>(st.peer_xchg[0]) + poff) + i);
+                for (int r = 1; r < st.world; ++r)
+                    v += __ldcg(reinterpret_cast<const TC*>(reinterpret_cast<const unsigned char*>(st.peer_xchg[r]) + poff) + i);
+                S[i] = v;
+            }
+            if (blockIdx.x == gridDim.x - 1 && (int)threadIdx.x < 3 * KP) {
+                const bool is_max = (int)threadIdx.x >= 2 * KP;
+                double v = 0.0;
+                for (int r = 0; r < st.world; ++r) {
+                    const double u = __ldcg(reinterpret_cast<const double*>(
+                        reinterpret_cast<const unsigned char*>(st.peer_xchg[r]) + poff + st.xchg_hs_off) + threadIdx.x);
+                    v = (r == 0) ? u : (is_max ? (u > v ? u : v) : v + u);
+                }
+                hstats[threadIdx.x] = v;
+            }
+            grid_barrier(bar, gridDim.x);
+        }
     }
 
     // ---- phase A: num = W * (G^T S), den = colsum(G) (x) rowsum(H')   (updates.py:58-60) ----

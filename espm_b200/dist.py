@@ -135,6 +135,123 @@ class Shard:
         return np.concatenate([o.cpu().numpy()[:, :s] for o, s in zip(out, sizes)], axis=1)
 
 
+class _DevMem:
+    """Read/write view of raw device memory for torch (``__cuda_array_interface__``, no ownership)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False),
+                                         "version": 2}
+
+
+def _up(a, b):
+    return (a + b - 1) // b * b
+
+
+class PeerShard(Shard):
+    """Sharded fit whose per-iteration exchanges run INSIDE the kernels through CUDA-IPC peer memory over
+    NVLink (ESPM_FLAG_PEER, include/espm_b200.h): no host-launched collective on the critical path.
+    torch.distributed is still used for the one-off set-up (IPC handles, initial halo / statistics) and for
+    gathering results."""
+
+    use_peer = True
+
+    def __init__(self, rank=None, world=None, group=None):
+        super().__init__(rank, world, group)
+        if self.world > L.MAX_RANKS:
+            raise ValueError("at most %d pixel shards are supported" % L.MAX_RANKS)
+        self.region = None
+        self.opened = []
+        self.bases = None
+        self.meta = None
+        self._lib = None
+
+    def setup_peer(self, eng):
+        """Allocate this rank's region (flags | exchange buffers | 3 H buffers), map every peer's region and
+        fill the peer fields of ``eng.st``.  Returns the three H tensors (views of the region)."""
+        import ctypes
+        lib = L.load()
+        self._lib = lib
+        st = eng.st
+        sz = 8 if st.c_dtype == L.F64 else 4
+        hs_off = _up(st.n_pad * st.kp * sz, 128)
+        stride = _up(hs_off + 3 * st.kp * 8, 256)
+        x_off = L.PF_WORDS * 4
+        h_bytes = _up(st.k * st.ldh * sz, 256)
+        h_off = [_up(x_off + 2 * stride, 256) + i * h_bytes for i in range(3)]
+        total = h_off[2] + h_bytes
+        ptr = ctypes.c_void_p()
+        L.check(lib.espm_peer_alloc(total, ctypes.byref(ptr)))
+        self.region = ptr.value
+        handle = ctypes.create_string_buffer(64)
+        L.check(lib.espm_peer_export(ctypes.c_void_p(self.region), handle))
+        mine = dict(handle=handle.raw, ldh=int(st.ldh), p_loc=int(st.p_loc), h_off=h_off, x_off=x_off, halo=int(st.halo))
+        metas = [None] * self.world
+        dist.all_gather_object(metas, mine, group=self.group)
+        bases = []
+        for r, m in enumerate(metas):
+            if r == self.rank:
+                bases.append(self.region)
+                continue
+            p = ctypes.c_void_p()
+            L.check(lib.espm_peer_open(m["handle"], ctypes.byref(p)))
+            self.opened.append(p.value)
+            bases.append(p.value)
+        self.bases, self.meta = bases, metas
+        st.rank, st.world = self.rank, self.world
+        st.xchg_stride, st.xchg_hs_off = stride, hs_off
+        for r in range(self.world):
+            st.peer_flags[r] = bases[r]
+            st.peer_xchg[r] = bases[r] + metas[r]["x_off"]
+        st.flags |= L.FLAG_PEER | L.FLAG_FUSED_WREDUCE
+        tdt = torch.float64 if st.c_dtype == L.F64 else torch.float32
+        raw = torch.as_tensor(_DevMem(self.region, total), device=eng.device)
+        H = []
+        for i in range(3):
+            t = raw[h_off[i]:h_off[i] + st.k * st.ldh * sz].view(tdt).view(st.k, st.ldh)
+            t.fill_(1.0)
+            H.append(t)
+        dist.barrier(group=self.group)          # every region is mapped and initialised before any kernel runs
+        return H
+
+    def halo_targets(self, eng, ibuf):
+        """(prev pointer, prev ldh, next pointer, next ldh) for pushing the boundary rows of H buffer ``ibuf``."""
+        if eng.ny <= 0:
+            return 0, 0, 0, 0
+        sz = 8 if eng.st.c_dtype == L.F64 else 4
+        pp = pl = npn = nl = 0
+        if self.rank > 0:
+            m = self.meta[self.rank - 1]
+            pp = self.bases[self.rank - 1] + m["h_off"][ibuf] + (m["halo"] + m["p_loc"]) * sz
+            pl = m["ldh"]
+        if self.rank < self.world - 1:
+            m = self.meta[self.rank + 1]
+            npn = self.bases[self.rank + 1] + m["h_off"][ibuf] + (m["halo"] - eng.ny) * sz
+            nl = m["ldh"]
+        return pp, pl, npn, nl
+
+    def close(self):
+        """Collective: unmap the peers' regions and free this rank's (after every rank is done with them)."""
+        import ctypes
+        if self.region is None:
+            return
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        for p in self.opened:
+            self._lib.espm_peer_close(ctypes.c_void_p(p))
+        self.opened = []
+        dist.barrier(group=self.group)
+        self._lib.espm_peer_free(ctypes.c_void_p(self.region))
+        self.region = None
+
+
+def make_shard(group=None):
+    """PeerShard when the process group runs NCCL on one box (and ESPM_B200_PEER != 0), else Shard."""
+    import os
+    if dist.get_backend(group) == "nccl" and os.environ.get("ESPM_B200_PEER", "1") != "0":
+        return PeerShard(group=group)
+    return Shard(group=group)
+
+
 def combine_record_arrays(allr):
     """(world, m, NSCALARS) -> (m, NSCALARS): sums for the additive loss parts, max for rel_H, OR for
     flags; everything else is replicated and taken from rank 0."""

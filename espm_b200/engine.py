@@ -166,7 +166,12 @@ class FitEngine:
 
         # ---- state buffers (rotated by pointer) ----
         # H pad pixels hold 1 so that padded pixels give y > 0 (their X is 0: they contribute nothing)
-        self.Hbuf = [torch.ones(k, ldh, dtype=cdt, device=dev) for _ in range(3)]
+        self.peer = shard is not None and getattr(shard, "use_peer", False)
+        self._seq_s = self._seq_m = 0
+        if self.peer:
+            self.Hbuf = shard.setup_peer(self)       # H lives in CUDA-IPC memory the neighbours can write
+        else:
+            self.Hbuf = [torch.ones(k, ldh, dtype=cdt, device=dev) for _ in range(3)]
         self.Wbuf = [zeros(self.m, k) for _ in range(2)]
         self.GWbuf = [zeros(n_pad, kp) for _ in range(2)]
         self.GWcbuf = [zeros(n_pad, kp) for _ in range(2)]
@@ -200,7 +205,7 @@ class FitEngine:
         st.xlogy_part, st.px_part = self.xlogy_part.data_ptr(), self.px_part.data_ptr()
         st.bisect_mask, st.dev_flags = self.mask.data_ptr(), self.dev_flags.data_ptr()
         st.coop_part = self.coop_part.data_ptr()
-        if shard is None:
+        if shard is None or self.peer:
             st.flags |= L.FLAG_FUSED_WREDUCE      # w_finish folds the W-pass partials itself
 
         # ---- constant inputs ----
@@ -259,6 +264,8 @@ class FitEngine:
             st.flags |= L.FLAG_HAVE_HPREV
         else:
             st.flags &= ~L.FLAG_HAVE_HPREV
+        if self.peer:
+            st.nb_prev_halo, st.nb_prev_ldh, st.nb_next_halo, st.nb_next_ldh = self.shard.halo_targets(self, hn)
 
     def _set_record(self, slot):
         if not 0 <= slot < self.max_records:
@@ -431,6 +438,13 @@ class FitEngine:
         self._bind()
 
     # ------------------------------------------------------------------ multi-GPU hooks (dist.py)
+    def close(self):
+        """Release peer memory (collective when sharded through peer memory); the engine is unusable after."""
+        if self.peer and self.shard is not None:
+            self.Hbuf = None
+            self.shard.close()
+            self.peer = False
+
     def _sync_hstats(self):
         if self.shard is not None:
             self.shard.allreduce_hstats(self.hstats[self.ihs[1]], self.st.kp)
@@ -443,6 +457,8 @@ class FitEngine:
     def evaluate(self, slot):
         """Phase A on (W_cur, H_cur): fills scalar record ``slot`` (loss parts, rel_H, flags)."""
         self._set_record(slot)
+        self._seq_m += 1
+        self.st.seq_m = self._seq_m                          # mask exchange of this evaluation (peer mode)
         self._call(self.lib.espm_h_pass, "h_pass")
         self._call(self.lib.espm_h_finish, "h_finish")      # its last CTA also writes the scalar record
 
@@ -451,12 +467,15 @@ class FitEngine:
         st = self.st
         self._set_record(slot)
         if st.flags & L.FLAG_SIMPLEX_H:
-            if self.shard is not None:
+            if self.shard is not None and not self.peer:
                 self.shard.gather_masks(self.mask)
             self._call(self.lib.espm_h_apply, "h_apply")
-        self._exchange_halo(self.ih[2])
+        if not self.peer:
+            self._exchange_halo(self.ih[2])
+        self._seq_s += 1
+        st.seq_s = self._seq_s                               # S exchange of this update (peer mode)
         self._call(self.lib.espm_w_pass, "w_pass")
-        if self.shard is not None:
+        if self.shard is not None and not self.peer:
             self._call(self.lib.espm_w_reduce, "w_reduce")
             self.shard.allreduce_sum(self.s_sum)
             self._sync_hstats()

@@ -254,8 +254,8 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
         if config.distributed:
             import torch.distributed as dist
             if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-                from .dist import Shard
-                shard = Shard()
+                from .dist import make_shard
+                shard = make_shard()
         eng = FitEngine(Xv, None if self._identity_G else G, W0, H0,
                         shape_2d=self.shape_2d, lambda_L=self.lambda_L, mu=self.mu, epsilon_reg=self.epsilon_reg,
                         log_shift=self.log_shift, dicotomy_tol=self.dicotomy_tol, dicotomy_tol_w=_DICOTOMY_TOL,
@@ -301,6 +301,7 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
             self.W_ = self.W_ / self.norm_factor_
         GW = self.G_ @ self.W_ if not self._identity_G else self.W_.copy()
         self.n_components_ = self.H_.shape[0]
+        eng.close()
         self._engine = None            # release the device copy of X
         if self.hspy_comp:                                             # base.py:415-420
             self.components_ = GW.T
@@ -318,6 +319,9 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
 
     def _check_flags(self, rec):
         flags = int(rec[L.S_DEV_FLAGS])
+        if flags & L.DEV_PEER_TIMEOUT:
+            raise RuntimeError("espm_b200: a peer rank did not answer within the exchange time-out; "
+                               "the sharded fit is invalid")
         if flags & L.DEV_NONFINITE:
             raise FloatingPointError("espm_b200: non-finite values in the H update (zero row in G W?)")
         if flags & (L.DEV_BRACKET | L.DEV_NEGATIVE):

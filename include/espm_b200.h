@@ -39,6 +39,12 @@ extern "C" {
 #define ESPM_STAGE_BYTES 16384    /* bytes of X per pipeline stage (one bulk copy) */
 #define ESPM_MAX_K 16             /* largest supported n_components */
 #define ESPM_COOP_BLOCKS 32        /* CTAs of the cooperative w_finish kernel */
+#define ESPM_MAX_RANKS 16          /* largest number of pixel shards (GPUs of one NVLink domain) */
+/* layout of a rank's peer flag block (uint32 words), see ESPM_FLAG_PEER */
+#define ESPM_PF_SFLAG 0            /* [r]: rank r published its S / H' statistics with this sequence number */
+#define ESPM_PF_MFLAG 16           /* [r]: rank r pushed its bisection trace mask with this sequence number */
+#define ESPM_PF_MASK  32           /* [4*r .. 4*r+3]: rank r's 128-bit trace mask */
+#define ESPM_PF_WORDS 128
 #define ESPM_NSCALARS 24          /* doubles per slot of the per-iteration scalar record */
 #define ESPM_MAXIT_DICHOTOMY 100  /* espm/conf.py:59 */
 
@@ -64,6 +70,7 @@ typedef enum espm_status {
 #define ESPM_FLAG_SIMPLEX_ROWS (1u << 10) /* simplex_W restricted to simplex_rows (updates.py:62-65) */
 #define ESPM_FLAG_HQ          (1u << 11) /* algo="l2_surrogate": quadratic surrogate H step (updates.py:263-301) */
 #define ESPM_FLAG_FUSED_WREDUCE (1u << 12) /* espm_w_finish also does the work of espm_w_reduce (single-GPU fits) */
+#define ESPM_FLAG_PEER        (1u << 13) /* pixel-sharded fit exchanging through peer memory (NVLink), see below */
 
 /* bits of the device-side error word (espm_state.dev_flags[0]) */
 #define ESPM_DEV_NONFINITE    (1u << 0)  /* non-finite ratio sums (x/0): caller must redo with CLAMP_Y */
@@ -71,6 +78,7 @@ typedef enum espm_status {
 #define ESPM_DEV_NEGATIVE     (1u << 2)  /* negative num/denum (updates.py:148-149, dicotomy.py:17-19) */
 #define ESPM_DEV_GW_BELOW_LS  (1u << 3)  /* some GW entry < log_shift: loss needs ESPM_FLAG_LOSS_DUAL */
 #define ESPM_DEV_GW_ZERO_ROW  (1u << 4)  /* some row of GW is all zero: updates need ESPM_FLAG_CLAMP_Y */
+#define ESPM_DEV_PEER_TIMEOUT (1u << 5)  /* a peer rank did not signal within ~1 s: results of this fit are invalid */
 
 /* layout of one scalar record (doubles), written by espm_h_scalars / espm_w_finish */
 enum {
@@ -172,6 +180,25 @@ typedef struct espm_state {
                              * [2] h_finish completion ticket, [3] grid-barrier counter of w_finish (start at 0) */
     double* scalars;        /* ESPM_NSCALARS doubles: the record being filled */
     double* coop_part;      /* ESPM_COOP_BLOCKS x (2*ESPM_MAX_K + 1) doubles: per-CTA partials of w_finish */
+    /* ---- ESPM_FLAG_PEER: exchange between the pixel shards through CUDA-IPC peer memory over NVLink ----
+     * No host-launched collective sits on the per-iteration path: the kernels signal and wait on flag words
+     * (system-scope release/acquire) and move the few KiB that cross ranks with plain peer loads / stores.
+     *   - espm_w_finish publishes this rank's S and H' statistics in its exchange buffer, raises its S flag on
+     *     every rank, waits for all ranks and folds the peers' buffers in rank order (identical everywhere);
+     *   - the H update pushes its first / last image row into the neighbours' halo columns (Laplacian);
+     *   - espm_h_finish pushes the 128-bit bisection trace mask to every rank, espm_h_apply waits for all. */
+    int32_t rank;           /* this shard */
+    int32_t world;          /* number of shards (<= ESPM_MAX_RANKS) */
+    uint32_t seq_s;         /* sequence number of the coming S exchange (strictly increasing, > 0) */
+    uint32_t seq_m;         /* sequence number of the mask exchange (set before espm_h_finish, kept for espm_h_apply) */
+    int32_t nb_prev_ldh;    /* row stride (elements) of the previous rank's H buffers */
+    int32_t nb_next_ldh;
+    int64_t xchg_stride;    /* bytes between the two parities of an exchange buffer */
+    int64_t xchg_hs_off;    /* byte offset of the 3*kp statistics doubles inside one parity */
+    void* nb_prev_halo;     /* in the previous rank's H_next: where my FIRST image row goes (row kk at + kk*ldh) or NULL */
+    void* nb_next_halo;     /* in the next rank's H_next: where my LAST image row goes, or NULL */
+    void* peer_xchg[ESPM_MAX_RANKS];       /* every rank's exchange buffer: 2 x {S [n_pad][kp], statistics} */
+    uint32_t* peer_flags[ESPM_MAX_RANKS];  /* every rank's flag block (ESPM_PF_WORDS words, zero at start) */
 } espm_state;
 
 /* library / device */
@@ -258,6 +285,14 @@ int espm_w_reduce(const espm_state* st, void* stream);
  * the next H pass; with ESPM_FLAG_FUSED_WREDUCE also s_sum and hstats_next (espm_w_reduce).  One
  * cooperative kernel of ESPM_COOP_BLOCKS CTAs. */
 int espm_w_finish(const espm_state* st, void* stream);
+
+/* Peer memory for ESPM_FLAG_PEER: cudaMalloc'ed (zero-filled) regions that other processes of the same
+ * box map through CUDA IPC.  handle64 is the 64-byte cudaIpcMemHandle_t. */
+int espm_peer_alloc(int64_t bytes, void** ptr_out);
+int espm_peer_export(void* ptr, unsigned char* handle64);
+int espm_peer_open(const unsigned char* handle64, void** ptr_out);
+int espm_peer_close(void* ptr);
+int espm_peer_free(void* ptr);
 
 /* Standalone operator used by the unit-level API: nu = dichotomy_simplex(num, den) (dicotomy.py:4-55).
  * num/den: k x p (c dtype, row stride p), nu_out: p.  its_out (device int32) receives it*. */

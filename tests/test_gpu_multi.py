@@ -64,13 +64,14 @@ def _data(tag):
     return X, G, W0, H0
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, peer):
     if ROOT not in sys.path:
         sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    os.environ["ESPM_B200_PEER"] = "1" if peer else "0"
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
@@ -93,7 +94,9 @@ def _worker(rank, world, port, out_dir):
         dist.destroy_process_group()
 
 
-def test_sharded_fit_matches_oracle(tmp_path):
+@pytest.mark.parametrize("peer", [True, False], ids=["peer-memory", "nccl"])
+def test_sharded_fit_matches_oracle(tmp_path, peer):
+    """Both exchange paths: inside the kernels through CUDA-IPC peer memory (default), and NCCL."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -101,7 +104,7 @@ def test_sharded_fit_matches_oracle(tmp_path):
     from conftest import rel_err
     from oracle import smooth_nmf_oracle as orc
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), peer), nprocs=world, join=True)
     r0 = dict(np.load(tmp_path / "rank0.npz"))
     r1 = dict(np.load(tmp_path / "rank1.npz"))
     for tag, kw in CASES.items():
