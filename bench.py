@@ -31,7 +31,18 @@ WORKLOADS = {
     "C3": dict(nx=512, ny=512, n=2048, k=4, n_elements=25,
                kw=dict(simplex_H=True, simplex_W=False, lambda_L=2.0, mu=0.05)),
 }
-KERNELS_PER_ITER = 7   # h_pass, h_finish, h_scalars, h_apply, w_pass, w_reduce, w_finish
+
+
+def load_traffic(workload, dtype, world, kernel):
+    """ncu-measured DRAM bytes per launch of `kernel` (profiles/traffic.json), or None when no capture of
+    this exact configuration is committed."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as fh:
+            ent = json.load(fh).get("%s/%s/%d" % (workload, dtype, world))
+        return None if ent is None else ent.get(kernel)
+    except (OSError, ValueError):
+        return None
 
 
 def load_peaks():
@@ -189,11 +200,13 @@ def main():
     eng.profile = {}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    launches0 = eng.n_launches
     e0.record()
     for i in range(W + 1, W + K + 1):
         eng.advance(i)
         eng.evaluate(i)
     e1.record()
+    n_launches = eng.n_launches - launches0
     barrier()
     clocks = sampler.stop() if sampler else None
     ms = e0.elapsed_time(e1)
@@ -227,7 +240,8 @@ def main():
     kernel_ms = {nm: float(np.mean([a.elapsed_time(b) for a, b in ev])) for nm, ev in eng.profile.items()}
     eng.profile, eng.profile_names = None, ("h_pass", "w_pass")
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": load_traffic(args.workload, args.dtype, world, dom),
+                "peak_source": peak_src,
                 "bytes_per_launch": bytes_launch,
                 "h_pass_ms": h_ms, "w_pass_ms": w_ms,
                 "h_pass_gbs": bytes_launch / (h_ms * 1e-3) / 1e9, "w_pass_gbs": bytes_launch / (w_ms * 1e-3) / 1e9,
@@ -297,7 +311,7 @@ def main():
     line = {"metric": "smoothnmf_iterations_per_s", "value": value, "unit": "it/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic", "config": config, "roofline": roofline, "cpu_baseline": cpu,
-            "e2e": e2e, "gpu_launches": KERNELS_PER_ITER * K, "clocks": clocks,
+            "e2e": e2e, "gpu_launches": n_launches, "clocks": clocks,
             "check": {"loss_kl_sumY": float(recs[L.S_SUMY]), "bisect_its_H": float(recs[L.S_BISECT_ITS_H]),
                       "dev_flags": float(recs[L.S_DEV_FLAGS])}}
     print(json.dumps(line))

@@ -128,20 +128,18 @@ __device__ __forceinline__ int first_clear_bit(const uint32_t* mask, int maxit) 
     return maxit;
 }
 
-// Lock-step trace for one column: records for every iteration j whether |f(new_j)| > tol.
-// Exits early when every later midpoint is provably within tol (f is monotone on the bracket) or when
-// the bracket is stationary in floating point (then new, and the bit, never change again).
-template <typename TC, int KP>
-__device__ __forceinline__ void simplex_trace(const TC (&num)[KP], const TC (&den)[KP], int k, TC ls, TC tol,
-                                              int maxit, Mask128& bits, uint32_t& err) {
-    TC a, b;
-    simplex_bracket<TC, KP>(num, den, k, a, b);
-    TC fa = simplex_f<TC, KP>(num, den, a, k, ls);
-    TC fb = simplex_f<TC, KP>(num, den, b, k, ls);
+// Lock-step trace of one column's bisection (dicotomy.py:138-171) for a monotone f with f(a) > 0 > f(b):
+// records for every iteration j whether |f(new_j)| > tol.  Exits early when every later midpoint is
+// provably within tol (f is monotone on the bracket) or when the bracket is stationary in floating
+// point (then new, and the bit, never change again).
+template <typename TC, typename F>
+__device__ __forceinline__ void bisect_trace(TC a, TC b, F&& f, TC tol, int maxit, Mask128& bits, uint32_t& err) {
+    TC fa = f(a);
+    TC fb = f(b);
     // dicotomy.py:141-144 preconditions
     if (!(fa > TC(0)) || !(fb < TC(0))) err |= ESPM_DEV_BRACKET;
     TC nw = (a + b) / TC(2);
-    TC fn = simplex_f<TC, KP>(num, den, nw, k, ls);
+    TC fn = f(nw);
     for (int j = 0; j < maxit; ++j) {
         const bool bad = Num<TC>::vabs(fn) > tol;
         if (bad) bits.set(j);
@@ -158,18 +156,16 @@ __device__ __forceinline__ void simplex_trace(const TC (&num)[KP], const TC (&de
             fa = fn;
         }
         nw = (a + b) / TC(2);
-        fn = simplex_f<TC, KP>(num, den, nw, k, ls);
+        fn = f(nw);
     }
 }
 
 // Replays exactly `its` updates of dicotomy.py:152-168 and returns new.
-template <typename TC, int KP>
-__device__ __forceinline__ TC simplex_replay(const TC (&num)[KP], const TC (&den)[KP], int k, TC ls, int its) {
-    TC a, b;
-    simplex_bracket<TC, KP>(num, den, k, a, b);
-    TC fa = simplex_f<TC, KP>(num, den, a, k, ls);
+template <typename TC, typename F>
+__device__ __forceinline__ TC bisect_replay(TC a, TC b, F&& f, int its) {
+    TC fa = f(a);
     TC nw = (a + b) / TC(2);
-    TC fn = simplex_f<TC, KP>(num, den, nw, k, ls);
+    TC fn = f(nw);
     for (int j = 0; j < its; ++j) {
         if (nw == a || nw == b) break;  // stationary: new no longer changes
         if (fa * fn <= TC(0)) {
@@ -179,9 +175,82 @@ __device__ __forceinline__ TC simplex_replay(const TC (&num)[KP], const TC (&den
             fa = fn;
         }
         nw = (a + b) / TC(2);
-        fn = simplex_f<TC, KP>(num, den, nw, k, ls);
+        fn = f(nw);
     }
     return nw;
+}
+
+template <typename TC, int KP>
+__device__ __forceinline__ void simplex_trace(const TC (&num)[KP], const TC (&den)[KP], int k, TC ls, TC tol,
+                                              int maxit, Mask128& bits, uint32_t& err) {
+    TC a, b;
+    simplex_bracket<TC, KP>(num, den, k, a, b);
+    bisect_trace<TC>(a, b, [&](TC x) { return simplex_f<TC, KP>(num, den, x, k, ls); }, tol, maxit, bits, err);
+}
+
+template <typename TC, int KP>
+__device__ __forceinline__ TC simplex_replay(const TC (&num)[KP], const TC (&den)[KP], int k, TC ls, int its) {
+    TC a, b;
+    simplex_bracket<TC, KP>(num, den, k, a, b);
+    return bisect_replay<TC>(a, b, [&](TC x) { return simplex_f<TC, KP>(num, den, x, k, ls); }, its);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Quadratic-surrogate simplex function (algo="l2_surrogate", dicotomy.py:57-81), always in fp64:
+//   f(x) = 2a - sum_k max( sqrt((b_k + x)^2 + 4 a c_k) - x - b_k, 2 a ls )
+// increasing in x; bracket (f > 0 at nu_max, f < 0 at nu_min) of dicotomy.py:74-75.  Written with
+// explicit round-to-nearest operations (no FMA contraction) so that the sign decisions of the
+// bisection follow NumPy's.
+// ------------------------------------------------------------------------------------------------
+template <int KP>
+__device__ __forceinline__ double acc_f(const double (&c)[KP], const double (&b)[KP], double x, int k, double a,
+                                        double ls) {
+    const double four_a = 4.0 * a, floor_v = __dmul_rn(ls * 2.0, a);
+    double s = 0.0;
+#pragma unroll
+    for (int kk = 0; kk < KP; ++kk)
+        if (kk < k) {
+            const double t = __dadd_rn(b[kk], x);
+            const double q = __dadd_rn(__dmul_rn(t, t), __dmul_rn(four_a, c[kk]));
+            double g = __dsub_rn(__dsub_rn(sqrt(q), x), b[kk]);
+            g = fmax(g, floor_v);
+            s = (kk == 0) ? g : __dadd_rn(s, g);
+        }
+    return __dsub_rn(2.0 * a, s);
+}
+template <int KP>
+__device__ __forceinline__ void acc_bracket(const double (&c)[KP], const double (&b)[KP], int k, double a,
+                                            double& nu_max, double& nu_min) {
+    double mx = -Num<double>::inf(), sb = 0.0;
+#pragma unroll
+    for (int kk = 0; kk < KP; ++kk)
+        if (kk < k) {
+            const double v = __dadd_rn(__dadd_rn(__ddiv_rn(__dmul_rn(b[kk], b[kk]), a), 2.0 * a),
+                                       __dmul_rn(2.0, __dadd_rn(b[kk], c[kk])));
+            mx = fmax(mx, v);
+            sb = (kk == 0) ? b[kk] : __dadd_rn(sb, b[kk]);
+        }
+    nu_max = __dadd_rn(__dmul_rn(__dmul_rn((double)k, mx), 1.5), 1e-3);
+    nu_min = __dsub_rn(__dmul_rn(__ddiv_rn(-__dadd_rn(2.0 * a, sb), (double)k), 1.1), 1e-3);
+}
+template <int KP>
+__device__ __forceinline__ void acc_trace(const double (&c)[KP], const double (&b)[KP], int k, double a, double ls,
+                                          double tol, int maxit, Mask128& bits, uint32_t& err) {
+    double lo, hi;
+    acc_bracket<KP>(c, b, k, a, lo, hi);
+    bisect_trace<double>(lo, hi, [&](double x) { return acc_f<KP>(c, b, x, k, a, ls); }, tol, maxit, bits, err);
+}
+template <int KP>
+__device__ __forceinline__ double acc_replay(const double (&c)[KP], const double (&b)[KP], int k, double a, double ls,
+                                             int its) {
+    double lo, hi;
+    acc_bracket<KP>(c, b, k, a, lo, hi);
+    return bisect_replay<double>(lo, hi, [&](double x) { return acc_f<KP>(c, b, x, k, a, ls); }, its);
+}
+// updates.py:289: H' = (-b + sqrt(b^2 + 4 a c)) / (2 a)
+__device__ __forceinline__ double hq_root(double c, double b, double a) {
+    const double q = __dadd_rn(__dmul_rn(b, b), __dmul_rn(4.0 * a, c));
+    return __ddiv_rn(__dadd_rn(-b, sqrt(q)), 2.0 * a);
 }
 
 // OR-reduce a per-thread mask over the block and merge it into the global mask / error word.

@@ -80,6 +80,7 @@ class FitEngine:
         self.x_local = x_local
         self.profile = None          # set to {} to record CUDA events around kernel launches
         self.profile_names = ("h_pass", "w_pass")
+        self.n_launches = 0          # kernels launched through the C ABI (bench.py reports the count)
         k = W0.shape[1]
         self.n, self.p, self.k = n, p, k
         self.identity_G = G is None
@@ -276,6 +277,7 @@ class FitEngine:
         """Launch one C-ABI entry point on the current stream.  With ``self.profile`` set to a dict,
         calls whose name is in ``self.profile_names`` (or every named call when that is None) are
         bracketed by CUDA events."""
+        self.n_launches += 1
         if self.profile is None or name is None or (self.profile_names is not None
                                                     and name not in self.profile_names):
             L.check(fn(ctypes.byref(self.st), self.stream))
