@@ -120,6 +120,8 @@ _EXPORTS = {
     "espm_peer_close": (ctypes.c_int, [_vp]),
     "espm_peer_free": (ctypes.c_int, [_vp]),
     "espm_dichotomy_simplex": (ctypes.c_int, [_i32, _i32, _i64, _vp, _vp, _f64, _f64, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "espm_dichotomy_simplex_acc": (ctypes.c_int, [_i32, _i32, _i64, _f64, _vp, _vp, _f64, _f64, _i32, _vp, _vp, _vp,
+                                                  _vp, _vp]),
 }
 
 _lib = None

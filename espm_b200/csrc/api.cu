@@ -71,10 +71,6 @@ static int check_state(const espm_state* st) {
             return ESPM_ERR_BAD_ARG;
         }
     }
-    if (st->flags & ESPM_FLAG_HQ) {
-        set_error("algo=l2_surrogate is not implemented on the device yet");
-        return ESPM_ERR_UNSUPPORTED;
-    }
     return ESPM_OK;
 }
 
@@ -99,9 +95,11 @@ static XPassArgs make_args(const espm_state* st, bool w_pass) {
     a.nsplit = st->h_nsplit;
     a.w_upc = st->w_upc;
     a.depth = w_pass ? st->w_depth : st->h_depth;
-    a.clamp_y = (st->flags & ESPM_FLAG_CLAMP_Y) ? 1 : 0;
+    // the quadratic-surrogate H step divides by GWH + log_shift and has no NaN fallback (updates.py:280)
+    a.clamp_y = ((st->flags & ESPM_FLAG_CLAMP_Y) && (w_pass || !(st->flags & ESPM_FLAG_HQ))) ? 1 : 0;
     a.dual = (st->flags & ESPM_FLAG_LOSS_DUAL) ? 1 : 0;
     a.log_shift = st->log_shift;
+    a.y_shift = (!w_pass && (st->flags & ESPM_FLAG_HQ)) ? st->log_shift : 0.0;
     return a;
 }
 
@@ -395,16 +393,33 @@ int espm_peer_free(void* ptr) {
     return ESPM_OK;
 }
 
+static int dicho_common(int32_t c_dtype, int32_t k, int64_t p, const void* num, const void* den, double log_shift,
+                        double tol, int32_t maxit, double acc_a, void* nu_out, uint32_t* mask4, uint32_t* dev_flags,
+                        int32_t* its_out, void* stream) {
+    const int kp = pad_k(k);
+    if (kp < 0 || p < 1 || !num || !den || !nu_out || !mask4 || !dev_flags) {
+        set_error("dichotomy_simplex: bad arguments (k=%d p=%lld)", k, (long long)p);
+        return ESPM_ERR_BAD_ARG;
+    }
+    if (maxit <= 0 || maxit > 127) maxit = ESPM_MAXIT_DICHOTOMY;
+    DichoArgs d{k, kp, maxit, (long long)p, num, den, log_shift, tol, acc_a, nu_out, mask4, dev_flags, its_out};
+    return c_dtype == ESPM_F64 ? dicho_launch_f64(d, (cudaStream_t)stream) : dicho_launch_f32(d, (cudaStream_t)stream);
+}
+
 int espm_dichotomy_simplex(int32_t c_dtype, int32_t k, int64_t p, const void* num, const void* den, double log_shift,
                            double tol, int32_t maxit, void* nu_out, uint32_t* mask4, uint32_t* dev_flags,
                            int32_t* its_out, void* stream) {
-    const int kp = pad_k(k);
-    if (kp < 0 || p < 1) {
-        set_error("dichotomy_simplex: unsupported shape k=%d p=%lld", k, (long long)p);
+    return dicho_common(c_dtype, k, p, num, den, log_shift, tol, maxit, 0.0, nu_out, mask4, dev_flags, its_out, stream);
+}
+
+int espm_dichotomy_simplex_acc(int32_t c_dtype, int32_t k, int64_t p, double a, const void* b, const void* minus_c,
+                               double log_shift, double tol, int32_t maxit, void* nu_out, uint32_t* mask4,
+                               uint32_t* dev_flags, int32_t* its_out, void* stream) {
+    if (!(a > 0.0)) {
+        set_error("dichotomy_simplex_acc needs a > 0 (got %g)", a);
         return ESPM_ERR_BAD_ARG;
     }
-    DichoArgs d{k, kp, maxit, (long long)p, num, den, log_shift, tol, nu_out, mask4, dev_flags, its_out};
-    return c_dtype == ESPM_F64 ? dicho_launch_f64(d, (cudaStream_t)stream) : dicho_launch_f32(d, (cudaStream_t)stream);
+    return dicho_common(c_dtype, k, p, minus_c, b, log_shift, tol, maxit, a, nu_out, mask4, dev_flags, its_out, stream);
 }
 
 }  // extern "C"

@@ -340,6 +340,8 @@ __global__ void __launch_bounds__(PX_THREADS) h_finish_kernel(const espm_state s
     const bool lap = st.flags & ESPM_FLAG_LAPLACIAN;
     const bool use_mu = st.flags & ESPM_FLAG_MU;
     const bool simplex = st.flags & ESPM_FLAG_SIMPLEX_H;
+    const bool hq = st.flags & ESPM_FLAG_HQ;   // algo="l2_surrogate" (updates.py:263-301)
+    const bool quad = hq && lap;               // quadratic root / dichotomy_simplex_acc instead of num/(den+nu)
 
     constexpr int NV = 3 + 3 * KP;
     double vals[NV];
@@ -401,19 +403,30 @@ __global__ void __launch_bounds__(PX_THREADS) h_finish_kernel(const espm_state s
                     const double rr = (double)Num<TC>::vabs(h[kk] - hp) / ((double)h[kk] + st.tol * meanH);
                     relh = rr > relh ? rr : relh;
                 }
-                // ---- updates.py:132-142 ----
                 TC nm = s;
                 TC dn = gwstats[kk];
-                if (use_mu) dn = dn + (TC)st.mu[kk] / (h[kk] + (TC)st.eps_reg);
-                if (lap) {
-                    const TC lam = (TC)st.lambda_L;
-                    const TC ls_max = lam * (TC)st.sigma * (TC)hstats[2 * KP + kk];
-                    nm = nm + ls_max;
-                    dn = dn + ls_max + lam * HL[kk];
+                if (hq) {
+                    // ---- updates.py:280-284: minus_c = H * s (s formed with y + ls), b; mu does not enter ----
+                    if (lap) {
+                        const TC lam = (TC)st.lambda_L;
+                        dn = dn + lam * HL[kk] - (lam * (TC)st.sigma) * h[kk];
+                    }
+                    num[kk] = h[kk] * nm;
+                    den[kk] = dn;
+                    if (num[kk] < TC(0) || (!lap && den[kk] < TC(0))) err |= ESPM_DEV_NEGATIVE;
+                } else {
+                    // ---- updates.py:132-142 ----
+                    if (use_mu) dn = dn + (TC)st.mu[kk] / (h[kk] + (TC)st.eps_reg);
+                    if (lap) {
+                        const TC lam = (TC)st.lambda_L;
+                        const TC ls_max = lam * (TC)st.sigma * (TC)hstats[2 * KP + kk];
+                        nm = nm + ls_max;
+                        dn = dn + ls_max + lam * HL[kk];
+                    }
+                    num[kk] = h[kk] * nm;
+                    den[kk] = dn;
+                    if (num[kk] < TC(0) || den[kk] < TC(0)) err |= ESPM_DEV_NEGATIVE;
                 }
-                num[kk] = h[kk] * nm;
-                den[kk] = dn;
-                if (num[kk] < TC(0) || den[kk] < TC(0)) err |= ESPM_DEV_NEGATIVE;
             } else {
                 h[kk] = HL[kk] = num[kk] = TC(0);
                 den[kk] = TC(1);
@@ -440,11 +453,19 @@ __global__ void __launch_bounds__(PX_THREADS) h_finish_kernel(const espm_state s
                 numd[kk] = (double)num[kk];
                 dend[kk] = (double)den[kk];
             }
-            simplex_trace<double, KP>(numd, dend, k, st.log_shift, st.dicotomy_tol, st.maxit, bits, err);
+            if (quad)   // dicotomy.py:57-81 on (a, b, minus_c)
+                acc_trace<KP>(numd, dend, k, st.lambda_L * st.sigma, st.log_shift, st.dicotomy_tol, st.maxit, bits, err);
+            else
+                simplex_trace<double, KP>(numd, dend, k, st.log_shift, st.dicotomy_tol, st.maxit, bits, err);
         } else {
-            TC hn[KP];  // updates.py:152 with nu = 0
+            TC hn[KP];  // updates.py:152 with nu = 0 (updates.py:289 for the quadratic surrogate)
 #pragma unroll
-            for (int kk = 0; kk < KP; ++kk) hn[kk] = (kk < k) ? Num<TC>::vmax(num[kk] / den[kk], ls) : TC(0);
+            for (int kk = 0; kk < KP; ++kk) {
+                if (kk >= k) hn[kk] = TC(0);
+                else if (quad)
+                    hn[kk] = (TC)fmax(hq_root((double)num[kk], (double)den[kk], st.lambda_L * st.sigma), st.log_shift);
+                else hn[kk] = Num<TC>::vmax(num[kk] / den[kk], ls);
+            }
             store_h_next<TC, KP>(st, j, k, hn, vals);
         }
     }
@@ -513,10 +534,18 @@ __global__ void __launch_bounds__(PX_THREADS) h_apply_kernel(const espm_state st
             num[kk] = (kk < k) ? (double)num_i[(size_t)kk * st.p_pad + j] : 0.0;
             den[kk] = (kk < k) ? (double)den_i[(size_t)kk * st.p_pad + j] : 1.0;
         }
-        const double nu = simplex_replay<double, KP>(num, den, k, st.log_shift, its);
+        if ((st.flags & ESPM_FLAG_HQ) && (st.flags & ESPM_FLAG_LAPLACIAN)) {   // updates.py:286-289
+            const double a = st.lambda_L * st.sigma;
+            const double nu = acc_replay<KP>(num, den, k, a, st.log_shift, its);
 #pragma unroll
-        for (int kk = 0; kk < KP; ++kk)
-            hn[kk] = (kk < k) ? (TC)fmax(num[kk] / (den[kk] + nu), st.log_shift) : TC(0);
+            for (int kk = 0; kk < KP; ++kk)
+                hn[kk] = (kk < k) ? (TC)fmax(hq_root(num[kk], den[kk] + nu, a), st.log_shift) : TC(0);
+        } else {
+            const double nu = simplex_replay<double, KP>(num, den, k, st.log_shift, its);
+#pragma unroll
+            for (int kk = 0; kk < KP; ++kk)
+                hn[kk] = (kk < k) ? (TC)fmax(num[kk] / (den[kk] + nu), st.log_shift) : TC(0);
+        }
         store_h_next<TC, KP>(st, j, k, hn, vals);
     }
     // only the H_next statistics are produced here; keep the loss partials written by h_finish
@@ -846,10 +875,13 @@ __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_sta
     }
 
     // ---- phase A: num = W * (G^T S), den = colsum(G) (x) rowsum(H')   (updates.py:58-60) ----
+    bool nonfinite = false;
     if (ident) {
         for (int i = gthread; i < m * k; i += gthreads) {
             const int mm = i / k, kk = i - mm * k;
-            wnum[i] = W[i] * S[(size_t)mm * KP + kk];
+            const TC sv = S[(size_t)mm * KP + kk];
+            nonfinite |= !(Num<TC>::vabs(sv) < Num<TC>::inf());
+            wnum[i] = W[i] * sv;
             wden[i] = (TC)hstats[kk];
         }
     } else {
@@ -867,6 +899,7 @@ __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_sta
 #pragma unroll
             for (int kk = 0; kk < KP; ++kk) {
                 const TC v = warp_sum(acc[kk]);
+                nonfinite |= (kk < k) && !(Num<TC>::vabs(v) < Num<TC>::inf());
                 if (lane == 0 && kk < k) {
                     wnum[mm * k + kk] = W[mm * k + kk] * v;
                     wden[mm * k + kk] = colsumG[mm] * (TC)hstats[kk];
@@ -874,6 +907,8 @@ __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_sta
             }
         }
     }
+    // x / 0 in the W pass (updates.py:53-56): the caller redoes the step with ESPM_FLAG_CLAMP_Y
+    if (__any_sync(0xffffffffu, nonfinite) && lane == 0) atomicOr(&st.dev_flags[0], ESPM_DEV_NONFINITE);
     grid_barrier(bar, gridDim.x);
 
     // ---- phase B (CTA 0): simplex_W, W', rel_W ----
@@ -1097,10 +1132,11 @@ __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_sta
 
 // ------------------------------------------------------------------------------------------------
 // Standalone dichotomy_simplex(num, den) -> nu  (dicotomy.py:4-55), two kernels: trace, replay.
+// acc_a > 0 selects dichotomy_simplex_acc(a, b = den, minus_c = num) (dicotomy.py:57-81, fp64 only).
 // ------------------------------------------------------------------------------------------------
 template <typename TC, int KP>
 __global__ void __launch_bounds__(PX_THREADS) dicho_trace_kernel(const TC* num_i, const TC* den_i, long long p, int k,
-                                                                 double ls_d, double tol_d, int maxit,
+                                                                 double ls_d, double tol_d, int maxit, double acc_a,
                                                                  uint32_t* gmask, uint32_t* gflags) {
     const long long j = (long long)blockIdx.x * PX_THREADS + threadIdx.x;
     Mask128 bits;
@@ -1109,25 +1145,36 @@ __global__ void __launch_bounds__(PX_THREADS) dicho_trace_kernel(const TC* num_i
     if (j < p) {
         TC num[KP], den[KP];
         TC nsum = TC(0);
+        const bool acc = acc_a > 0.0;
 #pragma unroll
         for (int kk = 0; kk < KP; ++kk) {
             num[kk] = (kk < k) ? num_i[(size_t)kk * p + j] : TC(0);
             den[kk] = (kk < k) ? den_i[(size_t)kk * p + j] : TC(1);
             if (kk < k) {
                 nsum += num[kk];
-                if (num[kk] < TC(0) || den[kk] < TC(0)) err |= ESPM_DEV_NEGATIVE;
+                if (num[kk] < TC(0) || (!acc && den[kk] < TC(0))) err |= ESPM_DEV_NEGATIVE;
             }
         }
-        if (!(nsum > TC(0))) err |= ESPM_DEV_NEGATIVE;  // dicotomy.py:19
-        simplex_trace<TC, KP>(num, den, k, (TC)ls_d, (TC)tol_d, maxit, bits, err);
+        if (acc) {
+            double c[KP], b[KP];
+#pragma unroll
+            for (int kk = 0; kk < KP; ++kk) {
+                c[kk] = (double)num[kk];
+                b[kk] = (double)den[kk];
+            }
+            acc_trace<KP>(c, b, k, acc_a, ls_d, tol_d, maxit, bits, err);
+        } else {
+            if (!(nsum > TC(0))) err |= ESPM_DEV_NEGATIVE;  // dicotomy.py:19
+            simplex_trace<TC, KP>(num, den, k, (TC)ls_d, (TC)tol_d, maxit, bits, err);
+        }
     }
     merge_mask(bits, err, gmask, gflags);
 }
 
 template <typename TC, int KP>
 __global__ void __launch_bounds__(PX_THREADS) dicho_apply_kernel(const TC* num_i, const TC* den_i, long long p, int k,
-                                                                 double ls_d, int maxit, const uint32_t* gmask,
-                                                                 TC* nu_out, int* its_out) {
+                                                                 double ls_d, int maxit, double acc_a,
+                                                                 const uint32_t* gmask, TC* nu_out, int* its_out) {
     const long long j = (long long)blockIdx.x * PX_THREADS + threadIdx.x;
     const int its = first_clear_bit(gmask, maxit);
     if (j == 0 && its_out) *its_out = its;
@@ -1138,7 +1185,17 @@ __global__ void __launch_bounds__(PX_THREADS) dicho_apply_kernel(const TC* num_i
             num[kk] = (kk < k) ? num_i[(size_t)kk * p + j] : TC(0);
             den[kk] = (kk < k) ? den_i[(size_t)kk * p + j] : TC(1);
         }
-        nu_out[j] = simplex_replay<TC, KP>(num, den, k, (TC)ls_d, its);
+        if (acc_a > 0.0) {
+            double c[KP], b[KP];
+#pragma unroll
+            for (int kk = 0; kk < KP; ++kk) {
+                c[kk] = (double)num[kk];
+                b[kk] = (double)den[kk];
+            }
+            nu_out[j] = (TC)acc_replay<KP>(c, b, k, acc_a, ls_d, its);
+        } else {
+            nu_out[j] = simplex_replay<TC, KP>(num, den, k, (TC)ls_d, its);
+        }
     }
 }
 

@@ -20,6 +20,7 @@ struct DichoArgs {
     const void* num;
     const void* den;
     double log_shift, tol;
+    double acc_a;   // > 0: dichotomy_simplex_acc with this `a` (num = minus_c, den = b)
     void* nu_out;
     uint32_t* mask4;
     uint32_t* dev_flags;
@@ -89,11 +90,11 @@ static int dicho_launch_t(const DichoArgs& d, cudaStream_t s) {
     const int blocks = (int)((d.p + PX_THREADS - 1) / PX_THREADS);
     ESPM_CUDA_CHECK(cudaMemsetAsync(d.mask4, 0, 4 * sizeof(uint32_t), s));
     ESPM_KP_SWITCH(d.kp, (dicho_trace_kernel<TC, KP><<<blocks, PX_THREADS, 0, s>>>(
-                             (const TC*)d.num, (const TC*)d.den, d.p, d.k, d.log_shift, d.tol, d.maxit, d.mask4,
-                             d.dev_flags)));
+                             (const TC*)d.num, (const TC*)d.den, d.p, d.k, d.log_shift, d.tol, d.maxit, d.acc_a,
+                             d.mask4, d.dev_flags)));
     ESPM_CUDA_CHECK(cudaGetLastError());
     ESPM_KP_SWITCH(d.kp, (dicho_apply_kernel<TC, KP><<<blocks, PX_THREADS, 0, s>>>(
-                             (const TC*)d.num, (const TC*)d.den, d.p, d.k, d.log_shift, d.maxit, d.mask4,
+                             (const TC*)d.num, (const TC*)d.den, d.p, d.k, d.log_shift, d.maxit, d.acc_a, d.mask4,
                              (TC*)d.nu_out, d.its_out)));
     ESPM_CUDA_CHECK(cudaGetLastError());
     return ESPM_OK;

@@ -33,6 +33,7 @@ struct XPassArgs {
     int depth;           // pipeline stages
     int clamp_y, dual;   // SAFE variants only
     double log_shift;
+    double y_shift;      // H pass: ratio = x / (y + y_shift); log_shift for algo="l2_surrogate" (updates.py:280), else 0
 };
 
 template <typename TX, typename TC, int KP, bool SAFE>
@@ -245,6 +246,10 @@ h_pass_kernel(const XPassArgs a) {
                     h2[kk][j] = make_float2(h[kk][2 * j], h[kk][2 * j + 1]);
                     num2[kk][j] = make_float2(0.f, 0.f);
                 }
+            // y starts from y_shift (0, or log_shift for the quadratic surrogate): fma(gw, h, 0) == gw * h.
+            // With a shift the loss below sees log(y + ls) instead of log(y): 1e-14 / y relative, far below
+            // fp32 resolution.
+            const float2 ysh = dup2((float)a.y_shift);
             for (int st = s0; st < s1; ++st, ring.next(pos)) {
                 ring.consumer_wait(pos);
                 const unsigned char* xs = ring.stage(pos.slot);
@@ -259,7 +264,7 @@ h_pass_kernel(const XPassArgs a) {
                     const float2 x2[2] = {make_float2(xv.x, xv.y), make_float2(xv.z, xv.w)};
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
-                        float2 y = __fmul2_rn(dup2(gw[0]), h2[0][j]);
+                        float2 y = __ffma2_rn(dup2(gw[0]), h2[0][j], ysh);
 #pragma unroll
                         for (int kk = 1; kk < KP; ++kk) y = __ffma2_rn(dup2(gw[kk]), h2[kk][j], y);
                         const float2 r = __fmul2_rn(x2[j], make_float2(rcp_ftz(y.x), rcp_ftz(y.y)));
@@ -282,6 +287,7 @@ h_pass_kernel(const XPassArgs a) {
                 }
         } else {
             TC hc[SAFE ? KP : 1][PPL];
+            const TC ysh = (TC)a.y_shift;
 #pragma unroll
             for (int kk = 0; kk < KP; ++kk)
 #pragma unroll
@@ -317,7 +323,7 @@ h_pass_kernel(const XPassArgs a) {
                         }
                     }
 #pragma unroll
-                    for (int q = 0; q < PPL; ++q) r[q] = Num<TC>::ratio((TC)xv[q], y[q]);
+                    for (int q = 0; q < PPL; ++q) r[q] = Num<TC>::ratio((TC)xv[q], y[q] + ysh);
 #pragma unroll
                     for (int kk = 0; kk < KP; ++kk)
 #pragma unroll

@@ -56,7 +56,7 @@ class FitEngine:
                  log_shift=1e-14, dicotomy_tol=1e-5, dicotomy_tol_w=1e-5, tol=1e-4, sigma=8.0,
                  simplex_H=False, simplex_W=True, simplex_rows=None, fixed_H=None, fixed_W=None,
                  x_scale=1.0, max_records=512, device=None, shard=None, c_dtype=None, clamp_init=True,
-                 x_local=False, ingest=None):
+                 x_local=False, ingest=None, algo="log_surrogate"):
         """
         X : (n, p) array-like view (any strides; C order or the transposed hyperspy layout are
             uploaded without a host copy).  G : (n, m) array or None (identity).  W0 : (m, k), H0 : (k, p).
@@ -69,6 +69,7 @@ class FitEngine:
         """
         self.lib = L.load()
         self.clamp_init = clamp_init
+        self.clamped = False
         if not torch.cuda.is_available():
             raise L.EspmError("espm_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -135,6 +136,11 @@ class FitEngine:
             flags |= L.FLAG_SIMPLEX_W
         if self.identity_G:
             flags |= L.FLAG_G_IDENTITY
+        if algo == "l2_surrogate":
+            flags |= L.FLAG_HQ                   # quadratic-surrogate H step (updates.py:263-301)
+        elif algo != "log_surrogate":
+            raise NotImplementedError("espm_b200: algo=%r is not available on the device" % (algo,))
+        self.algo = algo
         mu_arr = np.zeros(L.MAX_K)
         if np.isscalar(mu):
             mu_arr[:k] = float(mu)
@@ -562,6 +568,18 @@ class FitEngine:
     def set_WH(self, W, H):
         """Overwrite the current iterate (e.g. after rescaled_DH) and refresh the derived buffers."""
         self._init_WH(W, H)
+
+    def enable_clamp(self):
+        """Switch to the reference's NaN fallback (updates.py:129-131, 54-56: GWH = max(GWH, log_shift)) and to
+        the separately clamped GW of the loss (measures.py:493); clears the sticky device error word."""
+        self.st.flags |= L.FLAG_CLAMP_Y | L.FLAG_LOSS_DUAL
+        self.clamped = True
+        self.dev_flags[0] = 0
+
+    def gw_flags_init(self):
+        """ESPM_DEV_GW_* bits of the initial G W (one small D2H)."""
+        rec = self.records[self.max_records - 1].cpu().numpy()
+        return int(rec[L.S_GW_FLAGS])
 
     def set_flag(self, flag, on=True):
         if on:

@@ -6,7 +6,7 @@ Same constructor arguments, ``fit`` / ``fit_transform`` / ``inverse_transform`` 
 initialises and runs the stop tests; every pass over X happens in the CUDA kernels behind
 ``espm_b200.engine.FitEngine``.  There is no CPU fallback: without a CUDA device ``fit`` raises.
 
-Supported on the device: ``algo="log_surrogate"`` (the default) with the KL loss, ``simplex_H`` /
+Supported on the device: ``algo="log_surrogate"`` (the default) and ``"l2_surrogate"`` with the KL loss, ``simplex_H`` /
 ``simplex_W``, ``mu`` (scalar or per phase), ``lambda_L`` with ``shape_2d`` (5-point Laplacian) or
 without (identity), ``fixed_H`` / ``fixed_W``, ``normalize``, ``G`` as ``None`` / ndarray / physical
 model, ``hspy_comp``.  Other ``algo`` values, ``l2=True`` and ``linesearch=True`` raise
@@ -133,9 +133,10 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
             reset("l2", False, "The l2 parameter must be False when using the algorithm " + self.algo)
 
     def _require_supported(self):
-        if self.algo != "log_surrogate":
+        if self.algo not in ("log_surrogate", "l2_surrogate"):
             raise NotImplementedError(
-                "espm_b200 runs algo='log_surrogate' on the device; algo=%r is not available yet" % self.algo)
+                "espm_b200 runs algo='log_surrogate' and 'l2_surrogate' on the device; algo=%r is not "
+                "available yet" % self.algo)
         if self.l2:
             raise NotImplementedError("espm_b200: the Frobenius loss (l2=True) is not available yet")
         if self.linesearch:
@@ -261,9 +262,15 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
                         log_shift=self.log_shift, dicotomy_tol=self.dicotomy_tol, dicotomy_tol_w=_DICOTOMY_TOL,
                         tol=self.tol, sigma=float(self.gamma_), simplex_H=self.simplex_H, simplex_W=self.simplex_W,
                         simplex_rows=simplex_rows, fixed_H=self.fixed_H, fixed_W=self.fixed_W,
-                        max_records=max(max_iter, 1) + 8, shard=shard,
+                        max_records=max(max_iter, 1) + 8, shard=shard, algo=self.algo,
                         ingest=dict(eps=self.log_shift, normalize=self.n_components if self.normalize else None))
         self._engine = eng
+        gwf = eng.gw_flags_init()
+        if gwf & L.DEV_GW_ZERO_ROW:        # x / 0 would appear in the first pass: updates.py:129-131, 54-56
+            eng.enable_clamp()
+        elif gwf & L.DEV_GW_BELOW_LS:      # measures.py:493: the loss clamps G W, the updates do not
+            eng.set_flag(L.FLAG_LOSS_DUAL)
+        self._init_WH = (W0, H0)
         # device-side prologue results: const_KL_ (base.py:200-201), norm_factor_ (base.py:264-267)
         self.const_KL_ = eng.const_KL
         if self.normalize:
@@ -303,6 +310,7 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
         self.n_components_ = self.H_.shape[0]
         eng.close()
         self._engine = None            # release the device copy of X
+        self._init_WH = None
         if self.hspy_comp:                                             # base.py:415-420
             self.components_ = GW.T
             return self.H_.T
@@ -335,6 +343,12 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
             eng.advance(it)
             eng.evaluate(it)
         recs = eng.read_records(0, max_iter + 1)
+        if not eng.clamped and any(int(r[L.S_DEV_FLAGS]) & L.DEV_NONFINITE for r in recs):
+            # x / 0 appeared mid-fit (a row of G W became zero): the reference then clamps GWH
+            # (updates.py:129-131, 54-56).  Restart from the initial factors with the clamped kernels.
+            eng.enable_clamp()
+            eng.set_WH(*self._init_WH)
+            return self._run_batch(eng, max_iter)
         self._eval_init = self._loss_from_record(recs[0])
         for it in range(1, max_iter + 1):
             self._append(recs[it])
@@ -346,6 +360,10 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
         """The reference's while-loop with its ordered stop tests (base.py:313-393)."""
         eng.evaluate(0)
         rec = eng.read_records(0, 1)[0]
+        if int(rec[L.S_DEV_FLAGS]) & L.DEV_NONFINITE and not eng.clamped:
+            eng.enable_clamp()
+            eng.evaluate(0)
+            rec = eng.read_records(0, 1)[0]
         self._check_flags(rec)
         eval_init = self._loss_from_record(rec)                        # base.py:295
         self._eval_init = eval_init
@@ -356,6 +374,13 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
             eng.advance(it)
             eng.evaluate(it)
             rec = eng.read_records(it, it + 1)[0]
+            if int(rec[L.S_DEV_FLAGS]) & L.DEV_NONFINITE and not eng.clamped:
+                # x / 0 in this H pass: redo it like the reference's NaN fallback (updates.py:129-131)
+                rel_w = rec[L.S_REL_W]
+                eng.enable_clamp()
+                eng.evaluate(it)
+                rec = eng.read_records(it, it + 1)[0]
+                rec[L.S_REL_W] = rel_w
             self._check_flags(rec)
             eval_after = self._append(rec)                             # base.py:320-351
             self.n_iter_ = it

@@ -2,6 +2,7 @@
 names and argument meaning, executed by the CUDA kernels.
 
     multiplicative_step_h / multiplicative_step_w   espm/estimators/updates.py:83 / :6
+    multiplicative_step_hq                           espm/estimators/updates.py:263
     dichotomy_simplex                                espm/estimators/dicotomy.py:4
     KLdiv_loss / log_reg / trace_xtLx                espm/measures.py:456 / :524 / :560
     create_laplacian_matrix                          espm/utils.py:39 (returns the image shape: the
@@ -126,7 +127,33 @@ def multiplicative_step_h(X, G, W, H, simplex_H=False, mu=0, log_shift=_LS, epsi
     Ge = None if (G is None or _is_identity(np.asarray(G))) else G
     eng = _engine(X, Ge, W, H, shape_2d=shape_2d, lambda_L=lambda_L, mu=mu, epsilon_reg=epsilon_reg,
                   log_shift=log_shift, dicotomy_tol=dicotomy_tol, sigma=sigmaL, simplex_H=simplex_H,
-                  simplex_W=False, fixed_H=fixed_H, max_records=8)
+                  simplex_W=False, fixed_H=fixed_H, max_records=8, clamp_init=bool(safe))   # updates.py:104-105
+    Hn, rec = eng.step_h_only()
+    if int(rec[_L.S_DEV_FLAGS]) & _L.DEV_NONFINITE:      # updates.py:129-131: NaN -> GWH = max(GWH, log_shift)
+        eng.enable_clamp()
+        Hn, rec = eng.step_h_only()
+    _raise_flags(rec)
+    if return_its:
+        return Hn, int(rec[_L.S_BISECT_ITS_H])
+    return Hn
+
+
+def multiplicative_step_hq(X, G, W, H, simplex_H=True, log_shift=_LS, safe=True, dicotomy_tol=_TOL, lambda_L=0,
+                           L=None, sigmaL=_SIGMA, fixed_H=None, return_its=False):
+    """updates.py:263-301: the quadratic-surrogate H step of ``algo="l2_surrogate"``."""
+    p = np.shape(H)[1]
+    shape_2d = None
+    if lambda_L != 0:
+        if L is None:
+            raise ValueError("Please provide the laplacian")          # updates.py:267-269
+        shape_2d, _ = _shape_from_L(L, p)
+    if simplex_H and log_shift > 0 and np.shape(H)[0] * log_shift >= 1:
+        raise ValueError("No solution exists!")                       # dicotomy.py:71-72
+    Ge = None if (G is None or _is_identity(np.asarray(G))) else G
+    # updates.py:263-301 never clamps W, H (only asserts when safe): upload them as given
+    eng = _engine(X, Ge, W, H, shape_2d=shape_2d, lambda_L=lambda_L, log_shift=log_shift,
+                  dicotomy_tol=dicotomy_tol, sigma=sigmaL, simplex_H=simplex_H, simplex_W=False, fixed_H=fixed_H,
+                  max_records=8, algo="l2_surrogate", clamp_init=False)
     Hn, rec = eng.step_h_only()
     _raise_flags(rec)
     if return_its:
@@ -147,8 +174,11 @@ def multiplicative_step_w(X, G, W, H, simplex_W=False, log_shift=_LS, safe=True,
         raise ValueError("No solution exists!")
     Ge = None if (G is None or _is_identity(np.asarray(G))) else G
     eng = _engine(X, Ge, W, H, log_shift=log_shift, simplex_H=False, simplex_W=simplex_W, simplex_rows=rows,
-                  fixed_W=fixed_W, max_records=8)
+                  fixed_W=fixed_W, max_records=8, clamp_init=bool(safe))                        # updates.py:26-27
     Wn, rec = eng.step_w_only()
+    if int(rec[_L.S_DEV_FLAGS]) & _L.DEV_NONFINITE:      # updates.py:54-56
+        eng.enable_clamp()
+        Wn, rec = eng.step_w_only()
     _raise_flags(rec)
     return Wn
 
@@ -181,6 +211,41 @@ def dichotomy_simplex(num, denum, log_shift=_LS, tol=_TOL, maxit=_MAXIT, return_
     f = int(flags[0].item())
     if f & (_L.DEV_BRACKET | _L.DEV_NEGATIVE):
         raise AssertionError("dichotomy_simplex: preconditions violated (dicotomy.py:17-19,141-144)")
+    out = nu.cpu().numpy()
+    n_it = int(its.item())
+    if n_it >= maxit:
+        print("Dicotomy stopped for maximum number of iterations")
+    if return_its:
+        return out, n_it
+    return out
+
+
+def dichotomy_simplex_acc(a, b, minus_c, log_shift=_LS, tol=_TOL, maxit=_MAXIT, return_its=False):
+    """dicotomy.py:57-81: the bisection of the quadratic-surrogate H step, with the reference's bracket
+    and lock-step stop test."""
+    lib = _L.load()
+    assert a >= 0                                                       # dicotomy.py:67-68
+    b = np.asarray(b, dtype=np.float64)
+    minus_c = np.asarray(minus_c, dtype=np.float64)
+    assert (minus_c >= 0).all()
+    if b.ndim == 1:
+        b, minus_c = b[:, None], minus_c[:, None]
+    k, p = b.shape
+    if log_shift > 0 and k * log_shift >= 1:
+        raise ValueError("No solution exists!")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    d_b = torch.as_tensor(np.ascontiguousarray(b)).to(dev)
+    d_c = torch.as_tensor(np.ascontiguousarray(minus_c)).to(dev)
+    nu = torch.empty(p, dtype=torch.float64, device=dev)
+    mask = torch.zeros(4, dtype=torch.int32, device=dev)
+    flags = torch.zeros(4, dtype=torch.int32, device=dev)
+    its = torch.zeros(1, dtype=torch.int32, device=dev)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    _L.check(lib.espm_dichotomy_simplex_acc(_L.F64, k, p, float(a), d_b.data_ptr(), d_c.data_ptr(), float(log_shift),
+                                           float(tol), int(maxit), nu.data_ptr(), mask.data_ptr(), flags.data_ptr(),
+                                           its.data_ptr(), stream))
+    if int(flags[0].item()) & (_L.DEV_BRACKET | _L.DEV_NEGATIVE):
+        raise AssertionError("dichotomy_simplex_acc: preconditions violated (dicotomy.py:67-68,141-144)")
     out = nu.cpu().numpy()
     n_it = int(its.item())
     if n_it >= maxit:

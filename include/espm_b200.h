@@ -68,7 +68,9 @@ typedef enum espm_status {
 #define ESPM_FLAG_LAPLACIAN   (1u << 8)  /* lambda_L != 0 (updates.py:93-96, 138-141) */
 #define ESPM_FLAG_HAVE_HPREV  (1u << 9)  /* H_prev is valid: h_finish also emits rel_H of the current iterate */
 #define ESPM_FLAG_SIMPLEX_ROWS (1u << 10) /* simplex_W restricted to simplex_rows (updates.py:62-65) */
-#define ESPM_FLAG_HQ          (1u << 11) /* algo="l2_surrogate": quadratic surrogate H step (updates.py:263-301) */
+#define ESPM_FLAG_HQ          (1u << 11) /* algo="l2_surrogate": quadratic surrogate H step (updates.py:263-301):
+                                          * ratio = x / (GWH + log_shift), b = colsum(GW) + lambda (HL - sigma H),
+                                          * H' = (-(b+nu) + sqrt((b+nu)^2 + 4 a c)) / 2a with a = lambda sigma */
 #define ESPM_FLAG_FUSED_WREDUCE (1u << 12) /* espm_w_finish also does the work of espm_w_reduce (single-GPU fits) */
 #define ESPM_FLAG_PEER        (1u << 13) /* pixel-sharded fit exchanging through peer memory (NVLink), see below */
 
@@ -299,6 +301,13 @@ int espm_peer_free(void* ptr);
 int espm_dichotomy_simplex(int32_t c_dtype, int32_t k, int64_t p, const void* num, const void* den,
                            double log_shift, double tol, int32_t maxit, void* nu_out,
                            uint32_t* mask4, uint32_t* dev_flags, int32_t* its_out, void* stream);
+
+/* nu = dichotomy_simplex_acc(a, b, minus_c) (dicotomy.py:57-81), the bisection of the quadratic-surrogate
+ * H step (updates.py:286-289).  a > 0 scalar; b, minus_c: k x p.  Evaluated in fp64 whatever c_dtype. */
+int espm_dichotomy_simplex_acc(int32_t c_dtype, int32_t k, int64_t p, double a, const void* b,
+                               const void* minus_c, double log_shift, double tol, int32_t maxit,
+                               void* nu_out, uint32_t* mask4, uint32_t* dev_flags, int32_t* its_out,
+                               void* stream);
 
 #ifdef __cplusplus
 }

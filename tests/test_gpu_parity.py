@@ -65,6 +65,41 @@ def test_step_h_accepts_reference_sparse_laplacian(ops, golden_steps):
     assert rel_err(out, g["h_simplex_mu_lap"]) < STEP_TOL_F64
 
 
+def test_step_hq_golden(ops, golden_steps):
+    """algo="l2_surrogate": quadratic-surrogate H step (updates.py:263-301) and its bisection (dicotomy.py:57-81)."""
+    g = golden_steps
+    X, G, W, H = g["X"], g["G"], g["W0"], g["H0"]
+    Lg = ops.create_laplacian_matrix(int(g["nx"]), int(g["ny"]))
+    out = ops.multiplicative_step_hq(X, G, W, H, simplex_H=True, lambda_L=1.5, L=Lg)
+    assert rel_err(out, g["hq_simplex_lap"]) < STEP_TOL_F64
+    assert np.max(np.abs(out.sum(0) - 1)) < 1e-4
+    assert rel_err(ops.multiplicative_step_hq(X, G, W, H, simplex_H=False), g["hq_plain"]) < STEP_TOL_F64
+    assert rel_err(ops.multiplicative_step_hq(X, G, W, H, simplex_H=True), g["hq_simplex"]) < STEP_TOL_F64
+    with pytest.raises(ValueError):
+        ops.multiplicative_step_hq(X, G, W, H, lambda_L=1.0, L=None)
+
+
+@pytest.mark.parametrize("n,nx,ny,k,m,lam", [(517, 33, 19, 5, 7, 0.7), (300, 16, 16, 8, 12, 3.0), (64, 3, 130, 2, 4, 0.0)])
+def test_step_hq_vs_oracle(ops, orc, n, nx, ny, k, m, lam):
+    rng = np.random.default_rng(n + k)
+    X, G, W0, H0 = _problem(rng, n, nx, ny, k, m)
+    Lg = ops.create_laplacian_matrix(nx, ny)
+    for simplex in (True, False):
+        ref = orc.multiplicative_step_hq(X, G, W0, H0, simplex_H=simplex, lambda_L=lam, shape_2d=(nx, ny), safe=False)
+        out = ops.multiplicative_step_hq(X, G, W0, H0, simplex_H=simplex, lambda_L=lam, L=Lg, safe=False)
+        assert rel_err(out, ref) < STEP_TOL_F64
+    # fp32 mode against the fp64 oracle on the fp32-rounded inputs.  (The 64-channel case is too ill-conditioned
+    # for the 1e-5 bar in ANY fp32 arithmetic: NumPy's own fp32 evaluation of updates.py:263-301 is 1.13e-5 off.)
+    if n < 100:
+        return
+    X32, G32, W32, H32 = (a.astype(np.float32) for a in (X, G, W0, H0))
+    ref = orc.multiplicative_step_hq(X32.astype(np.float64), G32.astype(np.float64), W32.astype(np.float64),
+                                     H32.astype(np.float64), simplex_H=True, lambda_L=lam, shape_2d=(nx, ny), safe=False)
+    out = ops.multiplicative_step_hq(X32, G32, W32, H32, simplex_H=True, lambda_L=lam, L=Lg, safe=False)
+    assert out.dtype == np.float32
+    assert rel_err(out, ref) < STEP_TOL_F32
+
+
 def test_step_w_golden(ops, golden_steps):
     g = golden_steps
     X, G, W, H1 = g["X"], g["G"], g["W0"], g["h_simplex"]
@@ -120,6 +155,20 @@ def test_bisection_golden(ops, golden_bisect):
     assert np.max(np.abs(f)) <= 1e-5
     with pytest.raises(ValueError):
         ops.dichotomy_simplex(np.ones((4, 2)), np.ones((4, 2)), log_shift=0.3)
+    # quadratic-surrogate bisection (dicotomy.py:57-81)
+    nu = ops.dichotomy_simplex_acc(3.0, g["acc_b"], g["acc_mc"], 1e-14, 1e-5)
+    assert rel_err(nu, g["acc_nu"]) < 1e-13
+
+
+def test_bisection_acc_lockstep_count_matches_oracle(ops, orc):
+    rng = np.random.default_rng(12)
+    for k, p, a in ((3, 1000, 8.0), (5, 4097, 0.4), (8, 300, 16.0)):
+        b = rng.normal(size=(k, p))                    # b may be negative (lambda (HL - sigma H))
+        mc = rng.uniform(size=(k, p)) * (rng.uniform(size=(k, p)) > 0.3)
+        ref, its_ref = orc.dichotomy_simplex_acc(a, b.copy(), mc.copy(), 1e-14, 1e-6, return_its=True)
+        nu, its = ops.dichotomy_simplex_acc(a, b, mc, 1e-14, 1e-6, return_its=True)
+        assert its == its_ref
+        assert rel_err(nu, ref) < 1e-12
 
 
 def test_bisection_lockstep_count_matches_oracle(ops, orc):
@@ -230,6 +279,58 @@ def test_mixed_mode_fp32_storage_fp64_math(ops, orc):
     assert rel_err(h, ref) < STEP_TOL_F64
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_zero_rows_of_G_take_the_reference_nan_fallback(ops, orc, dtype):
+    """A channel where G is zero gives GWH = 0: X / GWH is inf / NaN and the reference falls back to
+    GWH = max(GWH, log_shift) (updates.py:129-131, 54-56); the loss clamps G W separately (measures.py:493)."""
+    rng = np.random.default_rng(5)
+    n, nx, ny, k, m = 200, 12, 11, 3, 6
+    X, G, W0, H0 = _problem(rng, n, nx, ny, k, m)
+    G[17, :] = 0.0
+    G[101, :] = 0.0
+    G[150, :] = 1e-17                                       # G W < log_shift but not zero
+    X[17, ::3] = 2.0
+    X[101, :] = 0.0
+    X, G, W0, H0 = (a.astype(dtype) for a in (X, G, W0, H0))
+    X64, G64, W64, H64 = (a.astype(np.float64) for a in (X, G, W0, H0))
+    tol = STEP_TOL_F64 if dtype == np.float64 else STEP_TOL_F32
+    ref_h = orc.multiplicative_step_h(X64, G64, W64, H64, simplex_H=True)
+    assert rel_err(ops.multiplicative_step_h(X, G, W0, H0, simplex_H=True), ref_h) < tol
+    ref_w = orc.multiplicative_step_w(X64, G64, W64, ref_h, simplex_W=False)
+    assert rel_err(ops.multiplicative_step_w(X, G, W0, ref_h.astype(dtype), simplex_W=False), ref_w) < tol
+    from espm_b200 import SmoothNMF
+    kw = dict(simplex_H=True, simplex_W=False, lambda_L=0.5, shape_2d=(nx, ny), tol=0, no_stop_criterion=True,
+              max_iter=8)
+    ref = orc.fit(X64, G64, W64, H64, **kw)
+    for verbose in (0, 1):                                  # batched and checked loop variants
+        est = SmoothNMF(n_components=k, G=G, verbose=verbose, **kw)
+        est.fit_transform(X, W=W0.copy(), H=H0.copy())
+        ttol = 1e-9 if dtype == np.float64 else TRAJ_TOL
+        assert rel_err(est.losses_, ref["losses"]) < ttol
+        assert rel_err(est.W_, ref["W"]) < ttol * 10
+        assert rel_err(est.H_, ref["H"]) < ttol * 10
+
+
+def test_zero_row_of_GW_appearing_mid_fit(orc):
+    """fixed_W zeros make a row of G W vanish after the first W update: the x / 0 then shows up mid-fit."""
+    rng = np.random.default_rng(6)
+    n, nx, ny, k, m = 120, 9, 8, 3, 5
+    X, G, W0, H0 = _problem(rng, n, nx, ny, k, m)
+    G[40, :] = 0.0
+    G[40, 1] = 0.7                                          # channel 40 only sees element 1 ...
+    fixed_W = -np.ones_like(W0)
+    fixed_W[1, :] = 0.0                                     # ... which is pinned to zero
+    from espm_b200 import SmoothNMF
+    kw = dict(simplex_H=True, simplex_W=False, shape_2d=(nx, ny), tol=0, no_stop_criterion=True, max_iter=6,
+              fixed_W=fixed_W)
+    ref = orc.fit(X, G, W0, H0, **kw)
+    for verbose in (0, 1):
+        est = SmoothNMF(n_components=k, G=G, verbose=verbose, **kw)
+        est.fit_transform(X, W=W0.copy(), H=H0.copy())
+        assert rel_err(est.losses_, ref["losses"]) < 1e-9
+        assert rel_err(est.H_, ref["H"]) < 1e-8
+
+
 # ---------------------------------------------------------------------------------- full fits
 FIT_CASES = {
     "c1": dict(simplex_H=True, simplex_W=False),
@@ -239,6 +340,7 @@ FIT_CASES = {
     "none": dict(simplex_H=False, simplex_W=False),
     "norm": dict(simplex_H=True, simplex_W=False, normalize=True, mu=0.02),
     "stop": dict(simplex_H=True, simplex_W=False, tol=2e-3, max_iter=200, no_stop_criterion=False),
+    "hq": dict(simplex_H=True, simplex_W=False, lambda_L=1.0, algo="l2_surrogate"),
 }
 
 
