@@ -35,6 +35,11 @@ def golden_bisect():
 
 
 @pytest.fixture(scope="session")
+def golden_variants():
+    return load_golden("variants_small.npz")
+
+
+@pytest.fixture(scope="session")
 def golden_fits():
     return load_golden("fits_small.npz")
 

@@ -160,3 +160,81 @@ def test_fit_fixed_and_identity_and_model(golden_fits):
     assert rel_err(res["losses"], g["pm__losses"]) < 1e-11
     assert rel_err(res["W"], g["pm__W"]) < 1e-10
     assert rel_err(res["G"], g["pm__G"]) < 1e-12
+
+
+# ---------------------------------------------------------------------------------- alternative update rules
+VARIANT_FITS = {
+    "l2": dict(simplex_H=True, simplex_W=False, lambda_L=0.8, algo="l2_surrogate", l2=True),
+    "l2w": dict(simplex_H=False, simplex_W=False, lambda_L=0.0, algo="l2_surrogate", l2=True),
+    "bmd": dict(simplex_H=True, simplex_W=False, lambda_L=0.5, mu=0.03, algo="bmd"),
+    "pg": dict(simplex_H=True, simplex_W=False, lambda_L=0.4, mu=0.02, algo="projected_gradient", gamma=[80.0, 4000.0]),
+    "pgdef": dict(simplex_H=False, simplex_W=False, algo="projected_gradient"),
+    "ls_log": dict(simplex_H=True, simplex_W=False, lambda_L=1.0, mu=0.02, linesearch=True),
+    "ls_hq": dict(simplex_H=True, simplex_W=False, lambda_L=1.0, algo="l2_surrogate", linesearch=True),
+    "ls_bmd": dict(simplex_H=True, simplex_W=False, lambda_L=0.5, algo="bmd", linesearch=True),
+    "ls_pg": dict(simplex_H=True, simplex_W=False, lambda_L=0.4, algo="projected_gradient", gamma=[80.0, 4000.0],
+                  linesearch=True),
+    "truth": dict(simplex_H=True, simplex_W=False, lambda_L=0.3, track=True),
+    "truth_free": dict(simplex_H=False, simplex_W=False, track=True),
+}
+
+
+def variant_inputs(g, tag):
+    """(X, G, W0, H0, shape_2d) of a variants_small.npz fit: the bmd fits run on the identity-G problem."""
+    if "bmd" in tag:
+        return g["I__X"], None, g["I__W0"], g["I__H0"], (5, 6)
+    return g["S__X"], g["S__G"], g["S__W0"], g["S__H0"], tuple(int(v) for v in g["S__shape"])
+
+
+def test_variant_steps(golden_variants):
+    g = golden_variants
+    X, G, W0, H0 = g["S__X"], g["S__G"], g["S__W0"], g["S__H0"]
+    sh = tuple(int(v) for v in g["S__shape"])
+    mu = g["S__mu_vec"]
+    assert rel_err(orc.multiplicative_step_h(X, G, W0, H0, simplex_H=False, l2=True), g["h_l2"]) < 1e-12
+    assert rel_err(orc.multiplicative_step_h(X, G, W0, H0, simplex_H=True, l2=True), g["h_l2_simplex"]) < 1e-12
+    assert rel_err(orc.multiplicative_step_w(X, G, W0, H0, simplex_W=False, l2=True), g["w_l2"]) < 1e-12
+    assert rel_err(orc.multiplicative_step_h(X, G, W0, H0, simplex_H=False, use_bregman=True), g["h_bmd"]) < 1e-12
+    out = orc.multiplicative_step_h(X, G, W0, H0, simplex_H=True, mu=mu, lambda_L=1.5, shape_2d=sh, use_bregman=True)
+    assert rel_err(out, g["h_bmd_simplex_mu_lap"]) < 1e-12
+    out = orc.multiplicative_step_w(g["I__X"], np.eye(40), g["I__W0"], g["I__H0"], use_bregman=True)
+    assert rel_err(out, g["w_bmd_identity"]) < 1e-12
+    out = orc.multiplicative_step_w(g["I__X"], g["I__Gsq"], g["I__W0sq"], g["I__H0"], use_bregman=True)
+    assert rel_err(out, g["w_bmd_square"]) < 1e-12
+    assert rel_err(orc.gradH(X, G, W0, H0, mu=mu, lambda_L=0.7, shape_2d=sh, epsilon_reg=0.5), g["gradH"]) < 1e-11
+    assert rel_err(orc.gradH(X, G, W0, H0, l2=True), g["gradH_l2"]) < 1e-11
+    assert rel_err(orc.gradW(X, G, W0, H0), g["gradW"]) < 1e-11
+    assert rel_err(orc.gradW(X, G, W0, H0, l2=True), g["gradW_l2"]) < 1e-11
+    out = orc.proj_grad_step_h(X, G, W0, H0, 60.0, simplex_H=True, mu=mu, lambda_L=0.7, shape_2d=sh)
+    assert rel_err(out, g["pg_h_simplex"]) < 1e-11
+    assert rel_err(orc.proj_grad_step_h(X, G, W0, H0, 60.0, simplex_H=False), g["pg_h_plain"]) < 1e-11
+    assert rel_err(orc.proj_grad_step_h(X, G, W0, H0, 400.0, simplex_H=True, l2=True), g["pg_h_l2"]) < 1e-11
+    assert rel_err(orc.proj_grad_step_w(X, G, W0, H0, 3000.0, simplex_W=False), g["pg_w"]) < 1e-11
+    assert rel_err(orc.proj_grad_step_w(X, G, W0, H0, 2.0e4, simplex_W=False, l2=True), g["pg_w_l2"]) < 1e-11
+    with pytest.raises(NotImplementedError):
+        orc.proj_grad_step_w(X, G, W0, H0, 3000.0, simplex_W=True)
+    assert rel_err(orc.estimate_Lipschitz_bound_h(1e-14, X, G, 3, lambda_L=0.7, mu=0.1, epsilon_reg=0.5), g["lip_h"]) < 1e-12
+    assert rel_err(orc.estimate_Lipschitz_bound_w(1e-14, X, G, 3), g["lip_w"]) < 1e-12
+    nu = orc.dichotomy_simplex_projected_gradient(g["pgd_a"].copy(), log_shift=1e-14, tol=1e-6)
+    assert rel_err(nu, g["pgd_nu"]) < 1e-13
+    assert rel_err(orc.diff_surrogate(H0, g["S__H1"], sh, sigmaL=8, algo="log_surrogate"), g["diff_log"]) < 1e-10
+    assert rel_err(orc.diff_surrogate(H0, g["S__H1"], sh, sigmaL=0.3, algo="l2_surrogate"), g["diff_l2"]) < 1e-10
+
+
+@pytest.mark.parametrize("tag", sorted(VARIANT_FITS))
+def test_variant_fit_trajectories(golden_variants, tag):
+    g = golden_variants
+    X, G, W0, H0, sh = variant_inputs(g, tag)
+    kw = dict(tol=0, no_stop_criterion=True, max_iter=10, shape_2d=sh)
+    kw.update(VARIANT_FITS[tag])
+    if kw.pop("track", False):
+        kw.update(true_D=g["S__true_D"], true_H=g["S__true_H"])
+    res = orc.fit(X, G, W0, H0, **kw)
+    assert res["n_iter"] == int(g[tag + "__n_iter"])
+    assert rel_err(res["losses"], g[tag + "__losses"]) < 1e-10
+    assert rel_err(res["W"], g[tag + "__W"]) < 1e-9
+    assert rel_err(res["H"], g[tag + "__H"]) < 1e-9
+    assert rel_err(res["reconstruction_err"], g[tag + "__rec"]) < 1e-10
+    np.testing.assert_allclose(res["detailed_losses"], g[tag + "__detailed"], rtol=1e-9, atol=1e-18)   # incl. gamma
+    if tag.startswith("truth"):
+        assert rel_err(res["true_losses"], g[tag + "__true_losses"]) < 1e-10
