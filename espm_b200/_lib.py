@@ -76,6 +76,7 @@ class EspmState(ctypes.Structure):
         ("rank", _i32), ("world", _i32), ("seq_s", _u32), ("seq_m", _u32), ("nb_prev_ldh", _i32), ("nb_next_ldh", _i32),
         ("xchg_stride", _i64), ("xchg_hs_off", _i64), ("nb_prev_halo", _vp), ("nb_next_halo", _vp),
         ("peer_xchg", _vp * MAX_RANKS), ("peer_flags", _vp * MAX_RANKS),
+        ("bisect_dec", _vp),
     ]
 
 

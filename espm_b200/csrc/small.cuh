@@ -114,6 +114,17 @@ struct Mask128 {
     __device__ __forceinline__ void set_from(int j, int end) {  // bits [j, end)
         for (int i = j; i < end; ++i) set(i);
     }
+    __device__ __forceinline__ void or_word(int wi, uint32_t v) {
+        w[0] |= (wi == 0) ? v : 0u;
+        w[1] |= (wi == 1) ? v : 0u;
+        w[2] |= (wi == 2) ? v : 0u;
+        w[3] |= (wi == 3) ? v : 0u;
+    }
+    __device__ __forceinline__ bool get(int j) const {
+        const int wi = j >> 5;
+        const uint32_t v = (wi == 0) ? w[0] : (wi == 1) ? w[1] : (wi == 2) ? w[2] : w[3];
+        return (v >> (j & 31)) & 1u;
+    }
 };
 
 // first clear bit in [0, maxit) of the global trace mask, or maxit (dicotomy.py:152,169-171)
@@ -247,6 +258,170 @@ __device__ __forceinline__ double acc_replay(const double (&c)[KP], const double
     acc_bracket<KP>(c, b, k, a, lo, hi);
     return bisect_replay<double>(lo, hi, [&](double x) { return acc_f<KP>(c, b, x, k, a, ls); }, its);
 }
+// ------------------------------------------------------------------------------------------------
+// Recorded lock-step bisection of the H update (h_finish traces, h_apply replays).
+//
+// The reference's loop (dicotomy.py:152-168) needs, per midpoint, only two facts about f(new):
+//   le0 : f(new) <= 0   (then b = new, else a = new; f(a) > 0 is an invariant of the loop)
+//   bad : |f(new)| > tol (the global stop test ORs this over all pixels)
+// An evaluator returns both.  The KL evaluator first SCREENS f in fp32 (one MUFU.RCP per phase instead
+// of a correctly rounded fp64 quotient) and accepts the answer only when it is certain, i.e. when
+// |f32| and | |f32| - tol | exceed a bound on |f32 - f_exact|; otherwise it evaluates f exactly like the
+// reference (simplex_f).  Bound: fl32(x + den) 2^-24, rcp.approx 2^-23, fl32(num) 2^-24, product 2^-24
+// => 3.0e-7 relative per term; (k-1) fp32 additions of partial sums <= s => 6e-8 (k-1) s; the final s - 1
+// 6e-8 |f|.  The margin used is 1.25 x that bound: (4.5e-7 + 7.5e-8 (k-1)) s + 1e-7 |f| + 2e-8.
+// Pixels whose num has entries outside [1e-30, 1e30] (fp32 under/overflow) are never screened.
+// The trace also records the decisions, so that the replay of the it* global iterations is pure
+// bracket arithmetic for every iteration the trace has seen.
+// ------------------------------------------------------------------------------------------------
+struct Cls {
+    bool le0, bad;
+};
+
+template <int KP>
+struct KlEval {
+    const double (&num)[KP];
+    const double (&den)[KP];
+    float numf[KP];
+    int k;
+    double ls, tol;
+    float lsf, tolf, mrel;
+    bool screen;
+    __device__ __forceinline__ KlEval(const double (&num_)[KP], const double (&den_)[KP], int k_, double ls_, double tol_)
+        : num(num_), den(den_), k(k_), ls(ls_), tol(tol_) {
+        lsf = (float)ls_;
+        tolf = (float)tol_;
+        mrel = 4.5e-7f + 7.5e-8f * (float)(k_ - 1);   // 1.25 x (2.98e-7 per term + 5.96e-8 per addition)
+        screen = true;
+#pragma unroll
+        for (int kk = 0; kk < KP; ++kk) {
+            numf[kk] = (kk < k) ? (float)num[kk] : 0.f;
+            if (kk < k && num[kk] != 0.0 && !(num[kk] >= 1e-30 && num[kk] <= 1e30)) screen = false;
+        }
+    }
+    __device__ __forceinline__ double exact(double x) const { return simplex_f<double, KP>(num, den, x, k, ls); }
+    // fp32 screen: returns false when the fp32 value cannot be trusted
+    __device__ __forceinline__ bool screen_f(double x, float& f, float& margin) const {
+        float sacc = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < KP; ++kk)
+            if (kk < k) {
+                const float t = __double2float_rn(x + den[kk]);
+                float r;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
+                const float q = fmaxf(numf[kk] * r, lsf);
+                sacc = (kk == 0) ? q : sacc + q;
+            }
+        f = sacc - 1.0f;
+        margin = mrel * sacc + 1e-7f * fabsf(f) + 2e-8f;
+        return true;
+    }
+    __device__ __forceinline__ Cls operator()(double x) const {
+        if (screen) {
+            float f, margin;
+            screen_f(x, f, margin);
+            const float af = fabsf(f);
+            if (af > margin && fabsf(af - tolf) > margin + 1e-7f * tolf) return Cls{f <= 0.f, af > tolf};
+        }
+        const double fe = exact(x);
+        return Cls{fe <= 0.0, fabs(fe) > tol};
+    }
+    __device__ __forceinline__ bool le0(double x) const {
+        if (screen) {
+            float f, margin;
+            screen_f(x, f, margin);
+            if (fabsf(f) > margin) return f <= 0.f;
+        }
+        return exact(x) <= 0.0;
+    }
+};
+
+template <int KP>
+struct AccEval {   // quadratic surrogate (dicotomy.py:57-81): always exact
+    const double (&c)[KP];
+    const double (&b)[KP];
+    int k;
+    double a, ls, tol;
+    __device__ __forceinline__ AccEval(const double (&c_)[KP], const double (&b_)[KP], int k_, double a_, double ls_,
+                                       double tol_)
+        : c(c_), b(b_), k(k_), a(a_), ls(ls_), tol(tol_) {}
+    __device__ __forceinline__ double exact(double x) const { return acc_f<KP>(c, b, x, k, a, ls); }
+    __device__ __forceinline__ Cls operator()(double x) const {
+        const double fe = exact(x);
+        return Cls{fe <= 0.0, fabs(fe) > tol};
+    }
+    __device__ __forceinline__ bool le0(double x) const { return exact(x) <= 0.0; }
+};
+
+// word 4 of a pixel's decision record: iterations seen by the trace | stationary flag
+constexpr uint32_t BIS_STATIONARY = 1u << 8;
+
+template <typename E>
+__device__ __forceinline__ void bisect_trace_rec(double a, double b, const E& ev, int maxit, Mask128& bad, Mask128& dec,
+                                                 uint32_t& seen, uint32_t& err) {
+    const double fa = ev.exact(a), fb = ev.exact(b);
+    if (!(fa > 0.0) || !(fb < 0.0)) err |= ESPM_DEV_BRACKET;   // dicotomy.py:141-144
+    bool a_ok = fa <= ev.tol, b_ok = -fb <= ev.tol;          // is the end of the bracket already within tol?
+    double nw = (a + b) * 0.5;
+    int j = 0, widx = 0;
+    uint32_t stat = 0u;
+    uint32_t wb = 0u, wd = 0u, bit = 1u;    // bits of the current 32-iteration word
+    for (; j < maxit; ++j) {
+        const Cls c = ev(nw);
+        if (c.bad) wb |= bit;
+        if (a_ok && b_ok) break;            // f is monotone: every later midpoint is within tol as well
+        if (nw == a || nw == b) {           // stationary in floating point: new (and its bit) never change again
+            if (c.bad) bad.set_from(j + 1, maxit);
+            stat = BIS_STATIONARY;
+            break;
+        }
+        if (c.le0) {
+            b = nw;
+            b_ok = !c.bad;
+            wd |= bit;
+        } else {
+            a = nw;
+            a_ok = !c.bad;
+        }
+        nw = (a + b) * 0.5;
+        bit <<= 1;
+        if (bit == 0u) {
+            bad.or_word(widx, wb);
+            dec.or_word(widx, wd);
+            wb = wd = 0u;
+            bit = 1u;
+            ++widx;
+        }
+    }
+    bad.or_word(widx, wb);
+    dec.or_word(widx, wd);
+    seen = (uint32_t)j | stat;
+}
+
+// new after exactly `its` updates of dicotomy.py:152-168: recorded decisions first, evaluations after
+template <typename E>
+__device__ __forceinline__ double bisect_replay_rec(double a, double b, const E& ev, int its, const Mask128& dec,
+                                                    uint32_t seen) {
+    const int e = (int)(seen & 0xffu);
+    const int jb = its < e ? its : e;
+    double nw = (a + b) * 0.5;
+    int j = 0;
+    for (; j < jb; ++j) {
+        if (dec.get(j)) b = nw;
+        else a = nw;
+        nw = (a + b) * 0.5;
+    }
+    if (!(seen & BIS_STATIONARY)) {
+        for (; j < its; ++j) {
+            if (nw == a || nw == b) break;
+            if (ev.le0(nw)) b = nw;
+            else a = nw;
+            nw = (a + b) * 0.5;
+        }
+    }
+    return nw;
+}
+
 // updates.py:289: H' = (-b + sqrt(b^2 + 4 a c)) / (2 a)
 __device__ __forceinline__ double hq_root(double c, double b, double a) {
     const double q = __dadd_rn(__dmul_rn(b, b), __dmul_rn(4.0 * a, c));
@@ -400,7 +575,7 @@ __global__ void __launch_bounds__(PX_THREADS) h_finish_kernel(const espm_state s
                 if (lap) lapl += (double)(h[kk] * HL[kk]);
                 if (st.flags & ESPM_FLAG_HAVE_HPREV) {  // base.py:324
                     const TC hp = Hp[(size_t)kk * st.ldh + j];
-                    const double rr = (double)Num<TC>::vabs(h[kk] - hp) / ((double)h[kk] + st.tol * meanH);
+                    const double rr = (double)Num<TC>::vabs(h[kk] - hp) * Num<double>::rcp((double)h[kk] + st.tol * meanH);
                     relh = rr > relh ? rr : relh;
                 }
                 TC nm = s;
@@ -453,10 +628,25 @@ __global__ void __launch_bounds__(PX_THREADS) h_finish_kernel(const espm_state s
                 numd[kk] = (double)num[kk];
                 dend[kk] = (double)den[kk];
             }
-            if (quad)   // dicotomy.py:57-81 on (a, b, minus_c)
-                acc_trace<KP>(numd, dend, k, st.lambda_L * st.sigma, st.log_shift, st.dicotomy_tol, st.maxit, bits, err);
-            else
-                simplex_trace<double, KP>(numd, dend, k, st.log_shift, st.dicotomy_tol, st.maxit, bits, err);
+            Mask128 dec;
+            dec.clear();
+            uint32_t seen = 0u;
+            if (quad) {   // dicotomy.py:57-81 on (a, b, minus_c)
+                const double qa = st.lambda_L * st.sigma;
+                double lo, hi;
+                acc_bracket<KP>(numd, dend, k, qa, lo, hi);
+                bisect_trace_rec(lo, hi, AccEval<KP>(numd, dend, k, qa, st.log_shift, st.dicotomy_tol), st.maxit, bits,
+                                 dec, seen, err);
+            } else {
+                double lo, hi;
+                simplex_bracket<double, KP>(numd, dend, k, lo, hi);
+                bisect_trace_rec(lo, hi, KlEval<KP>(numd, dend, k, st.log_shift, st.dicotomy_tol), st.maxit, bits, dec,
+                                 seen, err);
+            }
+            uint32_t* rec = st.bisect_dec + j;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) rec[(size_t)w * st.p_pad] = dec.w[w];
+            rec[(size_t)4 * st.p_pad] = seen;
         } else {
             TC hn[KP];  // updates.py:152 with nu = 0 (updates.py:289 for the quadratic surrogate)
 #pragma unroll
@@ -534,14 +724,25 @@ __global__ void __launch_bounds__(PX_THREADS) h_apply_kernel(const espm_state st
             num[kk] = (kk < k) ? (double)num_i[(size_t)kk * st.p_pad + j] : 0.0;
             den[kk] = (kk < k) ? (double)den_i[(size_t)kk * st.p_pad + j] : 1.0;
         }
+        Mask128 dec;
+        const uint32_t* rec = st.bisect_dec + j;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) dec.w[w] = rec[(size_t)w * st.p_pad];
+        const uint32_t seen = rec[(size_t)4 * st.p_pad];
         if ((st.flags & ESPM_FLAG_HQ) && (st.flags & ESPM_FLAG_LAPLACIAN)) {   // updates.py:286-289
             const double a = st.lambda_L * st.sigma;
-            const double nu = acc_replay<KP>(num, den, k, a, st.log_shift, its);
+            double lo, hi;
+            acc_bracket<KP>(num, den, k, a, lo, hi);
+            const double nu = bisect_replay_rec(lo, hi, AccEval<KP>(num, den, k, a, st.log_shift, st.dicotomy_tol), its,
+                                                dec, seen);
 #pragma unroll
             for (int kk = 0; kk < KP; ++kk)
                 hn[kk] = (kk < k) ? (TC)fmax(hq_root(num[kk], den[kk] + nu, a), st.log_shift) : TC(0);
         } else {
-            const double nu = simplex_replay<double, KP>(num, den, k, st.log_shift, its);
+            double lo, hi;
+            simplex_bracket<double, KP>(num, den, k, lo, hi);
+            const double nu = bisect_replay_rec(lo, hi, KlEval<KP>(num, den, k, st.log_shift, st.dicotomy_tol), its, dec,
+                                                seen);
 #pragma unroll
             for (int kk = 0; kk < KP; ++kk)
                 hn[kk] = (kk < k) ? (TC)fmax(num[kk] / (den[kk] + nu), st.log_shift) : TC(0);

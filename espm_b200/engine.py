@@ -199,6 +199,8 @@ class FitEngine:
         self.xlogy_part = zeros(max(st.h_grid, 1), dtype=torch.float64)
         self.px_part = zeros(st.px_blocks, 3 + 3 * kp, dtype=torch.float64)
         self.mask = torch.zeros(4 * max(self.world, 1), dtype=torch.int32, device=dev)
+        self.bisect_dec = torch.zeros(5 * p_pad if simplex_H else 1, dtype=torch.int32, device=dev)
+        st.bisect_dec = self.bisect_dec.data_ptr()
         self.dev_flags = torch.zeros(8, dtype=torch.int32, device=dev)
         self.coop_part = zeros(L.COOP_BLOCKS * (2 * L.MAX_K + 1), dtype=torch.float64)
         self.max_records = int(max_records)

@@ -201,6 +201,11 @@ typedef struct espm_state {
     void* nb_next_halo;     /* in the next rank's H_next: where my LAST image row goes, or NULL */
     void* peer_xchg[ESPM_MAX_RANKS];       /* every rank's exchange buffer: 2 x {S [n_pad][kp], statistics} */
     uint32_t* peer_flags[ESPM_MAX_RANKS];  /* every rank's flag block (ESPM_PF_WORDS words, zero at start) */
+    /* ---- recorded bisection (simplex_H): espm_h_finish writes, espm_h_apply reads ----
+     * [5][p_pad] words per pixel: words 0..3 = bit j set <=> iteration j of dicotomy.py:152-168 moved the
+     * upper end (b = new); word 4 = number of iterations the trace evaluated | 1<<8 if the bracket became
+     * stationary.  The replay of the it* global iterations follows these bits instead of re-evaluating f. */
+    uint32_t* bisect_dec;
 } espm_state;
 
 /* library / device */
