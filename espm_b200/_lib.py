@@ -32,6 +32,11 @@ FLAG_SIMPLEX_ROWS = 1 << 10
 FLAG_HQ = 1 << 11
 FLAG_FUSED_WREDUCE = 1 << 12
 FLAG_PEER = 1 << 13
+FLAG_BMD = 1 << 14
+FLAG_PG = 1 << 15
+FLAG_L2 = 1 << 16
+FLAG_L2_H = 1 << 17
+FLAG_LINESEARCH = 1 << 18
 COOP_BLOCKS = 32
 
 # device error word
@@ -44,7 +49,7 @@ DEV_PEER_TIMEOUT = 1 << 5
 
 # scalar record slots
 S_XLOGY, S_SUMY, S_LOGREG, S_LAPL, S_REL_H, S_REL_W, S_BISECT_ITS_H, S_BISECT_ITS_W, S_DEV_FLAGS, \
-    S_MEAN_H, S_MEAN_W, S_GW_FLAGS = range(12)
+    S_MEAN_H, S_MEAN_W, S_GW_FLAGS, S_GAMMA, S_LS_D = range(14)
 
 _i32, _u32, _i64, _f64, _vp = ctypes.c_int32, ctypes.c_uint32, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
 
@@ -77,6 +82,9 @@ class EspmState(ctypes.Structure):
         ("xchg_stride", _i64), ("xchg_hs_off", _i64), ("nb_prev_halo", _vp), ("nb_next_halo", _vp),
         ("peer_xchg", _vp * MAX_RANKS), ("peer_flags", _vp * MAX_RANKS),
         ("bisect_dec", _vp),
+        ("gamma_h", _f64), ("gamma_w", _f64), ("x_total", _f64),
+        ("x_colsum", _vp), ("x_rowsum", _vp), ("GG", _vp), ("gram_gw", _vp), ("gram_h", _vp), ("sigma_dev", _vp),
+        ("ls_part", _vp),
     ]
 
 
@@ -121,6 +129,10 @@ _EXPORTS = {
     "espm_peer_close": (ctypes.c_int, [_vp]),
     "espm_peer_free": (ctypes.c_int, [_vp]),
     "espm_dichotomy_simplex": (ctypes.c_int, [_i32, _i32, _i64, _vp, _vp, _f64, _f64, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "espm_gram": (ctypes.c_int, [ctypes.POINTER(EspmState), _i32, _vp]),
+    "espm_x_sums": (ctypes.c_int, [ctypes.POINTER(EspmState), _vp, _vp, _vp]),
+    "espm_linesearch": (ctypes.c_int, [ctypes.POINTER(EspmState), _vp]),
+    "espm_dichotomy_simplex_pg": (ctypes.c_int, [_i32, _i32, _i64, _vp, _f64, _f64, _i32, _vp, _vp, _vp, _vp, _vp]),
     "espm_dichotomy_simplex_acc": (ctypes.c_int, [_i32, _i32, _i64, _f64, _vp, _vp, _f64, _f64, _i32, _vp, _vp, _vp,
                                                   _vp, _vp]),
 }

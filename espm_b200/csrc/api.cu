@@ -42,7 +42,15 @@ static int sizes_of(const espm_state* st, int safe, XPassSizes* o) {
     return xpass_sizes<double, double>(st->kp, safe, o);
 }
 
-static bool is_safe(const espm_state* st) { return (st->flags & (ESPM_FLAG_CLAMP_Y | ESPM_FLAG_LOSS_DUAL)) != 0; }
+// the Frobenius branches never divide by G W H and their loss does not clamp (measures.py:350-385)
+static bool is_safe(const espm_state* st) {
+    return !(st->flags & (ESPM_FLAG_L2 | ESPM_FLAG_L2_H)) && (st->flags & (ESPM_FLAG_CLAMP_Y | ESPM_FLAG_LOSS_DUAL)) != 0;
+}
+static int h_mode(const espm_state* st) {
+    if (st->flags & ESPM_FLAG_L2_H) return XMODE_FROB;
+    return (st->flags & ESPM_FLAG_L2) ? XMODE_KL_FROB : XMODE_KL;
+}
+static int w_mode(const espm_state* st) { return (st->flags & ESPM_FLAG_L2) ? XMODE_FROB : XMODE_KL; }
 
 static int check_state(const espm_state* st) {
     if (!st) {
@@ -100,6 +108,8 @@ static XPassArgs make_args(const espm_state* st, bool w_pass) {
     a.dual = (st->flags & ESPM_FLAG_LOSS_DUAL) ? 1 : 0;
     a.log_shift = st->log_shift;
     a.y_shift = (!w_pass && (st->flags & ESPM_FLAG_HQ)) ? st->log_shift : 0.0;
+    a.n = st->n;
+    a.p_loc = st->p_loc;
     return a;
 }
 
@@ -185,7 +195,7 @@ int espm_plan(espm_state* st) {
     st->h_smem = z.fixed + depth * z.h_stride + z.h_tail;
     int occ = 0;
     {
-        XPassLaunch l{XPASS_H, st->kp, 1, 1, st->h_smem};
+        XPassLaunch l{XPASS_H, st->kp, 1, 1, st->h_smem, XMODE_KL};
         rc = fn(l, nullptr, &occ, 0);
         if (rc) return rc;
         if (occ < 1) {
@@ -228,7 +238,7 @@ int espm_plan(espm_state* st) {
         st->w_depth = wdepth;
         st->w_smem = z.fixed + wdepth * z.w_stride + z.w_tail;
         int wocc = 0;
-        XPassLaunch l{XPASS_W, st->kp, 1, 1, st->w_smem};
+        XPassLaunch l{XPASS_W, st->kp, 1, 1, st->w_smem, XMODE_KL};
         rc = fn(l, nullptr, &wocc, 0);
         if (rc) return rc;
         if (wocc < 1) {
@@ -321,6 +331,32 @@ int espm_h_scalars(const espm_state* st, void* stream) { return small(OP_H_SCALA
 int espm_w_reduce(const espm_state* st, void* stream) { return small(OP_W_REDUCE, st, stream); }
 int espm_w_finish(const espm_state* st, void* stream) { return small(OP_W_FINISH, st, stream); }
 
+int espm_linesearch(const espm_state* st, void* stream) {
+    if (st && (!st->sigma_dev || !st->ls_part)) {
+        set_error("espm_linesearch needs sigma_dev and ls_part");
+        return ESPM_ERR_BAD_ARG;
+    }
+    return small(OP_LINESEARCH, st, stream);
+}
+
+int espm_gram(const espm_state* st, int32_t which, void* stream) {
+    if (st && !(which == 0 ? st->gram_gw : st->gram_h)) {
+        set_error("espm_gram: output buffer is null");
+        return ESPM_ERR_BAD_ARG;
+    }
+    return small(which == 0 ? OP_GRAM_GW : OP_GRAM_H, st, stream);
+}
+
+int espm_x_sums(const espm_state* st, void* colsum_out, double* rowsum_part, void* stream) {
+    int rc = check_state(st);
+    if (rc) return rc;
+    if (!colsum_out || !rowsum_part) {
+        set_error("espm_x_sums: null output");
+        return ESPM_ERR_BAD_ARG;
+    }
+    return x_sums_launch(st, colsum_out, rowsum_part, (cudaStream_t)stream);
+}
+
 int espm_colsum_g(const espm_state* st, void* colsum_out, void* stream) {
     int rc = check_state(st);
     if (rc) return rc;
@@ -337,7 +373,7 @@ int espm_h_pass(const espm_state* st, void* stream) {
     if (rc) return rc;
     // (the kernel also clears the trace mask of the coming h_finish)
     XPassArgs a = make_args(st, false);
-    XPassLaunch l{XPASS_H, st->kp, is_safe(st) ? 1 : 0, st->h_grid, st->h_smem};
+    XPassLaunch l{XPASS_H, st->kp, is_safe(st) ? 1 : 0, st->h_grid, st->h_smem, h_mode(st)};
     return pick_xpass(st)(l, &a, nullptr, (cudaStream_t)stream);
 }
 
@@ -345,7 +381,7 @@ int espm_w_pass(const espm_state* st, void* stream) {
     int rc = check_state(st);
     if (rc) return rc;
     XPassArgs a = make_args(st, true);
-    XPassLaunch l{XPASS_W, st->kp, is_safe(st) ? 1 : 0, st->w_grid, st->w_smem};
+    XPassLaunch l{XPASS_W, st->kp, is_safe(st) ? 1 : 0, st->w_grid, st->w_smem, w_mode(st)};
     return pick_xpass(st)(l, &a, nullptr, (cudaStream_t)stream);
 }
 
@@ -410,6 +446,12 @@ int espm_dichotomy_simplex(int32_t c_dtype, int32_t k, int64_t p, const void* nu
                            double tol, int32_t maxit, void* nu_out, uint32_t* mask4, uint32_t* dev_flags,
                            int32_t* its_out, void* stream) {
     return dicho_common(c_dtype, k, p, num, den, log_shift, tol, maxit, 0.0, nu_out, mask4, dev_flags, its_out, stream);
+}
+
+int espm_dichotomy_simplex_pg(int32_t c_dtype, int32_t k, int64_t p, const void* a, double log_shift, double tol,
+                              int32_t maxit, void* nu_out, uint32_t* mask4, uint32_t* dev_flags, int32_t* its_out,
+                              void* stream) {
+    return dicho_common(c_dtype, k, p, a, a, log_shift, tol, maxit, -1.0, nu_out, mask4, dev_flags, its_out, stream);
 }
 
 int espm_dichotomy_simplex_acc(int32_t c_dtype, int32_t k, int64_t p, double a, const void* b, const void* minus_c,

@@ -51,6 +51,17 @@ int xt_const_launch(const espm_state* st, double* part, cudaStream_t s) {
     return ESPM_OK;
 }
 
+int x_sums_launch(const espm_state* st, void* colsum, double* rowsum_part, cudaStream_t s) {
+    if (st->x_dtype == ESPM_F32 && st->c_dtype == ESPM_F32)
+        x_sums_kernel<float, float><<<st->n_tiles, 128, 0, s>>>((const float*)st->Xt, st->n_pad, (float*)colsum, rowsum_part);
+    else if (st->x_dtype == ESPM_F32)
+        x_sums_kernel<float, double><<<st->n_tiles, 128, 0, s>>>((const float*)st->Xt, st->n_pad, (double*)colsum, rowsum_part);
+    else
+        x_sums_kernel<double, double><<<st->n_tiles, 128, 0, s>>>((const double*)st->Xt, st->n_pad, (double*)colsum, rowsum_part);
+    ESPM_CUDA_CHECK(cudaGetLastError());
+    return ESPM_OK;
+}
+
 int reduce_sum_launch(const double* in, long long n, double* out, cudaStream_t s) {
     reduce_sum_kernel<<<1, 1024, 0, s>>>(in, n, out);
     ESPM_CUDA_CHECK(cudaGetLastError());

@@ -158,4 +158,27 @@ __global__ void __launch_bounds__(1024) reduce_sum_kernel(const double* __restri
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Sums of X for the Bregman branches: one CTA per pixel tile of Xt ([n_pad][128]).
+//   colsum[j] = sum_c X[c][j]  (updates.py:121);  rowsum_part[tile][c] = sum_{j in tile} X[c][j]  (updates.py:43)
+// ------------------------------------------------------------------------------------------------
+template <typename TX, typename TC>
+__global__ void __launch_bounds__(128) x_sums_kernel(const TX* Xt, int n_pad, TC* colsum, double* rowsum_part) {
+    const TX* tile = Xt + (size_t)blockIdx.x * n_pad * TILE_PX;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double cs = 0.0;
+    __shared__ double sm[4];
+    for (int c = 0; c < n_pad; ++c) {
+        const double v = (double)tile[(size_t)c * TILE_PX + threadIdx.x];
+        cs += v;
+        const double r = warp_sum(v);
+        if (lane == 0) sm[warp] = r;
+        __syncthreads();
+        if (threadIdx.x == 0) rowsum_part[(size_t)blockIdx.x * n_pad + c] = (sm[0] + sm[1]) + (sm[2] + sm[3]);
+        __syncthreads();
+    }
+    colsum[(size_t)blockIdx.x * TILE_PX + threadIdx.x] = (TC)cs;
+}
+
+
 }  // namespace espm

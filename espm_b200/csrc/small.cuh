@@ -353,6 +353,42 @@ struct AccEval {   // quadratic surrogate (dicotomy.py:57-81): always exact
     __device__ __forceinline__ bool le0(double x) const { return exact(x) <= 0.0; }
 };
 
+template <int KP>
+struct PgEval {    // projected gradient (dicotomy.py:83-108): f(x) = sum_k max(a_k + x, ls) - 1, always exact
+    const double (&av)[KP];
+    int k;
+    double ls, tol;
+    __device__ __forceinline__ PgEval(const double (&a_)[KP], int k_, double ls_, double tol_)
+        : av(a_), k(k_), ls(ls_), tol(tol_) {}
+    __device__ __forceinline__ double exact(double x) const {
+        double s = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < KP; ++kk)
+            if (kk < k) {
+                const double g = fmax(__dadd_rn(av[kk], x), ls);
+                s = (kk == 0) ? g : __dadd_rn(s, g);
+            }
+        return __dsub_rn(s, 1.0);
+    }
+    __device__ __forceinline__ Cls operator()(double x) const {
+        const double fe = exact(x);
+        return Cls{fe <= 0.0, fabs(fe) > tol};
+    }
+    __device__ __forceinline__ bool le0(double x) const { return exact(x) <= 0.0; }
+    // dicotomy.py:99-100: (nu_max, nu_min) = (1/k - min a, -max a)
+    __device__ __forceinline__ void bracket(double& lo, double& hi) const {
+        double mn = av[0], mx = av[0];
+#pragma unroll
+        for (int kk = 1; kk < KP; ++kk)
+            if (kk < k) {
+                mn = fmin(mn, av[kk]);
+                mx = fmax(mx, av[kk]);
+            }
+        lo = __dsub_rn(__ddiv_rn(1.0, (double)k), mn);
+        hi = -mx;
+    }
+};
+
 // word 4 of a pixel's decision record: iterations seen by the trace | stationary flag
 constexpr uint32_t BIS_STATIONARY = 1u << 8;
 
@@ -517,6 +553,10 @@ __global__ void __launch_bounds__(PX_THREADS) h_finish_kernel(const espm_state s
     const bool simplex = st.flags & ESPM_FLAG_SIMPLEX_H;
     const bool hq = st.flags & ESPM_FLAG_HQ;   // algo="l2_surrogate" (updates.py:263-301)
     const bool quad = hq && lap;               // quadratic root / dichotomy_simplex_acc instead of num/(den+nu)
+    const bool bmd = st.flags & ESPM_FLAG_BMD; // use_bregman (updates.py:120-125)
+    const bool pg = st.flags & ESPM_FLAG_PG;   // proj_grad_step_h (updates.py:369-391)
+    const bool l2h = st.flags & ESPM_FLAG_L2_H;  // Frobenius H step / gradient (updates.py:109-118, 330-332)
+    const double sigma = st.sigma_dev ? *st.sigma_dev : st.sigma;   // gamma_ (device-resident under line search)
 
     constexpr int NV = 3 + 3 * KP;
     double vals[NV];
@@ -584,23 +624,58 @@ __global__ void __launch_bounds__(PX_THREADS) h_finish_kernel(const espm_state s
                     // ---- updates.py:280-284: minus_c = H * s (s formed with y + ls), b; mu does not enter ----
                     if (lap) {
                         const TC lam = (TC)st.lambda_L;
-                        dn = dn + lam * HL[kk] - (lam * (TC)st.sigma) * h[kk];
+                        dn = dn + lam * HL[kk] - (lam * (TC)sigma) * h[kk];
                     }
                     num[kk] = h[kk] * nm;
                     den[kk] = dn;
                     if (num[kk] < TC(0) || (!lap && den[kk] < TC(0))) err |= ESPM_DEV_NEGATIVE;
+                } else if (pg) {
+                    // ---- gradH (updates.py:316-345), new_H = H - 1/gamma * grad (updates.py:378) ----
+                    TC g;
+                    if (l2h) {
+                        TC dd = TC(0);   // ((G W)^T (G W) H)_kk
+#pragma unroll
+                        for (int k2 = 0; k2 < KP; ++k2)
+                            if (k2 < k) dd = fma((TC)st.gram_gw[kk * KP + k2], Hc[(size_t)k2 * st.ldh + j], dd);
+                        g = dd - s;
+                    } else {
+                        g = -s + dn;
+                    }
+                    if (use_mu) g = g + (TC)st.mu[kk] / (h[kk] + (TC)st.eps_reg);
+                    if (lap) {
+                        // lambda_L * L is formed in FLOAT32 by the reference (utils.py:57 stores float32 entries)
+                        const float lamf = (float)st.lambda_L;
+                        const TC cdeg = (st.ny > 0) ? (TC)((float)deg * lamf) : (TC)lamf;
+                        const TC nbs = (st.ny > 0) ? ((TC)deg * h[kk] - HL[kk]) : TC(0);   // sum of the neighbours
+                        g = g + (cdeg * h[kk] - (TC)lamf * nbs);
+                    }
+                    num[kk] = h[kk] - (TC)(1.0 / st.gamma_h) * g;
+                    den[kk] = g;   // the gradient itself (gradH of the operator-level API reads it back)
+                } else if (l2h) {
+                    // ---- updates.py:109-118: num = (G W)^T X, denum = (G W)^T (G W) H ----
+                    TC dd = TC(0);
+#pragma unroll
+                    for (int k2 = 0; k2 < KP; ++k2)
+                        if (k2 < k) dd = fma((TC)st.gram_gw[kk * KP + k2], Hc[(size_t)k2 * st.ldh + j], dd);
+                    num[kk] = h[kk] * s;
+                    den[kk] = dd;
                 } else {
-                    // ---- updates.py:132-142 ----
+                    // ---- updates.py:120-142 ----
+                    if (bmd) {   // sigmaR / H and the gradient of the data term (updates.py:121-125)
+                        const TC t = reinterpret_cast<const TC*>(st.x_colsum)[j] / h[kk];
+                        nm = t;
+                        dn = (-s + dn) + t;
+                    }
                     if (use_mu) dn = dn + (TC)st.mu[kk] / (h[kk] + (TC)st.eps_reg);
                     if (lap) {
                         const TC lam = (TC)st.lambda_L;
-                        const TC ls_max = lam * (TC)st.sigma * (TC)hstats[2 * KP + kk];
+                        const TC ls_max = lam * (TC)sigma * (TC)hstats[2 * KP + kk];
                         nm = nm + ls_max;
                         dn = dn + ls_max + lam * HL[kk];
                     }
                     num[kk] = h[kk] * nm;
                     den[kk] = dn;
-                    if (num[kk] < TC(0) || den[kk] < TC(0)) err |= ESPM_DEV_NEGATIVE;
+                    if (!bmd && (num[kk] < TC(0) || den[kk] < TC(0))) err |= ESPM_DEV_NEGATIVE;
                 }
             } else {
                 h[kk] = HL[kk] = num[kk] = TC(0);
@@ -631,8 +706,13 @@ __global__ void __launch_bounds__(PX_THREADS) h_finish_kernel(const espm_state s
             Mask128 dec;
             dec.clear();
             uint32_t seen = 0u;
-            if (quad) {   // dicotomy.py:57-81 on (a, b, minus_c)
-                const double qa = st.lambda_L * st.sigma;
+            if (pg) {     // dicotomy.py:83-108 on new_H
+                const PgEval<KP> ev(numd, k, st.log_shift, st.dicotomy_tol);
+                double lo, hi;
+                ev.bracket(lo, hi);
+                bisect_trace_rec(lo, hi, ev, st.maxit, bits, dec, seen, err);
+            } else if (quad) {   // dicotomy.py:57-81 on (a, b, minus_c)
+                const double qa = st.lambda_L * sigma;
                 double lo, hi;
                 acc_bracket<KP>(numd, dend, k, qa, lo, hi);
                 bisect_trace_rec(lo, hi, AccEval<KP>(numd, dend, k, qa, st.log_shift, st.dicotomy_tol), st.maxit, bits,
@@ -648,12 +728,21 @@ __global__ void __launch_bounds__(PX_THREADS) h_finish_kernel(const espm_state s
             for (int w = 0; w < 4; ++w) rec[(size_t)w * st.p_pad] = dec.w[w];
             rec[(size_t)4 * st.p_pad] = seen;
         } else {
+            if (pg) {   // keep new_H / grad readable (gradH, proj_grad_step_h of the operator-level API)
+#pragma unroll
+                for (int kk = 0; kk < KP; ++kk)
+                    if (kk < k) {
+                        reinterpret_cast<TC*>(st.num)[(size_t)kk * st.p_pad + j] = num[kk];
+                        reinterpret_cast<TC*>(st.den)[(size_t)kk * st.p_pad + j] = den[kk];
+                    }
+            }
             TC hn[KP];  // updates.py:152 with nu = 0 (updates.py:289 for the quadratic surrogate)
 #pragma unroll
             for (int kk = 0; kk < KP; ++kk) {
                 if (kk >= k) hn[kk] = TC(0);
+                else if (pg) hn[kk] = Num<TC>::vmax(num[kk], ls);                       // updates.py:387, nu = 0
                 else if (quad)
-                    hn[kk] = (TC)fmax(hq_root((double)num[kk], (double)den[kk], st.lambda_L * st.sigma), st.log_shift);
+                    hn[kk] = (TC)fmax(hq_root((double)num[kk], (double)den[kk], st.lambda_L * sigma), st.log_shift);
                 else hn[kk] = Num<TC>::vmax(num[kk] / den[kk], ls);
             }
             store_h_next<TC, KP>(st, j, k, hn, vals);
@@ -729,8 +818,15 @@ __global__ void __launch_bounds__(PX_THREADS) h_apply_kernel(const espm_state st
 #pragma unroll
         for (int w = 0; w < 4; ++w) dec.w[w] = rec[(size_t)w * st.p_pad];
         const uint32_t seen = rec[(size_t)4 * st.p_pad];
-        if ((st.flags & ESPM_FLAG_HQ) && (st.flags & ESPM_FLAG_LAPLACIAN)) {   // updates.py:286-289
-            const double a = st.lambda_L * st.sigma;
+        if (st.flags & ESPM_FLAG_PG) {                                         // updates.py:381-387
+            const PgEval<KP> ev(num, k, st.log_shift, st.dicotomy_tol);
+            double lo, hi;
+            ev.bracket(lo, hi);
+            const double nu = bisect_replay_rec(lo, hi, ev, its, dec, seen);
+#pragma unroll
+            for (int kk = 0; kk < KP; ++kk) hn[kk] = (kk < k) ? (TC)fmax(num[kk] + nu, st.log_shift) : TC(0);
+        } else if ((st.flags & ESPM_FLAG_HQ) && (st.flags & ESPM_FLAG_LAPLACIAN)) {   // updates.py:286-289
+            const double a = st.lambda_L * (st.sigma_dev ? *st.sigma_dev : st.sigma);
             double lo, hi;
             acc_bracket<KP>(num, den, k, a, lo, hi);
             const double nu = bisect_replay_rec(lo, hi, AccEval<KP>(num, den, k, a, st.log_shift, st.dicotomy_tol), its,
@@ -1077,13 +1173,42 @@ __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_sta
 
     // ---- phase A: num = W * (G^T S), den = colsum(G) (x) rowsum(H')   (updates.py:58-60) ----
     bool nonfinite = false;
+    const bool w_bmd = st.flags & ESPM_FLAG_BMD, w_pg = st.flags & ESPM_FLAG_PG, w_l2 = st.flags & ESPM_FLAG_L2;
+    // num / denum of one entry from v = (G^T S)[mm][kk] and cs_h = colsum(G)[mm] * rowsum(H')[kk]; trow = (G^T G W)[mm][:]
+    auto entry = [&](int mm, int kk, TC v, TC cs_h, const TC (&trow)[KP]) {
+        const int i = mm * k + kk;
+        TC ggwhh = TC(0);
+        if (w_l2) {   // (G^T G W H H^T)[mm][kk]  (updates.py:30-32)
+#pragma unroll
+            for (int k2 = 0; k2 < KP; ++k2)
+                if (k2 < k) ggwhh = fma(trow[k2], (TC)st.gram_h[k2 * KP + kk], ggwhh);
+        }
+        if (w_pg) {          // gradW + projected step (updates.py:303-314, 357)
+            const TC grad = w_l2 ? TC(2) * (ggwhh - v) : (-v + cs_h);
+            wnum[i] = W[i] - (TC)(1.0 / st.gamma_w) * grad;
+            wden[i] = grad;   // the gradient itself (gradW of the operator-level API reads it back)
+        } else if (w_l2) {   // new_W = W / GGWHH * GXH (updates.py:36)
+            wnum[i] = (W[i] / ggwhh) * v;
+            wden[i] = TC(1);
+        } else if (w_bmd) {  // updates.py:40-48
+            const TC sr = ident ? reinterpret_cast<const TC*>(st.x_rowsum)[mm] : (TC)st.x_total;
+            const TC gradg = -v + cs_h;
+            wnum[i] = sr * W[i];
+            wden[i] = gradg * W[i] + sr;
+        } else {             // updates.py:59-60
+            wnum[i] = W[i] * v;
+            wden[i] = cs_h;
+        }
+    };
     if (ident) {
         for (int i = gthread; i < m * k; i += gthreads) {
             const int mm = i / k, kk = i - mm * k;
             const TC sv = S[(size_t)mm * KP + kk];
             nonfinite |= !(Num<TC>::vabs(sv) < Num<TC>::inf());
-            wnum[i] = W[i] * sv;
-            wden[i] = (TC)hstats[kk];
+            TC trow[KP];
+#pragma unroll
+            for (int k2 = 0; k2 < KP; ++k2) trow[k2] = (k2 < k) ? W[mm * k + k2] : TC(0);   // G^T G = I
+            entry(mm, kk, sv, (TC)hstats[kk], trow);
         }
     } else {
         for (int mm = blockIdx.x * NWARPS + warp; mm < m; mm += gridDim.x * NWARPS) {
@@ -1097,14 +1222,25 @@ __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_sta
 #pragma unroll
                 for (int kk = 0; kk < KP; ++kk) acc[kk] = fma(g, srow[kk], acc[kk]);
             }
+            TC trow[KP];
+#pragma unroll
+            for (int k2 = 0; k2 < KP; ++k2) trow[k2] = TC(0);
+            if (w_l2) {   // row mm of (G^T G) W
+                const TC* GG = reinterpret_cast<const TC*>(st.GG);
+                for (int m2 = lane; m2 < m; m2 += 32) {
+                    const TC g = GG[(size_t)mm * m + m2];
+#pragma unroll
+                    for (int k2 = 0; k2 < KP; ++k2)
+                        if (k2 < k) trow[k2] = fma(g, W[m2 * k + k2], trow[k2]);
+                }
+#pragma unroll
+                for (int k2 = 0; k2 < KP; ++k2) trow[k2] = warp_sum(trow[k2]);
+            }
 #pragma unroll
             for (int kk = 0; kk < KP; ++kk) {
                 const TC v = warp_sum(acc[kk]);
                 nonfinite |= (kk < k) && !(Num<TC>::vabs(v) < Num<TC>::inf());
-                if (lane == 0 && kk < k) {
-                    wnum[mm * k + kk] = W[mm * k + kk] * v;
-                    wden[mm * k + kk] = colsumG[mm] * (TC)hstats[kk];
-                }
+                if (lane == 0 && kk < k) entry(mm, kk, v, colsumG[mm] * (TC)hstats[kk], trow);
             }
         }
     }
@@ -1213,7 +1349,7 @@ __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_sta
         const TC* fw = reinterpret_cast<const TC*>(st.fixed_W);
         double wsum = 0.0;
         for (int i = threadIdx.x; i < m * k; i += W_COOP_THREADS) {
-            TC v = Num<TC>::vmax(wnum[i] / wden[i], ls);
+            TC v = Num<TC>::vmax((st.flags & ESPM_FLAG_PG) ? wnum[i] : wnum[i] / wden[i], ls);
             if (st.flags & ESPM_FLAG_FIXED_W) {
                 const TC f = fw[i];
                 if (f >= TC(0)) v = f;
@@ -1332,6 +1468,121 @@ __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_sta
 }
 
 // ------------------------------------------------------------------------------------------------
+// Gram matrix of k vectors: out[a][b] = sum_r A(r, a) A(r, b), A(r, a) = A[r * ld_r + a * ld_a].
+// One CTA per (a, b) pair; fixed-order reduction.  Used for (G W)^T (G W) and H H^T (updates.py:31, 115).
+// ------------------------------------------------------------------------------------------------
+template <typename TC>
+__global__ void __launch_bounds__(256) gram_kernel(const TC* A, long long rows, long long ld_r, long long ld_a, int k,
+                                                   int kp, double* out) {
+    const int a = blockIdx.x / k, b = blockIdx.x % k;
+    __shared__ double sm[8];
+    double acc = 0.0;
+    for (long long r = threadIdx.x; r < rows; r += blockDim.x)
+        acc = fma((double)A[r * ld_r + a * ld_a], (double)A[r * ld_r + b * ld_a], acc);
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += sm[w];
+        out[a * kp + b] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Line search on the Laplacian surrogate (smooth_nmf.py:376-382; surrogates.py:5-53, 66-149), Ht = H_cur
+// (the iterate the surrogate was built at), H = H_next:
+//   t1 = sum (Ht L) Ht, t2 = sum (Ht L) H, b_inf = trace(H L H^T) / 2,
+//   t3 = sum_k max_j(H_kj) sum_j dgkl(Ht_kj, H_kj)   (log_surrogate, bmd)   |   sum (Ht - H)^2   (l2_surrogate)
+//   d = (2 t2 - t1 + sigma t3) / 2 - b_inf;   gamma_ <- gamma_ / 1.05 if d > 0 else gamma_ * 1.5
+// (diff_surrogate is called with its default lambda_L = 1, smooth_nmf.py:378.)
+// ------------------------------------------------------------------------------------------------
+template <typename TC, int KP>
+__global__ void __launch_bounds__(PX_THREADS) linesearch_kernel(const espm_state st) {
+    const int j = blockIdx.x * PX_THREADS + threadIdx.x;
+    const int k = st.k;
+    const bool quad = st.flags & ESPM_FLAG_HQ;
+    constexpr int NV = 4 + KP;   // t1, t2, trace(H L H), (quad: sum sq) , per-phase dgkl row sums
+    double vals[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) vals[i] = 0.0;
+    if (j < st.p_loc) {
+        const TC* Ho = reinterpret_cast<const TC*>(st.H_cur);
+        const TC* Hn = reinterpret_cast<const TC*>(st.H_next);
+        int deg = 0;
+        bool up = false, down = false, left = false, right = false;
+        if (st.ny > 0) {
+            const int il = j / st.ny, col = j - il * st.ny;
+            const int ig = st.row0 + il;
+            left = col > 0;
+            right = col < st.ny - 1;
+            up = ig > 0;
+            down = ig < st.nx - 1;
+            deg = (int)left + (int)right + (int)up + (int)down;
+        }
+#pragma unroll
+        for (int kk = 0; kk < KP; ++kk)
+            if (kk < k) {
+                const TC* ro = Ho + (size_t)kk * st.ldh;
+                const TC* rn = Hn + (size_t)kk * st.ldh;
+                const double ho = (double)ro[j], hn = (double)rn[j];
+                double lo = ho, ln = hn;   // (Ht L)_j and (H L)_j; identity when shape_2d is None
+                if (st.ny > 0) {
+                    double so = 0.0, sn = 0.0;
+                    if (up) { so += (double)ro[j - st.ny]; sn += (double)rn[j - st.ny]; }
+                    if (left) { so += (double)ro[j - 1]; sn += (double)rn[j - 1]; }
+                    if (right) { so += (double)ro[j + 1]; sn += (double)rn[j + 1]; }
+                    if (down) { so += (double)ro[j + st.ny]; sn += (double)rn[j + st.ny]; }
+                    lo = (double)deg * ho - so;
+                    ln = (double)deg * hn - sn;
+                }
+                vals[0] += lo * ho;
+                vals[1] += lo * hn;
+                vals[2] += ln * hn;
+                if (quad) vals[3] += (ho - hn) * (ho - hn);
+                else vals[4 + kk] = ho * log(ho / hn) - ho + hn;
+            }
+    }
+    block_reduce_vals<NV>(vals, NV, st.ls_part + (size_t)blockIdx.x * NV);
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(&st.dev_flags[4], 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // fold the per-CTA partials in index order; rowmax(H_next) from the px_part rows written by the H update
+    __shared__ double tot[NV + KP];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int stride = px_part_stride(KP);
+    for (int v = warp; v < NV + KP; v += PX_WARPS) {
+        const bool is_max = v >= NV;
+        double r = is_max ? -1e300 : 0.0;
+        for (int b = lane; b < (int)gridDim.x; b += 32) {
+            const double u = is_max ? st.px_part[(size_t)b * stride + 3 + 2 * KP + (v - NV)] : st.ls_part[(size_t)b * NV + v];
+            r = is_max ? (u > r ? u : r) : r + u;
+        }
+        r = is_max ? warp_max(r) : warp_sum(r);
+        if (lane == 0) tot[v] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double sigma = *st.sigma_dev;
+        double t3 = tot[3];
+        if (!quad) {
+            t3 = 0.0;
+            for (int kk = 0; kk < k; ++kk) t3 += tot[NV + kk] * tot[4 + kk];
+        }
+        const double d = 0.5 * (2.0 * tot[1] - tot[0] + sigma * t3) - 0.5 * tot[2];
+        const double g = d > 0.0 ? sigma / 1.05 : sigma * 1.5;
+        *st.sigma_dev = g;
+        st.scalars[ESPM_S_GAMMA] = g;
+        st.scalars[ESPM_S_LS_D] = d;
+        st.dev_flags[4] = 0u;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Standalone dichotomy_simplex(num, den) -> nu  (dicotomy.py:4-55), two kernels: trace, replay.
 // acc_a > 0 selects dichotomy_simplex_acc(a, b = den, minus_c = num) (dicotomy.py:57-81, fp64 only).
 // ------------------------------------------------------------------------------------------------
@@ -1346,17 +1597,29 @@ __global__ void __launch_bounds__(PX_THREADS) dicho_trace_kernel(const TC* num_i
     if (j < p) {
         TC num[KP], den[KP];
         TC nsum = TC(0);
-        const bool acc = acc_a > 0.0;
+        const bool acc = acc_a > 0.0, pgm = acc_a < 0.0;
 #pragma unroll
         for (int kk = 0; kk < KP; ++kk) {
             num[kk] = (kk < k) ? num_i[(size_t)kk * p + j] : TC(0);
-            den[kk] = (kk < k) ? den_i[(size_t)kk * p + j] : TC(1);
-            if (kk < k) {
+            den[kk] = (kk < k && !pgm) ? den_i[(size_t)kk * p + j] : TC(1);
+            if (kk < k && !pgm) {
                 nsum += num[kk];
                 if (num[kk] < TC(0) || (!acc && den[kk] < TC(0))) err |= ESPM_DEV_NEGATIVE;
             }
         }
-        if (acc) {
+        if (acc_a < 0.0) {   // projected gradient: num holds a (dicotomy.py:83-108)
+            double av[KP];
+#pragma unroll
+            for (int kk = 0; kk < KP; ++kk) av[kk] = (double)num[kk];
+            const PgEval<KP> ev(av, k, ls_d, tol_d);
+            double lo, hi;
+            ev.bracket(lo, hi);
+            Mask128 dec;
+            dec.clear();
+            uint32_t seen;
+            err = 0u;
+            bisect_trace_rec(lo, hi, ev, maxit, bits, dec, seen, err);
+        } else if (acc) {
             double c[KP], b[KP];
 #pragma unroll
             for (int kk = 0; kk < KP; ++kk) {
@@ -1384,9 +1647,19 @@ __global__ void __launch_bounds__(PX_THREADS) dicho_apply_kernel(const TC* num_i
 #pragma unroll
         for (int kk = 0; kk < KP; ++kk) {
             num[kk] = (kk < k) ? num_i[(size_t)kk * p + j] : TC(0);
-            den[kk] = (kk < k) ? den_i[(size_t)kk * p + j] : TC(1);
+            den[kk] = (kk < k && !(acc_a < 0.0)) ? den_i[(size_t)kk * p + j] : TC(1);
         }
-        if (acc_a > 0.0) {
+        if (acc_a < 0.0) {
+            double av[KP];
+#pragma unroll
+            for (int kk = 0; kk < KP; ++kk) av[kk] = (double)num[kk];
+            const PgEval<KP> ev(av, k, ls_d, 0.0);
+            double lo, hi;
+            ev.bracket(lo, hi);
+            Mask128 none;
+            none.clear();
+            nu_out[j] = (TC)bisect_replay_rec(lo, hi, ev, its, none, 0u);
+        } else if (acc_a > 0.0) {
             double c[KP], b[KP];
 #pragma unroll
             for (int kk = 0; kk < KP; ++kk) {

@@ -12,6 +12,9 @@ enum SmallOp {
     OP_W_REDUCE,
     OP_W_FINISH,
     OP_GW_PREPARE,
+    OP_LINESEARCH,
+    OP_GRAM_GW,
+    OP_GRAM_H,
 };
 
 struct DichoArgs {
@@ -76,6 +79,17 @@ static int small_launch_t(int op, const espm_state* st, cudaStream_t s) {
         }
         case OP_GW_PREPARE:
             gw_prepare_kernel<TC><<<1, 1024, 0, s>>>(*st);
+            break;
+        case OP_LINESEARCH:
+            ESPM_KP_SWITCH(kp, (linesearch_kernel<TC, KP><<<st->px_blocks, PX_THREADS, 0, s>>>(*st)));
+            break;
+        case OP_GRAM_GW:   // over the n real channels of GW_cur [n_pad][kp]
+            gram_kernel<TC><<<st->k * st->k, 256, 0, s>>>((const TC*)st->GW_cur, st->n, st->kp, 1, st->k, st->kp,
+                                                            st->gram_gw);
+            break;
+        case OP_GRAM_H:    // over the p_loc pixels of H_next [k][ldh]
+            gram_kernel<TC><<<st->k * st->k, 256, 0, s>>>((const TC*)st->H_next, st->p_loc, 1, st->ldh, st->k, st->kp,
+                                                            st->gram_h);
             break;
         default:
             set_error("unknown small op %d", op);

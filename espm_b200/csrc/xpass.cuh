@@ -34,7 +34,16 @@ struct XPassArgs {
     int clamp_y, dual;   // SAFE variants only
     double log_shift;
     double y_shift;      // H pass: ratio = x / (y + y_shift); log_shift for algo="l2_surrogate" (updates.py:280), else 0
+    int n, p_loc;        // real channel / pixel counts (the Frobenius loss masks the padding)
 };
+
+// MODE of the X passes (template parameter):
+//   XMODE_KL      ratio sums of x / y and the KL loss terms                      (updates.py:127-128, measures.py:497-503)
+//   XMODE_FROB    Frobenius branches: the "ratio" is x itself                   (updates.py:109-118, 29-36)
+//                 H pass: numraw = GW^T X, partial of sum (y - x)^2; W pass: S = X H'^T
+//   XMODE_KL_FROB H pass only: KL ratio sums, Frobenius loss (algo="l2_surrogate" with l2=True: the H step is
+//                 updates.py:263-301, the loss is 0.5 Frobenius_loss, base.py:197-198)
+constexpr int XMODE_KL = 0, XMODE_FROB = 1, XMODE_KL_FROB = 2;
 
 template <typename TX, typename TC, int KP, bool SAFE>
 struct XPassSmem {
@@ -172,13 +181,13 @@ struct Ring {
 // ------------------------------------------------------------------------------------------------
 // H pass
 // ------------------------------------------------------------------------------------------------
-template <typename TX, typename TC, int KP, bool SAFE>
+template <typename TX, typename TC, int KP, bool SAFE, int MODE = XMODE_KL>
 __global__ void __launch_bounds__(XPASS_THREADS, (XPassSmem<TX, TC, KP, SAFE>::H_OCC))
 h_pass_kernel(const XPassArgs a) {
     using G = PassGeom<TX, TC>;
     using S = XPassSmem<TX, TC, KP, SAFE>;
     constexpr int PPL = G::PPL;
-    constexpr bool FAST32 = !SAFE && sizeof(TX) == 4 && sizeof(TC) == 4;
+    constexpr bool FAST32 = MODE == XMODE_KL && !SAFE && sizeof(TX) == 4 && sizeof(TC) == 4;
     extern __shared__ __align__(128) unsigned char smem[];
     Ring<S::H_STRIDE> ring(smem, a.depth, S::BAR_BYTES + S::MISC_BYTES);
     double* misc = reinterpret_cast<double*>(smem + S::BAR_BYTES);
@@ -323,7 +332,10 @@ h_pass_kernel(const XPassArgs a) {
                         }
                     }
 #pragma unroll
-                    for (int q = 0; q < PPL; ++q) r[q] = Num<TC>::ratio((TC)xv[q], y[q] + ysh);
+                    for (int q = 0; q < PPL; ++q) {
+                        if constexpr (MODE == XMODE_FROB) r[q] = (TC)xv[q];
+                        else r[q] = Num<TC>::ratio((TC)xv[q], y[q] + ysh);
+                    }
 #pragma unroll
                     for (int kk = 0; kk < KP; ++kk)
 #pragma unroll
@@ -348,13 +360,23 @@ h_pass_kernel(const XPassArgs a) {
 #pragma unroll
                         for (int q = 0; q < PPL; ++q) yl[q] = y[q];
                     }
+                    if constexpr (MODE != XMODE_KL) {
+                        // 0.5 Frobenius_loss (measures.py:350-385) of the unclamped G W H; padding is masked out
+                        const bool c_real = st * G::CS + c < a.n;
 #pragma unroll
-                    for (int q = 0; q < PPL; ++q) {
-                        const TC x = (TC)xv[q];
-                        if (x > TC(0)) {
-                            xl = fma(Num<TC>::vmax(x, ls), Num<TC>::log2_fast(yl[q]), xl);
-                        } else {
-                            zl += __log2f((float)yl[q]);
+                        for (int q = 0; q < PPL; ++q) {
+                            const TC d = y[q] - (TC)xv[q];
+                            if (c_real && tile * TILE_PX + lane_px + q < a.p_loc) xl = fma(d, d, xl);
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < PPL; ++q) {
+                            const TC x = (TC)xv[q];
+                            if (x > TC(0)) {
+                                xl = fma(Num<TC>::vmax(x, ls), Num<TC>::log2_fast(yl[q]), xl);
+                            } else {
+                                zl += __log2f((float)yl[q]);
+                            }
                         }
                     }
                 }
@@ -390,7 +412,7 @@ h_pass_kernel(const XPassArgs a) {
     if (threadIdx.x == 0) {
         double s = 0.0;
         for (int w = 0; w < N_CONSUMER_WARPS; ++w) s += misc[w];
-        a.xlogy_part[blockIdx.x] = s * 0.6931471805599453094;  // log2 -> ln
+        a.xlogy_part[blockIdx.x] = (MODE != XMODE_KL) ? s : s * 0.6931471805599453094;  // log2 -> ln
     }
 }
 
@@ -411,14 +433,14 @@ __host__ __device__ inline int w_last_cta(int cb, int n_tiles, int upc) {
     return (int)((((long long)cb + 1) * n_tiles - 1) / upc);
 }
 
-template <typename TX, typename TC, int KP, bool SAFE>
+template <typename TX, typename TC, int KP, bool SAFE, int MODE = XMODE_KL>
 __global__ void __launch_bounds__(XPASS_THREADS, (XPassSmem<TX, TC, KP, SAFE>::W_OCC))
 w_pass_kernel(const XPassArgs a) {
     using G = PassGeom<TX, TC>;
     using S = XPassSmem<TX, TC, KP, SAFE>;
     constexpr int PPL = G::PPL;
     constexpr int CPW = G::CPW;
-    constexpr bool FAST32 = S::FAST32;
+    constexpr bool FAST32 = MODE == XMODE_KL && S::FAST32;
     constexpr bool ACC_REG = S::ACC_REG;
     extern __shared__ __align__(128) unsigned char smem[];
     Ring<S::W_STRIDE> ring(smem, a.depth, S::BAR_BYTES + S::MISC_BYTES);
@@ -587,13 +609,18 @@ w_pass_kernel(const XPassArgs a) {
                 }
 #pragma unroll
                 for (int q = 0; q < PPL; ++q) {
-                    TC y = gw[0] * h[0][q];
+                    TC rq;
+                    if constexpr (MODE == XMODE_FROB) {
+                        rq = (TC)xv[q];                       // S = X H'^T (updates.py:33)
+                    } else {
+                        TC y = gw[0] * h[0][q];
 #pragma unroll
-                    for (int kk = 1; kk < KP; ++kk) y = fma(gw[kk], h[kk][q], y);
-                    if constexpr (SAFE) {
-                        if (a.clamp_y) y = Num<TC>::vmax(y, ls);
+                        for (int kk = 1; kk < KP; ++kk) y = fma(gw[kk], h[kk][q], y);
+                        if constexpr (SAFE) {
+                            if (a.clamp_y) y = Num<TC>::vmax(y, ls);
+                        }
+                        rq = Num<TC>::ratio((TC)xv[q], y);
                     }
-                    const TC rq = Num<TC>::ratio((TC)xv[q], y);
 #pragma unroll
                     for (int kk = 0; kk < KP; ++kk) t[kk] = fma(rq, h[kk][q], t[kk]);
                 }

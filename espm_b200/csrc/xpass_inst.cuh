@@ -13,11 +13,23 @@ struct XPassLaunch {
     int safe;
     int grid;
     int smem;
+    int mode;   // XMODE_*
 };
 
 template <typename TX, typename TC, int KP, bool SAFE>
 static int xpass_do(const XPassLaunch& l, const XPassArgs* a, int* occ_out, cudaStream_t stream) {
-    auto kern = (l.kind == XPASS_H) ? h_pass_kernel<TX, TC, KP, SAFE> : w_pass_kernel<TX, TC, KP, SAFE>;
+    void (*kern)(const XPassArgs) =
+        (l.kind == XPASS_H) ? h_pass_kernel<TX, TC, KP, SAFE, XMODE_KL> : w_pass_kernel<TX, TC, KP, SAFE, XMODE_KL>;
+    if constexpr (!SAFE) {
+        // Frobenius variants (no division, so no clamped instances)
+        if (l.mode == XMODE_FROB)
+            kern = (l.kind == XPASS_H) ? h_pass_kernel<TX, TC, KP, false, XMODE_FROB> : w_pass_kernel<TX, TC, KP, false, XMODE_FROB>;
+        else if (l.mode == XMODE_KL_FROB && l.kind == XPASS_H)
+            kern = h_pass_kernel<TX, TC, KP, false, XMODE_KL_FROB>;
+    } else if (l.mode != XMODE_KL) {
+        set_error("the Frobenius X passes have no clamped (SAFE) instances");
+        return ESPM_ERR_UNSUPPORTED;
+    }
     ESPM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, l.smem));
     if (occ_out) {
         ESPM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ_out, kern, XPASS_THREADS, l.smem));

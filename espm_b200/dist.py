@@ -46,6 +46,15 @@ class Shard:
     def allreduce_sum(self, t):
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
 
+    def allreduce_max_scalar(self, t):
+        """Maximum over the ranks of a 0-d / 1-element float64 tensor (any device the backend accepts)."""
+        dev = t.device
+        v = t.reshape(1).clone()
+        if dist.get_backend(self.group) == "nccl" and v.device.type != "cuda":
+            v = v.cuda()
+        dist.all_reduce(v, op=dist.ReduceOp.MAX, group=self.group)
+        return v.to(dev)[0]
+
     def allreduce_hstats(self, hstats, kp):
         """hstats = {rowsum[kp], rowsum(max(.,ls))[kp], rowmax[kp]} (float64)."""
         dist.all_reduce(hstats[:2 * kp], op=dist.ReduceOp.SUM, group=self.group)

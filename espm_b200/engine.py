@@ -56,7 +56,8 @@ class FitEngine:
                  log_shift=1e-14, dicotomy_tol=1e-5, dicotomy_tol_w=1e-5, tol=1e-4, sigma=8.0,
                  simplex_H=False, simplex_W=True, simplex_rows=None, fixed_H=None, fixed_W=None,
                  x_scale=1.0, max_records=512, device=None, shard=None, c_dtype=None, clamp_init=True,
-                 x_local=False, ingest=None, algo="log_surrogate"):
+                 x_local=False, ingest=None, algo="log_surrogate", l2=False, l2_h=False, linesearch=False,
+                 gamma_pg=None):
         """
         X : (n, p) array-like view (any strides; C order or the transposed hyperspy layout are
             uploaded without a host copy).  G : (n, m) array or None (identity).  W0 : (m, k), H0 : (k, p).
@@ -138,9 +139,28 @@ class FitEngine:
             flags |= L.FLAG_G_IDENTITY
         if algo == "l2_surrogate":
             flags |= L.FLAG_HQ                   # quadratic-surrogate H step (updates.py:263-301)
+        elif algo == "bmd":
+            flags |= L.FLAG_BMD                  # use_bregman branches (updates.py:40-48, 120-125)
+        elif algo == "projected_gradient":
+            flags |= L.FLAG_PG                   # proj_grad_step_h / _w (updates.py:347-391)
         elif algo != "log_surrogate":
-            raise NotImplementedError("espm_b200: algo=%r is not available on the device" % (algo,))
+            raise ValueError("Unknown algorithm")                      # smooth_nmf.py:374
+        if l2:
+            flags |= L.FLAG_L2                   # Frobenius loss + W step (base.py:197-198, updates.py:29-36)
+        if l2_h:
+            flags |= L.FLAG_L2_H                 # Frobenius H step / gradient (updates.py:109-118, 330-332)
+        if flags & (L.FLAG_BMD | L.FLAG_PG | L.FLAG_L2):
+            flags &= ~L.FLAG_SIMPLEX_W           # those W branches have no simplex projection (updates.py:29-48)
+        if linesearch:
+            if flags & L.FLAG_PG:
+                raise NotImplementedError("espm_b200: linesearch with algo='projected_gradient' is not available")
+            if shard is not None:
+                raise NotImplementedError("espm_b200: linesearch is not available for pixel-sharded fits")
+            flags |= L.FLAG_LINESEARCH
+        if shard is not None and (l2 or l2_h):
+            raise NotImplementedError("espm_b200: the Frobenius branches are not available for pixel-sharded fits")
         self.algo = algo
+        self.gamma_pg = gamma_pg
         mu_arr = np.zeros(L.MAX_K)
         if np.isscalar(mu):
             mu_arr[:k] = float(mu)
@@ -201,6 +221,16 @@ class FitEngine:
         self.mask = torch.zeros(4 * max(self.world, 1), dtype=torch.int32, device=dev)
         self.bisect_dec = torch.zeros(5 * p_pad if simplex_H else 1, dtype=torch.int32, device=dev)
         st.bisect_dec = self.bisect_dec.data_ptr()
+        # ---- alternative update rules ----
+        self.gram = zeros(2, kp * kp, dtype=torch.float64)
+        st.gram_gw, st.gram_h = self.gram[0].data_ptr(), self.gram[1].data_ptr()
+        self.sigma_dev = None
+        if st.flags & L.FLAG_LINESEARCH:
+            self.sigma_dev = torch.full((1,), float(sigma), dtype=torch.float64, device=dev)
+            self.ls_part = zeros(st.px_blocks, 4 + kp, dtype=torch.float64)
+            st.sigma_dev, st.ls_part = self.sigma_dev.data_ptr(), self.ls_part.data_ptr()
+        if gamma_pg is not None:
+            st.gamma_h, st.gamma_w = float(gamma_pg[0]), float(gamma_pg[1])
         self.dev_flags = torch.zeros(8, dtype=torch.int32, device=dev)
         self.coop_part = zeros(L.COOP_BLOCKS * (2 * L.MAX_K + 1), dtype=torch.float64)
         self.max_records = int(max_records)
@@ -245,6 +275,9 @@ class FitEngine:
         self.norm_factor = None
         self.n_zero_rows = self.n_zero_cols = 0
         self._upload_x(X, x_scale, ingest)
+        self.x_colsum = self.x_rowsum = None
+        if st.flags & L.FLAG_BMD:
+            self.compute_x_sums()
         self.set_G(G, prepare=False)
         self._init_WH(W0, H0)
 
@@ -397,6 +430,25 @@ class FitEngine:
             self.shard.allreduce_sum(c)
         self.const_KL = float(c.item())
 
+    def compute_x_sums(self):
+        """Per-pixel and per-channel sums of the (repaired, normalised) X: sigmaR of the Bregman steps
+        (updates.py:43-45, 121) and the ingredients of the Lipschitz bounds (updates.py:393-413)."""
+        st = self.st
+        self.x_colsum = torch.zeros(st.p_pad, dtype=self.cdt, device=self.device)
+        part = torch.zeros(st.n_tiles, st.n_pad, dtype=torch.float64, device=self.device)
+        L.check(self.lib.espm_x_sums(ctypes.byref(st), ctypes.c_void_p(self.x_colsum.data_ptr()),
+                                     ctypes.c_void_p(part.data_ptr()), self.stream))
+        rows = part.sum(0)
+        if self.shard is not None:
+            self.shard.allreduce_sum(rows)
+        self.x_rowsum = rows.to(self.cdt)
+        self.x_total = float(rows[:self.n].sum().item())
+        st.x_colsum, st.x_rowsum, st.x_total = self.x_colsum.data_ptr(), self.x_rowsum.data_ptr(), self.x_total
+        return self.x_colsum, self.x_rowsum
+
+    def set_gamma_pg(self, gamma_h, gamma_w):
+        self.st.gamma_h, self.st.gamma_w = float(gamma_h), float(gamma_w)
+
     def set_G(self, G, prepare=True):
         """(Re)load G (base.py:269-274, 388-389).  ``prepare`` also recomputes GW for W_cur."""
         st = self.st
@@ -413,6 +465,9 @@ class FitEngine:
             if self.colsum_G is None:
                 self.colsum_G = torch.zeros(self.m, dtype=self.cdt, device=self.device)
             st.G, st.Gt, st.colsum_G = self.G.data_ptr(), self.Gt.data_ptr(), self.colsum_G.data_ptr()
+            if st.flags & L.FLAG_L2:
+                self.GG = (self.Gt @ self.G).contiguous()      # G^T G (updates.py:30), m x m, once per G
+                st.GG = self.GG.data_ptr()
             L.check(self.lib.espm_colsum_g(ctypes.byref(st), ctypes.c_void_p(self.colsum_G.data_ptr()), self.stream))
         if prepare:
             # GW for the CURRENT W under the new G: write into the `next` slot, then swap GW only
@@ -469,6 +524,8 @@ class FitEngine:
         self._set_record(slot)
         self._seq_m += 1
         self.st.seq_m = self._seq_m                          # mask exchange of this evaluation (peer mode)
+        if self.st.flags & L.FLAG_L2_H:
+            L.check(self.lib.espm_gram(ctypes.byref(self.st), 0, self.stream))   # (G W)^T (G W), updates.py:115
         self._call(self.lib.espm_h_pass, "h_pass")
         self._call(self.lib.espm_h_finish, "h_finish")      # its last CTA also writes the scalar record
 
@@ -482,6 +539,10 @@ class FitEngine:
             self._call(self.lib.espm_h_apply, "h_apply")
         if not self.peer:
             self._exchange_halo(self.ih[2])
+        if st.flags & L.FLAG_LINESEARCH:
+            self._call(self.lib.espm_linesearch, "linesearch")   # smooth_nmf.py:376-382, gamma_ stays on the device
+        if st.flags & L.FLAG_L2:
+            L.check(self.lib.espm_gram(ctypes.byref(st), 1, self.stream))        # H' H'^T, updates.py:31
         self._seq_s += 1
         st.seq_s = self._seq_s                               # S exchange of this update (peer mode)
         self._call(self.lib.espm_w_pass, "w_pass")
@@ -516,6 +577,8 @@ class FitEngine:
         self._call(self.lib.espm_h_stats)      # rebuilds Ht from H_next (= H_cur); hstats go to the `next` slot
         st.hstats_next = st.hstats_cur
         self._set_record(0)
+        if st.flags & L.FLAG_L2:
+            L.check(self.lib.espm_gram(ctypes.byref(st), 1, self.stream))
         self._call(self.lib.espm_w_pass)
         if self.shard is not None:
             self._call(self.lib.espm_w_reduce)

@@ -9,8 +9,8 @@ initialises and runs the stop tests; every pass over X happens in the CUDA kerne
 Supported on the device: ``algo="log_surrogate"`` (the default) and ``"l2_surrogate"`` with the KL loss, ``simplex_H`` /
 ``simplex_W``, ``mu`` (scalar or per phase), ``lambda_L`` with ``shape_2d`` (5-point Laplacian) or
 without (identity), ``fixed_H`` / ``fixed_W``, ``normalize``, ``G`` as ``None`` / ndarray / physical
-model, ``hspy_comp``.  Other ``algo`` values, ``l2=True`` and ``linesearch=True`` raise
-``NotImplementedError`` (SURVEY.md section 8f lists them as "next").
+model, ``hspy_comp``.  ``linesearch`` with ``projected_gradient`` and ground-truth tracking raise
+``NotImplementedError``.
 """
 import sys
 import time
@@ -133,14 +133,12 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
             reset("l2", False, "The l2 parameter must be False when using the algorithm " + self.algo)
 
     def _require_supported(self):
-        if self.algo not in ("log_surrogate", "l2_surrogate"):
-            raise NotImplementedError(
-                "espm_b200 runs algo='log_surrogate' and 'l2_surrogate' on the device; algo=%r is not "
-                "available yet" % self.algo)
-        if self.l2:
-            raise NotImplementedError("espm_b200: the Frobenius loss (l2=True) is not available yet")
-        if self.linesearch:
-            raise NotImplementedError("espm_b200: linesearch=True is not available yet")
+        if self.algo == "projected_gradient":
+            if self.simplex_W:                                          # updates.py:365-366
+                raise NotImplementedError(
+                    "Simplex constraint not implemented for W using the projected gradient method")
+            if self.linesearch:
+                raise NotImplementedError("espm_b200: linesearch with algo='projected_gradient' is not available yet")
         if self.true_D is not None and self.true_H is not None:
             raise NotImplementedError("espm_b200: ground-truth tracking (true_D/true_H) is not available yet")
 
@@ -173,13 +171,18 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
         raise AttributeError("%r object has no attribute %r" % (type(self).__name__, name))
 
     # ------------------------------------------------------------------ loss
-    def _loss_from_record(self, rec):
-        """base.py:203-205 + smooth_nmf.py:461-469 from one scalar record of the device."""
+    def _loss_from_record(self, rec, gamma=None):
+        """base.py:197-205 + smooth_nmf.py:461-473 from one scalar record of the device."""
         numel = self.GWH_numel_
-        kl = (rec[L.S_SUMY] - rec[L.S_XLOGY] + self.const_KL_) / numel
+        if self.l2:                      # 0.5 * Frobenius_loss: the H pass accumulated sum (G W H - X)^2
+            kl = 0.5 * rec[L.S_XLOGY] / numel
+        else:
+            kl = (rec[L.S_SUMY] - rec[L.S_XLOGY] + self.const_KL_) / numel
         reg = rec[L.S_LOGREG] / numel
         lap = 0.5 * self.lambda_L * rec[L.S_LAPL] / numel
-        self.detailed_loss_ = [kl, reg, lap, self.gamma_]
+        if gamma is None:
+            gamma = self.gamma_[0] if isinstance(self.gamma_, list) else self.gamma_
+        self.detailed_loss_ = [kl, reg, lap, gamma]
         return kl + reg + lap
 
     def __getstate__(self):
@@ -200,7 +203,7 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
                 self.const_KL_ = const
         val, det = full_loss(Xe, self.G_ if not self._identity_G else None, W, H, mu=self.mu,
                              epsilon_reg=self.epsilon_reg, lambda_L=self.lambda_L, shape_2d=self.shape_2d,
-                             log_shift=self.log_shift, const=const, average=average)
+                             log_shift=self.log_shift, const=const, average=average, l2=bool(self.l2))
         self.GWH_numel_ = Xe.shape[0] * H.shape[1]
         self.detailed_loss_ = det + [self.gamma_ if not isinstance(self.gamma_, list) else self.gamma_[0]]
         return val
@@ -242,7 +245,16 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
                                             self.simplex_H, self.simplex_W, self.log_shift, self.physics_model_)
         del X_init
         self.GWH_numel_ = n * p
-        self.gamma_ = _SIGMA_L if self.gamma is None else self.gamma   # smooth_nmf.py:290-306
+        pg = self.algo == "projected_gradient"
+        if self.algo == "bmd" and G_full.shape[0] != G_full.shape[1]:
+            # the reference's Bregman W step compares G with eye(n) (updates.py:42) and cannot broadcast otherwise
+            raise ValueError("operands could not be broadcast together with shapes (%d,%d) (%d,%d) "
+                             % (G_full.shape + (G_full.shape[0], G_full.shape[0])))
+        bmd_identity = self.algo == "bmd" and (self._identity_G or np.allclose(G_full, np.eye(G_full.shape[0])))
+        if self.gamma is not None:                                     # smooth_nmf.py:290-306
+            self.gamma_ = list(self.gamma) if isinstance(self.gamma, list) else self.gamma
+        elif not pg:
+            self.gamma_ = _SIGMA_L
         simplex_rows = None
         if self.physics_model_ is not None and self.simplex_W:
             simplex_rows = self.physics_model_.NMF_simplex()           # updates.py:62-65
@@ -257,14 +269,32 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
             if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
                 from .dist import make_shard
                 shard = make_shard()
-        eng = FitEngine(Xv, None if self._identity_G else G, W0, H0,
+        G_dev = None if (self._identity_G or bmd_identity) else G
+        eng = FitEngine(Xv, G_dev, W0, H0,
                         shape_2d=self.shape_2d, lambda_L=self.lambda_L, mu=self.mu, epsilon_reg=self.epsilon_reg,
                         log_shift=self.log_shift, dicotomy_tol=self.dicotomy_tol, dicotomy_tol_w=_DICOTOMY_TOL,
-                        tol=self.tol, sigma=float(self.gamma_), simplex_H=self.simplex_H, simplex_W=self.simplex_W,
-                        simplex_rows=simplex_rows, fixed_H=self.fixed_H, fixed_W=self.fixed_W,
-                        max_records=max(max_iter, 1) + 8, shard=shard, algo=self.algo,
+                        tol=self.tol, sigma=_SIGMA_L if pg else float(self.gamma_), simplex_H=self.simplex_H,
+                        simplex_W=self.simplex_W, simplex_rows=simplex_rows, fixed_H=self.fixed_H,
+                        fixed_W=None if pg else self.fixed_W,     # smooth_nmf.py:430-437 passes no fixed_W
+                        max_records=max(max_iter, 1) + 8, shard=shard, algo=self.algo, l2=bool(self.l2),
+                        linesearch=bool(self.linesearch), gamma_pg=self.gamma_ if pg and self.gamma is not None else None,
+                        clamp_init=True,
                         ingest=dict(eps=self.log_shift, normalize=self.n_components if self.normalize else None))
         self._engine = eng
+        if pg and self.gamma is None:
+            # estimate_Lipschitz_bound_h / _w (updates.py:393-413) with W = H = log_shift everywhere: they reduce to
+            # max_j colsum(X)_j / (k ls^2) + 2 lambda_L + mu eps   and   max_c rowsum(X)_c / (k ls^2 rowsum(G)_c^2)
+            cs, rs = eng.compute_x_sums()
+            k_, ls_ = self.n_components, self.log_shift
+            cmax = cs[:eng.p_loc].max().to("cpu", dtype=__import__("torch").float64)
+            if shard is not None:
+                cmax = shard.allreduce_max_scalar(cmax)
+            rsG = np.ones(n) if self._identity_G else np.asarray(G_full, dtype=np.float64).sum(1)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                gamma_W = float(np.max(rs[:n].cpu().numpy().astype(np.float64) / (k_ * ls_ ** 2 * rsG ** 2)))
+            gamma_H = float(cmax) / (k_ * ls_ ** 2) + 2 * self.lambda_L + self.mu * self.epsilon_reg
+            self.gamma_ = [gamma_H, gamma_W]
+            eng.set_gamma_pg(float(np.max(gamma_H)), gamma_W)
         gwf = eng.gw_flags_init()
         if gwf & L.DEV_GW_ZERO_ROW:        # x / 0 would appear in the first pass: updates.py:129-131, 54-56
             eng.enable_clamp()
@@ -319,6 +349,8 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
 
     # ---- loop variants -----------------------------------------------------------------------
     def _append(self, rec):
+        if self.linesearch and self.algo != "projected_gradient":
+            self.gamma_ = float(rec[L.S_GAMMA])        # gamma_ after this iteration's update (smooth_nmf.py:378-382)
         loss = self._loss_from_record(rec)
         self.losses_.append(loss)
         self.detailed_losses_.append(self.detailed_loss_)

@@ -113,9 +113,10 @@ def _raise_flags(rec):
 def multiplicative_step_h(X, G, W, H, simplex_H=False, mu=0, log_shift=_LS, epsilon_reg=1, safe=True,
                           dicotomy_tol=_TOL, lambda_L=0, L=None, l2=False, sigmaL=_SIGMA, fixed_H=None,
                           use_bregman=False, return_its=False):
-    """updates.py:83-156 (KL branch)."""
-    if l2 or use_bregman:
-        raise NotImplementedError("espm_b200: only the KL multiplicative update is implemented on the device")
+    """updates.py:83-156: the KL, Frobenius (``l2``) and Bregman (``use_bregman``) branches."""
+    if l2:                                                            # updates.py:110-114
+        assert lambda_L == 0
+        assert (mu == 0) if np.isscalar(mu) else (np.asarray(mu) == 0).all()
     p = np.shape(H)[1]
     shape_2d = None
     if lambda_L != 0:
@@ -127,7 +128,8 @@ def multiplicative_step_h(X, G, W, H, simplex_H=False, mu=0, log_shift=_LS, epsi
     Ge = None if (G is None or _is_identity(np.asarray(G))) else G
     eng = _engine(X, Ge, W, H, shape_2d=shape_2d, lambda_L=lambda_L, mu=mu, epsilon_reg=epsilon_reg,
                   log_shift=log_shift, dicotomy_tol=dicotomy_tol, sigma=sigmaL, simplex_H=simplex_H,
-                  simplex_W=False, fixed_H=fixed_H, max_records=8, clamp_init=bool(safe))   # updates.py:104-105
+                  simplex_W=False, fixed_H=fixed_H, max_records=8, clamp_init=bool(safe),   # updates.py:104-105
+                  algo="bmd" if (use_bregman and not l2) else "log_surrogate", l2_h=bool(l2))
     Hn, rec = eng.step_h_only()
     if int(rec[_L.S_DEV_FLAGS]) & _L.DEV_NONFINITE:      # updates.py:129-131: NaN -> GWH = max(GWH, log_shift)
         eng.enable_clamp()
@@ -163,9 +165,14 @@ def multiplicative_step_hq(X, G, W, H, simplex_H=True, log_shift=_LS, safe=True,
 
 def multiplicative_step_w(X, G, W, H, simplex_W=False, log_shift=_LS, safe=True, l2=False, fixed_W=None,
                           physics_model=None, use_bregman=False):
-    """updates.py:6-78 (KL branch)."""
-    if l2 or use_bregman:
-        raise NotImplementedError("espm_b200: only the KL multiplicative update is implemented on the device")
+    """updates.py:6-78: the KL, Frobenius (``l2``) and Bregman (``use_bregman``) branches."""
+    bmd = bool(use_bregman) and not l2
+    if bmd:
+        Gm = np.asarray(G)
+        if np.allclose(Gm, np.eye(Gm.shape[0])):     # updates.py:42 (raises for a non-square G, like the reference)
+            G = None
+    if l2 or bmd:
+        simplex_W = False                             # those branches never project (updates.py:29-48)
     rows = None
     if simplex_W and physics_model is not None:
         rows = physics_model.NMF_simplex()
@@ -174,13 +181,121 @@ def multiplicative_step_w(X, G, W, H, simplex_W=False, log_shift=_LS, safe=True,
         raise ValueError("No solution exists!")
     Ge = None if (G is None or _is_identity(np.asarray(G))) else G
     eng = _engine(X, Ge, W, H, log_shift=log_shift, simplex_H=False, simplex_W=simplex_W, simplex_rows=rows,
-                  fixed_W=fixed_W, max_records=8, clamp_init=bool(safe))                        # updates.py:26-27
+                  fixed_W=fixed_W, max_records=8, clamp_init=bool(safe),                        # updates.py:26-27
+                  algo="bmd" if bmd else "log_surrogate", l2=bool(l2))
     Wn, rec = eng.step_w_only()
     if int(rec[_L.S_DEV_FLAGS]) & _L.DEV_NONFINITE:      # updates.py:54-56
         eng.enable_clamp()
         Wn, rec = eng.step_w_only()
     _raise_flags(rec)
     return Wn
+
+
+def gradH(X, G, W, H, mu=0, lambda_L=0, L=None, epsilon_reg=1, log_shift=_LS, safe=False, l2=False):
+    """updates.py:316-345: gradient of the (KL or Frobenius) data term + regularisers with respect to H."""
+    p = np.shape(H)[1]
+    shape_2d = None
+    if lambda_L != 0:
+        if L is None:
+            raise ValueError("Please provide the laplacian")
+        shape_2d, _ = _shape_from_L(L, p)
+    Ge = None if (G is None or _is_identity(np.asarray(G))) else G
+    eng = _engine(X, Ge, W, H, shape_2d=shape_2d, lambda_L=lambda_L, mu=mu, epsilon_reg=epsilon_reg,
+                  log_shift=log_shift, simplex_H=False, simplex_W=False, max_records=8, clamp_init=bool(safe),
+                  algo="projected_gradient", l2_h=bool(l2), gamma_pg=(1.0, 1.0))
+    eng.evaluate(0)
+    return eng.den[:eng.k, :eng.p_loc].cpu().numpy()
+
+
+def gradW(X, G, W, H, log_shift=_LS, safe=False, l2=False):
+    """updates.py:303-314: gradient of the data term with respect to W."""
+    Ge = None if (G is None or _is_identity(np.asarray(G))) else G
+    eng = _engine(X, Ge, W, H, log_shift=log_shift, simplex_H=False, simplex_W=False, max_records=8,
+                  clamp_init=bool(safe), algo="projected_gradient", l2=bool(l2), gamma_pg=(1.0, 1.0))
+    eng.step_w_only()
+    return eng.w_den.cpu().numpy()
+
+
+def proj_grad_step_h(X, G, W, H, gamma, simplex_H=True, mu=0, log_shift=_LS, epsilon_reg=1, safe=True,
+                     dicotomy_tol=_TOL, lambda_L=0, L=None, l2=False, fixed_H=None, return_its=False):
+    """updates.py:369-391: gradient step in H, then projection on the simplex (dicotomy.py:83-108) / the orthant."""
+    p = np.shape(H)[1]
+    shape_2d = None
+    if lambda_L != 0:
+        if L is None:
+            raise ValueError("Please provide the laplacian")
+        shape_2d, _ = _shape_from_L(L, p)
+    if simplex_H and log_shift > 0 and np.shape(H)[0] * log_shift >= 1:
+        raise ValueError("No solution exists!")                       # dicotomy.py:94-96
+    Ge = None if (G is None or _is_identity(np.asarray(G))) else G
+    eng = _engine(X, Ge, W, H, shape_2d=shape_2d, lambda_L=lambda_L, mu=mu, epsilon_reg=epsilon_reg,
+                  log_shift=log_shift, dicotomy_tol=dicotomy_tol, simplex_H=simplex_H, simplex_W=False,
+                  fixed_H=fixed_H, max_records=8, clamp_init=bool(safe), algo="projected_gradient", l2_h=bool(l2),
+                  gamma_pg=(float(gamma), 1.0))
+    Hn, rec = eng.step_h_only()
+    if int(rec[_L.S_DEV_FLAGS]) & _L.DEV_BRACKET:
+        raise AssertionError("espm_b200: bisection preconditions violated (dicotomy.py:141-144)")
+    if return_its:
+        return Hn, int(rec[_L.S_BISECT_ITS_H])
+    return Hn
+
+
+def proj_grad_step_w(X, G, W, H, gamma, simplex_W=True, log_shift=_LS, safe=True, l2=False, fixed_W=None):
+    """updates.py:347-367: gradient step in W and projection on the orthant."""
+    Ge = None if (G is None or _is_identity(np.asarray(G))) else G
+    eng = _engine(X, Ge, W, H, log_shift=log_shift, simplex_H=False, simplex_W=False, fixed_W=fixed_W, max_records=8,
+                  clamp_init=bool(safe), algo="projected_gradient", l2=bool(l2), gamma_pg=(1.0, float(gamma)))
+    Wn, _ = eng.step_w_only()
+    if simplex_W:                                                     # updates.py:365-366 (after the step, like there)
+        raise NotImplementedError("Simplex constraint not implemented for W using the projected gradient method")
+    return Wn
+
+
+def estimate_Lipschitz_bound_w(log_shift, X, G, k):
+    """updates.py:393-401.  With W = H = log_shift everywhere the bound is max_c rowsum(X)_c / (k ls^2 rowsum(G)_c^2);
+    the sums of X come from the device."""
+    X = np.asarray(X)
+    eng = _engine(X, None, np.ones((X.shape[0], k), dtype=X.dtype if X.dtype in (np.float32, np.float64) else float),
+                  np.ones((k, X.shape[1])), simplex_H=False, simplex_W=False, max_records=8)
+    _, rs = eng.compute_x_sums()
+    rs = rs[:X.shape[0]].cpu().numpy().astype(np.float64)
+    rsG = np.ones(X.shape[0]) if G is None else np.asarray(G, dtype=np.float64).sum(1)
+    return float(np.max(rs / (k * log_shift ** 2 * rsG ** 2)))
+
+
+def estimate_Lipschitz_bound_h(log_shift, X, G, k, lambda_L=0, mu=0, epsilon_reg=1):
+    """updates.py:403-413: max_j colsum(X)_j / (k ls^2) + 2 lambda_L + mu eps (G cancels)."""
+    X = np.asarray(X)
+    eng = _engine(X, None, np.ones((X.shape[0], k), dtype=X.dtype if X.dtype in (np.float32, np.float64) else float),
+                  np.ones((k, X.shape[1])), simplex_H=False, simplex_W=False, max_records=8)
+    cs, _ = eng.compute_x_sums()
+    return float(cs[:X.shape[1]].max().item()) / (k * log_shift ** 2) + 2 * lambda_L + mu * epsilon_reg
+
+
+def dichotomy_simplex_projected_gradient(a, log_shift=_LS, tol=_TOL, maxit=_MAXIT, return_its=False):
+    """dicotomy.py:83-108: per-column root of sum_i max(a_i + x, log_shift) - 1."""
+    lib = _L.load()
+    a = np.asarray(a, dtype=np.float64)
+    if a.ndim == 1:
+        a = a[:, None]
+    k, p = a.shape
+    if log_shift > 0 and k * log_shift >= 1:
+        raise ValueError("No solution exists!")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    d_a = torch.as_tensor(np.ascontiguousarray(a)).to(dev)
+    nu = torch.empty(p, dtype=torch.float64, device=dev)
+    mask = torch.zeros(4, dtype=torch.int32, device=dev)
+    flags = torch.zeros(4, dtype=torch.int32, device=dev)
+    its = torch.zeros(1, dtype=torch.int32, device=dev)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    _L.check(lib.espm_dichotomy_simplex_pg(_L.F64, k, p, d_a.data_ptr(), float(log_shift), float(tol), int(maxit),
+                                          nu.data_ptr(), mask.data_ptr(), flags.data_ptr(), its.data_ptr(), stream))
+    if int(flags[0].item()) & _L.DEV_BRACKET:
+        raise AssertionError("dichotomy_simplex_projected_gradient: preconditions violated (dicotomy.py:141-144)")
+    out = nu.cpu().numpy()
+    if return_its:
+        return out, int(its.item())
+    return out
 
 
 def dichotomy_simplex(num, denum, log_shift=_LS, tol=_TOL, maxit=_MAXIT, return_its=False):
@@ -256,16 +371,31 @@ def dichotomy_simplex_acc(a, b, minus_c, log_shift=_LS, tol=_TOL, maxit=_MAXIT, 
 
 
 def full_loss(X, G, W, H, mu=0, epsilon_reg=1, lambda_L=0, shape_2d=None, log_shift=_LS, const=0.0,
-              average=True):
-    """KL + log-reg + Laplacian loss of (W, H) (base.py:167-207, smooth_nmf.py:457-475).
+              average=True, l2=False):
+    """KL (or 0.5 Frobenius, ``l2``) + log-reg + Laplacian loss of (W, H) (base.py:167-207, smooth_nmf.py:457-475).
     Returns (loss, [kl, log_reg, lapl])."""
     eng = _engine(X, G, W, H, shape_2d=shape_2d, lambda_L=lambda_L, mu=mu, epsilon_reg=epsilon_reg,
-                  log_shift=log_shift, simplex_H=False, simplex_W=False, max_records=8)
+                  log_shift=log_shift, simplex_H=False, simplex_W=False, max_records=8, l2=bool(l2),
+                  clamp_init=not l2)
     eng.evaluate(0)
     rec = eng.read_records(0, 1)[0]
     numel = X.shape[0] * np.shape(H)[1] if average else 1
     kl, reg, lap = eng.loss_parts(rec, const, numel)
+    if l2:
+        kl = 0.5 * rec[_L.S_XLOGY] / numel
     return kl + reg + lap, [kl, reg, lap]
+
+
+def Frobenius_loss(X, W, H, average=False):
+    """measures.py:350-385 with ``W`` playing the role of G W (n x k): sum (W H - X)^2."""
+    X = np.asarray(X)
+    if X.dtype not in (np.float32, np.float64):
+        X = X.astype(np.float64)
+    eng = _engine(X, None, W, H, log_shift=0.0, simplex_H=False, simplex_W=False, max_records=8, l2=True,
+                  clamp_init=False)
+    eng.evaluate(0)
+    val = eng.read_records(0, 1)[0][_L.S_XLOGY]
+    return val / X.size if average else val
 
 
 def KLdiv_loss(X, W, H, log_shift=_LS, average=False):

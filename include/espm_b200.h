@@ -73,6 +73,13 @@ typedef enum espm_status {
                                           * H' = (-(b+nu) + sqrt((b+nu)^2 + 4 a c)) / 2a with a = lambda sigma */
 #define ESPM_FLAG_FUSED_WREDUCE (1u << 12) /* espm_w_finish also does the work of espm_w_reduce (single-GPU fits) */
 #define ESPM_FLAG_PEER        (1u << 13) /* pixel-sharded fit exchanging through peer memory (NVLink), see below */
+#define ESPM_FLAG_BMD         (1u << 14) /* algo="bmd": the use_bregman branches (updates.py:40-48, 120-125) */
+#define ESPM_FLAG_PG          (1u << 15) /* algo="projected_gradient": proj_grad_step_h / _w (updates.py:347-391) */
+#define ESPM_FLAG_L2          (1u << 16) /* l2=True: 0.5 Frobenius loss (base.py:197-198, measures.py:350-385) and the
+                                          * Frobenius W step / W gradient (updates.py:29-36, 307-308) */
+#define ESPM_FLAG_L2_H        (1u << 17) /* Frobenius H step / H gradient (updates.py:109-118, 330-332); only reachable
+                                          * through the operator-level API, like in the reference */
+#define ESPM_FLAG_LINESEARCH  (1u << 18) /* smooth_nmf.py:376-386: gamma_ adapts from diff_surrogate; see sigma_dev */
 
 /* bits of the device-side error word (espm_state.dev_flags[0]) */
 #define ESPM_DEV_NONFINITE    (1u << 0)  /* non-finite ratio sums (x/0): caller must redo with CLAMP_Y */
@@ -95,7 +102,9 @@ enum {
     ESPM_S_DEV_FLAGS = 8, /* copy of the device error word */
     ESPM_S_MEAN_H = 9,
     ESPM_S_MEAN_W = 10,
-    ESPM_S_GW_FLAGS = 11  /* ESPM_DEV_GW_* bits of the GW produced for the NEXT H pass */
+    ESPM_S_GW_FLAGS = 11, /* ESPM_DEV_GW_* bits of the GW produced for the NEXT H pass */
+    ESPM_S_GAMMA = 12,    /* line search: gamma_ after this iteration's update (smooth_nmf.py:378-382) */
+    ESPM_S_LS_D = 13      /* line search: diff_surrogate(H_old, H_new) (surrogates.py:116-149) */
 };
 
 /*
@@ -206,6 +215,18 @@ typedef struct espm_state {
      * upper end (b = new); word 4 = number of iterations the trace evaluated | 1<<8 if the bracket became
      * stationary.  The replay of the it* global iterations follows these bits instead of re-evaluating f. */
     uint32_t* bisect_dec;
+    /* ---- alternative update rules (algo = "bmd" / "projected_gradient", l2 = True, linesearch) ---- */
+    double gamma_h;         /* projected gradient: step 1/gamma_h of proj_grad_step_h (updates.py:378) */
+    double gamma_w;         /* projected gradient: step 1/gamma_w of proj_grad_step_w (updates.py:357) */
+    double x_total;         /* sum(X): sigmaR of the Bregman W step when G is not the identity (updates.py:45) */
+    const void* x_colsum;   /* p_pad (c dtype): per-pixel sums of X, sigmaR of the Bregman H step (updates.py:121) */
+    const void* x_rowsum;   /* n_pad (c dtype): per-channel sums of X, sigmaR of the Bregman W step for G = identity */
+    const void* GG;         /* m x m (c dtype): G^T G of the Frobenius W step (updates.py:30); NULL when G = identity */
+    double* gram_gw;        /* kp*kp doubles: (G W_cur)^T (G W_cur), see espm_gram (updates.py:115) */
+    double* gram_h;         /* kp*kp doubles: H_next H_next^T over ALL pixels, see espm_gram (updates.py:31) */
+    double* sigma_dev;      /* line search: device-resident gamma_ read by espm_h_finish / espm_h_apply and updated by
+                             * espm_linesearch; NULL: the kernels use `sigma` */
+    double* ls_part;        /* px_blocks x (4 + kp) partial sums of espm_linesearch */
 } espm_state;
 
 /* library / device */
@@ -306,6 +327,21 @@ int espm_peer_free(void* ptr);
 int espm_dichotomy_simplex(int32_t c_dtype, int32_t k, int64_t p, const void* num, const void* den,
                            double log_shift, double tol, int32_t maxit, void* nu_out,
                            uint32_t* mask4, uint32_t* dev_flags, int32_t* its_out, void* stream);
+
+/* Gram matrices of the Frobenius branches: which = 0: gram_gw = GW_cur^T GW_cur (over the n real channels);
+ * which = 1: gram_h = H_next H_next^T over this rank's pixels (the caller sums the ranks). */
+int espm_gram(const espm_state* st, int32_t which, void* stream);
+/* Sums of X for the Bregman branches (from Xt, once per fit): colsum_out[p_pad] (c dtype, per pixel),
+ * rowsum_part[n_tiles][n_pad] doubles (per tile partials of the per-channel sums; the caller folds them). */
+int espm_x_sums(const espm_state* st, void* colsum_out, double* rowsum_part, void* stream);
+/* Line search on the Laplacian surrogate (smooth_nmf.py:376-382, surrogates.py:116-149) for (H_cur, H_next):
+ * d = diff_surrogate(H_cur, H_next, L, sigmaL = *sigma_dev, algo); *sigma_dev /= 1.05 if d > 0 else *= 1.5.
+ * Writes ESPM_S_GAMMA / ESPM_S_LS_D of st->scalars.  Run after espm_h_apply / espm_h_finish. */
+int espm_linesearch(const espm_state* st, void* stream);
+/* nu = dichotomy_simplex_projected_gradient(a) (dicotomy.py:83-108); a: k x p (c dtype, row stride p). */
+int espm_dichotomy_simplex_pg(int32_t c_dtype, int32_t k, int64_t p, const void* a, double log_shift, double tol,
+                              int32_t maxit, void* nu_out, uint32_t* mask4, uint32_t* dev_flags,
+                              int32_t* its_out, void* stream);
 
 /* nu = dichotomy_simplex_acc(a, b, minus_c) (dicotomy.py:57-81), the bisection of the quadratic-surrogate
  * H step (updates.py:286-289).  a > 0 scalar; b, minus_c: k x p.  Evaluated in fp64 whatever c_dtype. */
