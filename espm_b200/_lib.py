@@ -37,6 +37,7 @@ FLAG_PG = 1 << 15
 FLAG_L2 = 1 << 16
 FLAG_L2_H = 1 << 17
 FLAG_LINESEARCH = 1 << 18
+FLAG_EVAL_ONLY = 1 << 19
 COOP_BLOCKS = 32
 
 # device error word

@@ -332,8 +332,8 @@ int espm_w_reduce(const espm_state* st, void* stream) { return small(OP_W_REDUCE
 int espm_w_finish(const espm_state* st, void* stream) { return small(OP_W_FINISH, st, stream); }
 
 int espm_linesearch(const espm_state* st, void* stream) {
-    if (st && (!st->sigma_dev || !st->ls_part)) {
-        set_error("espm_linesearch needs sigma_dev and ls_part");
+    if (st && (!st->ls_part || (!st->sigma_dev && !(st->flags & ESPM_FLAG_PG)))) {
+        set_error("espm_linesearch needs ls_part (and sigma_dev for the surrogate algorithms)");
         return ESPM_ERR_BAD_ARG;
     }
     return small(OP_LINESEARCH, st, stream);

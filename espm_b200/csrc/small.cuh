@@ -686,7 +686,9 @@ __global__ void __launch_bounds__(PX_THREADS) h_finish_kernel(const espm_state s
         vals[1] = lapl;
         vals[2 + 2 * KP] = relh;
 
-        if (simplex) {
+        if (st.flags & ESPM_FLAG_EVAL_ONLY) {
+            // loss terms only
+        } else if (simplex) {
             TC* num_o = reinterpret_cast<TC*>(st.num);
             TC* den_o = reinterpret_cast<TC*>(st.den);
 #pragma unroll
@@ -748,8 +750,17 @@ __global__ void __launch_bounds__(PX_THREADS) h_finish_kernel(const espm_state s
             store_h_next<TC, KP>(st, j, k, hn, vals);
         }
     }
-    block_reduce_vals<NV>(vals, px_part_nsum(KP), st.px_part + (size_t)blockIdx.x * NV);
-    merge_mask(bits, err, simplex ? st.bisect_mask : nullptr, st.dev_flags);
+    if (st.flags & ESPM_FLAG_EVAL_ONLY) {
+        // keep the H_next statistics another kernel left in px_part: only the loss partials are ours
+        __shared__ double tmp[NV];
+        block_reduce_vals<NV>(vals, px_part_nsum(KP), tmp);
+        __syncthreads();
+        double* out = st.px_part + (size_t)blockIdx.x * NV;
+        if (threadIdx.x < 2 || threadIdx.x == 2 + 2 * KP) out[threadIdx.x] = tmp[threadIdx.x];
+    } else {
+        block_reduce_vals<NV>(vals, px_part_nsum(KP), st.px_part + (size_t)blockIdx.x * NV);
+    }
+    merge_mask(bits, err, (simplex && !(st.flags & ESPM_FLAG_EVAL_ONLY)) ? st.bisect_mask : nullptr, st.dev_flags);
     // The last CTA to finish folds every partial into the scalar record (what espm_h_scalars does),
     // in a fixed order that does not depend on which CTA that is.
     __shared__ bool is_last;
@@ -1536,6 +1547,12 @@ __global__ void __launch_bounds__(PX_THREADS) linesearch_kernel(const espm_state
                     lo = (double)deg * ho - so;
                     ln = (double)deg * hn - sn;
                 }
+                if (st.flags & ESPM_FLAG_PG) {   // quadratic surrogate of the projected gradient (surrogates.py:153-171)
+                    const double g = (double)reinterpret_cast<const TC*>(st.den)[(size_t)kk * st.p_pad + j];
+                    vals[0] += (hn - ho) * g;
+                    vals[1] += (hn - ho) * (hn - ho);
+                    continue;
+                }
                 vals[0] += lo * ho;
                 vals[1] += lo * hn;
                 vals[2] += ln * hn;
@@ -1566,7 +1583,11 @@ __global__ void __launch_bounds__(PX_THREADS) linesearch_kernel(const espm_state
         if (lane == 0) tot[v] = r;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && (st.flags & ESPM_FLAG_PG)) {
+        st.scalars[ESPM_S_LS_D] = tot[0];
+        st.scalars[ESPM_S_GAMMA] = tot[1];
+        st.dev_flags[4] = 0u;
+    } else if (threadIdx.x == 0) {
         const double sigma = *st.sigma_dev;
         double t3 = tot[3];
         if (!quad) {

@@ -151,12 +151,14 @@ class FitEngine:
             flags |= L.FLAG_L2_H                 # Frobenius H step / gradient (updates.py:109-118, 330-332)
         if flags & (L.FLAG_BMD | L.FLAG_PG | L.FLAG_L2):
             flags &= ~L.FLAG_SIMPLEX_W           # those W branches have no simplex projection (updates.py:29-48)
+        self.pg_ls = False
         if linesearch:
-            if flags & L.FLAG_PG:
-                raise NotImplementedError("espm_b200: linesearch with algo='projected_gradient' is not available")
             if shard is not None:
                 raise NotImplementedError("espm_b200: linesearch is not available for pixel-sharded fits")
-            flags |= L.FLAG_LINESEARCH
+            if flags & L.FLAG_PG:
+                self.pg_ls = True                # quadratic-surrogate line search (smooth_nmf.py:383-401, 438-447)
+            else:
+                flags |= L.FLAG_LINESEARCH
         if shard is not None and (l2 or l2_h):
             raise NotImplementedError("espm_b200: the Frobenius branches are not available for pixel-sharded fits")
         self.algo = algo
@@ -229,6 +231,11 @@ class FitEngine:
             self.sigma_dev = torch.full((1,), float(sigma), dtype=torch.float64, device=dev)
             self.ls_part = zeros(st.px_blocks, 4 + kp, dtype=torch.float64)
             st.sigma_dev, st.ls_part = self.sigma_dev.data_ptr(), self.ls_part.data_ptr()
+        if self.pg_ls:
+            self.ls_part = zeros(st.px_blocks, 4 + kp, dtype=torch.float64)
+            st.ls_part = self.ls_part.data_ptr()
+        self._eval_slot = 0
+        self._pg_w_pending = None
         if gamma_pg is not None:
             st.gamma_h, st.gamma_w = float(gamma_pg[0]), float(gamma_pg[1])
         self.dev_flags = torch.zeros(8, dtype=torch.int32, device=dev)
@@ -522,6 +529,7 @@ class FitEngine:
     def evaluate(self, slot):
         """Phase A on (W_cur, H_cur): fills scalar record ``slot`` (loss parts, rel_H, flags)."""
         self._set_record(slot)
+        self._eval_slot = slot
         self._seq_m += 1
         self.st.seq_m = self._seq_m                          # mask exchange of this evaluation (peer mode)
         if self.st.flags & L.FLAG_L2_H:
@@ -539,6 +547,9 @@ class FitEngine:
             self._call(self.lib.espm_h_apply, "h_apply")
         if not self.peer:
             self._exchange_halo(self.ih[2])
+        if self.pg_ls:
+            self._pg_ls_h()
+            self._set_record(slot)
         if st.flags & L.FLAG_LINESEARCH:
             self._call(self.lib.espm_linesearch, "linesearch")   # smooth_nmf.py:376-382, gamma_ stays on the device
         if st.flags & L.FLAG_L2:
@@ -551,6 +562,8 @@ class FitEngine:
             self.shard.allreduce_sum(self.s_sum)
             self._sync_hstats()
         self._call(self.lib.espm_w_finish, "w_finish")
+        if self.pg_ls:
+            self._pg_ls_w_stage()
         hp, hc, hn = self.ih
         self.ih = [hc, hn, hp]
         self.iw = [self.iw[1], self.iw[0]]
@@ -633,6 +646,101 @@ class FitEngine:
     def set_WH(self, W, H):
         """Overwrite the current iterate (e.g. after rescaled_DH) and refresh the derived buffers."""
         self._init_WH(W, H)
+
+    # ------------------------------------------------------------------ ground-truth tracking (base.py:301-347)
+    def enable_truth(self, true_D, true_H):
+        """Keep X_true = true_D @ true_H on the device in the same tile-major layout as X, so that
+        ``loss(W, H, X=true_DH)`` (base.py:345) is one more H pass."""
+        if self.shard is not None:
+            raise NotImplementedError("espm_b200: ground-truth tracking is not available for pixel-sharded fits")
+        st = self.st
+        D = torch.as_tensor(np.ascontiguousarray(true_D), dtype=self.cdt).to(self.device)
+        Ht = torch.as_tensor(np.ascontiguousarray(true_H[:, self.j0:self.j1]), dtype=self.cdt).to(self.device)
+        xdt = _torch_dtype(self.x_code)
+        dense = (D @ Ht).to(xdt)                 # once per fit (setup, not the per-iteration path)
+        self.Xt_true = torch.empty_like(self.Xt)
+        keep = st.Xt
+        st.Xt = self.Xt_true.data_ptr()
+        L.check(self.lib.espm_retile_x(ctypes.byref(st), ctypes.c_void_p(dense.data_ptr()), self.x_code,
+                                       dense.stride(0), 1, 0, 1.0, None, self.stream))
+        torch.cuda.current_stream(self.device).synchronize()
+        st.Xt = keep
+        del dense
+        self.H_tmp = torch.ones(self.k, self.ldh, dtype=self.cdt, device=self.device)
+        self.hstats_tmp = torch.zeros(3 * st.kp, dtype=torch.float64, device=self.device)
+
+    def _eval_only(self, slot, xt_ptr=None, h_ptr=None, hstats_ptr=None):
+        """Loss terms of (W_cur, H) against X into scalar record ``slot`` without touching the iteration state
+        (the ``self.loss(W, H, X=...)`` calls of the reference): h_pass + h_finish with ESPM_FLAG_EVAL_ONLY."""
+        st = self.st
+        keep = (st.Xt, st.H_cur, st.hstats_cur, st.flags)
+        if xt_ptr is not None:
+            st.Xt = xt_ptr
+        if h_ptr is not None:
+            st.H_cur, st.hstats_cur = h_ptr, hstats_ptr
+        st.flags = (st.flags & ~L.FLAG_HAVE_HPREV) | L.FLAG_EVAL_ONLY
+        self._set_record(slot)
+        if st.flags & L.FLAG_L2_H:
+            L.check(self.lib.espm_gram(ctypes.byref(st), 0, self.stream))
+        self._call(self.lib.espm_h_pass)
+        self._call(self.lib.espm_h_finish)
+        st.Xt, st.H_cur, st.hstats_cur, st.flags = keep
+        self._bind()
+
+    def truth_loss(self, slot, H_t=None):
+        """Scalar record ``slot`` <- loss terms of (W_cur, H_t or H_cur) against X_true (base.py:345)."""
+        st = self.st
+        h_ptr = hs_ptr = None
+        if H_t is not None:
+            self.H_tmp[:, self.halo:self.halo + self.p_loc] = torch.as_tensor(
+                np.ascontiguousarray(H_t[:, self.j0:self.j1]), dtype=self.cdt).to(self.device)
+            h_ptr = self.H_tmp.data_ptr() + self.halo * self.H_tmp.element_size()
+            hs_ptr = self.hstats_tmp.data_ptr()
+            keep = (st.H_next, st.hstats_next)
+            st.H_next, st.hstats_next = h_ptr, hs_ptr
+            self._call(self.lib.espm_h_stats)                  # row statistics of H_t (sum Y of the loss)
+            st.H_next, st.hstats_next = keep
+        self._eval_only(slot, xt_ptr=self.Xt_true.data_ptr(), h_ptr=h_ptr, hstats_ptr=hs_ptr)
+
+    # ------------------------------------------------------------------ projected-gradient line search
+    def _unaveraged(self, rec):
+        """loss(W, H, average=False) (smooth_nmf.py:457-475) from a scalar record."""
+        kl = 0.5 * rec[L.S_XLOGY] if self.st.flags & L.FLAG_L2 else rec[L.S_SUMY] - rec[L.S_XLOGY] + self.const_KL
+        return kl + rec[L.S_LOGREG] + 0.5 * self.st.lambda_L * rec[L.S_LAPL]
+
+    def _pg_ls_h(self):
+        """smooth_nmf.py:383-401 for (H_cur -> H_next): d = f(Ht) + <H - Ht, grad f(Ht)> + gamma |H - Ht|^2 - f(H)."""
+        st = self.st
+        a1, a2 = self.max_records - 5, self.max_records - 6
+        rec0 = self.read_records(self._eval_slot, self._eval_slot + 1)[0]
+        self._set_record(a1)
+        self._call(self.lib.espm_linesearch)                   # sums of the quadratic surrogate (den = gradH(Ht))
+        self._call(self.lib.espm_h_stats)                      # row statistics of H_next for sum Y
+        self._eval_only(a2, h_ptr=st.H_next, hstats_ptr=st.hstats_next)
+        r1 = self.read_records(a1, a1 + 1)[0]
+        r2 = self.read_records(a2, a2 + 1)[0]
+        f_xt, f_x = self._unaveraged(rec0), self._unaveraged(r2)
+        d = f_xt + r1[L.S_LS_D] + st.gamma_h * r1[L.S_GAMMA] - f_x
+        st.gamma_h = st.gamma_h / 1.05 if d > 0 else st.gamma_h * 1.5
+        self._pg_f_x = f_x
+
+    def _pg_ls_w_stage(self):
+        """After the W step: keep what smooth_nmf.py:438-447 needs until loss(W', H') is known."""
+        Wold = self.Wbuf[self.iw[0]].double()
+        Wn = self.Wbuf[self.iw[1]].double()
+        grad = self.w_den.double()
+        dW = Wn - Wold
+        self._pg_w_pending = (self._pg_f_x, float((dW * grad).sum().item()), float((dW * dW).sum().item()))
+
+    def pg_ls_w_update(self, rec):
+        """gamma_[1] update once the record of the new iterate (f(W', H')) has been read."""
+        if self._pg_w_pending is None:
+            return
+        f_xt, s1, s2 = self._pg_w_pending
+        self._pg_w_pending = None
+        st = self.st
+        d = f_xt + s1 + st.gamma_w * s2 - self._unaveraged(rec)
+        st.gamma_w = st.gamma_w / 1.05 if d > 0 else st.gamma_w * 1.5
 
     def enable_clamp(self):
         """Switch to the reference's NaN fallback (updates.py:129-131, 54-56: GWH = max(GWH, log_shift)) and to

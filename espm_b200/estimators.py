@@ -23,8 +23,8 @@ from . import _lib as L
 from .conf import dicotomy_tol as _DICOTOMY_TOL
 from .conf import log_shift as _LOG_SHIFT
 from .conf import sigmaL as _SIGMA_L
-from .host import (initialize_factors, is_physical_model, normalization_factor, remove_zeros_lines,
-                   rescaled_DH)
+from .host import (find_min_angle, find_min_MSE, initialize_factors, is_physical_model, normalization_factor,
+                   remove_zeros_lines, rescaled_DH)
 
 
 class SmoothNMF(TransformerMixin, BaseEstimator):
@@ -137,10 +137,7 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
             if self.simplex_W:                                          # updates.py:365-366
                 raise NotImplementedError(
                     "Simplex constraint not implemented for W using the projected gradient method")
-            if self.linesearch:
-                raise NotImplementedError("espm_b200: linesearch with algo='projected_gradient' is not available yet")
-        if self.true_D is not None and self.true_H is not None:
-            raise NotImplementedError("espm_b200: ground-truth tracking (true_D/true_H) is not available yet")
+
 
     # ------------------------------------------------------------------ X_ (lazy)
     def _host_X(self, Xv):
@@ -312,7 +309,16 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
         algo_start = time.time()
         self.n_iter_ = 0
         self.losses_, self.rel_, self.detailed_losses_ = [], [], []
-        batch = (self.no_stop_criterion and self.physics_model_ is None
+        self._track = False
+        if self.true_D is not None and self.true_H is not None:        # base.py:301-308
+            if self.true_D.shape[1] == self.n_components and self.true_H.shape[0] == self.n_components:
+                self.angles_, self.mse_, self.true_losses_ = [], [], []
+                eng.enable_truth(self.true_D, self.true_H)
+                self._track = True
+            else:
+                print("The chosen number of components does not match the number of components of the provided "
+                      "truth. The ground truth will be ignored.")
+        batch = (self.no_stop_criterion and self.physics_model_ is None and not self._track and not eng.pg_ls
                  and not (self.verbose > 0 and self.eval_print > 0))
         try:
             if batch:
@@ -351,6 +357,10 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
     def _append(self, rec):
         if self.linesearch and self.algo != "projected_gradient":
             self.gamma_ = float(rec[L.S_GAMMA])        # gamma_ after this iteration's update (smooth_nmf.py:378-382)
+        elif self.linesearch:
+            eng = self._engine
+            eng.pg_ls_w_update(rec)                    # smooth_nmf.py:438-447 needs loss(W', H') = this record
+            self.gamma_ = [eng.st.gamma_h, eng.st.gamma_w]
         loss = self._loss_from_record(rec)
         self.losses_.append(loss)
         self.detailed_losses_.append(self.detailed_loss_)
@@ -404,6 +414,8 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
         while True:
             it = self.n_iter_ + 1
             eng.advance(it)
+            if self._track:
+                self._track_truth(eng)
             eng.evaluate(it)
             rec = eng.read_records(it, it + 1)[0]
             if int(rec[L.S_DEV_FLAGS]) & L.DEV_NONFINITE and not eng.clamped:
@@ -448,6 +460,22 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
                 self._final_rec = rec2
             else:
                 eval_before = eval_after
+
+    def _track_truth(self, eng):
+        """base.py:335-347: angles / MSE against the ground truth and the loss on true_D @ true_H."""
+        W, H = eng.get_W(), eng.get_H()
+        rescale = not (self.simplex_H or self.simplex_W)
+        if rescale:
+            W, H = rescaled_DH(W, H)
+        GW = self.G_ @ W if not self._identity_G else W
+        self.angles_.append(find_min_angle(self.true_D.T, GW.T))
+        self.mse_.append(find_min_MSE(self.true_H, H))
+        slot = eng.max_records - 4
+        eng.truth_loss(slot, H if rescale else None)
+        rec = eng.read_records(slot, slot + 1)[0]
+        keep = self.__dict__.get("detailed_loss_")
+        self.true_losses_.append(self._loss_from_record(rec))
+        self.detailed_loss_ = keep
 
     def fit(self, X, y=None, **params):
         """Learn the model (base.py:422-441)."""

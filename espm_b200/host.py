@@ -88,3 +88,36 @@ def initialize_factors(X, G, W, H, n_components, init, random_state, simplex_H, 
     W = np.maximum(W, log_shift)
     H = np.maximum(H, log_shift)
     return G_dense, W, H
+
+
+# ---- ground-truth tracking (base.py:335-347; measures.py:10-50, 125-153, 166-207, 256-285, 579-627) -------------
+def _unique_min(matrix):
+    """measures.py:166-207: assignment with distinct rows that minimises the sum (brute force over permutations)."""
+    from itertools import permutations
+    n = matrix.shape[0]
+    perms = list(permutations(range(n), n))
+    sums = []
+    for perm in perms:
+        acc = 0
+        for i in range(n):
+            acc += matrix[perm[i], i]
+        sums.append(acc)
+    best = perms[sums.index(min(sums))]
+    return [matrix[best[i], i] for i in range(n)], best
+
+
+def find_min_angle(true_vectors, algo_vectors):
+    """measures.py:125-153 with unique=True: spectral angles (degrees) of the best one-to-one match."""
+    v1 = true_vectors / np.sqrt(np.sum(true_vectors ** 2, axis=1, keepdims=True))
+    v2 = algo_vectors / np.sqrt(np.sum(algo_vectors ** 2, axis=1, keepdims=True))
+    ang = np.arccos(np.clip(v1 @ v2.T, -1.0, 1.0)) * 180 / np.pi
+    return _unique_min(ang)[0]
+
+
+def find_min_MSE(true_maps, algo_maps):
+    """measures.py:256-285 with unique=True on the squared distances of measures.py:579-627."""
+    xx = (true_maps * true_maps).sum(axis=1)
+    yy = (algo_maps * algo_maps).sum(axis=1)
+    xy = np.dot(true_maps, algo_maps.T)
+    d = abs(np.kron(np.ones((algo_maps.shape[0], 1)), xx).T + np.kron(np.ones((true_maps.shape[0], 1)), yy) - 2 * xy)
+    return _unique_min(d / true_maps.shape[1])[0]

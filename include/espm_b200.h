@@ -79,6 +79,8 @@ typedef enum espm_status {
                                           * Frobenius W step / W gradient (updates.py:29-36, 307-308) */
 #define ESPM_FLAG_L2_H        (1u << 17) /* Frobenius H step / H gradient (updates.py:109-118, 330-332); only reachable
                                           * through the operator-level API, like in the reference */
+#define ESPM_FLAG_EVAL_ONLY   (1u << 19) /* espm_h_finish only evaluates the loss terms of (W_cur, H_cur): no update, no
+                                          * bisection, H_next / Ht untouched (loss(W, H, X=...) calls of the reference) */
 #define ESPM_FLAG_LINESEARCH  (1u << 18) /* smooth_nmf.py:376-386: gamma_ adapts from diff_surrogate; see sigma_dev */
 
 /* bits of the device-side error word (espm_state.dev_flags[0]) */
@@ -338,6 +340,9 @@ int espm_x_sums(const espm_state* st, void* colsum_out, double* rowsum_part, voi
  * d = diff_surrogate(H_cur, H_next, L, sigmaL = *sigma_dev, algo); *sigma_dev /= 1.05 if d > 0 else *= 1.5.
  * Writes ESPM_S_GAMMA / ESPM_S_LS_D of st->scalars.  Run after espm_h_apply / espm_h_finish. */
 int espm_linesearch(const espm_state* st, void* stream);
+/* With ESPM_FLAG_PG the same entry point produces the two sums of the quadratic surrogate of the projected-gradient
+ * line search (surrogates.py:153-171, smooth_nmf.py:383-401) for (H_cur, H_next) and the gradient left in `den` by
+ * espm_h_finish: ESPM_S_LS_D = sum (H_next - H_cur) * grad, ESPM_S_GAMMA = sum (H_next - H_cur)^2. */
 /* nu = dichotomy_simplex_projected_gradient(a) (dicotomy.py:83-108); a: k x p (c dtype, row stride p). */
 int espm_dichotomy_simplex_pg(int32_t c_dtype, int32_t k, int64_t p, const void* a, double log_shift, double tol,
                               int32_t maxit, void* nu_out, uint32_t* mask4, uint32_t* dev_flags,

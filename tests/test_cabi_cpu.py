@@ -48,7 +48,7 @@ def test_constants_match_header():
         assert m and int(m.group(1)) == val, name
     for name in ("SIMPLEX_H", "SIMPLEX_W", "G_IDENTITY", "CLAMP_Y", "LOSS_DUAL", "FIXED_H", "FIXED_W", "MU",
                  "LAPLACIAN", "HAVE_HPREV", "SIMPLEX_ROWS", "HQ", "FUSED_WREDUCE", "PEER", "BMD", "PG", "L2", "L2_H",
-                 "LINESEARCH"):
+                 "LINESEARCH", "EVAL_ONLY"):
         m = re.search(r"#define\s+ESPM_FLAG_%s\s+\(1u << (\d+)\)" % name, header)
         assert m and (1 << int(m.group(1))) == getattr(_lib, "FLAG_" + name), name
 

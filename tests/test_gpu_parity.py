@@ -454,9 +454,6 @@ def test_fit_physical_model_refresh(golden_fits):
 def test_unsupported_variants_fail_loudly():
     from espm_b200 import SmoothNMF
     X = np.random.default_rng(0).poisson(3.0, size=(20, 12)).astype(float)
-    for kw in (dict(true_D=np.ones((20, 2)), true_H=np.ones((2, 12))),):
-        with pytest.raises(NotImplementedError):
-            SmoothNMF(n_components=2, max_iter=2, verbose=0, **kw).fit_transform(X)
     with pytest.raises(ValueError):
         SmoothNMF(n_components=2, max_iter=2, verbose=0).fit_transform(-X)
 

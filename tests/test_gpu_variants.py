@@ -87,7 +87,7 @@ def test_projected_gradient_golden(ops, golden_variants):
     assert np.max(np.abs(f)) <= 1e-6
 
 
-@pytest.mark.parametrize("tag", sorted(t for t in VARIANT_FITS if not t.startswith("truth") and t != "ls_pg"))
+@pytest.mark.parametrize("tag", sorted(t for t in VARIANT_FITS if not t.startswith("truth")))
 @pytest.mark.parametrize("verbose", [0, 1])
 def test_variant_fit_trajectory_golden(golden_variants, tag, verbose):
     from espm_b200 import SmoothNMF
@@ -130,13 +130,33 @@ def test_variant_fits_fp32_vs_oracle(orc, golden_variants):
             assert rel_err(est.H_, ref["H"]) < 50 * TRAJ_TOL, tag
 
 
+@pytest.mark.parametrize("tag", ["truth", "truth_free"])
+def test_ground_truth_tracking(golden_variants, tag):
+    """true_D / true_H: per-iteration angles, MSE and the loss on true_D @ true_H (base.py:301-347)."""
+    from espm_b200 import SmoothNMF
+    g = golden_variants
+    X, G, W0, H0, sh = variant_inputs(g, tag)
+    kw = dict(tol=0, no_stop_criterion=True, max_iter=10, shape_2d=sh, verbose=0)
+    kw.update(VARIANT_FITS[tag])
+    kw.pop("track")
+    est = SmoothNMF(n_components=3, G=G, true_D=g["S__true_D"], true_H=g["S__true_H"], **kw)
+    est.fit_transform(X, W=W0.copy(), H=H0.copy())
+    assert rel_err(est.losses_, g[tag + "__losses"]) < 1e-9
+    assert rel_err(est.true_losses_, g[tag + "__true_losses"]) < 1e-8
+    assert rel_err(est.H_, g[tag + "__H"]) < 1e-8
+    np.testing.assert_allclose(np.array(est.angles_), g[tag + "__angles"], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(np.array(est.mse_), g[tag + "__mse"], rtol=1e-7, atol=1e-14)
+    # a truth with another number of components is ignored with the reference's message (base.py:307-308)
+    est2 = SmoothNMF(n_components=3, G=G, true_D=g["S__true_D"][:, :2], true_H=g["S__true_H"][:2], **kw)
+    est2.fit_transform(X, W=W0.copy(), H=H0.copy())
+    assert not hasattr(est2, "true_losses_")
+    assert rel_err(est2.losses_, g[tag + "__losses"]) < 1e-9
+
+
 def test_variant_guards():
     from espm_b200 import SmoothNMF
     X = np.random.default_rng(0).poisson(3.0, size=(20, 12)).astype(float)
     with pytest.raises(NotImplementedError):      # updates.py:365-366
         SmoothNMF(n_components=2, max_iter=2, verbose=0, algo="projected_gradient", simplex_W=True).fit_transform(X)
-    with pytest.raises(NotImplementedError):
-        SmoothNMF(n_components=2, max_iter=2, verbose=0, algo="projected_gradient", simplex_W=False, lambda_L=1.0,
-                  linesearch=True).fit_transform(X)
     with pytest.raises(ValueError):               # bmd needs a square G (updates.py:42)
         SmoothNMF(n_components=2, max_iter=2, verbose=0, algo="bmd", G=np.ones((20, 3)), simplex_W=False).fit_transform(X)
