@@ -1,0 +1,144 @@
+"""Full-size parity (BASELINE.json configs C2 / C3): one complete iteration on the synthetic EDXS image, checked
+
+* for the H update: against the oracle's arithmetic on a random subset of pixels (the update of a pixel needs only
+  its own spectrum, the neighbouring H and the GLOBAL lock-step iteration count, which the device reports),
+* for the W update and the loss: against an independent chunked fp64 evaluation of updates.py:38-72 and
+  measures.py:493-503 (torch on the GPU, never our kernels),
+* through size-independent properties: simplex sums within dicotomy_tol, positivity, monotone loss.
+"""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+LS, SIGMA, TOL = 1e-14, 8.0, 1e-5
+
+
+def _setup(nx, ny, n, k, n_el, dtype, seed=93):
+    import torch
+    from espm_b200 import synth
+    prob = synth.make_problem(nx, ny, n, k, n_el, seed=seed)
+    dev = torch.device("cuda", 0)
+    tdt = torch.float32 if dtype == np.float32 else torch.float64
+    X = synth.poisson_X_torch(prob, 0, nx * ny, seed, dev, tdt)
+    W0, H0 = synth.init_factors(prob["G_full"].shape[1], k, nx * ny, seed, dtype=dtype)
+    return prob["G_full"].astype(dtype), X, W0, H0
+
+
+def _replay(num, den, its):
+    """dicotomy.py:152-168 for exactly `its` iterations (the global count reported by the device)."""
+    k = num.shape[0]
+    a = np.max(np.where(num > 0, num / 2 - den, -np.inf), axis=0)
+    b = k * np.max(num, axis=0) / 0.5 - np.min(den, axis=0)
+
+    def func(x):
+        return np.sum(np.maximum(num / (x + den), LS), axis=0) - 1
+
+    new = (a + b) / 2
+    fn = func(new)
+    own = None
+    for it in range(its):
+        if own is None and np.max(np.abs(fn)) <= TOL:
+            own = it
+        minus = func(a) * fn <= 0
+        b[minus] = new[minus]
+        a[~minus] = new[~minus]
+        new = (a + b) / 2
+        fn = func(new)
+    return new, (its if own is None else own)
+
+
+@pytest.mark.parametrize("cfg", ["C2-f64", "C3-f32"])
+def test_one_iteration_at_full_size(cfg):
+    import torch
+    from espm_b200 import _lib as L
+    from espm_b200.engine import FitEngine
+    from oracle import smooth_nmf_oracle as orc
+    if cfg == "C2-f64":
+        nx = ny = 256
+        n, k, n_el, dtype, tol = 2048, 3, 9, np.float64, 1e-10
+    else:
+        nx = ny = 512
+        n, k, n_el, dtype, tol = 2048, 4, 25, np.float32, 1e-5
+    lam, mu, eps = 2.0, 0.05, 1.0
+    G, X, W0, H0 = _setup(nx, ny, n, k, n_el, dtype)
+    p = nx * ny
+    eng = FitEngine(X, G, W0, H0, shape_2d=(nx, ny), lambda_L=lam, mu=mu, epsilon_reg=eps, simplex_H=True,
+                    simplex_W=False, tol=0.0, max_records=16, x_local=True)
+    eng.evaluate(0)
+    eng.advance(1)
+    eng.evaluate(1)
+    recs = eng.read_records(0, 2)
+    H1, W1 = eng.get_H().astype(np.float64), eng.get_W().astype(np.float64)
+    assert int(recs[0][L.S_DEV_FLAGS]) == 0 and int(recs[1][L.S_DEV_FLAGS]) == 0
+    its = int(recs[0][L.S_BISECT_ITS_H])
+    assert 5 < its < 60
+
+    # ---- properties over ALL pixels ----
+    assert np.all(np.isfinite(H1)) and np.all(H1 >= LS)
+    assert np.max(np.abs(H1.sum(0) - 1.0)) <= TOL * 1.001 + (1e-6 if dtype == np.float32 else 0)
+
+    # ---- H update on a random pixel subset, oracle arithmetic (updates.py:127-152) ----
+    G64, W64, H64 = G.astype(np.float64), np.maximum(W0.astype(np.float64), LS), np.maximum(H0.astype(np.float64), LS)
+    rng = np.random.default_rng(7)
+    J = np.sort(rng.choice(p, size=768, replace=False))
+    XJ = X[:, torch.as_tensor(J, device=X.device)].double().cpu().numpy()
+    GW = G64 @ W64
+    HL = orc.laplacian_apply(H64, (nx, ny))[:, J]
+    HJ = H64[:, J]
+    num = GW.T @ (XJ / (GW @ HJ))
+    den = np.sum(GW, axis=0, keepdims=True).T + mu / (HJ + eps)
+    maxH = np.max(H64, axis=1, keepdims=True)
+    num = HJ * (num + lam * SIGMA * maxH)
+    den = den + lam * SIGMA * maxH + lam * HL
+    nu, own = _replay(num, den, its)
+    assert own <= its            # the global count is the slowest pixel's
+    ref_HJ = np.maximum(num / (den + nu), LS)
+    assert rel_err(H1[:, J], ref_HJ) < tol
+
+    # ---- W update + loss: independent chunked fp64 evaluation on the GPU ----
+    dev = X.device
+    GWd = torch.as_tensor(GW, device=dev)
+    H1d = torch.as_tensor(H1, device=dev)
+    S = torch.zeros(n, k, dtype=torch.float64, device=dev)
+    for a in range(0, p, 32768):
+        b = min(a + 32768, p)
+        Xc = X[:, a:b].double()
+        S += (Xc / (GWd @ H1d[:, a:b])) @ H1d[:, a:b].T
+    numW = W64 * (G64.T @ S.cpu().numpy())
+    denW = np.sum(G64, axis=0, keepdims=True).T @ np.sum(H1, axis=1, keepdims=True).T
+    ref_W = np.maximum(numW / denW, LS)
+    assert rel_err(W1, ref_W) < tol
+    GW1 = torch.as_tensor(np.maximum(G64 @ W1, LS), device=dev)
+    sumY, xlogy = 0.0, 0.0
+    for a in range(0, p, 32768):
+        b = min(a + 32768, p)
+        Y = GW1 @ torch.clamp(H1d[:, a:b], min=LS)
+        sumY += float(Y.sum())
+        xlogy += float((torch.clamp(X[:, a:b].double(), min=LS) * torch.log(Y)).sum())
+    ltol = 1e-11 if dtype == np.float64 else 2e-6
+    assert abs(recs[1][L.S_SUMY] - sumY) < ltol * abs(sumY)
+    assert abs(recs[1][L.S_XLOGY] - xlogy) < ltol * abs(xlogy)
+    eng.close()
+
+
+def test_loss_decreases_at_full_size():
+    """C3 (512 x 512 x 2048, fp32): ten iterations through the estimator; the regularised loss decreases monotonically
+    (the surrogate is a majoriser, test_estimators.py:72-98) and the abundances stay on the simplex."""
+    import torch
+    from espm_b200 import SmoothNMF
+    nx = ny = 512
+    G, X, W0, H0 = _setup(nx, ny, 2048, 4, 25, np.float32)
+    est = SmoothNMF(n_components=4, G=G, shape_2d=(nx, ny), simplex_H=True, simplex_W=False, lambda_L=2.0, mu=0.05,
+                    tol=0.0, no_stop_criterion=True, max_iter=10, verbose=0)
+    Xh = torch.empty(X.shape, dtype=X.dtype, pin_memory=True)
+    Xh.copy_(X)
+    del X
+    est.fit_transform(Xh.numpy(), W=W0.copy(), H=H0.copy())
+    losses = np.array(est.losses_)
+    assert losses.shape == (10,) and np.all(np.isfinite(losses))
+    assert np.all(np.diff(losses) < 0)
+    assert np.max(np.abs(est.H_.sum(0) - 1.0)) <= 1.1e-5
+    assert est.W_.shape == (27, 4) and np.all(est.W_ >= 1e-14)
