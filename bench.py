@@ -30,6 +30,12 @@ WORKLOADS = {
                kw=dict(simplex_H=True, simplex_W=False, lambda_L=2.0, mu=0.05)),
     "C3": dict(nx=512, ny=512, n=2048, k=4, n_elements=25,
                kw=dict(simplex_H=True, simplex_W=False, lambda_L=2.0, mu=0.05)),
+    # configs[3]: 1024x1024 px x 4096 ch (17.2 GB fp32), 5 phases + Laplacian; --algo l2_surrogate for the "L2" reading
+    "C4": dict(nx=1024, ny=1024, n=4096, k=5, n_elements=25,
+               kw=dict(simplex_H=True, simplex_W=False, lambda_L=2.0, mu=0.05)),
+    # configs[4]: free NMF (G=None), simplex_W, 8 components; independent images = replicas (one image per rank)
+    "C5": dict(nx=512, ny=512, n=2048, k=8, n_elements=25, identity=True,
+               kw=dict(simplex_H=False, simplex_W=True)),
 }
 
 
@@ -114,11 +120,17 @@ def main():
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--seed", type=int, default=93)
+    ap.add_argument("--algo", default="log_surrogate", choices=["log_surrogate", "l2_surrogate"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-rows", type=int, default=48, help="image rows of the CPU-baseline crop")
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload])
+    wl["kw"] = dict(wl["kw"])
+    if args.algo != "log_surrogate":
+        wl["kw"]["algo"] = args.algo
+        wl["kw"].pop("mu", None)          # updates.py:263-301 has no log regulariser
+    replicas = bool(wl.get("identity"))   # C5: independent images, one per rank, no sharding
     nx, ny, n, k = wl["nx"], wl["ny"], wl["n"], wl["k"]
     p = nx * ny
     rank = int(os.environ.get("RANK", "0"))
@@ -171,18 +183,19 @@ def main():
     shard = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    if world > 1 and not replicas:
         from espm_b200.dist import make_shard, shard_bounds
         shard = make_shard()
         j0, j1, _ = shard_bounds(p, nx, ny, rank, world)
     else:
         j0, j1 = 0, p
     tdt = torch.float32 if args.dtype == "f32" else torch.float64
-    X_loc = synth.poisson_X_torch(prob, j0, j1, args.seed, dev, tdt)
-    W0, H0 = synth.init_factors(prob["G_full"].shape[1], k, p, args.seed, dtype=np_dtype)
-    G = prob["G_full"].astype(np_dtype)
+    X_loc = synth.poisson_X_torch(prob, j0, j1, args.seed + (rank if replicas else 0), dev, tdt)
+    G = None if replicas else prob["G_full"].astype(np_dtype)
+    W0, H0 = synth.init_factors(n if replicas else prob["G_full"].shape[1], k, p, args.seed, dtype=np_dtype)
     eng = FitEngine(X_loc, G, W0, H0, shape_2d=(nx, ny), max_records=W + K + 16, shard=shard, x_local=True,
                     tol=0.0, **wl["kw"])
-    x_bytes_total = n * p * np_dtype().itemsize
+    x_bytes_total = n * p * np_dtype().itemsize * (world if replicas else 1)
 
     def barrier():
         if world > 1:
@@ -216,7 +229,7 @@ def main():
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms = float(t_ms.item())
-    value = K / (ms * 1e-3)
+    value = K / (ms * 1e-3) * (world if replicas else 1)     # replicas: every rank iterates its own image
 
     # per-kernel durations of the two X passes inside the timed region
     def mean_ms(name):
@@ -258,7 +271,7 @@ def main():
         # the user's host buffer: the whole image in pinned host memory (every rank reads its own rows)
         X_host = torch.empty((n, p), dtype=tdt, pin_memory=True)
         X_host[:, j0:j1].copy_(X_loc)
-        if world > 1:
+        if world > 1 and not replicas:
             # assemble the full image on every rank, as a user would hold it
             parts = [torch.empty((n, b - a), dtype=tdt, device=dev) for a, b in
                      [shard_bounds(p, nx, ny, r, world)[:2] for r in range(world)]]
@@ -269,7 +282,7 @@ def main():
             del parts
         del X_loc
         torch.cuda.synchronize()
-        espm_b200.config.distributed = world > 1
+        espm_b200.config.distributed = world > 1 and not replicas
         est = SmoothNMF(n_components=k, G=G, shape_2d=(nx, ny), tol=0.0, no_stop_criterion=True, max_iter=K,
                         verbose=0, **wl["kw"])
         import contextlib
@@ -289,8 +302,9 @@ def main():
         if world > 1:
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
         dt = float(t_e.item())
-        e2e = {"value": K / dt, "unit": "it/s",
-               "h2d_bytes_per_step": (x_bytes_total + (W0.nbytes + H0.nbytes + G.nbytes) * world) / K,
+        g_bytes = 0 if G is None else G.nbytes
+        e2e = {"value": K / dt * (world if replicas else 1), "unit": "it/s",
+               "h2d_bytes_per_step": (x_bytes_total + (W0.nbytes + H0.nbytes + g_bytes) * world) / K,
                "d2h_bytes_per_step": (est.W_.nbytes + est.H_.nbytes + (K + 1) * L.NSCALARS * 8 * world) / K,
                "what": "SmoothNMF.fit_transform(X in pinned host memory, max_iter=%d): H2D of X + re-tiling + %d "
                        "iterations + D2H of W, H and the loss history, after one untimed warm-up fit of %d iterations; "
@@ -315,7 +329,7 @@ def main():
                              rows, nx, rows * ny, n, dtc, its_crop)}
 
     line = {"metric": "smoothnmf_iterations_per_s", "value": value, "unit": "it/s", "n_gpus": world, "steps": K,
-            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak" if replicas else "strong", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic", "config": config, "roofline": roofline, "cpu_baseline": cpu,
             "e2e": e2e, "gpu_launches": n_launches, "clocks": clocks,
             "check": {"loss_kl_sumY": float(recs[L.S_SUMY]), "bisect_its_H": float(recs[L.S_BISECT_ITS_H]),

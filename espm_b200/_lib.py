@@ -109,6 +109,7 @@ _EXPORTS = {
     "espm_device_count": (ctypes.c_int, []),
     "espm_plan": (ctypes.c_int, [ctypes.POINTER(EspmState)]),
     "espm_plan_info": (ctypes.c_int, [ctypes.POINTER(EspmState), ctypes.POINTER(_i32)]),
+    "espm_upload_2d": (ctypes.c_int, [_vp, _i64, _vp, _i64, _i64, _i64, _vp]),
     "espm_retile_x": (ctypes.c_int, [ctypes.POINTER(EspmState), _vp, _i32, _i64, _i64, _i64, _f64,
                                      ctypes.POINTER(EspmIngest), _vp]),
     "espm_xt_fixup": (ctypes.c_int, [ctypes.POINTER(EspmState), _vp, _vp, _f64, _f64, _vp]),

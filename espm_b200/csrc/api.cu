@@ -276,6 +276,17 @@ int espm_plan_info(const espm_state* st, int32_t* info8) {
     return ESPM_OK;
 }
 
+int espm_upload_2d(void* dst, int64_t dpitch_bytes, const void* src_host, int64_t spitch_bytes, int64_t width_bytes,
+                   int64_t height, void* stream) {
+    if (!dst || !src_host || width_bytes <= 0 || height <= 0 || dpitch_bytes < width_bytes || spitch_bytes < width_bytes) {
+        set_error("espm_upload_2d: bad arguments");
+        return ESPM_ERR_BAD_ARG;
+    }
+    ESPM_CUDA_CHECK(cudaMemcpy2DAsync(dst, (size_t)dpitch_bytes, src_host, (size_t)spitch_bytes, (size_t)width_bytes,
+                                      (size_t)height, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return ESPM_OK;
+}
+
 int espm_retile_x(const espm_state* st, const void* src, int32_t src_dtype, int64_t stride_c, int64_t stride_p,
                   int64_t j0, double scale, const espm_ingest* stats, void* stream) {
     int rc = check_state(st);

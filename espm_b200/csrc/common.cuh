@@ -4,6 +4,9 @@
 #include <stdint.h>
 #include <math.h>
 
+#include <cstdlib>
+#include <utility>
+
 #include "../../include/espm_b200.h"
 
 #ifndef __CUDA_ARCH__
@@ -85,6 +88,34 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last() {
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// ---------------------------------------------------------------- programmatic dependent launch
+// The per-iteration kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization: a kernel's CTAs
+// may be scheduled while the previous kernel of the stream drains.  pdl_wait() (griddepcontrol.wait) is the FIRST
+// statement of every such kernel -- nothing of the predecessor is read or overwritten before it returns, so the only
+// effect is that launch latency and CTA start-up overlap the predecessor's tail.  pdl_trigger() lets the next kernel
+// of the stream do the same with us.  Both are no-ops for kernels launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    static const bool enabled = [] {   // ESPM_B200_PDL=0 restores plain stream-ordered launches (A/B measurements)
+        const char* e = getenv("ESPM_B200_PDL");
+        return !(e && e[0] == '0');
+    }();
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = enabled ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
 // ---------------------------------------------------------------- arithmetic traits

@@ -540,6 +540,8 @@ __device__ __forceinline__ void h_scalars_block(const espm_state& st);
 // ------------------------------------------------------------------------------------------------
 template <typename TC, int KP>
 __global__ void __launch_bounds__(PX_THREADS) h_finish_kernel(const espm_state st) {
+    pdl_wait();
+    pdl_trigger();
     const int j = blockIdx.x * PX_THREADS + threadIdx.x;
     const bool active = j < st.p_loc;
     const int k = st.k;
@@ -789,6 +791,8 @@ __global__ void __launch_bounds__(PX_THREADS) h_finish_kernel(const espm_state s
 // ------------------------------------------------------------------------------------------------
 template <typename TC, int KP>
 __global__ void __launch_bounds__(PX_THREADS) h_apply_kernel(const espm_state st) {
+    pdl_wait();
+    pdl_trigger();
     const int j = blockIdx.x * PX_THREADS + threadIdx.x;
     const int k = st.k;
     const TC ls = (TC)st.log_shift;
@@ -1111,6 +1115,7 @@ __device__ __forceinline__ void grid_barrier(uint32_t* ctr, uint32_t nblocks) {
 
 template <typename TC, int KP>
 __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_state st) {
+    pdl_trigger();   // (launched in plain stream order itself; lets the next H pass set up while we run)
     __shared__ double sm[8 * 2 * ESPM_MAX_K + 8];
     __shared__ double col_a[ESPM_MAX_K], col_b[ESPM_MAX_K], col_fa[ESPM_MAX_K], col_new[ESPM_MAX_K],
         col_fn[ESPM_MAX_K];
@@ -1278,7 +1283,7 @@ __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_sta
                 TB sacc = 0.0;
                 for (int i = lane; i < nrows; i += 32) {
                     const int o = row_of(i) * k + kk;
-                    sacc += fmax((TB)wnum[o] / (x + (TB)wden[o]), lsb);
+                    sacc += fmax(simplex_quot<TB>((TB)wnum[o], x + (TB)wden[o]), lsb);   // correctly rounded, ~4x cheaper
                 }
                 return warp_sum(sacc) - 1.0;
             };

@@ -50,10 +50,10 @@ static int small_launch_t(int op, const espm_state* st, cudaStream_t s) {
     const int kp = st->kp;
     switch (op) {
         case OP_H_FINISH:
-            ESPM_KP_SWITCH(kp, (h_finish_kernel<TC, KP><<<st->px_blocks, PX_THREADS, 0, s>>>(*st)));
+            ESPM_KP_SWITCH(kp, ESPM_CUDA_CHECK(launch_pdl(h_finish_kernel<TC, KP>, dim3(st->px_blocks), dim3(PX_THREADS), 0, s, *st)));
             break;
         case OP_H_APPLY:
-            ESPM_KP_SWITCH(kp, (h_apply_kernel<TC, KP><<<st->px_blocks, PX_THREADS, 0, s>>>(*st)));
+            ESPM_KP_SWITCH(kp, ESPM_CUDA_CHECK(launch_pdl(h_apply_kernel<TC, KP>, dim3(st->px_blocks), dim3(PX_THREADS), 0, s, *st)));
             break;
         case OP_H_STATS:
             ESPM_KP_SWITCH(kp, (h_stats_kernel<TC, KP><<<st->px_blocks, PX_THREADS, 0, s>>>(*st)));

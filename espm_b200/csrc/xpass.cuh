@@ -194,7 +194,9 @@ h_pass_kernel(const XPassArgs a) {
     TC* red = reinterpret_cast<TC*>(smem + S::BAR_BYTES + S::MISC_BYTES + (size_t)a.depth * S::H_STRIDE);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) ring.init();
+    if (threadIdx.x == 0) ring.init();      // shared memory only: may overlap the previous kernel's tail
+    pdl_wait();
+    pdl_trigger();
     if (blockIdx.x == 0 && threadIdx.x < 4 && a.bisect_mask) a.bisect_mask[threadIdx.x] = 0u;
     __syncthreads();
 
@@ -457,8 +459,10 @@ w_pass_kernel(const XPassArgs a) {
     const int n_units = (u1 > u0) ? (int)(u1 - u0) : 0;
     const int cb0 = (int)(u0 / a.n_tiles), tile0 = (int)(u0 - (long long)cb0 * a.n_tiles);
 
-    if (threadIdx.x == 0) ring.init();
+    if (threadIdx.x == 0) ring.init();      // shared memory only: may overlap the previous kernel's tail
     for (int i = threadIdx.x; i < G::HALVES * G::CS * KP; i += blockDim.x) tail[i] = TC(0);
+    pdl_wait();
+    pdl_trigger();
     __syncthreads();
 
     if (warp == N_CONSUMER_WARPS) {

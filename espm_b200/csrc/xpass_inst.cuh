@@ -35,8 +35,7 @@ static int xpass_do(const XPassLaunch& l, const XPassArgs* a, int* occ_out, cuda
         ESPM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ_out, kern, XPASS_THREADS, l.smem));
         return ESPM_OK;
     }
-    kern<<<l.grid, XPASS_THREADS, l.smem, stream>>>(*a);
-    ESPM_CUDA_CHECK(cudaGetLastError());
+    ESPM_CUDA_CHECK(launch_pdl(kern, dim3(l.grid), dim3(XPASS_THREADS), (size_t)l.smem, stream, *a));
     return ESPM_OK;
 }
 

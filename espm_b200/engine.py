@@ -375,9 +375,16 @@ class FitEngine:
                 sc, sp = 1, self.n
             else:
                 slab = Xv[:, j0:j1]
-                if not slab.flags.c_contiguous:
-                    slab = np.ascontiguousarray(slab)
-                d = torch.from_numpy(slab).to(self.device)
+                if slab.flags.c_contiguous:
+                    d = torch.from_numpy(slab).to(self.device)
+                elif slab.strides[1] == slab.itemsize and slab.strides[0] >= slab.shape[1] * slab.itemsize:
+                    # this rank's columns of a C-ordered image: strided rows, copied without a host-side pass
+                    d = torch.empty(slab.shape, dtype=xdt, device=self.device)
+                    L.check(self.lib.espm_upload_2d(
+                        ctypes.c_void_p(d.data_ptr()), slab.shape[1] * slab.itemsize, ctypes.c_void_p(slab.ctypes.data),
+                        slab.strides[0], slab.shape[1] * slab.itemsize, slab.shape[0], self.stream))
+                else:
+                    d = torch.from_numpy(np.ascontiguousarray(slab)).to(self.device)
                 sc, sp = slab.shape[1], 1
         src = ctypes.c_void_p(d.data_ptr())
         if ingest is None:

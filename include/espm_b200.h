@@ -271,6 +271,10 @@ typedef struct espm_ingest {
     uint32_t* flags;
     double* sum_part;
 } espm_ingest;
+/* Strided host -> device copy (cudaMemcpy2DAsync): `height` rows of `width_bytes`, source rows `spitch_bytes` apart.
+ * Lets a rank upload its pixel slab X[:, j0:j1] of a C-ordered host image without a host-side copy. */
+int espm_upload_2d(void* dst, int64_t dpitch_bytes, const void* src_host, int64_t spitch_bytes, int64_t width_bytes,
+                   int64_t height, void* stream);
 int espm_retile_x(const espm_state* st, const void* src, int32_t src_dtype, int64_t stride_c,
                   int64_t stride_p, int64_t j0, double scale, const espm_ingest* stats, void* stream);
 int espm_xt_fixup(const espm_state* st, const int32_t* row_zero, const int32_t* col_zero, double eps,
