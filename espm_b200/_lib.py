@@ -115,6 +115,7 @@ _EXPORTS = {
     "espm_xt_fixup": (ctypes.c_int, [ctypes.POINTER(EspmState), _vp, _vp, _f64, _f64, _vp]),
     "espm_xt_const": (ctypes.c_int, [ctypes.POINTER(EspmState), _vp, _vp]),
     "espm_reduce_sum": (ctypes.c_int, [_vp, _i64, _vp, _vp]),
+    "espm_log2_table": (ctypes.c_int, [_vp, _i64, _vp, _vp]),
     "espm_gw_prepare": (ctypes.c_int, [ctypes.POINTER(EspmState), _vp]),
     "espm_colsum_g": (ctypes.c_int, [ctypes.POINTER(EspmState), _vp, _vp]),
     "espm_h_stats": (ctypes.c_int, [ctypes.POINTER(EspmState), _vp]),

@@ -319,6 +319,14 @@ int espm_xt_const(const espm_state* st, double* part_out, void* stream) {
     return xt_const_launch(st, part_out, (cudaStream_t)stream);
 }
 
+int espm_log2_table(const double* y, int64_t n, double* out, void* stream) {
+    if (!y || !out || n < 0) {
+        set_error("espm_log2_table: bad arguments");
+        return ESPM_ERR_BAD_ARG;
+    }
+    return log2_table_launch(y, (long long)n, out, (cudaStream_t)stream);
+}
+
 int espm_reduce_sum(const double* in, int64_t n, double* out, void* stream) {
     if (!in || !out || n < 0) {
         set_error("espm_reduce_sum: bad arguments");

@@ -147,7 +147,16 @@ struct Num<double> {
         r = fma(r, e, r);
         return r;
     }
-    static __device__ __forceinline__ double ratio(double x, double y) { return x * rcp(y); }
+    // x / y of the streaming passes: the seed is good to 2^-19.9 (scripts/probes/rcp_probe.cu), so ONE cubic step
+    // r (1 + e + e^2), e = 1 - y r, leaves e^3 = 2^-59.7: 3 DFMA instead of 4, max error 1 ulp on the reciprocal
+    // (measured over 2^24 arguments); the step tolerance of the fp64 mode is 1e-10.
+    static __device__ __forceinline__ double ratio(double x, double y) {
+        double r;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));
+        const double e = fma(-y, r, 1.0);
+        const double t = fma(e, e, e);
+        return x * fma(r, t, r);
+    }
     static __device__ __forceinline__ double log2_fast(double y) { return log2(y); }
     static __device__ __forceinline__ double vmax(double a, double b) { return fmax(a, b); }
     static __device__ __forceinline__ double vmin(double a, double b) { return fmin(a, b); }
@@ -156,6 +165,70 @@ struct Num<double> {
     static __device__ __forceinline__ double vlog(double a) { return log(a); }
     static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
 };
+
+// Table-driven log2 of a double for the streaming H pass (the CUDA library log2 is ~35 DP-pipe instructions, which
+// made the fp64 H pass DP-bound at 0.41 of the HBM peak): y = 2^e m, i = top 7 mantissa bits of m,
+// r = m * inv_i - 1 with inv_i = 1 / (1 + (i + 0.5) / 128)  (|r| <= 2^-8, one exact FMA),
+// log2(y) = e - log2(inv_i) + r * P(r), P of degree 4 fitted to log2(1 + r) / r on |r| <= 2^-8 (truncation
+// 3e-17).  8 DP instructions; absolute error <= 2 ulp of the result (the final additions), checked against a
+// long-double evaluation in tests/test_log2_table.py.  Zero / subnormal / negative / non-finite arguments take
+// the library path.
+constexpr int LOG2TAB_N = 128;
+// The 16-byte entries are replicated LOG2TAB_R = 4 times in shared memory: a lane reads copy (lane & 3), and copy c of
+// entry i lives at 16-byte slot (i & 63) * 8 + c * 2 + (i >> 6), i.e. in bank groups {2c, 2c + 1}.  An LDS.128 is
+// served per quarter warp (8 lanes), so lookups with unrelated i collide only between the two lanes that share a copy
+// (expected 1.5 wavefronts per quarter instead of 2.6 for a single copy: the single-copy table spent 40 % of the
+// kernel's shared-memory wavefronts on bank conflicts, profiles/r01f_summary.md).
+constexpr int LOG2TAB_R = 4;
+constexpr int LOG2TAB_BYTES = LOG2TAB_N * LOG2TAB_R * 16;
+__device__ __forceinline__ void log2tab_fill(double2* tab, int tid, int nthreads) {
+    for (int i = tid; i < LOG2TAB_N; i += nthreads) {
+        const double inv = 1.0 / (1.0 + ((double)i + 0.5) * (1.0 / LOG2TAB_N));
+        const double2 v = make_double2(inv, -log2(inv));
+#pragma unroll
+        for (int c = 0; c < LOG2TAB_R; ++c) tab[(i & 63) * 8 + c * 2 + (i >> 6)] = v;
+    }
+}
+// this lane's view of the table: byte offset of its copy folded into the base pointer
+__device__ __forceinline__ const double2* log2tab_lane(const double2* tab, int lane) { return tab + (lane & 3) * 2; }
+// entry of mantissa index i = hi[19:13] in the lane's copy: slot (i & 63) * 8 + (i >> 6)
+__device__ __forceinline__ double2 log2tab_get(const double2* lane_tab, int hi) {
+    const unsigned off = (((unsigned)hi >> 6) & 0x1f80u) | (((unsigned)hi >> 15) & 0x10u);   // bytes
+    return *reinterpret_cast<const double2*>(reinterpret_cast<const unsigned char*>(lane_tab) + off);
+}
+// polynomial coefficients in constant memory: DFMA takes them as c[bank][offset] operands (64-bit immediates
+// would cost two UMOVs each)
+static __device__ __constant__ double LOG2_C[5] = {0x1.71547652b82ffp+0, -0x1.715476529026dp-1, 0x1.ec709dc2ea15bp-2,
+                                                   -0x1.7155b049ac044p-2, 0x1.277837d2b64aap-2};
+// Branch-free core: valid for normal positive y.  `range` accumulates max((unsigned)(hi - 0x00100000)); the caller
+// tests log2_range_bad(range) once per batch and redoes the batch with the library log2 if it fires.
+// `tab` is the lane's view (log2tab_lane).
+__device__ __forceinline__ double log2_tab_core(double y, const double2* tab, unsigned& range) {
+    const int hi = __double2hiint(y);
+    const unsigned t = (unsigned)hi - 0x00100000u;
+    range = t > range ? t : range;
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(y));
+    const double2 tv = log2tab_get(tab, hi);
+    const double r = fma(m, tv.x, -1.0);
+    double p = LOG2_C[4];
+    p = fma(p, r, LOG2_C[3]);
+    p = fma(p, r, LOG2_C[2]);
+    p = fma(p, r, LOG2_C[1]);
+    p = fma(p, r, LOG2_C[0]);
+    return fma(p, r, tv.y + (double)((hi >> 20) - 1023));
+}
+__device__ __forceinline__ bool log2_range_bad(unsigned range) { return range >= 0x7fe00000u; }
+__device__ __forceinline__ double log2_tab(double y, const double2* tab) {
+    unsigned range = 0u;
+    const double v = log2_tab_core(y, tab, range);
+    return log2_range_bad(range) ? log2(y) : v;
+}
+// max(x, b) for x >= 0, b >= 0 (no NaN): the IEEE order of non-negative doubles is the order of their bit patterns,
+// so this is integer compare + select instead of the 7-instruction DSETP.MAX sequence.
+__device__ __forceinline__ double max_nonneg(double x, double b) {
+    const long long xb = __double_as_longlong(x), bb = __double_as_longlong(b);
+    return __longlong_as_double(xb > bb ? xb : bb);
+}
 
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {

@@ -62,6 +62,22 @@ int x_sums_launch(const espm_state* st, void* colsum, double* rowsum_part, cudaS
     return ESPM_OK;
 }
 
+// out[i] = log2_tab(y[i]): the table-driven log2 of the fp64 H pass, exposed for the accuracy test
+__global__ void __launch_bounds__(256) log2_table_kernel(const double* y, long long n, double* out) {
+    __shared__ double2 tab[LOG2TAB_N * LOG2TAB_R];
+    log2tab_fill(tab, threadIdx.x, blockDim.x);
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = log2_tab(y[i], log2tab_lane(tab, threadIdx.x & 31));
+}
+
+int log2_table_launch(const double* y, long long n, double* out, cudaStream_t s) {
+    const int grid = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
+    if (grid > 0) log2_table_kernel<<<grid, 256, 0, s>>>(y, n, out);
+    ESPM_CUDA_CHECK(cudaGetLastError());
+    return ESPM_OK;
+}
+
 int reduce_sum_launch(const double* in, long long n, double* out, cudaStream_t s) {
     reduce_sum_kernel<<<1, 1024, 0, s>>>(in, n, out);
     ESPM_CUDA_CHECK(cudaGetLastError());

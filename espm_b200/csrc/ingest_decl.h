@@ -18,5 +18,6 @@ int xt_fixup_launch(const espm_state* st, const int32_t* row_zero, const int32_t
                     cudaStream_t s);
 int xt_const_launch(const espm_state* st, double* part, cudaStream_t s);
 int x_sums_launch(const espm_state* st, void* colsum, double* rowsum_part, cudaStream_t s);
+int log2_table_launch(const double* y, long long n, double* out, cudaStream_t s);
 int reduce_sum_launch(const double* in, long long n, double* out, cudaStream_t s);
 }  // namespace espm

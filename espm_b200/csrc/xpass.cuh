@@ -57,6 +57,8 @@ struct XPassSmem {
     static constexpr int BAR_BYTES = 256;  // up to 16 full + 16 empty barriers
     static constexpr int MISC_BYTES = 128;
     static constexpr int RED_BYTES = G::NSLOT * KP * TILE_PX * (int)sizeof(TC);          // H pass epilogue
+    static constexpr int LOGTAB_BYTES = sizeof(TC) == 8 ? LOG2TAB_BYTES : 0;             // fp64 H pass: log2_tab()
+    static constexpr int HTAIL_BYTES = RED_BYTES + LOGTAB_BYTES;
     static constexpr int WACC_BYTES = G::HALVES * G::CS * KP * (int)sizeof(TC);           // W pass flush / accumulator
     static constexpr int WTAIL_BYTES = GW_BYTES_AL + WACC_BYTES;                          // + GW rows of the channel block
     // the W pass keeps CPW x KP ratio sums per lane in registers when they fit, else in shared memory
@@ -188,10 +190,15 @@ h_pass_kernel(const XPassArgs a) {
     using S = XPassSmem<TX, TC, KP, SAFE>;
     constexpr int PPL = G::PPL;
     constexpr bool FAST32 = MODE == XMODE_KL && !SAFE && sizeof(TX) == 4 && sizeof(TC) == 4;
+    constexpr bool FAST64 = MODE == XMODE_KL && !SAFE && sizeof(TC) == 8;   // table log2, branch-free loss terms
     extern __shared__ __align__(128) unsigned char smem[];
     Ring<S::H_STRIDE> ring(smem, a.depth, S::BAR_BYTES + S::MISC_BYTES);
     double* misc = reinterpret_cast<double*>(smem + S::BAR_BYTES);
     TC* red = reinterpret_cast<TC*>(smem + S::BAR_BYTES + S::MISC_BYTES + (size_t)a.depth * S::H_STRIDE);
+    [[maybe_unused]] const double2* ltab = log2tab_lane(
+        reinterpret_cast<const double2*>(reinterpret_cast<unsigned char*>(red) + S::RED_BYTES), threadIdx.x & 31);
+    if constexpr (sizeof(TC) == 8 && MODE == XMODE_KL)
+        log2tab_fill(reinterpret_cast<double2*>(reinterpret_cast<unsigned char*>(red) + S::RED_BYTES), threadIdx.x, XPASS_THREADS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) ring.init();      // shared memory only: may overlap the previous kernel's tail
@@ -299,6 +306,8 @@ h_pass_kernel(const XPassArgs a) {
         } else {
             TC hc[SAFE ? KP : 1][PPL];
             const TC ysh = (TC)a.y_shift;
+            const bool shifted = a.y_shift != 0.0;
+            [[maybe_unused]] unsigned lrange = 0u;
 #pragma unroll
             for (int kk = 0; kk < KP; ++kk)
 #pragma unroll
@@ -336,7 +345,7 @@ h_pass_kernel(const XPassArgs a) {
 #pragma unroll
                     for (int q = 0; q < PPL; ++q) {
                         if constexpr (MODE == XMODE_FROB) r[q] = (TC)xv[q];
-                        else r[q] = Num<TC>::ratio((TC)xv[q], y[q] + ysh);
+                        else r[q] = Num<TC>::ratio((TC)xv[q], shifted ? y[q] + ysh : y[q]);
                     }
 #pragma unroll
                     for (int kk = 0; kk < KP; ++kk)
@@ -374,10 +383,39 @@ h_pass_kernel(const XPassArgs a) {
 #pragma unroll
                         for (int q = 0; q < PPL; ++q) {
                             const TC x = (TC)xv[q];
-                            if (x > TC(0)) {
+                            if constexpr (FAST64) {
+                                // branch-free: max(x, ls) * log2(y) for every element (measures.py:497-503 as written);
+                                // X >= 0 was checked at ingest (base.py:528)
+                                xl = fma(max_nonneg(x, ls), log2_tab_core(y[q], ltab, lrange), xl);
+                            } else if constexpr (sizeof(TC) == 8) {
+                                xl = fma(Num<TC>::vmax(x, ls), log2_tab(yl[q], ltab), xl);
+                            } else if (x > TC(0)) {
                                 xl = fma(Num<TC>::vmax(x, ls), Num<TC>::log2_fast(yl[q]), xl);
                             } else {
                                 zl += __log2f((float)yl[q]);
+                            }
+                        }
+                    }
+                }
+                if constexpr (FAST64) {
+                    if (__any_sync(0xffffffffu, log2_range_bad(lrange))) {
+                        // some y of this stage is zero / subnormal / negative / non-finite: redo the stage's loss terms
+                        // with the library log2 (cold path)
+                        xl = TC(0);
+                        lrange = 0u;
+#pragma unroll 1
+                        for (int ci = 0; ci < G::CPW; ++ci) {
+                            const int c = slot + ci * G::NSLOT;
+                            TX xv[PPL];
+                            TC gw[KP];
+                            lds_vec<TX, PPL>(xv, xs + ((size_t)c * TILE_PX + lane_px) * sizeof(TX));
+                            lds_gw<TC, KP>(gw, gs + (size_t)c * KP * sizeof(TC));
+#pragma unroll
+                            for (int q = 0; q < PPL; ++q) {
+                                TC yq = gw[0] * h[0][q];
+#pragma unroll
+                                for (int kk = 1; kk < KP; ++kk) yq = fma(gw[kk], h[kk][q], yq);
+                                xl = fma(Num<TC>::vmax((TC)xv[q], ls), (TC)log2((double)yq), xl);
                             }
                         }
                     }

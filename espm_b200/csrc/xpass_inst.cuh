@@ -76,7 +76,7 @@ static void xpass_sizes_kp(int safe, XPassSizes* o) {
     using S1 = XPassSmem<TX, TC, KP, true>;
     o->h_stride = safe ? S1::H_STRIDE : S0::H_STRIDE;
     o->w_stride = S0::W_STRIDE;
-    o->h_tail = S0::RED_BYTES;
+    o->h_tail = S0::HTAIL_BYTES;
     o->w_tail = S0::WTAIL_BYTES;
     o->fixed = S0::BAR_BYTES + S0::MISC_BYTES;
     o->cs = S0::G::CS;

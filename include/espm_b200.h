@@ -281,6 +281,9 @@ int espm_xt_fixup(const espm_state* st, const int32_t* row_zero, const int32_t* 
                   double scale, void* stream);
 int espm_xt_const(const espm_state* st, double* part_out, void* stream);
 int espm_reduce_sum(const double* in, int64_t n, double* out, void* stream);
+/* Diagnostic: out[i] = log2(y[i]) evaluated by the table-driven routine the fp64 H pass uses for the
+ * max(X, ls) * log(Y) term of KLdiv_loss (measures.py:497-503); y, out: n device doubles. */
+int espm_log2_table(const double* y, int64_t n, double* out, void* stream);
 
 /* GW_next = G.W_next (+pad rows), gwstats_next, ESPM_DEV_GW_* flags.  base.py:189, updates.py:107. */
 int espm_gw_prepare(const espm_state* st, void* stream);
