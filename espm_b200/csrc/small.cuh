@@ -392,12 +392,35 @@ struct PgEval {    // projected gradient (dicotomy.py:83-108): f(x) = sum_k max(
 // word 4 of a pixel's decision record: iterations seen by the trace | stationary flag
 constexpr uint32_t BIS_STATIONARY = 1u << 8;
 
+// sign and size class of f at a bracket end; the KL evaluator answers from its fp32 screen when that is certain
+// (f(a) >= 1 and f(b) <= -1/2 by construction of the bracket, dicotomy.py:29-49, so it practically always is)
+struct End {
+    bool pos, neg, bad;
+};
+template <typename E>
+__device__ __forceinline__ End end_of(const E& ev, double x) {
+    const double f = ev.exact(x);
+    return End{f > 0.0, f < 0.0, fabs(f) > ev.tol};
+}
+template <int KP>
+__device__ __forceinline__ End end_of(const KlEval<KP>& ev, double x) {
+    if (ev.screen) {
+        float f, margin;
+        ev.screen_f(x, f, margin);
+        const float af = fabsf(f);
+        if (af > margin && fabsf(af - ev.tolf) > margin + 1e-7f * ev.tolf) return End{f > 0.f, f < 0.f, af > ev.tolf};
+    }
+    const double f = ev.exact(x);
+    return End{f > 0.0, f < 0.0, fabs(f) > ev.tol};
+}
+
 template <typename E>
 __device__ __forceinline__ void bisect_trace_rec(double a, double b, const E& ev, int maxit, Mask128& bad, Mask128& dec,
                                                  uint32_t& seen, uint32_t& err) {
-    const double fa = ev.exact(a), fb = ev.exact(b);
-    if (!(fa > 0.0) || !(fb < 0.0)) err |= ESPM_DEV_BRACKET;   // dicotomy.py:141-144
-    bool a_ok = fa <= ev.tol, b_ok = -fb <= ev.tol;          // is the end of the bracket already within tol?
+    // f at the two ends: only their signs and whether they are within tol matter (dicotomy.py:141-144)
+    const End ea = end_of(ev, a), eb = end_of(ev, b);
+    if (!ea.pos || !eb.neg) err |= ESPM_DEV_BRACKET;
+    bool a_ok = !ea.bad, b_ok = !eb.bad;                     // is the end of the bracket already within tol?
     double nw = (a + b) * 0.5;
     int j = 0, widx = 0;
     uint32_t stat = 0u;
@@ -539,7 +562,7 @@ __device__ __forceinline__ void h_scalars_block(const espm_state& st);
 // h_finish: per-pixel assembly (updates.py:132-152) + loss regularisers + rel_H + bisection trace
 // ------------------------------------------------------------------------------------------------
 template <typename TC, int KP>
-__global__ void __launch_bounds__(PX_THREADS) h_finish_kernel(const espm_state st) {
+__global__ void __launch_bounds__(PX_THREADS, 4) h_finish_kernel(const espm_state st) {
     pdl_wait();
     pdl_trigger();
     const int j = blockIdx.x * PX_THREADS + threadIdx.x;
@@ -752,13 +775,16 @@ __global__ void __launch_bounds__(PX_THREADS) h_finish_kernel(const espm_state s
             store_h_next<TC, KP>(st, j, k, hn, vals);
         }
     }
-    if (st.flags & ESPM_FLAG_EVAL_ONLY) {
-        // keep the H_next statistics another kernel left in px_part: only the loss partials are ours
-        __shared__ double tmp[NV];
-        block_reduce_vals<NV>(vals, px_part_nsum(KP), tmp);
+    if ((st.flags & ESPM_FLAG_EVAL_ONLY) || simplex) {
+        // only the loss partials and rel_H are ours: the H_next statistics in px_part come from another kernel
+        // (evaluation only) or from the h_apply that follows (simplex_H), which writes the other columns
+        const double v3[3] = {vals[0], vals[1], vals[2 + 2 * KP]};
+        __shared__ double tmp[3];
+        block_reduce_vals<3>(v3, 2, tmp);
         __syncthreads();
         double* out = st.px_part + (size_t)blockIdx.x * NV;
-        if (threadIdx.x < 2 || threadIdx.x == 2 + 2 * KP) out[threadIdx.x] = tmp[threadIdx.x];
+        if (threadIdx.x < 2) out[threadIdx.x] = tmp[threadIdx.x];
+        if (threadIdx.x == 2) out[2 + 2 * KP] = tmp[2];
     } else {
         block_reduce_vals<NV>(vals, px_part_nsum(KP), st.px_part + (size_t)blockIdx.x * NV);
     }
@@ -899,25 +925,43 @@ __global__ void __launch_bounds__(PX_THREADS) h_stats_kernel(const espm_state st
 // ------------------------------------------------------------------------------------------------
 // Reduce the px_part rows into hstats_next = {rowsum[kp], rowsumc[kp], rowmax[kp]} (one CTA).
 // ------------------------------------------------------------------------------------------------
+// Every thread takes whole px_part rows (blocks tid, tid + nthreads, ...): all its loads are independent, so the fold
+// is one L2 round trip instead of px_blocks / 32 dependent ones; then lane butterfly and warps in index order
+// (fixed order => deterministic).  Callable with up to 8 warps; hstats_out may be shared or global memory.
+template <int KP>
 __device__ __forceinline__ void reduce_hstats_block(const espm_state& st, double* hstats_out) {
-    const int kp = st.kp, stride = px_part_stride(kp);
+    constexpr int NVAL = 3 * KP, STRIDE = 3 + 3 * KP;
+    __shared__ double red[8][NVAL];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    for (int v = warp; v < 3 * kp; v += nwarps) {
-        const bool is_max = v >= 2 * kp;
-        const int col = is_max ? (3 + 2 * kp + (v - 2 * kp)) : (2 + v);
-        double r = is_max ? -1e300 : 0.0;
-        for (int b = lane; b < st.px_blocks; b += 32) {
-            const double u = st.px_part[(size_t)b * stride + col];
-            r = is_max ? (u > r ? u : r) : r + u;
-        }
-        r = is_max ? warp_max(r) : warp_sum(r);
-        if (lane == 0) hstats_out[v] = r;
+    double acc[NVAL];
+#pragma unroll
+    for (int v = 0; v < NVAL; ++v) acc[v] = (v >= 2 * KP) ? -1e300 : 0.0;
+    for (int b = threadIdx.x; b < st.px_blocks; b += blockDim.x) {
+        const double* row = st.px_part + (size_t)b * STRIDE;
+        double u[NVAL];
+#pragma unroll
+        for (int v = 0; v < NVAL; ++v) u[v] = row[(v >= 2 * KP) ? (3 + v) : (2 + v)];
+#pragma unroll
+        for (int v = 0; v < NVAL; ++v) acc[v] = (v >= 2 * KP) ? (u[v] > acc[v] ? u[v] : acc[v]) : acc[v] + u[v];
     }
+#pragma unroll
+    for (int v = 0; v < NVAL; ++v) {
+        const double r = (v >= 2 * KP) ? warp_max(acc[v]) : warp_sum(acc[v]);
+        if (lane == 0) red[warp][v] = r;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < NVAL) {
+        const int v = threadIdx.x;
+        double r = red[0][v];
+        for (int w = 1; w < nwarps; ++w) r = (v >= 2 * KP) ? (red[w][v] > r ? red[w][v] : r) : r + red[w][v];
+        hstats_out[v] = r;
+    }
+    __syncthreads();
 }
 
-template <typename TC>
+template <typename TC, int KP>
 __global__ void __launch_bounds__(256) hstats_reduce_kernel(const espm_state st) {
-    reduce_hstats_block(st, reinterpret_cast<double*>(st.hstats_next));
+    reduce_hstats_block<KP>(st, reinterpret_cast<double*>(st.hstats_next));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -982,10 +1026,10 @@ __global__ void __launch_bounds__(256) h_scalars_kernel(const espm_state st) {
 // ------------------------------------------------------------------------------------------------
 // w_reduce: s_sum[c][k] = sum_r s_part[r][c][k]; the last block reduces the H_next statistics.
 // ------------------------------------------------------------------------------------------------
-template <typename TC>
+template <typename TC, int KP>
 __global__ void __launch_bounds__(256) w_reduce_kernel(const espm_state st) {
     if (blockIdx.x == gridDim.x - 1) {
-        reduce_hstats_block(st, reinterpret_cast<double*>(st.hstats_next));
+        reduce_hstats_block<KP>(st, reinterpret_cast<double*>(st.hstats_next));
         return;
     }
     const size_t total = (size_t)st.n_pad * st.kp;
@@ -1088,15 +1132,22 @@ __global__ void __launch_bounds__(256) colsum_g_kernel(const TC* Gt, int n, int 
 
 // ------------------------------------------------------------------------------------------------
 // w_finish: the W update (updates.py:58-76) + GW' for the next H pass, as ONE cooperative kernel of
-// W_COOP_BLOCKS CTAs separated by grid barriers:
-//   phase 0 (all CTAs, optional)  s_sum = sum of the W-pass partial slots; H' row statistics
-//   phase A (all CTAs)            num = W * (G^T S),  den = colsum(G) (x) rowsum(H')
-//   phase B (CTA 0)               simplex_W lock-step bisection, W' = max(num/den, ls), fixed_W, rel_W
+// W_COOP_BLOCKS CTAs.  Grid barriers cost ~4 us each at this size, so the phases are arranged to need as few as
+// possible (single GPU, no simplex_W, m k <= W_SM_MAX: ONE barrier; was four):
+//   phase 0 (all CTAs, optional)  s_sum = sum of the W-pass partial slots; H' row statistics (every CTA folds them
+//                                 for itself into shared memory: nothing below waits for another CTA's phase 0)
+//   phase A (one CTA per row of G^T) num = W * (G^T S),  den = colsum(G) (x) rowsum(H'); S rows are folded from the
+//                                 partial slots on the fly when the fit is not sharded
+//   -- grid barrier --
+//   phase B                       W' = max(num/den, ls), fixed_W, rel_W: redundantly in every CTA (W' stays in shared
+//                                 memory, CTA 0 writes it out) unless simplex_W or a large m (then CTA 0 + a barrier)
 //   phase C (all CTAs)            GW' = G W' (+ pad rows, clamped copy), per-CTA column sums / flags
-//   phase D (CTA 0)               column sums in CTA order (deterministic), flags
+//   phase D (last CTA to finish)  column sums in CTA order (deterministic), flags
+// Sharded fits (ESPM_FLAG_PEER) add the exchange of S between phase 0 and phase A (two more barriers).
 // ------------------------------------------------------------------------------------------------
 constexpr int W_COOP_BLOCKS = 32;
 constexpr int W_COOP_THREADS = 256;
+constexpr int W_SM_MAX = 1024;   // m*k up to which W' is kept in shared memory by every CTA
 
 // Grid barrier for a cooperative launch: monotonically increasing arrival counter, every CTA arrives
 // exactly once per barrier, so the target of an arrival is the next multiple of the grid size.
@@ -1121,9 +1172,15 @@ __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_sta
         col_fn[ESPM_MAX_K];
     __shared__ int s_its;
     __shared__ uint32_t s_err;
+    __shared__ double hs_sm[3 * ESPM_MAX_K];
+    __shared__ TC wsm[W_SM_MAX];
+    __shared__ bool s_last;
     const int k = st.k, m = st.m, n = st.n;
     const TC ls = (TC)st.log_shift;
     const bool ident = st.flags & ESPM_FLAG_G_IDENTITY;
+    // single-GPU fused mode: phase A folds the partial slots itself and every CTA has its own H' statistics
+    const bool fly = (st.flags & ESPM_FLAG_FUSED_WREDUCE) && !(st.flags & ESPM_FLAG_PEER);
+    const bool redundant_b = !(st.flags & ESPM_FLAG_SIMPLEX_W) && m * k <= W_SM_MAX;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int NWARPS = W_COOP_THREADS / 32;
     const int gthread = blockIdx.x * W_COOP_THREADS + threadIdx.x;
@@ -1157,8 +1214,14 @@ __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_sta
             for (int r = 1; r <= last - first; ++r) v += part[(size_t)r * total + i];
             Sloc[i] = v;
         }
-        if (blockIdx.x == gridDim.x - 1) reduce_hstats_block(st, hsloc);
-        grid_barrier(bar, gridDim.x);
+        if (fly) {
+            reduce_hstats_block<KP>(st, hs_sm);                   // every CTA, for itself
+            __syncthreads();
+            if (blockIdx.x == gridDim.x - 1 && (int)threadIdx.x < 3 * KP) hstats[threadIdx.x] = hs_sm[threadIdx.x];
+        } else {
+            if (blockIdx.x == gridDim.x - 1) reduce_hstats_block<KP>(st, hsloc);
+            grid_barrier(bar, gridDim.x);
+        }
         if (peer) {
             if (blockIdx.x == 0 && (int)threadIdx.x < st.world) {
                 __threadfence_system();
@@ -1216,56 +1279,107 @@ __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_sta
             wden[i] = cs_h;
         }
     };
+    const double* hs = fly ? hs_sm : hstats;
+    // S[c][:] -- from s_sum, or (fly) summed from the W-pass partial slots in slot order, exactly like phase 0
+    const size_t s_total = (size_t)st.n_pad * KP;
+    const TC* s_part = reinterpret_cast<const TC*>(st.s_part);
+    auto load_srow = [&](int c, TC (&srow)[KP]) {
+        if (fly) {
+            const int cb = c / st.cs;
+            const int first = (int)(((long long)cb * st.n_tiles) / st.w_upc);
+            const int last = (int)((((long long)cb + 1) * st.n_tiles - 1) / st.w_upc);
+            const int nr = last - first;           // slots 0..nr hold partial sums of this channel block
+            constexpr int RU = 6;                  // slots loaded at once (independent loads: one L2 round trip)
+            TC t[RU][KP];
+            lds_row<TC, KP>(srow, s_part + (size_t)c * KP);
+#pragma unroll
+            for (int r = 0; r < RU; ++r) {
+                if (r < nr) lds_row<TC, KP>(t[r], s_part + (size_t)(r + 1) * s_total + (size_t)c * KP);
+            }
+#pragma unroll
+            for (int r = 0; r < RU; ++r) {
+                if (r < nr) {
+#pragma unroll
+                    for (int kk = 0; kk < KP; ++kk) srow[kk] += t[r][kk];
+                }
+            }
+            for (int r = RU + 1; r <= nr; ++r) {
+                TC u[KP];
+                lds_row<TC, KP>(u, s_part + (size_t)r * s_total + (size_t)c * KP);
+#pragma unroll
+                for (int kk = 0; kk < KP; ++kk) srow[kk] += u[kk];
+            }
+        } else {
+            lds_row<TC, KP>(srow, S + (size_t)c * KP);
+        }
+    };
     if (ident) {
         for (int i = gthread; i < m * k; i += gthreads) {
             const int mm = i / k, kk = i - mm * k;
-            const TC sv = S[(size_t)mm * KP + kk];
+            TC srow[KP];
+            load_srow(mm, srow);
+            TC sv = srow[0];
+#pragma unroll
+            for (int k2 = 1; k2 < KP; ++k2)
+                if (k2 == kk) sv = srow[k2];
             nonfinite |= !(Num<TC>::vabs(sv) < Num<TC>::inf());
             TC trow[KP];
 #pragma unroll
             for (int k2 = 0; k2 < KP; ++k2) trow[k2] = (k2 < k) ? W[mm * k + k2] : TC(0);   // G^T G = I
-            entry(mm, kk, sv, (TC)hstats[kk], trow);
+            entry(mm, kk, sv, (TC)hs[kk], trow);
         }
     } else {
-        for (int mm = blockIdx.x * NWARPS + warp; mm < m; mm += gridDim.x * NWARPS) {
+        // one CTA per row of G^T: the 8 warps split the channels, partial sums meet in shared memory (fixed order)
+        TC* accsm = reinterpret_cast<TC*>(sm);   // [NWARPS][KP]
+        for (int mm = blockIdx.x; mm < m; mm += gridDim.x) {
             TC acc[KP];
 #pragma unroll
             for (int kk = 0; kk < KP; ++kk) acc[kk] = TC(0);
-            for (int c = lane; c < n; c += 32) {
+#pragma unroll 2
+            for (int c = threadIdx.x; c < n; c += W_COOP_THREADS) {
                 const TC g = Gt[(size_t)mm * n + c];
                 TC srow[KP];
-                lds_row<TC, KP>(srow, S + (size_t)c * KP);
+                load_srow(c, srow);
 #pragma unroll
                 for (int kk = 0; kk < KP; ++kk) acc[kk] = fma(g, srow[kk], acc[kk]);
-            }
-            TC trow[KP];
-#pragma unroll
-            for (int k2 = 0; k2 < KP; ++k2) trow[k2] = TC(0);
-            if (w_l2) {   // row mm of (G^T G) W
-                const TC* GG = reinterpret_cast<const TC*>(st.GG);
-                for (int m2 = lane; m2 < m; m2 += 32) {
-                    const TC g = GG[(size_t)mm * m + m2];
-#pragma unroll
-                    for (int k2 = 0; k2 < KP; ++k2)
-                        if (k2 < k) trow[k2] = fma(g, W[m2 * k + k2], trow[k2]);
-                }
-#pragma unroll
-                for (int k2 = 0; k2 < KP; ++k2) trow[k2] = warp_sum(trow[k2]);
             }
 #pragma unroll
             for (int kk = 0; kk < KP; ++kk) {
                 const TC v = warp_sum(acc[kk]);
-                nonfinite |= (kk < k) && !(Num<TC>::vabs(v) < Num<TC>::inf());
-                if (lane == 0 && kk < k) entry(mm, kk, v, colsumG[mm] * (TC)hstats[kk], trow);
+                if (lane == 0) accsm[warp * KP + kk] = v;
             }
+            __syncthreads();
+            if (warp == 0) {
+                TC trow[KP];
+#pragma unroll
+                for (int k2 = 0; k2 < KP; ++k2) trow[k2] = TC(0);
+                if (w_l2) {   // row mm of (G^T G) W
+                    const TC* GG = reinterpret_cast<const TC*>(st.GG);
+                    for (int m2 = lane; m2 < m; m2 += 32) {
+                        const TC g = GG[(size_t)mm * m + m2];
+#pragma unroll
+                        for (int k2 = 0; k2 < KP; ++k2)
+                            if (k2 < k) trow[k2] = fma(g, W[m2 * k + k2], trow[k2]);
+                    }
+#pragma unroll
+                    for (int k2 = 0; k2 < KP; ++k2) trow[k2] = warp_sum(trow[k2]);
+                }
+                if (lane < k) {
+                    TC v = accsm[lane];
+                    for (int w = 1; w < NWARPS; ++w) v += accsm[w * KP + lane];
+                    nonfinite |= !(Num<TC>::vabs(v) < Num<TC>::inf());
+                    entry(mm, lane, v, colsumG[mm] * (TC)hs[lane], trow);
+                }
+            }
+            __syncthreads();
         }
     }
     // x / 0 in the W pass (updates.py:53-56): the caller redoes the step with ESPM_FLAG_CLAMP_Y
     if (__any_sync(0xffffffffu, nonfinite) && lane == 0) atomicOr(&st.dev_flags[0], ESPM_DEV_NONFINITE);
     grid_barrier(bar, gridDim.x);
 
-    // ---- phase B (CTA 0): simplex_W, W', rel_W ----
-    if (blockIdx.x == 0) {
+    // ---- phase B (CTA 0, or every CTA when W' fits in shared memory and there is no bisection): W', rel_W ----
+    if (blockIdx.x == 0 || redundant_b) {
         if (threadIdx.x == 0) {
             s_its = 0;
             s_err = 0u;
@@ -1370,9 +1484,13 @@ __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_sta
                 const TC f = fw[i];
                 if (f >= TC(0)) v = f;
             }
-            Wn[i] = v;
+            if (blockIdx.x == 0) Wn[i] = v;
+            if (redundant_b) wsm[i] = v;
             wsum += (double)v;
         }
+        __syncthreads();
+      if (blockIdx.x == 0) {   // the scalars of the record are CTA 0's business
+        const TC* Wsee = redundant_b ? wsm : Wn;
         wsum = warp_sum(wsum);
         if (lane == 0) sm[warp] = wsum;
         __syncthreads();
@@ -1382,7 +1500,7 @@ __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_sta
         __syncthreads();
         double rel = 0.0;
         for (int i = threadIdx.x; i < m * k; i += W_COOP_THREADS) {
-            const double wn = (double)Wn[i], wo = (double)W[i];
+            const double wn = (double)Wsee[i], wo = (double)W[i];
             const double r = fabs(wn - wo) / (wn + st.tol * meanW);
             rel = r > rel ? r : rel;
         }
@@ -1397,11 +1515,14 @@ __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_sta
             st.scalars[ESPM_S_MEAN_W] = meanW;
             if (s_err) atomicOr(&st.dev_flags[0], s_err);
         }
+      }
     }
-    grid_barrier(bar, gridDim.x);
+    if (redundant_b) __syncthreads();
+    else grid_barrier(bar, gridDim.x);
 
     // ---- phase C: GW' = G W' for the next H pass (updates.py:107), one channel per thread ----
     {
+        const TC* Wsrc = redundant_b ? wsm : Wn;
         TC* GW = reinterpret_cast<TC*>(st.GW_next);
         TC* GWc = reinterpret_cast<TC*>(st.GWc_next);
         double cs[KP], csc[KP];
@@ -1417,13 +1538,14 @@ __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_sta
             } else if (ident) {
 #pragma unroll
                 for (int kk = 0; kk < KP; ++kk)
-                    if (kk < k) v[kk] = Wn[(size_t)c * k + kk];
+                    if (kk < k) v[kk] = Wsrc[(size_t)c * k + kk];
             } else {
+#pragma unroll 8
                 for (int mm = 0; mm < m; ++mm) {
                     const TC g = Gt[(size_t)mm * n + c];   // coalesced over the channels of a warp
 #pragma unroll
                     for (int kk = 0; kk < KP; ++kk)
-                        if (kk < k) v[kk] = fma(g, Wn[(size_t)mm * k + kk], v[kk]);
+                        if (kk < k) v[kk] = fma(g, Wsrc[(size_t)mm * k + kk], v[kk]);
                 }
             }
             bool all_zero = true;
@@ -1464,21 +1586,26 @@ __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_sta
         }
         if (threadIdx.x == 0) part[2 * ESPM_MAX_K] = (double)s_err;
     }
-    grid_barrier(bar, gridDim.x);
-
-    // ---- phase D (CTA 0): column sums over the CTAs in index order ----
-    if (blockIdx.x == 0) {
+    // ---- phase D (the last CTA to get here): column sums over the CTAs in index order ----
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&st.dev_flags[4], 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
         TC* gwstats = reinterpret_cast<TC*>(st.gwstats_next);
         if (threadIdx.x < 2 * KP) {
             double a = 0.0;
-            for (int b = 0; b < (int)gridDim.x; ++b) a += st.coop_part[(size_t)b * (2 * ESPM_MAX_K + 1) + threadIdx.x];
+            for (int b = 0; b < (int)gridDim.x; ++b) a += __ldcg(st.coop_part + (size_t)b * (2 * ESPM_MAX_K + 1) + threadIdx.x);
             gwstats[threadIdx.x] = (TC)a;
         }
         if (threadIdx.x == 0) {
             uint32_t f = 0u;
-            for (int b = 0; b < (int)gridDim.x; ++b) f |= (uint32_t)st.coop_part[(size_t)b * (2 * ESPM_MAX_K + 1) + 2 * ESPM_MAX_K];
+            for (int b = 0; b < (int)gridDim.x; ++b)
+                f |= (uint32_t)__ldcg(st.coop_part + (size_t)b * (2 * ESPM_MAX_K + 1) + 2 * ESPM_MAX_K);
             st.dev_flags[1] = f;
             st.scalars[ESPM_S_GW_FLAGS] = (double)f;
+            st.dev_flags[4] = 0u;
         }
     }
 }

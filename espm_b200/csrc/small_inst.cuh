@@ -57,7 +57,7 @@ static int small_launch_t(int op, const espm_state* st, cudaStream_t s) {
             break;
         case OP_H_STATS:
             ESPM_KP_SWITCH(kp, (h_stats_kernel<TC, KP><<<st->px_blocks, PX_THREADS, 0, s>>>(*st)));
-            hstats_reduce_kernel<TC><<<1, 256, 0, s>>>(*st);
+            ESPM_KP_SWITCH(kp, (hstats_reduce_kernel<TC, KP><<<1, 256, 0, s>>>(*st)));
             break;
         case OP_H_SCALARS:
             h_scalars_kernel<TC><<<1, 256, 0, s>>>(*st);
@@ -65,7 +65,7 @@ static int small_launch_t(int op, const espm_state* st, cudaStream_t s) {
         case OP_W_REDUCE: {
             const size_t total = (size_t)st->n_pad * st->kp;
             const int blocks = (int)((total + 255) / 256) + 1;
-            w_reduce_kernel<TC><<<blocks, 256, 0, s>>>(*st);
+            ESPM_KP_SWITCH(kp, (w_reduce_kernel<TC, KP><<<blocks, 256, 0, s>>>(*st)));
             break;
         }
         case OP_W_FINISH: {

@@ -190,7 +190,8 @@ typedef struct espm_state {
     double* px_part;        /* px_blocks x (4 + 3*kp) partials of the per-pixel kernels */
     uint32_t* bisect_mask;  /* 4 words: bit j set <=> max|f_j| > tol somewhere (lock-step trace) */
     uint32_t* dev_flags;    /* 8 words: [0] sticky ESPM_DEV_* error bits, [1] ESPM_DEV_GW_* of GW_next,
-                             * [2] h_finish completion ticket, [3] grid-barrier counter of w_finish (start at 0) */
+                             * [2] h_finish completion ticket, [3] grid-barrier counter of w_finish (start at 0),
+                             * [4] w_finish completion ticket */
     double* scalars;        /* ESPM_NSCALARS doubles: the record being filled */
     double* coop_part;      /* ESPM_COOP_BLOCKS x (2*ESPM_MAX_K + 1) doubles: per-CTA partials of w_finish */
     /* ---- ESPM_FLAG_PEER: exchange between the pixel shards through CUDA-IPC peer memory over NVLink ----
