@@ -1,5 +1,6 @@
 // C ABI of libespm_b200.so (see include/espm_b200.h): argument checking, launch planning and kernel
 // dispatch.  No device memory is owned here; the host passes every buffer.
+#include <cstdlib>
 #include <cstdarg>
 #include <cstddef>
 #include <cstdio>
@@ -187,6 +188,10 @@ int espm_plan(espm_state* st) {
     // ---- H pass ----
     int depth = (budget_for(z.h_occ) - z.fixed - z.h_tail) / z.h_stride;
     if (depth > 8) depth = 8;
+    if (const char* e = getenv("ESPM_B200_HDEPTH")) {
+        const int d = atoi(e);
+        if (d >= 2 && d < depth) depth = d;
+    }
     if (depth < 2) {
         set_error("shared memory budget too small for the H pass (kp=%d)", st->kp);
         return ESPM_ERR_UNSUPPORTED;
@@ -231,6 +236,16 @@ int espm_plan(espm_state* st) {
     {
         int wdepth = (budget_for(z.w_occ) - z.fixed - z.w_tail) / z.w_stride;
         if (wdepth > 8) wdepth = 8;
+        // Measured on B200 (C3 f32, profiles/r01f_summary.md): the W pass is FASTER with a shallow ring -- 6 stages
+        // 0.347 ms, 5: 0.340, 4: 0.323, 3: 0.316, 2: 0.344.  Consecutive units of a CTA are 1 MiB apart in Xt (same
+        // channel block, next tile), so every stage in flight opens another DRAM page; three stages per CTA keep the
+        // HBM queues short enough for the 592 concurrent streams.  ESPM_B200_WDEPTH overrides (experiments).
+        int wcap = 3;
+        if (const char* e = getenv("ESPM_B200_WDEPTH")) {
+            const int d = atoi(e);
+            if (d >= 2) wcap = d;
+        }
+        if (wdepth > wcap) wdepth = wcap;
         if (wdepth < 2) {
             set_error("shared memory budget too small for the W pass (kp=%d)", st->kp);
             return ESPM_ERR_UNSUPPORTED;
