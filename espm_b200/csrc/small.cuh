@@ -1147,6 +1147,8 @@ __global__ void __launch_bounds__(256) colsum_g_kernel(const TC* Gt, int n, int 
 // ------------------------------------------------------------------------------------------------
 constexpr int W_COOP_BLOCKS = 32;
 constexpr int W_COOP_THREADS = 256;
+constexpr int W_COOP_STRIDE = 2 * ESPM_MAX_K + 4;   // doubles per CTA row of coop_part: 2 KP column sums, [2 MAX_K] flags,
+                                                  // [2 MAX_K + 1] sum of W' slice, [2 MAX_K + 2] rel_W of the slice
 constexpr int W_SM_MAX = 1024;   // m*k up to which W' is kept in shared memory by every CTA
 
 // Grid barrier for a cooperative launch: monotonically increasing arrival counter, every CTA arrives
@@ -1168,8 +1170,6 @@ template <typename TC, int KP>
 __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_state st) {
     pdl_trigger();   // (launched in plain stream order itself; lets the next H pass set up while we run)
     __shared__ double sm[8 * 2 * ESPM_MAX_K + 8];
-    __shared__ double col_a[ESPM_MAX_K], col_b[ESPM_MAX_K], col_fa[ESPM_MAX_K], col_new[ESPM_MAX_K],
-        col_fn[ESPM_MAX_K];
     __shared__ int s_its;
     __shared__ uint32_t s_err;
     __shared__ double hs_sm[3 * ESPM_MAX_K];
@@ -1378,147 +1378,202 @@ __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_sta
     if (__any_sync(0xffffffffu, nonfinite) && lane == 0) atomicOr(&st.dev_flags[0], ESPM_DEV_NONFINITE);
     grid_barrier(bar, gridDim.x);
 
-    // ---- phase B (CTA 0, or every CTA when W' fits in shared memory and there is no bisection): W', rel_W ----
-    if (blockIdx.x == 0 || redundant_b) {
-        if (threadIdx.x == 0) {
-            s_its = 0;
-            s_err = 0u;
-        }
-        __syncthreads();
-        // simplex_W: lock-step bisection over the k columns (updates.py:61-68, dicotomy.py)
-        if (st.flags & ESPM_FLAG_SIMPLEX_W) {
-            const bool sub = st.flags & ESPM_FLAG_SIMPLEX_ROWS;
-            const int nrows = sub ? st.n_simplex_rows : m;
-            typedef double TB;  // the bisection runs in fp64 in every mode (m x k data)
-            const TB tol = st.dicotomy_tol_w;
-            const TB lsb = st.log_shift;
-            auto row_of = [&](int i) { return sub ? st.simplex_rows[i] : i; };
-            auto feval = [&](int kk, TB x) {  // warp-collective: sum_rows max(num/(x+den), ls) - 1
-                TB sacc = 0.0;
-                for (int i = lane; i < nrows; i += 32) {
-                    const int o = row_of(i) * k + kk;
-                    sacc += fmax(simplex_quot<TB>((TB)wnum[o], x + (TB)wden[o]), lsb);   // correctly rounded, ~4x cheaper
+    if (threadIdx.x == 0) {
+        s_its = 0;
+        s_err = 0u;
+    }
+    __syncthreads();
+    // ---- simplex_W (updates.py:61-68): lock-step bisection over the k columns of (num, den), dicotomy.py:4-55,111-173.
+    // One CTA per column: all 256 threads share the sum over the rows, so a column costs rows/256 quotients per thread
+    // and evaluation instead of rows/32 (the whole bisection used to run in the warps of CTA 0: 0.15 ms at C5).  The
+    // global stop test couples the columns only through the iteration count, so -- like the H update -- every column is
+    // TRACED on its own (which iterations still have |f| > tol, which way each one went), the traces are OR-ed after one
+    // grid barrier, and every column is replayed for the common count.
+    if (st.flags & ESPM_FLAG_SIMPLEX_W) {
+        const bool sub = st.flags & ESPM_FLAG_SIMPLEX_ROWS;
+        const int nrows = sub ? st.n_simplex_rows : m;
+        auto row_of = [&](int i) { return sub ? st.simplex_rows[i] : i; };
+        double* redsm = sm;   // [NWARPS] partial sums, [NWARPS..] scratch of the bracket
+        uint32_t* pub = reinterpret_cast<uint32_t*>(st.coop_part + (size_t)blockIdx.x * W_COOP_STRIDE);
+        Mask128 bad, dec;
+        bad.clear();
+        dec.clear();
+        uint32_t seen = 0u;
+        double lo = 0.0, hi = 0.0;
+        const int kk = blockIdx.x;      // this CTA's column (grids of W_COOP_BLOCKS >= ESPM_MAX_K CTAs)
+        struct ColEval {               // block-collective evaluator: every thread gets the same value
+            const TC* wnum;
+            const TC* wden;
+            const int* rows;
+            double* red;
+            int k, kk, nrows;
+            double ls, tol;
+            __device__ __forceinline__ double exact(double x) const {
+                double sacc = 0.0;
+                for (int i = threadIdx.x; i < nrows; i += W_COOP_THREADS) {
+                    const int o = (rows ? rows[i] : i) * k + kk;
+                    sacc += fmax(simplex_quot<double>((double)__ldcg(wnum + o), x + (double)__ldcg(wden + o)), ls);
                 }
-                return warp_sum(sacc) - 1.0;
-            };
-            for (int kk = warp; kk < k; kk += NWARPS) {
-                TB amax = -Num<TB>::inf(), nmax = -Num<TB>::inf(), dmin = Num<TB>::inf(), nsum = 0.0;
-                bool neg = false;
-                for (int i = lane; i < nrows; i += 32) {
-                    const int o = row_of(i) * k + kk;
-                    const TB nv = (TB)wnum[o], dv = (TB)wden[o];
-                    if (nv > 0.0) amax = fmax(amax, nv / 2.0 - dv);
-                    nmax = fmax(nmax, nv);
-                    dmin = fmin(dmin, dv);
-                    nsum += nv;
-                    neg |= (nv < 0.0) || (dv < 0.0);
-                }
-                amax = warp_max(amax);
-                nmax = warp_max(nmax);
-                dmin = -warp_max(-dmin);
-                nsum = warp_sum(nsum);
-                neg = __any_sync(0xffffffffu, neg);
-                const TB a = amax, b = (TB)nrows * nmax / 0.5 - dmin;
-                const TB fa = feval(kk, a), fb = feval(kk, b);
-                const TB nw = (a + b) / 2.0;
-                const TB fn = feval(kk, nw);
-                if (lane == 0) {
-                    uint32_t e = 0u;
-                    if (!(fa > 0.0) || !(fb < 0.0)) e |= ESPM_DEV_BRACKET;
-                    if (neg || !(nsum > 0.0)) e |= ESPM_DEV_NEGATIVE;
-                    if (e) atomicOr(&s_err, e);
-                    col_a[kk] = a;
-                    col_b[kk] = b;
-                    col_fa[kk] = fa;
-                    col_new[kk] = nw;
-                    col_fn[kk] = fn;
-                }
+                sacc = warp_sum(sacc);
+                if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sacc;
+                __syncthreads();
+                double t = red[0];
+                for (int w = 1; w < W_COOP_THREADS / 32; ++w) t += red[w];
+                __syncthreads();
+                return t - 1.0;
+            }
+            __device__ __forceinline__ Cls operator()(double x) const {
+                const double fe = exact(x);
+                return Cls{fe <= 0.0, fabs(fe) > tol};
+            }
+            __device__ __forceinline__ bool le0(double x) const { return exact(x) <= 0.0; }
+        };
+        const ColEval ev{wnum, wden, sub ? st.simplex_rows : nullptr, redsm, k, kk, nrows, st.log_shift,
+                         st.dicotomy_tol_w};
+        if (kk < k) {
+            // bracket of dicotomy.py:29-49 over the rows of this column
+            double amax = -Num<double>::inf(), nmax = -Num<double>::inf(), dmin = Num<double>::inf(), nsum = 0.0;
+            bool neg = false;
+            for (int i = threadIdx.x; i < nrows; i += W_COOP_THREADS) {
+                const int o = row_of(i) * k + kk;
+                const double nv = (double)__ldcg(wnum + o), dv = (double)__ldcg(wden + o);
+                if (nv > 0.0) amax = fmax(amax, nv / 2.0 - dv);
+                nmax = fmax(nmax, nv);
+                dmin = fmin(dmin, dv);
+                nsum += nv;
+                neg |= (nv < 0.0) || (dv < 0.0);
+            }
+            amax = warp_max(amax);
+            nmax = warp_max(nmax);
+            dmin = -warp_max(-dmin);
+            nsum = warp_sum(nsum);
+            if (lane == 0) {
+                redsm[NWARPS + warp] = amax;
+                redsm[2 * NWARPS + warp] = nmax;
+                redsm[3 * NWARPS + warp] = dmin;
+                redsm[4 * NWARPS + warp] = nsum;
+            }
+            const int any_neg = __syncthreads_or((int)neg);
+            amax = redsm[NWARPS], nmax = redsm[2 * NWARPS], dmin = redsm[3 * NWARPS], nsum = redsm[4 * NWARPS];
+            for (int w = 1; w < NWARPS; ++w) {
+                amax = fmax(amax, redsm[NWARPS + w]);
+                nmax = fmax(nmax, redsm[2 * NWARPS + w]);
+                dmin = fmin(dmin, redsm[3 * NWARPS + w]);
+                nsum += redsm[4 * NWARPS + w];
             }
             __syncthreads();
-            int it = 0;
-            while (true) {
-                double worst = 0.0;
-                for (int kk = 0; kk < k; ++kk) {
-                    const double v = fabs(col_fn[kk]);
-                    worst = v > worst ? v : worst;
-                }
-                if (!(worst > (double)tol)) break;  // dicotomy.py:152
-                it += 1;
-                __syncthreads();
-                for (int kk = warp; kk < k; kk += NWARPS) {
-                    TB a = col_a[kk], b = col_b[kk], fa = col_fa[kk], nw = col_new[kk], fn = col_fn[kk];
-                    if (fa * fn <= 0.0) {
-                        b = nw;
-                    } else {
-                        a = nw;
-                        fa = fn;
-                    }
-                    nw = (a + b) / 2.0;
-                    fn = feval(kk, nw);
-                    if (lane == 0) {
-                        col_a[kk] = a;
-                        col_b[kk] = b;
-                        col_fa[kk] = fa;
-                        col_new[kk] = nw;
-                        col_fn[kk] = fn;
-                    }
-                }
-                __syncthreads();
-                if (it >= st.maxit) break;  // dicotomy.py:169-171
+            lo = amax;
+            hi = (double)nrows * nmax / 0.5 - dmin;
+            uint32_t e = 0u;
+            if (any_neg || !(nsum > 0.0)) e |= ESPM_DEV_NEGATIVE;
+            bisect_trace_rec(lo, hi, ev, st.maxit, bad, dec, seen, e);
+            if (threadIdx.x == 0) {
+#pragma unroll
+                for (int w = 0; w < 4; ++w) pub[w] = bad.w[w];
+                if (e) atomicOr(&st.dev_flags[0], e);
             }
-            if (threadIdx.x == 0) s_its = it;
+        }
+        grid_barrier(bar, gridDim.x);
+        uint32_t gmask[4] = {0u, 0u, 0u, 0u};
+        for (int c = 0; c < k; ++c) {
+            const uint32_t* pc = reinterpret_cast<const uint32_t*>(st.coop_part + (size_t)c * W_COOP_STRIDE);
+#pragma unroll
+            for (int w = 0; w < 4; ++w) gmask[w] |= __ldcg(pc + w);
+        }
+        const int its = first_clear_bit(gmask, st.maxit);
+        if (threadIdx.x == 0) s_its = its;   // every CTA: the last one to finish writes the record
+        if (kk < k) {
+            const double nu = bisect_replay_rec(lo, hi, ev, its, dec, seen);
             // denum[rows] += nu (updates.py:65,68)
-            for (int i = threadIdx.x; i < nrows * k; i += W_COOP_THREADS) {
-                const int r = row_of(i / k), kk = i % k;
-                wden[r * k + kk] += (TC)col_new[kk];
+            for (int i = threadIdx.x; i < nrows; i += W_COOP_THREADS) {
+                const int o = row_of(i) * k + kk;
+                wden[o] = __ldcg(wden + o) + (TC)nu;
             }
-            __syncthreads();
         }
+        grid_barrier(bar, gridDim.x);
+    }
 
-        // W' = max(num/den, ls), fixed_W (updates.py:70-76); rel_W (base.py:323)
-        const TC* fw = reinterpret_cast<const TC*>(st.fixed_W);
+    // ---- phase B: W' = max(num/den, ls), fixed_W (updates.py:70-76); rel_W (base.py:323) ----
+    // small m k without bisection: every CTA computes all of W' into shared memory (no barrier before phase C);
+    // otherwise every CTA takes a slice (a single CTA needed 40 us for the 2048 x 8 entries of C5), one barrier.
+    const TC* fw = reinterpret_cast<const TC*>(st.fixed_W);
+    auto w_entry = [&](int i) {
+        const TC nv = __ldcg(wnum + i), dv = __ldcg(wden + i);   // L2: written by other CTAs in this launch
+        TC v = Num<TC>::vmax((st.flags & ESPM_FLAG_PG) ? nv : nv / dv, ls);
+        if (st.flags & ESPM_FLAG_FIXED_W) {
+            const TC f = fw[i];
+            if (f >= TC(0)) v = f;
+        }
+        return v;
+    };
+    auto block_sum = [&](double v) {      // fixed order; every thread gets the result
+        v = warp_sum(v);
+        if (lane == 0) sm[warp] = v;
+        __syncthreads();
+        double t = sm[0];
+        for (int w = 1; w < NWARPS; ++w) t += sm[w];
+        __syncthreads();
+        return t;
+    };
+    auto block_max = [&](double v) {
+        v = warp_max(v);
+        if (lane == 0) sm[warp] = v;
+        __syncthreads();
+        double t = sm[0];
+        for (int w = 1; w < NWARPS; ++w) t = sm[w] > t ? sm[w] : t;
+        __syncthreads();
+        return t;
+    };
+    if (redundant_b) {
         double wsum = 0.0;
         for (int i = threadIdx.x; i < m * k; i += W_COOP_THREADS) {
-            TC v = Num<TC>::vmax((st.flags & ESPM_FLAG_PG) ? wnum[i] : wnum[i] / wden[i], ls);
-            if (st.flags & ESPM_FLAG_FIXED_W) {
-                const TC f = fw[i];
-                if (f >= TC(0)) v = f;
-            }
+            const TC v = w_entry(i);
             if (blockIdx.x == 0) Wn[i] = v;
-            if (redundant_b) wsm[i] = v;
+            wsm[i] = v;
             wsum += (double)v;
         }
         __syncthreads();
-      if (blockIdx.x == 0) {   // the scalars of the record are CTA 0's business
-        const TC* Wsee = redundant_b ? wsm : Wn;
-        wsum = warp_sum(wsum);
-        if (lane == 0) sm[warp] = wsum;
-        __syncthreads();
+        if (blockIdx.x == 0) {   // the scalars of the record are CTA 0's business
+            const double meanW = block_sum(wsum) / (double)(m * k);
+            double rel = 0.0;
+            for (int i = threadIdx.x; i < m * k; i += W_COOP_THREADS) {
+                const double wn = (double)wsm[i], wo = (double)W[i];
+                const double r = fabs(wn - wo) / (wn + st.tol * meanW);
+                rel = r > rel ? r : rel;
+            }
+            rel = block_max(rel);
+            if (threadIdx.x == 0) {
+                st.scalars[ESPM_S_REL_W] = rel;
+                st.scalars[ESPM_S_BISECT_ITS_W] = (double)s_its;
+                st.scalars[ESPM_S_MEAN_W] = meanW;
+            }
+        }
+    } else {
+        const int total = m * k, per = (total + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int i0 = blockIdx.x * per, i1 = (i0 + per < total) ? i0 + per : total;
+        double* row = st.coop_part + (size_t)blockIdx.x * W_COOP_STRIDE;
+        double wsum = 0.0;
+        for (int i = i0 + threadIdx.x; i < i1; i += W_COOP_THREADS) {
+            const TC v = w_entry(i);
+            Wn[i] = v;
+            wsum += (double)v;
+        }
+        wsum = block_sum(wsum);
+        if (threadIdx.x == 0) row[2 * ESPM_MAX_K + 1] = wsum;
+        grid_barrier(bar, gridDim.x);
         double meanW = 0.0;
-        for (int w = 0; w < NWARPS; ++w) meanW += sm[w];
-        meanW /= (double)(m * k);
-        __syncthreads();
+        for (int b = 0; b < (int)gridDim.x; ++b) meanW += __ldcg(st.coop_part + (size_t)b * W_COOP_STRIDE + 2 * ESPM_MAX_K + 1);
+        meanW /= (double)total;
         double rel = 0.0;
-        for (int i = threadIdx.x; i < m * k; i += W_COOP_THREADS) {
-            const double wn = (double)Wsee[i], wo = (double)W[i];
+        for (int i = i0 + threadIdx.x; i < i1; i += W_COOP_THREADS) {
+            const double wn = (double)Wn[i], wo = (double)W[i];   // Wn[i]: this thread's own store
             const double r = fabs(wn - wo) / (wn + st.tol * meanW);
             rel = r > rel ? r : rel;
         }
-        rel = warp_max(rel);
-        if (lane == 0) sm[warp] = rel;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double r = sm[0];
-            for (int w = 1; w < NWARPS; ++w) r = sm[w] > r ? sm[w] : r;
-            st.scalars[ESPM_S_REL_W] = r;
-            st.scalars[ESPM_S_BISECT_ITS_W] = (double)s_its;
-            st.scalars[ESPM_S_MEAN_W] = meanW;
-            if (s_err) atomicOr(&st.dev_flags[0], s_err);
-        }
-      }
+        rel = block_max(rel);
+        if (threadIdx.x == 0) row[2 * ESPM_MAX_K + 2] = rel;
     }
-    if (redundant_b) __syncthreads();
-    else grid_barrier(bar, gridDim.x);
+    __syncthreads();
 
     // ---- phase C: GW' = G W' for the next H pass (updates.py:107), one channel per thread ----
     {
@@ -1578,7 +1633,7 @@ __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_sta
         __syncthreads();
         if (lane == 0 && f) atomicOr(&s_err, f);
         __syncthreads();
-        double* part = st.coop_part + (size_t)blockIdx.x * (2 * ESPM_MAX_K + 1);
+        double* part = st.coop_part + (size_t)blockIdx.x * W_COOP_STRIDE;
         if (threadIdx.x < 2 * KP) {
             double a = 0.0;
             for (int w = 0; w < NWARPS; ++w) a += sm[w * 2 * KP + threadIdx.x];
@@ -1596,15 +1651,26 @@ __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_sta
         TC* gwstats = reinterpret_cast<TC*>(st.gwstats_next);
         if (threadIdx.x < 2 * KP) {
             double a = 0.0;
-            for (int b = 0; b < (int)gridDim.x; ++b) a += __ldcg(st.coop_part + (size_t)b * (2 * ESPM_MAX_K + 1) + threadIdx.x);
+            for (int b = 0; b < (int)gridDim.x; ++b) a += __ldcg(st.coop_part + (size_t)b * W_COOP_STRIDE + threadIdx.x);
             gwstats[threadIdx.x] = (TC)a;
         }
         if (threadIdx.x == 0) {
             uint32_t f = 0u;
             for (int b = 0; b < (int)gridDim.x; ++b)
-                f |= (uint32_t)__ldcg(st.coop_part + (size_t)b * (2 * ESPM_MAX_K + 1) + 2 * ESPM_MAX_K);
+                f |= (uint32_t)__ldcg(st.coop_part + (size_t)b * W_COOP_STRIDE + 2 * ESPM_MAX_K);
             st.dev_flags[1] = f;
             st.scalars[ESPM_S_GW_FLAGS] = (double)f;
+            if (!redundant_b) {   // scalars of the sliced phase B, folded in CTA order
+                double ws = 0.0, rel = 0.0;
+                for (int b = 0; b < (int)gridDim.x; ++b) {
+                    ws += __ldcg(st.coop_part + (size_t)b * W_COOP_STRIDE + 2 * ESPM_MAX_K + 1);
+                    const double r = __ldcg(st.coop_part + (size_t)b * W_COOP_STRIDE + 2 * ESPM_MAX_K + 2);
+                    rel = r > rel ? r : rel;
+                }
+                st.scalars[ESPM_S_REL_W] = rel;
+                st.scalars[ESPM_S_BISECT_ITS_W] = (double)s_its;
+                st.scalars[ESPM_S_MEAN_W] = ws / (double)(m * k);
+            }
             st.dev_flags[4] = 0u;
         }
     }

@@ -239,7 +239,7 @@ class FitEngine:
         if gamma_pg is not None:
             st.gamma_h, st.gamma_w = float(gamma_pg[0]), float(gamma_pg[1])
         self.dev_flags = torch.zeros(8, dtype=torch.int32, device=dev)
-        self.coop_part = zeros(L.COOP_BLOCKS * (2 * L.MAX_K + 1), dtype=torch.float64)
+        self.coop_part = zeros(L.COOP_BLOCKS * (2 * L.MAX_K + 4), dtype=torch.float64)
         self.max_records = int(max_records)
         self.records = zeros(self.max_records, L.NSCALARS, dtype=torch.float64)
         st.numraw, st.num, st.den = self.numraw.data_ptr(), self.num.data_ptr(), self.den.data_ptr()

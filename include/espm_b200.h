@@ -193,7 +193,7 @@ typedef struct espm_state {
                              * [2] h_finish completion ticket, [3] grid-barrier counter of w_finish (start at 0),
                              * [4] w_finish completion ticket */
     double* scalars;        /* ESPM_NSCALARS doubles: the record being filled */
-    double* coop_part;      /* ESPM_COOP_BLOCKS x (2*ESPM_MAX_K + 1) doubles: per-CTA partials of w_finish */
+    double* coop_part;      /* ESPM_COOP_BLOCKS x (2*ESPM_MAX_K + 4) doubles: per-CTA partials of w_finish */
     /* ---- ESPM_FLAG_PEER: exchange between the pixel shards through CUDA-IPC peer memory over NVLink ----
      * No host-launched collective sits on the per-iteration path: the kernels signal and wait on flag words
      * (system-scope release/acquire) and move the few KiB that cross ranks with plain peer loads / stores.
