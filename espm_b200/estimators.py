@@ -236,11 +236,28 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
             G = self.G
         self._identity_G = G is None
         n, p = Xv.shape
-        # initial factors (updates.py:160-223): only a missing factor needs the data on the host
-        X_init = Xv if (W is not None and H is not None) else self._host_X(Xv)
-        G_full, W0, H0 = initialize_factors(X_init, G, W, H, self.n_components, self.init, self.random_state,
-                                            self.simplex_H, self.simplex_W, self.log_shift, self.physics_model_)
-        del X_init
+        from . import config
+        distributed = False
+        if config.distributed:
+            import torch.distributed as dist
+            distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        # initial factors (updates.py:160-223).  Given factors are only clamped; one missing factor needs a least-squares
+        # solve against the data on the host; when BOTH are missing (the reference's default call) the NNDSVD of
+        # scikit-learn runs its randomized SVD on the device against the X the engine holds (init_device.py), so the
+        # engine is created first, with placeholders, and receives the real factors afterwards.
+        device_init = (W is None and H is None and not distributed and config.device_init
+                       and self.n_components + 10 <= n < p)      # tall factorisations of init_device.py
+        if device_init:
+            c_np = np.result_type(Xv.dtype, *([] if G is None else [np.asarray(G).dtype]))
+            m_cols = n if G is None else np.asarray(G).shape[1]
+            G_full = np.diag(np.ones(n).astype(Xv.dtype)) if G is None else np.asarray(G)
+            W0 = np.ones((m_cols, self.n_components), dtype=c_np)
+            H0 = np.ones((self.n_components, p), dtype=c_np)
+        else:
+            X_init = Xv if (W is not None and H is not None) else self._host_X(Xv)
+            G_full, W0, H0 = initialize_factors(X_init, G, W, H, self.n_components, self.init, self.random_state,
+                                                self.simplex_H, self.simplex_W, self.log_shift, self.physics_model_)
+            del X_init
         self.GWH_numel_ = n * p
         pg = self.algo == "projected_gradient"
         if self.algo == "bmd" and G_full.shape[0] != G_full.shape[1]:
@@ -260,12 +277,9 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
             check_shape_2d(self.shape_2d, p)
         max_iter = int(self.max_iter)
         shard = None
-        from . import config
-        if config.distributed:
-            import torch.distributed as dist
-            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-                from .dist import make_shard
-                shard = make_shard()
+        if distributed:
+            from .dist import make_shard
+            shard = make_shard()
         G_dev = None if (self._identity_G or bmd_identity) else G
         eng = FitEngine(Xv, G_dev, W0, H0,
                         shape_2d=self.shape_2d, lambda_L=self.lambda_L, mu=self.mu, epsilon_reg=self.epsilon_reg,
@@ -278,6 +292,13 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
                         clamp_init=True,
                         ingest=dict(eps=self.log_shift, normalize=self.n_components if self.normalize else None))
         self._engine = eng
+        if device_init:
+            from .init_device import initialize_nmf_device
+            _, W0, H0 = initialize_factors(
+                Xv, G, None, None, self.n_components, self.init, self.random_state, self.simplex_H, self.simplex_W,
+                self.log_shift, self.physics_model_,
+                nmf_init=lambda k_, init_, rs_: initialize_nmf_device(eng, k_, init_, rs_))
+            eng.set_WH(W0, H0)
         if pg and self.gamma is None:
             # estimate_Lipschitz_bound_h / _w (updates.py:393-413) with W = H = log_shift everywhere: they reduce to
             # max_j colsum(X)_j / (k ls^2) + 2 lambda_L + mu eps   and   max_c rowsum(X)_c / (k ls^2 rowsum(G)_c^2)

@@ -44,7 +44,7 @@ def rescaled_DH(D, H):
 
 
 def initialize_factors(X, G, W, H, n_components, init, random_state, simplex_H, simplex_W, log_shift,
-                       physics_model=None):
+                       physics_model=None, nmf_init=None):
     """Initial (G, W, H) following updates.py:160-223.
 
     Missing factors come from scikit-learn's NMF initialisation plus least squares; user-supplied
@@ -58,8 +58,11 @@ def initialize_factors(X, G, W, H, n_components, init, random_state, simplex_H, 
         G_dense = np.asarray(G)
     if W is None:
         if H is None:
-            from sklearn.decomposition._nmf import _initialize_nmf
-            D, H = _initialize_nmf(X, n_components=n_components, init=init, random_state=random_state)
+            if nmf_init is not None:     # NNDSVD with the SVD on the device (init_device.py); X may be None then
+                D, H = nmf_init(n_components, init, random_state)
+            else:
+                from sklearn.decomposition._nmf import _initialize_nmf
+                D, H = _initialize_nmf(X, n_components=n_components, init=init, random_state=random_state)
             if simplex_H:
                 H = np.nan_to_num(H, nan=1.0 / H.shape[0])
                 scale = np.sum(H, axis=0, keepdims=True)
