@@ -5,7 +5,7 @@ the host."""
 import numpy as np
 import pytest
 
-pytestmark = pytest.mark.gpu
+gpu = pytest.mark.gpu
 
 
 def problem(dtype, seed=5, n=96, nx=20, ny=24, k=3, m=7):
@@ -30,6 +30,7 @@ def engine_for(X, G, k):
                      ingest=dict(eps=1e-14, normalize=None))
 
 
+@gpu
 @pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-9), (np.float32, 2e-3)])
 @pytest.mark.parametrize("init", [None, "nndsvd", "nndsvdar", "random"])
 def test_initialize_nmf_device_matches_sklearn(dtype, tol, init):
@@ -49,6 +50,7 @@ def test_initialize_nmf_device_matches_sklearn(dtype, tol, init):
         assert np.array_equal(Wd == 0, Ws == 0) and np.array_equal(Hd == 0, Hs == 0)
 
 
+@gpu
 @pytest.mark.parametrize("identity", [False, True])
 def test_default_fit_device_init_equals_host_init(identity):
     import espm_b200
@@ -71,3 +73,30 @@ def test_default_fit_device_init_equals_host_init(identity):
     assert np.max(np.abs(l_dev - l_host) / np.abs(l_host)) < 1e-7
     assert np.max(np.abs(W_dev - W_host)) <= 1e-6 * np.abs(W_host).max()
     assert np.max(np.abs(H_dev - H_host)) <= 1e-6 * np.abs(H_host).max()
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-11), (np.float32, 1e-4)])
+def test_init_host_logic_with_cpu_tensors(dtype, tol):
+    """The host side of init_device.py (random stream, LU row permutation, svd_flip, NNDSVD split, tile-major
+    indexing) with the tensor algebra on CPU tensors: no CUDA involved, no engine -- a stand-in object carries Xt."""
+    import types
+    import torch
+    from sklearn.decomposition._nmf import _initialize_nmf
+    from espm_b200.host import remove_zeros_lines
+    from espm_b200.init_device import initialize_nmf_device
+    X, _, _, k = problem(dtype)
+    Xp = remove_zeros_lines(X, 1e-14)
+    n, p = Xp.shape
+    n_pad, nt = (n + 31) // 32 * 32, (p + 127) // 128
+    Xt = np.zeros((nt, n_pad, 128), dtype=dtype)
+    for t in range(nt):
+        w = min(128, p - t * 128)
+        Xt[t, :n, :w] = Xp[:, t * 128:t * 128 + w]
+    eng = types.SimpleNamespace(n=n, p_loc=p, Xt=torch.from_numpy(Xt.reshape(-1)),
+                                st=types.SimpleNamespace(n_pad=n_pad, n_tiles=nt))
+    for init in (None, "nndsvd", "nndsvdar", "random"):
+        Wd, Hd = initialize_nmf_device(eng, k, init, random_state=3)
+        Ws, Hs = _initialize_nmf(Xp, k, init=init, random_state=3)
+        assert Wd.dtype == Ws.dtype and Hd.dtype == Hs.dtype
+        assert np.max(np.abs(Wd - Ws)) <= tol * np.abs(Ws).max()
+        assert np.max(np.abs(Hd - Hs)) <= tol * np.abs(Hs).max()
