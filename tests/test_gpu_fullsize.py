@@ -142,3 +142,60 @@ def test_loss_decreases_at_full_size():
     assert np.all(np.diff(losses) < 0)
     assert np.max(np.abs(est.H_.sum(0) - 1.0)) <= 1.1e-5
     assert est.W_.shape == (27, 4) and np.all(est.W_ >= 1e-14)
+
+
+def test_free_nmf_simplex_w_at_full_size():
+    """C5 (G=None, 8 components, simplex_W, 512 x 512 x 2048, fp32): one complete iteration.  The H update has no
+    bisection here; the W update bisects its 8 columns over 2048 rows in lock step (updates.py:61-68) -- one CTA per
+    column traces, all replay the common count.  Checked against an independent chunked fp64 evaluation (torch on the
+    GPU, never our kernels) with the device's iteration count, and through the simplex sums."""
+    import torch
+    from espm_b200 import _lib as L
+    from espm_b200.engine import FitEngine
+    nx = ny = 512
+    n, k, dtype, tol = 2048, 8, np.float32, 2e-5
+    _, X, W0, H0 = _setup(nx, ny, n, k, 25, dtype)
+    W0, H0 = _setup_identity_factors(n, k, nx * ny, dtype)
+    p = nx * ny
+    eng = FitEngine(X, None, W0, H0, shape_2d=(nx, ny), simplex_H=False, simplex_W=True, tol=0.0, max_records=16,
+                    x_local=True, dicotomy_tol_w=TOL)
+    eng.evaluate(0)
+    eng.advance(1)
+    eng.evaluate(1)
+    recs = eng.read_records(0, 2)
+    H1, W1 = eng.get_H().astype(np.float64), eng.get_W().astype(np.float64)
+    assert int(recs[0][L.S_DEV_FLAGS]) == 0 and int(recs[1][L.S_DEV_FLAGS]) == 0
+    its = int(recs[1][L.S_BISECT_ITS_W])
+    assert 5 < its < 80
+    assert np.all(np.isfinite(W1)) and np.all(W1 >= LS) and np.all(np.isfinite(H1)) and np.all(H1 >= LS)
+    assert np.max(np.abs(W1.sum(0) - 1.0)) <= TOL * 1.001 + 2e-6          # columns of W on the simplex
+
+    dev = X.device
+    W64, H64 = np.maximum(W0.astype(np.float64), LS), np.maximum(H0.astype(np.float64), LS)
+    Wd, Hd = torch.as_tensor(W64, device=dev), torch.as_tensor(H64, device=dev)
+    # H update (updates.py:127-152 without regularisation / simplex): H' = H * (W^T (X / WH)) / colsum(W)
+    num = torch.zeros(k, p, dtype=torch.float64, device=dev)
+    for a in range(0, p, 32768):
+        b = min(a + 32768, p)
+        num[:, a:b] = Wd.T @ (X[:, a:b].double() / (Wd @ Hd[:, a:b]))
+    ref_H = np.maximum((H64 * num.cpu().numpy()) / np.sum(W64, axis=0, keepdims=True).T, LS)
+    assert rel_err(H1, ref_H) < tol
+    # W update (updates.py:38-72 with G = I): num = W * ((X / W H') H'^T), den = rowsum(H') + nu
+    H1d = torch.as_tensor(H1, device=dev)
+    S = torch.zeros(n, k, dtype=torch.float64, device=dev)
+    for a in range(0, p, 32768):
+        b = min(a + 32768, p)
+        S += (X[:, a:b].double() / (Wd @ H1d[:, a:b])) @ H1d[:, a:b].T
+    numW = W64 * S.cpu().numpy()
+    denW = np.ones((n, 1)) @ np.sum(H1, axis=1, keepdims=True).T
+    nu, own = _replay(numW, denW, its)
+    assert abs(own - its) <= 1
+    ref_W = np.maximum(numW / (denW + nu), LS)
+    big = ref_W > 1e-6 * ref_W.max()          # entries at the log_shift floor carry no relative information in fp32
+    assert rel_err(W1[big], ref_W[big]) < tol
+    eng.close()
+
+
+def _setup_identity_factors(n, k, p, dtype, seed=93):
+    from espm_b200 import synth
+    return synth.init_factors(n, k, p, seed, dtype=dtype)
