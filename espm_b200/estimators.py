@@ -6,11 +6,13 @@ Same constructor arguments, ``fit`` / ``fit_transform`` / ``inverse_transform`` 
 initialises and runs the stop tests; every pass over X happens in the CUDA kernels behind
 ``espm_b200.engine.FitEngine``.  There is no CPU fallback: without a CUDA device ``fit`` raises.
 
-Supported on the device: ``algo="log_surrogate"`` (the default) and ``"l2_surrogate"`` with the KL loss, ``simplex_H`` /
-``simplex_W``, ``mu`` (scalar or per phase), ``lambda_L`` with ``shape_2d`` (5-point Laplacian) or
-without (identity), ``fixed_H`` / ``fixed_W``, ``normalize``, ``G`` as ``None`` / ndarray / physical
-model, ``hspy_comp``.  ``linesearch`` with ``projected_gradient`` and ground-truth tracking raise
-``NotImplementedError``.
+On the device: every ``algo`` of the reference (``"log_surrogate"``, ``"l2_surrogate"``, ``"bmd"``,
+``"projected_gradient"``), the KL and (``l2=True``) Frobenius losses, ``simplex_H`` / ``simplex_W``, ``mu`` (scalar or
+per phase), ``lambda_L`` with ``shape_2d`` (5-point Laplacian) or without (identity), ``fixed_H`` / ``fixed_W``,
+``normalize``, ``linesearch``, ground-truth tracking (``true_D`` / ``true_H``), ``G`` as ``None`` / ndarray / physical
+model, ``hspy_comp``; the NNDSVD initialisation of a call without ``W`` and ``H`` runs its randomized SVD on the device
+too (``init_device.py``).  Pixel-sharded fits (one process per GPU) support the KL algorithms; ``linesearch``,
+``l2=True`` and truth tracking raise ``NotImplementedError`` there.
 """
 import sys
 import time
