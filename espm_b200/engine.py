@@ -159,8 +159,6 @@ class FitEngine:
                 self.pg_ls = True                # quadratic-surrogate line search (smooth_nmf.py:383-401, 438-447)
             else:
                 flags |= L.FLAG_LINESEARCH
-        if shard is not None and (l2 or l2_h):
-            raise NotImplementedError("espm_b200: the Frobenius branches are not available for pixel-sharded fits")
         self.algo = algo
         self.gamma_pg = gamma_pg
         mu_arr = np.zeros(L.MAX_K)
@@ -561,6 +559,8 @@ class FitEngine:
             self._call(self.lib.espm_linesearch, "linesearch")   # smooth_nmf.py:376-382, gamma_ stays on the device
         if st.flags & L.FLAG_L2:
             L.check(self.lib.espm_gram(ctypes.byref(st), 1, self.stream))        # H' H'^T, updates.py:31
+            if self.shard is not None:
+                self.shard.allreduce_sum(self.gram[1])                           # k x k sums over the pixel shards
         self._seq_s += 1
         st.seq_s = self._seq_s                               # S exchange of this update (peer mode)
         self._call(self.lib.espm_w_pass, "w_pass")

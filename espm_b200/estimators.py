@@ -11,8 +11,8 @@ On the device: every ``algo`` of the reference (``"log_surrogate"``, ``"l2_surro
 per phase), ``lambda_L`` with ``shape_2d`` (5-point Laplacian) or without (identity), ``fixed_H`` / ``fixed_W``,
 ``normalize``, ``linesearch``, ground-truth tracking (``true_D`` / ``true_H``), ``G`` as ``None`` / ndarray / physical
 model, ``hspy_comp``; the NNDSVD initialisation of a call without ``W`` and ``H`` runs its randomized SVD on the device
-too (``init_device.py``).  Pixel-sharded fits (one process per GPU) support the KL algorithms; ``linesearch``,
-``l2=True`` and truth tracking raise ``NotImplementedError`` there.
+too (``init_device.py``).  Pixel-sharded fits (one process per GPU) support every algorithm and loss; ``linesearch`` and
+truth tracking raise ``NotImplementedError`` there.
 """
 import sys
 import time

@@ -48,6 +48,9 @@ CASES = {
     "simplex_H_lap_mu": dict(simplex_H=True, simplex_W=False, lambda_L=2.0, mu=0.05),
     "simplex_W": dict(simplex_H=False, simplex_W=True, lambda_L=0.5),
     "normalize": dict(simplex_H=True, simplex_W=False, normalize=True, mu=0.02),
+    "l2_frobenius": dict(simplex_H=True, simplex_W=False, lambda_L=0.8, algo="l2_surrogate", l2=True),
+    "proj_grad": dict(simplex_H=True, simplex_W=False, lambda_L=0.4, mu=0.02, algo="projected_gradient",
+                      gamma=[3000.0, 4.0e5]),      # a stable step size: the trajectory is not chaotic
 }
 NX, NY = 37, 29          # 37 rows do not divide evenly: ragged shards
 
