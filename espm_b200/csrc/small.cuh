@@ -1168,7 +1168,8 @@ __device__ __forceinline__ void grid_barrier(uint32_t* ctr, uint32_t nblocks) {
 
 template <typename TC, int KP>
 __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_state st) {
-    pdl_trigger();   // (launched in plain stream order itself; lets the next H pass set up while we run)
+    pdl_wait();      // results of the W pass (and of everything before it) are visible from here on
+    pdl_trigger();   // lets the next H pass set up while we run
     __shared__ double sm[8 * 2 * ESPM_MAX_K + 8];
     __shared__ int s_its;
     __shared__ uint32_t s_err;

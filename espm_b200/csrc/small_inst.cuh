@@ -74,7 +74,25 @@ static int small_launch_t(int op, const espm_state* st, cudaStream_t s) {
             void* args[] = {&copy};
             const void* fn = nullptr;
             ESPM_KP_SWITCH(kp, (fn = (const void*)w_finish_kernel<TC, KP>));
-            ESPM_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(W_COOP_BLOCKS), dim3(W_COOP_THREADS), args, 0, s));
+            // cooperative (grid barriers) AND programmatic dependent launch: the CTAs become resident while the W
+            // pass drains and wait in griddepcontrol.wait (ESPM_B200_PDL=0: plain stream order)
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(W_COOP_BLOCKS);
+            cfg.blockDim = dim3(W_COOP_THREADS);
+            cfg.dynamicSmemBytes = 0;
+            cfg.stream = s;
+            static const bool pdl = [] {
+                const char* e = getenv("ESPM_B200_PDL");
+                return !(e && e[0] == '0');
+            }();
+            cudaLaunchAttribute attr[2];
+            attr[0].id = cudaLaunchAttributeCooperative;
+            attr[0].val.cooperative = 1;
+            attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[1].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = pdl ? 2 : 1;
+            ESPM_CUDA_CHECK(cudaLaunchKernelExC(&cfg, fn, args));
             break;
         }
         case OP_GW_PREPARE:
