@@ -98,6 +98,12 @@ def cpu_baseline(prob, wl, X_crop, rows_crop, steps, seed):
     Every operation of the reference is linear in the pixel count, so it/s scales as p_crop / p."""
     from oracle import smooth_nmf_oracle as orc
     from espm_b200 import synth
+    try:
+        # torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm is meant to use every host core
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
     nx, ny, k = wl["nx"], wl["ny"], wl["k"]
     p_crop = rows_crop * ny
     W0, H0 = synth.init_factors(prob["G_full"].shape[1], k, nx * ny, seed)
