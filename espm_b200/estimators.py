@@ -79,48 +79,47 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
     def _more_tags(self):
         return {"requires_positive_X": True}
 
+    # (parameter, accepted types, replacement, subject of the two printed lines, wording of the requirement, shown value)
+    _TYPE_RULES = (
+        ("lambda_L", (int, float), 0.0, "The regularization parameter lambda_L", "a float or int", "0.0"),
+        ("linesearch", bool, False, "The linesearch parameter", "a boolean", "False"),
+        ("mu", (int, float, np.ndarray), 0, "The regularization parameter mu", "a float, int or np.ndarray", "0"),
+        ("epsilon_reg", (int, float), 1, "The regularization parameter epsilon_reg", "a float or int", "1"),
+        ("algo", str, "log_surrogate", "The algorithm", "a string", "'log_surrogate'"),
+        ("simplex_H", bool, False, "The simplex_H parameter", "a boolean", "False"),
+        ("simplex_W", bool, True, "The simplex_W parameter", "a boolean", "True"),
+        ("dicotomy_tol", (int, float), 1e-3, "The dicotomy_tol parameter", "a float or int", "1e-3"),
+        ("gamma", (int, float, list, type(None)), None, "The gamma parameter", "a float, int, or list", "None"),
+        ("verbose", (bool, int), 1, "The verbose parameter", "a boolean or int", "1"),
+        ("debug", bool, False, "The debug parameter", "a boolean", "False"),
+        ("l2", bool, False, "The l2 parameter", "a boolean", "False"),
+        ("n_components", int, 2, "The n_components parameter", "an int", "2"),
+    )
+
     def check_params(self):
-        """Soft validation: bad values are reported and reset, never raised (smooth_nmf.py:145-237)."""
-        def reset(name, value, why):
-            print(why)
-            print("The %s parameter is set to %r" % (name, value))
+        """Soft validation: bad values are reported on stdout and reset, never raised; the two printed lines per
+        correction are the reference's (smooth_nmf.py:145-237), types first, then values, then the combinations."""
+        def correct(name, value, subject, requirement, shown):
+            print("%s %s" % (subject, requirement))
+            print("%s is set to %s" % (subject, shown))
             setattr(self, name, value)
 
-        if not isinstance(self.lambda_L, (int, float)):
-            reset("lambda_L", 0.0, "The regularization parameter lambda_L must be a float or int")
-        if not isinstance(self.linesearch, bool):
-            reset("linesearch", False, "The linesearch parameter must be a boolean")
-        if not isinstance(self.mu, (int, float, np.ndarray)):
-            reset("mu", 0, "The regularization parameter mu must be a float, int or np.ndarray")
-        if not isinstance(self.epsilon_reg, (int, float)):
-            reset("epsilon_reg", 1, "The regularization parameter epsilon_reg must be a float or int")
-        if not isinstance(self.algo, str):
-            reset("algo", "log_surrogate", "The algorithm parameter must be a string")
-        if not isinstance(self.simplex_H, bool):
-            reset("simplex_H", False, "The simplex_H parameter must be a boolean")
-        if not isinstance(self.simplex_W, bool):
-            reset("simplex_W", True, "The simplex_W parameter must be a boolean")
-        if not isinstance(self.dicotomy_tol, (int, float)):
-            reset("dicotomy_tol", 1e-3, "The dicotomy_tol parameter must be a float or int")
-        if self.gamma is not None and not isinstance(self.gamma, (int, float, list)):
-            reset("gamma", None, "The gamma parameter must be a float, int, or list")
-        if not isinstance(self.verbose, (bool, int)):
-            reset("verbose", 1, "The verbose parameter must be a boolean or int")
-        if not isinstance(self.debug, bool):
-            reset("debug", False, "The debug parameter must be a boolean")
-        if not isinstance(self.l2, bool):
-            reset("l2", False, "The l2 parameter must be a boolean")
-        if not isinstance(self.n_components, int):
-            reset("n_components", 2, "The n_components parameter must be an int")
+        for name, types, value, subject, wording, shown in self._TYPE_RULES:
+            if not isinstance(getattr(self, name), types):
+                # the reference words the type complaint about `algo` differently from its reset line
+                lead = "The algorithm parameter" if name == "algo" else subject
+                print("%s must be %s" % (lead, wording))
+                print("%s is set to %s" % (subject, shown))
+                setattr(self, name, value)
         if self.algo not in ("l2_surrogate", "log_surrogate", "projected_gradient", "bmd"):
-            reset("algo", "log_surrogate",
-                  "The algorithm must be 'l2_surrogate', 'log_surrogate', 'bmd' or 'projected_gradient'")
+            correct("algo", "log_surrogate", "The algorithm",
+                    "must be 'l2_surrogate', 'log_surrogate', 'bmd' or 'projected_gradient'", "'log_surrogate'")
         if not (self.lambda_L >= 0):
-            reset("lambda_L", 0, "The regularization parameter lambda_L must be non-negative")
+            correct("lambda_L", 0, "The regularization parameter lambda_L", "must be non-negative", "0")
         if not (self.epsilon_reg > 0.0):
-            reset("epsilon_reg", 1.0, "The regularization parameter epsilon_reg must be positive")
+            correct("epsilon_reg", 1.0, "The regularization parameter epsilon_reg", "must be positive", "1")
         if not np.all(np.array(self.mu) >= 0):
-            reset("mu", 0, "The regularization parameter mu must be non-negative")
+            correct("mu", 0, "The regularization parameter mu", "must be non-negative", "0")
         if self.simplex_H and self.simplex_W:
             print("The simplex constraint must be applied to either W or H or none of them")
             print("The simplex constraint is applied to W and not to H")
@@ -128,11 +127,13 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
             self.simplex_H = False
         if self.linesearch:
             if self.l2:
-                reset("l2", False, "The l2 parameter must be False when using linesearch")
+                correct("l2", False, "The l2 parameter", "must be False when using linesearch", "False")
             if not (self.lambda_L > 0):
-                reset("lambda_L", 1, "The regularization parameter lambda_L must be non-zero when using linesearch")
+                print("The regularization parameter lambda_L must be non-zero when using linesearch")
+                print("The regularization parameter lambda_L is set to 1")
+                self.lambda_L = 1
         if self.algo != "l2_surrogate" and self.l2:
-            reset("l2", False, "The l2 parameter must be False when using the algorithm " + self.algo)
+            correct("l2", False, "The l2 parameter", "must be False when using the algorithm " + self.algo, "False")
 
     def _require_supported(self):
         if self.algo == "projected_gradient":
