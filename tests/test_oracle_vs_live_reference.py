@@ -1,0 +1,54 @@
+"""The oracle against the UNMODIFIED reference run live (only where the reference tree is present, i.e. the build
+container): randomised small problems and flag combinations beyond the committed golden vectors.  This is the second
+pin of oracle/smooth_nmf_oracle.py (the first being tests/golden/*.npz, which the same reference produced)."""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import rel_err
+from oracle import ref_import
+from oracle import smooth_nmf_oracle as orc
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+from gen_golden import synth_problem  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not ref_import.reference_available(), reason="reference tree not present")
+
+CONFIGS = [
+    dict(simplex_H=True, simplex_W=False),
+    dict(simplex_H=True, simplex_W=False, lambda_L=1.3, mu=0.04),
+    dict(simplex_H=False, simplex_W=True, lambda_L=0.7),
+    dict(simplex_H=False, simplex_W=False, mu=0.1),
+    dict(simplex_H=True, simplex_W=False, normalize=True, mu=0.02),
+    dict(simplex_H=True, simplex_W=False, lambda_L=0.9, algo="l2_surrogate"),
+    dict(simplex_H=True, simplex_W=False, lambda_L=0.6, linesearch=True),
+    dict(simplex_H=True, simplex_W=False, lambda_L=0.5, mu=0.03, algo="bmd", identity=True),
+    dict(simplex_H=False, simplex_W=True, identity=True),
+]
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+@pytest.mark.parametrize("ci", range(len(CONFIGS)))
+def test_oracle_equals_live_reference(seed, ci):
+    ref = ref_import.load_reference()
+    kw = dict(CONFIGS[ci])
+    identity = kw.pop("identity", False)
+    rng = np.random.default_rng(1000 * seed + ci)
+    nx, ny = int(rng.integers(4, 9)), int(rng.integers(4, 9))
+    n, k, m = int(rng.integers(40, 90)), int(rng.integers(2, 5)), int(rng.integers(5, 9))
+    pr = synth_problem(rng, n, nx, ny, k, m, counts=float(rng.uniform(10, 60)), identity_G=identity)
+    X, G, W0, H0 = pr["X"], pr["G"], pr["W0"], pr["H0"]
+    common = dict(tol=0, no_stop_criterion=True, max_iter=9, shape_2d=(nx, ny))
+    est = ref.estimators.SmoothNMF(n_components=k, G=G, verbose=0, **common, **kw)
+    with contextlib.redirect_stdout(io.StringIO()):
+        est.fit_transform(X.copy(), W=W0.copy(), H=H0.copy())
+    res = orc.fit(X, G, W0, H0, **common, **kw)
+    assert res["n_iter"] == est.n_iter_
+    assert rel_err(res["losses"], np.array(est.losses_)) < 1e-10
+    assert rel_err(res["W"], est.W_) < 1e-9
+    assert rel_err(res["H"], est.H_) < 1e-9
+    assert rel_err(res["rel"], np.array(est.rel_)) < 1e-7
