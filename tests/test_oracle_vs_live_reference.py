@@ -52,3 +52,25 @@ def test_oracle_equals_live_reference(seed, ci):
     assert rel_err(res["W"], est.W_) < 1e-9
     assert rel_err(res["H"], est.H_) < 1e-9
     assert rel_err(res["rel"], np.array(est.rel_)) < 1e-7
+
+
+@pytest.mark.parametrize("case", ["both_missing", "only_H_given", "only_W_given", "both_given", "identity_both_missing"])
+@pytest.mark.parametrize("simplex", ["H", "W", "none"])
+def test_initialize_factors_equals_reference(case, simplex):
+    """espm_b200.host.initialize_factors (row a11) against initialize_algorithms (updates.py:160-223), same random
+    state: NNDSVD through scikit-learn, least squares for one missing factor, simplex rescale, clamp."""
+    from espm_b200.host import initialize_factors
+    ref = ref_import.load_reference()
+    rng = np.random.default_rng(77)
+    identity = case.startswith("identity")
+    pr = synth_problem(rng, 60, 6, 7, 3, 7, identity_G=identity)
+    X, G = pr["X"], pr["G"]
+    X = np.maximum(X, 1e-14)
+    W = pr["W0"].copy() if case in ("only_W_given", "both_given") else None
+    H = pr["H0"].copy() if case in ("only_H_given", "both_given") else None
+    sH, sW = simplex == "H", simplex == "W"
+    Gr, Wr, Hr = ref.updates.initialize_algorithms(X, G, None if W is None else W.copy(), None if H is None else H.copy(),
+                                                   3, None, 5, sH, sW)
+    Go, Wo, Ho = initialize_factors(X, G, W, H, 3, None, 5, sH, sW, 1e-14)
+    assert np.array_equal(Go, Gr)
+    assert rel_err(Wo, Wr) < 1e-12 and rel_err(Ho, Hr) < 1e-12
