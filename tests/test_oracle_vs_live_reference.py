@@ -74,3 +74,29 @@ def test_initialize_factors_equals_reference(case, simplex):
     Go, Wo, Ho = initialize_factors(X, G, W, H, 3, None, 5, sH, sW, 1e-14)
     assert np.array_equal(Go, Gr)
     assert rel_err(Wo, Wr) < 1e-12 and rel_err(Ho, Hr) < 1e-12
+
+
+def test_host_helpers_equal_reference():
+    """rescaled_DH (utils.py:79-96, row a15), normalization_factor (base.py:16-18), remove_zeros_lines
+    (base.py:519-528) and the truth-tracking measures find_min_angle / find_min_MSE (measures.py:125-153, 258-285,
+    row a16) of espm_b200.host against the reference's functions."""
+    from espm_b200 import host
+    ref = ref_import.load_reference()
+    rng = np.random.default_rng(5)
+    D = rng.uniform(0.1, 1.0, size=(40, 3))
+    H = rng.uniform(0.05, 1.0, size=(3, 90))
+    Dr, Hr = ref.utils.rescaled_DH(D.copy(), H.copy())
+    Do, Ho = host.rescaled_DH(D.copy(), H.copy())
+    assert rel_err(Do, Dr) < 1e-12 and rel_err(Ho, Hr) < 1e-12
+    X = rng.poisson(0.3, size=(40, 90)).astype(float)
+    X[7, :] = 0
+    X[:, 11] = 0
+    assert host.normalization_factor(X, 3) == ref.estimators.base.normalization_factor(X, 3)
+    est = ref.estimators.SmoothNMF(n_components=3, verbose=0)
+    assert np.array_equal(host.remove_zeros_lines(X, 1e-14), est.remove_zeros_lines(X, 1e-14))
+    with pytest.raises(ValueError):
+        host.remove_zeros_lines(-np.ones((3, 3)), 1e-14)
+    tv, av = rng.uniform(size=(3, 40)), rng.uniform(size=(3, 40))
+    assert np.allclose(host.find_min_angle(tv, av), ref.measures.find_min_angle(tv, av, unique=True), rtol=1e-12)
+    tm, am = rng.uniform(size=(3, 90)), rng.uniform(size=(3, 90))
+    assert np.allclose(host.find_min_MSE(tm, am), ref.measures.find_min_MSE(tm, am, unique=True), rtol=1e-12)
