@@ -74,3 +74,33 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not pat.search(text), (dirpath, f)
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/espm_b200.h must be consumable from C (the drop-in boundary is a C ABI): compile a C99 translation unit
+    with -pedantic, link it against the shared library and call two entry points that need no GPU."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    from espm_b200 import _lib
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "espm_b200.h"\n'
+        "int main(void) {\n"
+        "    long long out[8];\n"
+        "    espm_state st;\n"
+        "    if (espm_state_layout((int64_t*)out) != 0) return 2;\n"
+        "    if (out[0] != (long long)sizeof(st)) return 3;\n"
+        '    printf("%d %lld\\n", espm_version(), out[0]);\n'
+        "    return 0;\n}\n")
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(_lib.LIBPATH)
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+           "-o", str(exe), "-L", libdir, "-lespm_b200", "-Wl,-rpath," + libdir]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    version, size = r.stdout.split()
+    assert int(version) > 0 and int(size) == ctypes.sizeof(_lib.EspmState)
