@@ -30,6 +30,10 @@ WORKLOADS = {
                kw=dict(simplex_H=True, simplex_W=False, lambda_L=2.0, mu=0.05)),
     "C3": dict(nx=512, ny=512, n=2048, k=4, n_elements=25,
                kw=dict(simplex_H=True, simplex_W=False, lambda_L=2.0, mu=0.05)),
+    # one rank's slab of C3 on 8 GPUs (64 image rows) as a single-GPU problem: profiling of the k x p / m x k
+    # kernels at the shard size that limits strong scaling (ncu cannot attach to a multi-rank run)
+    "C3r8": dict(nx=64, ny=512, n=2048, k=4, n_elements=25,
+                 kw=dict(simplex_H=True, simplex_W=False, lambda_L=2.0, mu=0.05)),
     # configs[3]: 1024x1024 px x 4096 ch (17.2 GB fp32), 5 phases + Laplacian; --algo l2_surrogate for the "L2" reading
     "C4": dict(nx=1024, ny=1024, n=4096, k=5, n_elements=25,
                kw=dict(simplex_H=True, simplex_W=False, lambda_L=2.0, mu=0.05)),
@@ -167,6 +171,8 @@ def main():
     ap.add_argument("--algo", default="log_surrogate", choices=["log_surrogate", "l2_surrogate"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-selfcheck", action="store_true",
+                    help="N > 1: skip the comparison with an unsharded run of the same image on rank 0")
     ap.add_argument("--cpu-rows", type=int, default=48, help="image rows of the CPU-baseline crop")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
@@ -287,6 +293,13 @@ def main():
     dom_ms = max(h_ms, w_ms)
     achieved = bytes_launch / (dom_ms * 1e-3) / 1e9
     recs = eng.read_records(W + K, W + K + 1)[0]
+    W_end = eng.get_W().astype(np.float64)
+    check = {"loss_kl_sumY": float(recs[L.S_SUMY]), "loss_kl_xlogy": float(recs[L.S_XLOGY]),
+             "kl_raw": float(recs[L.S_SUMY] - recs[L.S_XLOGY]), "bisect_its_H": float(recs[L.S_BISECT_ITS_H]),
+             "dev_flags": float(recs[L.S_DEV_FLAGS]), "W_sum": float(W_end.sum()),
+             "W_l2": float(np.sqrt((W_end ** 2).sum())), "iterations": W + K,
+             "what": "state after warmup+steps iterations; X is seeded per global 32768-pixel chunk, so these "
+                     "values are comparable across --gpus 1/2/4/8"}
     # warm per-kernel durations of EVERY launch of an iteration (separate untimed loop: events between
     # all launches perturb the pipeline, so this is diagnostic only)
     eng.profile, eng.profile_names = {}, None
@@ -304,6 +317,32 @@ def main():
                 "h_pass_gbs": bytes_launch / (h_ms * 1e-3) / 1e9, "w_pass_gbs": bytes_launch / (w_ms * 1e-3) / 1e9,
                 "iteration_frac": (2 * bytes_launch / (ms / K * 1e-3) / 1e9) / peak, "kernel_ms": kernel_ms}
 
+    if world > 1 and not replicas and rank == 0 and not args.no_selfcheck:
+        # (after the last use of the sharded engine: the peers' kernels wait for this rank with a ~1 s time-out)
+        # The sharded result against the UNSHARDED engine on the same image, same iterations (rank 0 only, outside
+        # every timed region): W, the KL sums and the lock-step bisection count must agree.
+        X_full = synth.poisson_X_torch(prob, 0, p, args.seed, dev, tdt)
+        eng1 = FitEngine(X_full, G, W0, H0, shape_2d=(nx, ny), max_records=W + K + 16, shard=None, x_local=True,
+                         tol=0.0, **wl["kw"])
+        del X_full
+        eng1.evaluate(0)
+        for i in range(1, W + K + 1):
+            eng1.advance(i)
+            eng1.evaluate(i)
+        r1 = eng1.read_records(0, W + K + 1)
+        W1 = eng1.get_W().astype(np.float64)
+        kl1 = float(r1[W + K][L.S_SUMY] - r1[W + K][L.S_XLOGY])
+        check["vs_unsharded"] = {
+            "W_max_rel_diff": float(np.max(np.abs(W_end - W1) / np.maximum(np.abs(W1), 1e-300))),
+            "kl_raw_rel_diff": abs(check["kl_raw"] - kl1) / abs(kl1),
+            "bisect_its_equal": bool(recs[L.S_BISECT_ITS_H] == r1[W + K][L.S_BISECT_ITS_H]),
+            "unsharded_kl_raw": kl1, "unsharded_W_sum": float(W1.sum())}
+        tol_chk = 1e-6 if args.dtype == "f32" else 1e-10
+        check["vs_unsharded"]["ok"] = bool(check["vs_unsharded"]["W_max_rel_diff"] <= 20 * tol_chk
+                                           and check["vs_unsharded"]["kl_raw_rel_diff"] <= tol_chk
+                                           and check["vs_unsharded"]["bisect_its_equal"])
+        eng1.close()
+        del eng1
     # ------------------------------------------------------------------ end to end through the public API
     e2e = None
     if not args.no_e2e:
@@ -382,8 +421,7 @@ def main():
             "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak" if replicas else "strong", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic", "config": config, "roofline": roofline, "cpu_baseline": cpu,
             "e2e": e2e, "gpu_launches": n_launches, "clocks": clocks,
-            "check": {"loss_kl_sumY": float(recs[L.S_SUMY]), "bisect_its_H": float(recs[L.S_BISECT_ITS_H]),
-                      "dev_flags": float(recs[L.S_DEV_FLAGS])}}
+            "check": check}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -195,15 +195,16 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
         from .ops import full_loss
         check_is_fitted(self, "G_")
         Xe = self.X_ if X is None else X
-        const = self.const_KL_
-        if X is not None or const is None:
-            # base.py:201 (the constant mixes X and self.X_ exactly like the reference)
-            const = float(np.sum(Xe * np.log(np.maximum(self.X_, self.log_shift))) - np.sum(Xe))
-            if self.const_KL_ is None:
-                self.const_KL_ = const
+        if self.const_KL_ is None and not self.l2:
+            # base.py:200-201: computed once (mixing X and self.X_ exactly like the reference), then reused for
+            # every later call, whatever X that call is given
+            self.const_KL_ = float(np.sum(Xe * np.log(np.maximum(self.X_, self.log_shift))) - np.sum(Xe))
+        # clamp=False: G W and H are clamped inside the KL term only (measures.py:493-495), not in the
+        # regularisers (smooth_nmf.py:461-466)
         val, det = full_loss(Xe, self.G_ if not self._identity_G else None, W, H, mu=self.mu,
                              epsilon_reg=self.epsilon_reg, lambda_L=self.lambda_L, shape_2d=self.shape_2d,
-                             log_shift=self.log_shift, const=const, average=average, l2=bool(self.l2))
+                             log_shift=self.log_shift, const=0.0 if self.l2 else self.const_KL_, average=average,
+                             l2=bool(self.l2), clamp=False)
         self.GWH_numel_ = Xe.shape[0] * H.shape[1]
         self.detailed_loss_ = det + [self.gamma_ if not isinstance(self.gamma_, list) else self.gamma_[0]]
         return val
@@ -328,7 +329,10 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
             self.norm_factor_ = eng.norm_factor
         self._x_fix = (eng.n_zero_rows > 0 or eng.n_zero_cols > 0, self.norm_factor_ if self.normalize else None)
         self.G_ = G_full
-        self.L_ = None  # the Laplacian is a stencil inside the kernels (utils.py:39-76 is never materialised)
+        # base.py:287-291.  The kernels apply the Laplacian as a stencil; L_ is the reference's matrix all the same
+        # (assembled on first use: `est.L_ @ x`, `.toarray()`, `.shape` work like on the scipy.sparse original)
+        from .ops import GridLaplacian
+        self.L_ = GridLaplacian(*self.shape_2d) if self.shape_2d is not None else GridLaplacian(None, identity=p)
 
         algo_start = time.time()
         self.n_iter_ = 0
@@ -371,6 +375,7 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
         eng.close()
         self._engine = None            # release the device copy of X
         self._init_WH = None
+        register_with_espm()
         if self.hspy_comp:                                             # base.py:415-420
             self.components_ = GW.T
             return self.H_.T
@@ -512,9 +517,34 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
         return self.G_ @ W @ self.H_
 
     def get_losses(self):
-        """Structured array of the loss history (base.py:479-517)."""
+        """Structured array of the loss history (base.py:479-517); with ``true_D`` / ``true_H`` also the angles,
+        the mean squared errors and the loss against the ground truth of every iteration."""
         names = ["full_loss"] + self.loss_names_ + ["rel_W", "rel_H"]
+        truth = self.true_D is not None and self.true_H is not None
+        if truth:
+            names += ["ang_p%d" % i for i in range(self.n_components)]
+            names += ["mse_p%d" % i for i in range(self.n_components)] + ["true_KL_loss"]
         dt = np.dtype([(name, "float64") for name in names])
-        rows = [(self.losses_[i],) + tuple(self.detailed_losses_[i]) + tuple(self.rel_[i])
-                for i in range(len(self.losses_))]
+        rows = []
+        for i in range(len(self.losses_)):
+            row = (self.losses_[i],) + tuple(self.detailed_losses_[i]) + tuple(self.rel_[i])
+            if truth:
+                row += tuple(self.angles_[i]) + tuple(self.mse_[i]) + (self.true_losses_[i],)
+            rows.append(row)
         return np.array(rows, dtype=dt)
+
+
+def register_with_espm():
+    """``isinstance(est, espm.estimators.NMFEstimator)`` is how the reference's hyperspy signal class recognises a
+    fitted espm estimator (eds_spim.py:607, 639).  NMFEstimator is an ABC (base.py:20), so the drop-in registers as
+    a virtual subclass -- only when espm is already imported: importing it here would pull in hyperspy / exspy."""
+    mod = sys.modules.get("espm.estimators")
+    base = getattr(mod, "NMFEstimator", None)
+    if base is None or not hasattr(base, "register"):
+        return False
+    if not issubclass(SmoothNMF, base):
+        base.register(SmoothNMF)
+    return True
+
+
+register_with_espm()

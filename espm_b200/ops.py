@@ -5,8 +5,8 @@ names and argument meaning, executed by the CUDA kernels.
     multiplicative_step_hq                           espm/estimators/updates.py:263
     dichotomy_simplex                                espm/estimators/dicotomy.py:4
     KLdiv_loss / log_reg / trace_xtLx                espm/measures.py:456 / :524 / :560
-    create_laplacian_matrix                          espm/utils.py:39 (returns the image shape: the
-                                                     Laplacian is a stencil inside the kernels)
+    create_laplacian_matrix                          espm/utils.py:39 (matrix-like object that also carries the
+                                                     image shape: the kernels apply a stencil)
 
 Inputs and outputs are NumPy arrays on the host (like the reference); each call uploads, runs the
 kernels once and downloads -- these entry points exist for parity tests and small problems, the
@@ -26,16 +26,80 @@ from .engine import FitEngine
 
 
 class GridLaplacian:
-    """Stand-in for the scipy.sparse matrix of ``create_laplacian_matrix``: remembers (nx, ny)."""
+    """The matrix ``create_laplacian_matrix`` returns in the reference (utils.py:39-76), or the identity the fit
+    uses when ``shape_2d`` is None (base.py:289-291).
 
-    def __init__(self, nx, ny):
-        self.shape_2d = (int(nx), int(ny))
-        self.shape = (nx * ny, nx * ny)
+    The kernels apply it as a 5-point stencil and only ever need ``shape_2d``; everything a caller can do with
+    the reference's scipy.sparse matrix (``L @ x``, ``x @ L``, ``.dot``, ``.toarray()``, ``.shape``, indexing,
+    ...) works as well: the float32 sparse matrix is assembled on first use and every other attribute is
+    delegated to it."""
+
+    __array_priority__ = 10.1        # like scipy.sparse: ndarray @ L defers to __rmatmul__
+    __array_ufunc__ = None
+    ndim = 2
+
+    def __init__(self, nx, ny=None, identity=None):
+        if identity is not None:
+            self.shape_2d = None
+            self._p = int(identity)
+        else:
+            self.shape_2d = (int(nx), int(ny))
+            self._p = int(nx) * int(ny)
+        self._mat = None
+
+    @property
+    def shape(self):
+        return (self._p, self._p)
+
+    @property
+    def dtype(self):
+        return np.dtype(np.float32)
+
+    def tosparse(self):
+        """scipy.sparse matrix with the reference's entries: diagonal = number of in-bounds 4-neighbours,
+        -1 for each neighbour, pixel index = i * ny + j (float32, utils.py:57)."""
+        if self._mat is None:
+            import scipy.sparse as sp
+            if self.shape_2d is None:
+                self._mat = sp.identity(self._p, dtype=np.float32, format="csr")
+            else:
+                def path(n):    # 1-D Neumann Laplacian of a path with n nodes
+                    d = np.full(n, 2.0, dtype=np.float32)
+                    d[0] = d[-1] = 1.0
+                    o = np.full(n - 1, -1.0, dtype=np.float32)
+                    return sp.diags([o, d, o], [-1, 0, 1], format="csr", dtype=np.float32)
+                nx, ny = self.shape_2d
+                eye = lambda n: sp.identity(n, dtype=np.float32, format="csr")   # noqa: E731
+                self._mat = (sp.kron(eye(nx), path(ny)) + sp.kron(path(nx), eye(ny))).tocsr().astype(np.float32)
+        return self._mat
+
+    def __matmul__(self, other):
+        return self.tosparse() @ other
+
+    def __rmatmul__(self, other):
+        return other @ self.tosparse()
+
+    def dot(self, other):
+        return self.tosparse().dot(other)
+
+    def __mul__(self, other):
+        return self.tosparse() * other
+
+    def __rmul__(self, other):
+        return other * self.tosparse()
+
+    def __getitem__(self, idx):
+        return self.tosparse()[idx]
+
+    def __getattr__(self, name):
+        if name.startswith("__") or name in ("_mat", "_p", "shape_2d"):
+            raise AttributeError(name)
+        return getattr(self.tosparse(), name)
 
 
 def create_laplacian_matrix(nx, ny=None):
-    """utils.py:39-76.  The 5-point Neumann Laplacian is applied as a stencil by the kernels, so this
-    only records the image shape."""
+    """utils.py:39-76.  Returns an object that behaves like the reference's sparse matrix and carries the image
+    shape for the kernels (which apply the 5-point Neumann Laplacian as a stencil)."""
     if ny is None:
         ny = nx
     assert nx > 1
@@ -58,6 +122,8 @@ def _shape_from_L(Lm, p):
     if Lm is None:
         return None, False
     if isinstance(Lm, GridLaplacian):
+        if Lm.shape != (p, p):
+            raise ValueError("Laplacian has shape %s, expected %s" % (Lm.shape, (p, p)))
         return Lm.shape_2d, True
     if isinstance(Lm, tuple):
         return (int(Lm[0]), int(Lm[1])), True
@@ -371,12 +437,16 @@ def dichotomy_simplex_acc(a, b, minus_c, log_shift=_LS, tol=_TOL, maxit=_MAXIT, 
 
 
 def full_loss(X, G, W, H, mu=0, epsilon_reg=1, lambda_L=0, shape_2d=None, log_shift=_LS, const=0.0,
-              average=True, l2=False):
+              average=True, l2=False, clamp=True):
     """KL (or 0.5 Frobenius, ``l2``) + log-reg + Laplacian loss of (W, H) (base.py:167-207, smooth_nmf.py:457-475).
-    Returns (loss, [kl, log_reg, lapl])."""
+    Returns (loss, [kl, log_reg, lapl]).  ``clamp=False`` uploads W and H as given: G W and H are then clamped to
+    ``log_shift`` inside the KL term only (measures.py:493-495), exactly like ``SmoothNMF.loss``; the default clamps
+    the factors themselves first, which is what the fit loop evaluates (its iterates are >= log_shift)."""
     eng = _engine(X, G, W, H, shape_2d=shape_2d, lambda_L=lambda_L, mu=mu, epsilon_reg=epsilon_reg,
                   log_shift=log_shift, simplex_H=False, simplex_W=False, max_records=8, l2=bool(l2),
-                  clamp_init=not l2)
+                  clamp_init=clamp and not l2)
+    if not clamp and not l2:
+        eng.set_flag(_L.FLAG_LOSS_DUAL)
     eng.evaluate(0)
     rec = eng.read_records(0, 1)[0]
     numel = X.shape[0] * np.shape(H)[1] if average else 1

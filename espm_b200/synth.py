@@ -80,15 +80,23 @@ def poisson_X_numpy(prob, j0, j1, seed, dtype=np.float32):
 
 
 def poisson_X_torch(prob, j0, j1, seed, device, dtype, chunk=32768):
-    """Device generation of the same distribution (different random stream), (n, j1-j0) tensor."""
+    """Device generation of the same distribution (different random stream), (n, j1-j0) tensor.
+
+    The random stream is seeded per GLOBAL chunk of `chunk` pixels, and a chunk is always drawn whole, so the
+    pixels [j0, j1) come out identical however the image is partitioned over ranks: 1-, 2-, 4- and 8-GPU runs of
+    bench.py stream the same X and their losses / W can be compared with each other."""
     import torch
-    gen = torch.Generator(device=device)
-    gen.manual_seed(seed * 1000003 + j0)
     Dd = torch.as_tensor(prob["counts"] * prob["D"] * prob["dens"][None, :], dtype=torch.float32, device=device)
     n = Dd.shape[0]
+    p = prob["H_true"].shape[1]
     X = torch.empty(n, j1 - j0, dtype=dtype, device=device)
-    for a in range(j0, j1, chunk):
-        b = min(a + chunk, j1)
+    gen = torch.Generator(device=device)
+    for c in range(j0 // chunk, (j1 + chunk - 1) // chunk):
+        a, b = c * chunk, min((c + 1) * chunk, p)
+        gen.manual_seed(seed * 1000003 + c)
         Ht = torch.as_tensor(prob["H_true"][:, a:b], dtype=torch.float32, device=device)
-        X[:, a - j0:b - j0] = torch.poisson(Dd @ Ht, generator=gen).to(dtype)
+        draw = torch.poisson(Dd @ Ht, generator=gen)
+        lo, hi = max(a, j0), min(b, j1)
+        X[:, lo - j0:hi - j0] = draw[:, lo - a:hi - a].to(dtype)
+        del draw
     return X

@@ -97,8 +97,12 @@ def trace_xtLx(H, shape_2d):
 # --------------------------------------------------------------------------------------------
 # Lock-step bisection (dicotomy.py)
 # --------------------------------------------------------------------------------------------
-def dicotomy(a, b, func, maxit, tol, return_its=False):
-    """dicotomy.py:111-173.  Vectorised bisection with a GLOBAL stop test (line 152)."""
+def dicotomy(a, b, func, maxit, tol, return_its=False, force_its=None):
+    """dicotomy.py:111-173.  Vectorised bisection with a GLOBAL stop test (line 152).
+
+    ``force_its`` (not in the reference; test infrastructure) runs exactly that many updates instead of applying the
+    stop test: the fp32 parity tests use it to evaluate "what the reference computes when its lock-step count is c"
+    when the fp32 device data and the fp64 oracle disagree on a knife-edge stop decision."""
     func_max = func(a)
     func_min = func(b)
     assert np.sum(func_min >= 0) == 0
@@ -108,7 +112,7 @@ def dicotomy(a, b, func, maxit, tol, return_its=False):
     it = 0
     new = (a + b) / 2
     func_new = func(new)
-    while np.max(np.abs(func_new)) > tol:
+    while (np.max(np.abs(func_new)) > tol) if force_its is None else (it < force_its):
         it += 1
         func_a = func(a)
         minus_bool = func_a * func_new <= 0
@@ -117,7 +121,7 @@ def dicotomy(a, b, func, maxit, tol, return_its=False):
         a[plus_bool] = new[plus_bool]
         new = (a + b) / 2
         func_new = func(new)
-        if it >= maxit:
+        if it >= maxit and force_its is None:
             break
     if return_its:
         return new, it
@@ -125,7 +129,7 @@ def dicotomy(a, b, func, maxit, tol, return_its=False):
 
 
 def dichotomy_simplex(num, denum, log_shift=LOG_SHIFT, tol=DICOTOMY_TOL, maxit=MAXIT_DICHOTOMY,
-                      return_its=False):
+                      return_its=False, force_its=None):
     """dicotomy.py:4-55: root of sum_i max(num_i/(x+den_i), log_shift) - 1 per column."""
     assert (num >= 0).all()
     assert (denum >= 0).all()
@@ -142,7 +146,7 @@ def dichotomy_simplex(num, denum, log_shift=LOG_SHIFT, tol=DICOTOMY_TOL, maxit=M
     def func(x):
         return np.sum(np.maximum(num / (x + denum), log_shift), axis=0) - 1
 
-    return dicotomy(a, b, func, maxit, tol, return_its=return_its)
+    return dicotomy(a, b, func, maxit, tol, return_its=return_its, force_its=force_its)
 
 
 def dichotomy_simplex_acc(a, b, minus_c, log_shift=LOG_SHIFT, tol=DICOTOMY_TOL,
@@ -178,8 +182,9 @@ def _mu_column(mu):
 
 def multiplicative_step_h(X, G, W, H, simplex_H=False, mu=0, log_shift=LOG_SHIFT, epsilon_reg=1,
                           safe=True, dicotomy_tol=DICOTOMY_TOL, lambda_L=0, shape_2d=None,
-                          sigmaL=SIGMA_L, fixed_H=None, return_its=False, l2=False, use_bregman=False):
-    """updates.py:83-156 (``L`` is replaced by ``shape_2d``: stencil Laplacian)."""
+                          sigmaL=SIGMA_L, fixed_H=None, return_its=False, l2=False, use_bregman=False,
+                          force_its=None):
+    """updates.py:83-156 (``L`` is replaced by ``shape_2d``: stencil Laplacian).  ``force_its``: see ``dicotomy``."""
     if lambda_L != 0:
         HL = laplacian_apply(H, shape_2d)                      # updates.py:96
     if safe:
@@ -218,7 +223,7 @@ def multiplicative_step_h(X, G, W, H, simplex_H=False, mu=0, log_shift=LOG_SHIFT
     its = 0
     if simplex_H:                                              # updates.py:143-146
         nu, its = dichotomy_simplex(num, denum, log_shift=log_shift, tol=dicotomy_tol,
-                                    return_its=True)
+                                    return_its=True, force_its=force_its)
     else:
         nu = 0
     if safe:

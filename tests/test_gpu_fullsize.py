@@ -50,6 +50,30 @@ def _replay(num, den, its):
     return new, (its if own is None else own)
 
 
+def _lockstep_count_torch(num, den):
+    """Iteration count of dicotomy.py:111-173 on (k, p) float64 device tensors."""
+    import torch
+    k = num.shape[0]
+    ninf = torch.full_like(num, -float("inf"))
+    a = torch.where(num > 0, num / 2 - den, ninf).max(0).values
+    b = k * num.max(0).values / 0.5 - den.min(0).values
+
+    def func(x):
+        return torch.clamp(num / (x + den), min=LS).sum(0) - 1
+
+    new = (a + b) / 2
+    fn = func(new)
+    it = 0
+    while float(fn.abs().max()) > TOL and it < 100:
+        it += 1
+        minus = func(a) * fn <= 0
+        b = torch.where(minus, new, b)
+        a = torch.where(minus, a, new)
+        new = (a + b) / 2
+        fn = func(new)
+    return it
+
+
 @pytest.mark.parametrize("cfg", ["C2-f64", "C3-f32"])
 def test_one_iteration_at_full_size(cfg):
     import torch
@@ -98,9 +122,25 @@ def test_one_iteration_at_full_size(cfg):
     ref_HJ = np.maximum(num / (den + nu), LS)
     assert rel_err(H1[:, J], ref_HJ) < tol
 
-    # ---- W update + loss: independent chunked fp64 evaluation on the GPU ----
+    # ---- the GLOBAL lock-step count (dicotomy.py:152) over ALL pixels: independent fp64 evaluation (torch on the GPU)
+    # of num / den from the same (fp32-rounded) inputs, then the reference's vectorised bisection.  This pins the count
+    # the fp32 kernels arrive at against what the reference computes in fp64 at this size.
     dev = X.device
     GWd = torch.as_tensor(GW, device=dev)
+    H64d = torch.as_tensor(H64, device=dev)
+    numA = torch.empty(k, p, dtype=torch.float64, device=dev)
+    for a in range(0, p, 32768):
+        b = min(a + 32768, p)
+        numA[:, a:b] = GWd.T @ (X[:, a:b].double() / (GWd @ H64d[:, a:b]))
+    maxHd = torch.as_tensor(maxH, device=dev)
+    HLd = torch.as_tensor(orc.laplacian_apply(H64, (nx, ny)), device=dev)
+    numA = H64d * (numA + lam * SIGMA * maxHd)
+    denA = GWd.sum(0)[:, None] + mu / (H64d + eps) + lam * SIGMA * maxHd + lam * HLd
+    its64 = _lockstep_count_torch(numA, denA)
+    assert its == its64, "device lock-step count %d, fp64 evaluation %d" % (its, its64)
+    del numA, denA, HLd
+
+    # ---- W update + loss: independent chunked fp64 evaluation on the GPU ----
     H1d = torch.as_tensor(H1, device=dev)
     S = torch.zeros(n, k, dtype=torch.float64, device=dev)
     for a in range(0, p, 32768):

@@ -1,6 +1,7 @@
-"""Pixel-sharded fit on 2 GPUs (one process per GPU, NCCL) against the single-process oracle.
+"""Pixel-sharded fit on 2 / 4 / 8 GPUs (one process per GPU, NCCL) against the single-process oracle, and at the
+benchmark size (C3) against the unsharded engine on the same data.
 
-Skipped on boxes with fewer than two GPUs.  The image rows are split across the ranks; every rank must
+Skipped on boxes with fewer GPUs than ranks.  The image rows are split across the ranks; every rank must
 end with the same W and the same loss history as the unsharded reference run.
 """
 import os
@@ -97,27 +98,117 @@ def _worker(rank, world, port, out_dir, peer):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("peer", [True, False], ids=["peer-memory", "nccl"])
-def test_sharded_fit_matches_oracle(tmp_path, peer):
-    """Both exchange paths: inside the kernels through CUDA-IPC peer memory (default), and NCCL."""
+def _need_gpus(world):
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("peer", [True, False], ids=["peer-memory", "nccl"])
+def test_sharded_fit_matches_oracle(tmp_path, peer, world):
+    """Both exchange paths: inside the kernels through CUDA-IPC peer memory (default), and NCCL; 2, 4 and 8 shards
+    (37 image rows: ragged shards of 4-5 rows at 8 ranks)."""
+    _need_gpus(world)
     import torch.multiprocessing as mp
     from conftest import rel_err
     from oracle import smooth_nmf_oracle as orc
-    world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), peer), nprocs=world, join=True)
-    r0 = dict(np.load(tmp_path / "rank0.npz"))
-    r1 = dict(np.load(tmp_path / "rank1.npz"))
+    res = [dict(np.load(tmp_path / ("rank%d.npz" % r))) for r in range(world)]
     for tag, kw in CASES.items():
         X, G, W0, H0 = _data(tag)
         ref = orc.fit(X, G, W0, H0, shape_2d=(NX, NY), tol=0, no_stop_criterion=True, max_iter=8, **kw)
-        for r in (r0, r1):
+        for r in res:
             assert rel_err(r[tag + "__losses"], ref["losses"]) < 1e-9, tag
             assert rel_err(r[tag + "__W"], ref["W"]) < 1e-8, tag
             assert rel_err(r[tag + "__H"], ref["H"]) < 1e-8, tag
             assert rel_err(r[tag + "__rel"], ref["rel"]) < 1e-6, tag
         # every rank holds the identical replicated result
-        assert np.array_equal(r0[tag + "__W"], r1[tag + "__W"]), tag
-        assert np.array_equal(r0[tag + "__losses"], r1[tag + "__losses"]), tag
+        for r in res[1:]:
+            assert np.array_equal(res[0][tag + "__W"], r[tag + "__W"]), tag
+            assert np.array_equal(res[0][tag + "__losses"], r[tag + "__losses"]), tag
+
+
+# ------------------------------------------------------------------------------------------------------------
+# The configuration the scaling benchmark times (C3: 512 x 512 px x 2048 ch, k = 4, fp32, Laplacian + mu,
+# simplex_H): the pixel-sharded engine against the UNSHARDED engine on the same image (synth.poisson_X_torch
+# seeds per global pixel chunk, so every partition streams identical data).
+# ------------------------------------------------------------------------------------------------------------
+C3 = dict(nx=512, ny=512, n=2048, k=4, n_el=25, seed=93, iters=2,
+          kw=dict(simplex_H=True, simplex_W=False, lambda_L=2.0, mu=0.05))
+
+
+def _run_c3(eng, iters):
+    eng.evaluate(0)
+    for i in range(1, iters + 1):
+        eng.advance(i)
+        eng.evaluate(i)
+    return eng.read_records(0, iters + 1)
+
+
+def _worker_c3(rank, world, port, out_dir, peer):
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["ESPM_B200_PEER"] = "1" if peer else "0"
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from espm_b200 import synth
+        from espm_b200.dist import make_shard, shard_bounds
+        from espm_b200.engine import FitEngine
+        c = C3
+        nx, ny, n, k = c["nx"], c["ny"], c["n"], c["k"]
+        p = nx * ny
+        prob = synth.make_problem(nx, ny, n, k, c["n_el"], seed=c["seed"])
+        G = prob["G_full"].astype(np.float32)
+        W0, H0 = synth.init_factors(G.shape[1], k, p, c["seed"], dtype=np.float32)
+        j0, j1, _ = shard_bounds(p, nx, ny, rank, world)
+        X_loc = synth.poisson_X_torch(prob, j0, j1, c["seed"], dev, torch.float32)
+        shard = make_shard()
+        assert getattr(shard, "use_peer", False) == peer
+        eng = FitEngine(X_loc, G, W0, H0, shape_2d=(nx, ny), max_records=16, shard=shard, x_local=True, tol=0.0,
+                        **c["kw"])
+        recs = _run_c3(eng, c["iters"])
+        res = dict(W=eng.get_W(), recs=recs, H=eng.get_H())
+        eng.close()
+        del eng, X_loc
+        if rank == 0:
+            X = synth.poisson_X_torch(prob, 0, p, c["seed"], dev, torch.float32)
+            eng1 = FitEngine(X, G, W0, H0, shape_2d=(nx, ny), max_records=16, x_local=True, tol=0.0, **c["kw"])
+            res["recs1"] = _run_c3(eng1, c["iters"])
+            res["W1"], res["H1"] = eng1.get_W(), eng1.get_H()
+        np.savez(os.path.join(out_dir, "c3_rank%d.npz" % rank), **res)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("peer", [True, False], ids=["peer-memory", "nccl"])
+def test_sharded_c3_iterations_match_unsharded(tmp_path, peer, world):
+    """Two full iterations at the benchmark size: W to 1e-6 (fp32 sums over 262144 pixels in another order), equal
+    lock-step bisection counts, loss sums to 1e-6, H to 1e-5, identical replicated state on every rank."""
+    _need_gpus(world)
+    import torch.multiprocessing as mp
+    from conftest import rel_err
+    from espm_b200 import _lib as L
+    mp.spawn(_worker_c3, args=(world, _free_port(), str(tmp_path), peer), nprocs=world, join=True)
+    res = [dict(np.load(tmp_path / ("c3_rank%d.npz" % r))) for r in range(world)]
+    r0 = res[0]
+    for r in res[1:]:
+        assert np.array_equal(r0["W"], r["W"])
+        assert np.array_equal(r0["recs"], r["recs"])
+    recs, recs1 = r0["recs"], r0["recs1"]
+    assert np.all(recs[:, L.S_DEV_FLAGS] == 0) and np.all(recs1[:, L.S_DEV_FLAGS] == 0)
+    assert np.array_equal(recs[:, L.S_BISECT_ITS_H], recs1[:, L.S_BISECT_ITS_H])      # dicotomy.py:152, global count
+    assert recs[0, L.S_BISECT_ITS_H] > 5
+    assert rel_err(r0["W"], r0["W1"]) < 1e-6
+    for s in (L.S_XLOGY, L.S_SUMY, L.S_LOGREG, L.S_LAPL):
+        assert rel_err(recs[:, s], recs1[:, s]) < 1e-6, s
+    assert rel_err(recs[1:, L.S_REL_W], recs1[1:, L.S_REL_W]) < 1e-4                  # base.py:323-324
+    assert rel_err(recs[1:, L.S_REL_H], recs1[1:, L.S_REL_H]) < 1e-4
+    assert rel_err(r0["H"], r0["H1"]) < 1e-5

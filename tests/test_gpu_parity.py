@@ -252,11 +252,20 @@ def test_one_iteration_vs_oracle_fp32(ops, orc, n, nx, ny, k, m):
     X, G, W0, H0 = [a.astype(np.float32) for a in _problem(rng, n, nx, ny, k, m)]
     Lg = ops.create_laplacian_matrix(nx, ny)
     args64 = [a.astype(np.float64) for a in (X, G, W0, H0)]
-    ref_h = orc.multiplicative_step_h(*args64, simplex_H=True, mu=0.05, lambda_L=2.0, shape_2d=(nx, ny))
-    h = ops.multiplicative_step_h(X, G, W0, H0, simplex_H=True, mu=0.05, lambda_L=2.0, L=Lg)
+    ref_h, its_ref = orc.multiplicative_step_h(*args64, simplex_H=True, mu=0.05, lambda_L=2.0, shape_2d=(nx, ny),
+                                               return_its=True)
+    h, its = ops.multiplicative_step_h(X, G, W0, H0, simplex_H=True, mu=0.05, lambda_L=2.0, L=Lg, return_its=True)
     assert h.dtype == np.float32
-    # the fp32 lock-step count may differ by rounding from the fp64 one: nu moves by <= tol-level amounts
-    assert rel_err(h, ref_h) < 2e-4
+    # The lock-step count (dicotomy.py:152) is a GLOBAL stop decision: it can flip by one when the worst pixel's
+    # |f| sits within fp32 rounding of tol, and nu then moves by one bisection step for every pixel.  North-star bar
+    # for the fp32 mode: 1e-5 on the step.  It holds against the reference evaluated at the SAME count; the counts
+    # themselves are required to agree (these seeded cases do) or to differ by that one knife-edge step.
+    assert abs(its - its_ref) <= 1
+    if its != its_ref:
+        ref_h = orc.multiplicative_step_h(*args64, simplex_H=True, mu=0.05, lambda_L=2.0, shape_2d=(nx, ny),
+                                          force_its=its)
+    assert rel_err(h, ref_h) < STEP_TOL_F32
+    assert its == its_ref, "fp32 lock-step count %d differs from the fp64 reference's %d" % (its, its_ref)
     ref_plain = orc.multiplicative_step_h(*args64, simplex_H=False, mu=0.05, lambda_L=2.0, shape_2d=(nx, ny))
     h_plain = ops.multiplicative_step_h(X, G, W0, H0, simplex_H=False, mu=0.05, lambda_L=2.0, L=Lg)
     assert rel_err(h_plain, ref_plain) < STEP_TOL_F32
@@ -518,3 +527,38 @@ def test_sklearn_check_estimator():
     with contextlib.redirect_stdout(io.StringIO()):
         check_estimator(SmoothNMF(n_components=3, max_iter=10, verbose=0))
         check_estimator(SmoothNMF(n_components=3, max_iter=10, verbose=0, lambda_L=2, mu=0.1))
+
+
+def test_hyperspy_decomposition_protocol(golden_fits):
+    """What hyperspy's ``decomposition(algorithm=est)`` and the reference's signal class do with the estimator
+    (eds_spim.py:597-612, 639-644): ``fit_transform`` on the (pixels, channels) matrix,
+    loadings = the return value, factors = ``components_.T``; afterwards ``isinstance(est, NMFEstimator)`` and reads
+    of ``W_ / G_ / H_`` (plot_1D_results, concentration_report) and of ``L_``."""
+    from espm_b200 import SmoothNMF
+    from oracle import ref_import
+    g = golden_fits
+    X = g["A__X"]                                   # (n, p)
+    nx, ny = (int(v) for v in g["A__shape"])
+    data = np.ascontiguousarray(X.T)                # hyperspy hands over (navigation = p, signal = n)
+    est = SmoothNMF(n_components=3, G=g["A__G"], simplex_H=True, simplex_W=False, hspy_comp=True, lambda_L=1.0,
+                    shape_2d=(nx, ny), tol=0, no_stop_criterion=True, max_iter=12, verbose=0)
+    loadings = est.fit_transform(data, W=g["A__W0"].copy(), H=g["A__H0"].copy())
+    factors = est.components_.T
+    n, p = X.shape
+    assert loadings.shape == (p, 3) and factors.shape == (n, 3)
+    assert rel_err(loadings, g["hspy__out"]) < 1e-8 and rel_err(est.components_, g["hspy__components"]) < 1e-8
+    # eds_spim.py:610-612: the 1-D model spectrum
+    W, G, Hm = est.W_, est.G_, est.H_.mean(axis=1)
+    assert (G @ W @ Hm).shape == (n,)
+    # eds_spim.py:642-645: explained intensity per element needs G (n x m), W (m x k), H (k x p)
+    assert G.shape[1] == W.shape[0] and W.shape[1] == est.H_.shape[0] == 3 and est.H_.shape[1] == p
+    # the fitted Laplacian is the reference's matrix (base.py:287-288)
+    Lref = np.asarray(est.L_.toarray())
+    assert Lref.shape == (p, p) and np.array_equal(np.diag(Lref)[:2], [2.0, 3.0])
+    tr = float(np.sum(est.H_.T * (est.L_ @ est.H_.T)))            # measures.py:577 with the fitted L_
+    assert abs(0.5 * 1.0 * tr / (n * p) - est.detailed_losses_[-1][2]) <= 1e-9 * abs(est.detailed_losses_[-1][2])
+    if ref_import.reference_available():
+        ref = ref_import.load_reference()
+        from espm_b200.estimators import register_with_espm
+        register_with_espm()
+        assert isinstance(est, ref.estimators.NMFEstimator)      # eds_spim.py:607, 639

@@ -146,6 +146,13 @@ def test_ground_truth_tracking(golden_variants, tag):
     assert rel_err(est.H_, g[tag + "__H"]) < 1e-8
     np.testing.assert_allclose(np.array(est.angles_), g[tag + "__angles"], rtol=1e-6, atol=1e-9)
     np.testing.assert_allclose(np.array(est.mse_), g[tag + "__mse"], rtol=1e-7, atol=1e-14)
+    # get_losses() exposes them with the reference's column names (base.py:479-498)
+    rec = est.get_losses()
+    assert rec.dtype.names[-7:] == ("ang_p0", "ang_p1", "ang_p2", "mse_p0", "mse_p1", "mse_p2", "true_KL_loss")
+    np.testing.assert_allclose(rec["ang_p1"], g[tag + "__angles"][:, 1], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(rec["mse_p2"], g[tag + "__mse"][:, 2], rtol=1e-7, atol=1e-14)
+    assert rel_err(rec["true_KL_loss"], g[tag + "__true_losses"]) < 1e-8
+    assert rel_err(rec["full_loss"], g[tag + "__losses"]) < 1e-9
     # a truth with another number of components is ignored with the reference's message (base.py:307-308)
     est2 = SmoothNMF(n_components=3, G=G, true_D=g["S__true_D"][:, :2], true_H=g["S__true_H"][:2], **kw)
     est2.fit_transform(X, W=W0.copy(), H=H0.copy())
