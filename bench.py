@@ -402,6 +402,9 @@ def main():
 
     if args.no_e2e:
         eng.close()
+    if world > 1 and not replicas:
+        from espm_b200.dist import release_peer_memory
+        release_peer_memory()          # collective: the peer region is cached across fits until here
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -80,7 +80,7 @@ class EspmState(ctypes.Structure):
         ("s_part", _vp), ("s_sum", _vp), ("Ht", _vp), ("w_num", _vp), ("w_den", _vp),
         ("xlogy_part", _vp), ("px_part", _vp), ("bisect_mask", _vp), ("dev_flags", _vp), ("scalars", _vp), ("coop_part", _vp),
         ("rank", _i32), ("world", _i32), ("seq_s", _u32), ("seq_m", _u32), ("nb_prev_ldh", _i32), ("nb_next_ldh", _i32),
-        ("xchg_stride", _i64), ("xchg_hs_off", _i64), ("nb_prev_halo", _vp), ("nb_next_halo", _vp),
+        ("xchg_stride", _i64), ("xchg_slot", _i64), ("xchg_hs_off", _i64), ("nb_prev_halo", _vp), ("nb_next_halo", _vp),
         ("peer_xchg", _vp * MAX_RANKS), ("peer_flags", _vp * MAX_RANKS),
         ("bisect_dec", _vp),
         ("gamma_h", _f64), ("gamma_w", _f64), ("x_total", _f64),

@@ -22,6 +22,21 @@ __device__ __forceinline__ void lds_row(T (&dst)[N], const T* src) {
         for (int i = 0; i < N; ++i) dst[i] = src[i];
     }
 }
+// the same through L2 only (ld.global.cg): data another GPU stored into this GPU's memory
+template <typename T, int N>
+__device__ __forceinline__ void ldcg_row(T (&dst)[N], const T* src) {
+    constexpr int BYTES = N * (int)sizeof(T);
+    if constexpr (BYTES % 16 == 0) {
+        const uint4* s4 = reinterpret_cast<const uint4*>(src);
+        uint4 tmp[BYTES / 16];
+#pragma unroll
+        for (int i = 0; i < BYTES / 16; ++i) tmp[i] = __ldcg(s4 + i);
+        memcpy(dst, tmp, BYTES);
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) dst[i] = __ldcg(src + i);
+    }
+}
 constexpr int PX_WARPS = PX_THREADS / 32;
 
 // ------------------------------------------------------------------------------------------------
@@ -1134,8 +1149,8 @@ __global__ void __launch_bounds__(256) colsum_g_kernel(const TC* Gt, int n, int 
 // w_finish: the W update (updates.py:58-76) + GW' for the next H pass, as ONE cooperative kernel of
 // W_COOP_BLOCKS CTAs.  Grid barriers cost ~4 us each at this size, so the phases are arranged to need as few as
 // possible (single GPU, no simplex_W, m k <= W_SM_MAX: ONE barrier; was four):
-//   phase 0 (all CTAs, optional)  s_sum = sum of the W-pass partial slots; H' row statistics (every CTA folds them
-//                                 for itself into shared memory: nothing below waits for another CTA's phase 0)
+//   phase 0 (all CTAs, optional)  H' row statistics (every CTA folds them for itself into shared memory: nothing below
+//                                 waits for another CTA's phase 0); sharded: push of the local S to every rank
 //   phase A (one CTA per row of G^T) num = W * (G^T S),  den = colsum(G) (x) rowsum(H'); S rows are folded from the
 //                                 partial slots on the fly when the fit is not sharded
 //   -- grid barrier --
@@ -1143,7 +1158,8 @@ __global__ void __launch_bounds__(256) colsum_g_kernel(const TC* Gt, int n, int 
 //                                 memory, CTA 0 writes it out) unless simplex_W or a large m (then CTA 0 + a barrier)
 //   phase C (all CTAs)            GW' = G W' (+ pad rows, clamped copy), per-CTA column sums / flags
 //   phase D (last CTA to finish)  column sums in CTA order (deterministic), flags
-// Sharded fits (ESPM_FLAG_PEER) add the exchange of S between phase 0 and phase A (two more barriers).
+// Sharded fits (ESPM_FLAG_PEER) exchange S in phase 0 by PUSHING it into every rank's receive buffer (remote stores +
+// one flag per rank); phase A folds the ranks' slots on the fly.  No additional grid barrier.
 // ------------------------------------------------------------------------------------------------
 constexpr int W_COOP_BLOCKS = 32;
 constexpr int W_COOP_THREADS = 256;
@@ -1179,8 +1195,9 @@ __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_sta
     const int k = st.k, m = st.m, n = st.n;
     const TC ls = (TC)st.log_shift;
     const bool ident = st.flags & ESPM_FLAG_G_IDENTITY;
-    // single-GPU fused mode: phase A folds the partial slots itself and every CTA has its own H' statistics
-    const bool fly = (st.flags & ESPM_FLAG_FUSED_WREDUCE) && !(st.flags & ESPM_FLAG_PEER);
+    // fused mode: phase A folds the W-pass partial slots (single GPU) or the ranks' receive slots (peer exchange)
+    // itself and every CTA has its own copy of the H' statistics
+    const bool fly = (st.flags & ESPM_FLAG_FUSED_WREDUCE) != 0;
     const bool redundant_b = !(st.flags & ESPM_FLAG_SIMPLEX_W) && m * k <= W_SM_MAX;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int NWARPS = W_COOP_THREADS / 32;
@@ -1197,58 +1214,61 @@ __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_sta
     TC* Wn = reinterpret_cast<TC*>(st.W_next);
 
     // ---- phase 0: fold the W-pass partial slots and the per-pixel statistics ----
-    if (st.flags & ESPM_FLAG_FUSED_WREDUCE) {
-        const bool peer = st.flags & ESPM_FLAG_PEER;
+    const bool peer = st.flags & ESPM_FLAG_PEER;
+    const size_t recv_off = (size_t)(st.seq_s & 1u) * st.xchg_stride;   // parity of this exchange in every rank's buffer
+    if (peer) {
+        // Sharded: PUSH model.  Every rank folds its own partial slots and stores the result into slot [rank] of the
+        // receive buffer of EVERY rank (its own included) -- remote stores over NVLink are fire-and-forget, so no
+        // thread ever waits for a remote load.  The last CTA to finish pushing raises this rank's flag everywhere;
+        // every CTA then waits for all flags and from there on reads only LOCAL memory: phase A folds the `world`
+        // slots in rank order (identical sums on every rank, no broadcast), exactly like the single-GPU path folds the
+        // W-pass partial slots.  No grid barrier before phase A.
         const size_t total = (size_t)st.n_pad * KP;
         const TC* part = reinterpret_cast<const TC*>(st.s_part);
-        // sharded: the local sums go to this rank's exchange buffer (parity = seq & 1), read by every rank
-        unsigned char* my_x = peer ? reinterpret_cast<unsigned char*>(st.peer_xchg[st.rank]) +
-                                         (size_t)(st.seq_s & 1u) * st.xchg_stride
-                                   : nullptr;
-        TC* Sloc = peer ? reinterpret_cast<TC*>(my_x) : S;
-        double* hsloc = peer ? reinterpret_cast<double*>(my_x + st.xchg_hs_off) : hstats;
+        const size_t my_off = recv_off + (size_t)st.rank * st.xchg_slot;
         for (size_t i = gthread; i < total; i += gthreads) {
             const int cb = (int)(i / ((size_t)st.cs * KP));
             const int first = (int)(((long long)cb * st.n_tiles) / st.w_upc);
             const int last = (int)((((long long)cb + 1) * st.n_tiles - 1) / st.w_upc);
             TC v = part[i];
             for (int r = 1; r <= last - first; ++r) v += part[(size_t)r * total + i];
-            Sloc[i] = v;
+            for (int r = 0; r < st.world; ++r)
+                reinterpret_cast<TC*>(reinterpret_cast<unsigned char*>(st.peer_xchg[r]) + my_off)[i] = v;
         }
-        if (fly) {
-            reduce_hstats_block<KP>(st, hs_sm);                   // every CTA, for itself
-            __syncthreads();
-            if (blockIdx.x == gridDim.x - 1 && (int)threadIdx.x < 3 * KP) hstats[threadIdx.x] = hs_sm[threadIdx.x];
-        } else {
-            if (blockIdx.x == gridDim.x - 1) reduce_hstats_block<KP>(st, hsloc);
-            grid_barrier(bar, gridDim.x);
+        if (blockIdx.x == gridDim.x - 1) {
+            reduce_hstats_block<KP>(st, hs_sm);
+            if ((int)threadIdx.x < 3 * KP)
+                for (int r = 0; r < st.world; ++r)
+                    reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(st.peer_xchg[r]) + my_off + st.xchg_hs_off)[threadIdx.x] =
+                        hs_sm[threadIdx.x];
         }
-        if (peer) {
-            if (blockIdx.x == 0 && (int)threadIdx.x < st.world) {
-                __threadfence_system();
-                st_release_sys(st.peer_flags[threadIdx.x] + ESPM_PF_SFLAG + st.rank, st.seq_s);
-            }
-            wait_peer_flags(st.peer_flags[st.rank] + ESPM_PF_SFLAG, st.world, st.seq_s, st.dev_flags);
-            // fold the ranks' buffers in rank order: every rank computes the identical sums (no broadcast)
-            const size_t poff = (size_t)(st.seq_s & 1u) * st.xchg_stride;
-            for (size_t i = gthread; i < total; i += gthreads) {
-                TC v = __ldcg(reinterpret_cast<const TC*>(reinterpret_cast<const unsigned char*>(st.peer_xchg[0]) + poff) + i);
-                for (int r = 1; r < st.world; ++r)
-                    v += __ldcg(reinterpret_cast<const TC*>(reinterpret_cast<const unsigned char*>(st.peer_xchg[r]) + poff) + i);
-                S[i] = v;
-            }
-            if (blockIdx.x == gridDim.x - 1 && (int)threadIdx.x < 3 * KP) {
-                const bool is_max = (int)threadIdx.x >= 2 * KP;
-                double v = 0.0;
-                for (int r = 0; r < st.world; ++r) {
-                    const double u = __ldcg(reinterpret_cast<const double*>(
-                        reinterpret_cast<const unsigned char*>(st.peer_xchg[r]) + poff + st.xchg_hs_off) + threadIdx.x);
-                    v = (r == 0) ? u : (is_max ? (u > v ? u : v) : v + u);
-                }
-                hstats[threadIdx.x] = v;
-            }
-            grid_barrier(bar, gridDim.x);
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = atomicAdd(&st.dev_flags[5], 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (s_last) {     // every CTA of this rank has pushed (and fenced): publish
+            __threadfence_system();
+            if ((int)threadIdx.x < st.world) st_release_sys(st.peer_flags[threadIdx.x] + ESPM_PF_SFLAG + st.rank, st.seq_s);
+            if (threadIdx.x == 0) st.dev_flags[5] = 0u;
         }
+        wait_peer_flags(st.peer_flags[st.rank] + ESPM_PF_SFLAG, st.world, st.seq_s, st.dev_flags);
+        // global H' statistics: every CTA folds the ranks' slots for itself (rank order)
+        if ((int)threadIdx.x < 3 * KP) {
+            const bool is_max = (int)threadIdx.x >= 2 * KP;
+            const unsigned char* base = reinterpret_cast<const unsigned char*>(st.peer_xchg[st.rank]) + recv_off + st.xchg_hs_off;
+            double v = 0.0;
+            for (int r = 0; r < st.world; ++r) {
+                const double u = __ldcg(reinterpret_cast<const double*>(base + (size_t)r * st.xchg_slot) + threadIdx.x);
+                v = (r == 0) ? u : (is_max ? (u > v ? u : v) : v + u);
+            }
+            hs_sm[threadIdx.x] = v;
+            if (blockIdx.x == gridDim.x - 1) hstats[threadIdx.x] = v;
+        }
+        __syncthreads();
+    } else if (st.flags & ESPM_FLAG_FUSED_WREDUCE) {
+        reduce_hstats_block<KP>(st, hs_sm);                   // every CTA, for itself
+        __syncthreads();
+        if (blockIdx.x == gridDim.x - 1 && (int)threadIdx.x < 3 * KP) hstats[threadIdx.x] = hs_sm[threadIdx.x];
     }
 
     // ---- phase A: num = W * (G^T S), den = colsum(G) (x) rowsum(H')   (updates.py:58-60) ----
@@ -1285,7 +1305,18 @@ __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_sta
     const size_t s_total = (size_t)st.n_pad * KP;
     const TC* s_part = reinterpret_cast<const TC*>(st.s_part);
     auto load_srow = [&](int c, TC (&srow)[KP]) {
-        if (fly) {
+        if (peer) {
+            // slots of the ranks in this rank's receive buffer (written by the peers, read through L2 only)
+            const unsigned char* base = reinterpret_cast<const unsigned char*>(st.peer_xchg[st.rank]) + recv_off;
+            ldcg_row<TC, KP>(srow, reinterpret_cast<const TC*>(base) + (size_t)c * KP);
+#pragma unroll 4
+            for (int r = 1; r < st.world; ++r) {
+                TC u[KP];
+                ldcg_row<TC, KP>(u, reinterpret_cast<const TC*>(base + (size_t)r * st.xchg_slot) + (size_t)c * KP);
+#pragma unroll
+                for (int kk = 0; kk < KP; ++kk) srow[kk] += u[kk];
+            }
+        } else if (fly) {
             const int cb = c / st.cs;
             const int first = (int)(((long long)cb * st.n_tiles) / st.w_upc);
             const int last = (int)((((long long)cb + 1) * st.n_tiles - 1) / st.w_upc);

@@ -156,6 +156,40 @@ def _up(a, b):
     return (a + b - 1) // b * b
 
 
+# One peer region per process is kept across fits (module level): allocating it, exporting / opening the CUDA-IPC
+# handles of `world` ranks and the barriers around that cost tens of milliseconds, more than a 20-iteration fit of the
+# benchmark image on 8 GPUs.  Key = everything that determines the layout; a different problem shape frees the old one.
+_REGION = None
+
+
+class _PeerRegion:
+    def __init__(self, key, region, total, bases, opened, metas, lib):
+        self.key, self.region, self.total = key, region, total
+        self.bases, self.opened, self.metas, self.lib = bases, opened, metas, lib
+        self.seq_s = self.seq_m = 0        # exchange sequence numbers continue across fits (flags are never reset)
+        self.group = None
+
+    def free(self, group):
+        """Collective: unmap the peers' regions, then free this rank's."""
+        import ctypes
+        torch.cuda.synchronize()
+        dist.barrier(group=group)
+        for p in self.opened:
+            self.lib.espm_peer_close(ctypes.c_void_p(p))
+        self.opened = []
+        dist.barrier(group=group)
+        self.lib.espm_peer_free(ctypes.c_void_p(self.region))
+        self.region = None
+
+
+def release_peer_memory(group=None):
+    """Collective: free the cached peer region (call on every rank, e.g. before destroying the process group)."""
+    global _REGION
+    if _REGION is not None and _REGION.region is not None:
+        _REGION.free(_REGION.group)
+    _REGION = None
+
+
 class PeerShard(Shard):
     """Sharded fit whose per-iteration exchanges run INSIDE the kernels through CUDA-IPC peer memory over
     NVLink (ESPM_FLAG_PEER, include/espm_b200.h): no host-launched collective on the critical path.
@@ -168,59 +202,108 @@ class PeerShard(Shard):
         super().__init__(rank, world, group)
         if self.world > L.MAX_RANKS:
             raise ValueError("at most %d pixel shards are supported" % L.MAX_RANKS)
-        self.region = None
-        self.opened = []
-        self.bases = None
-        self.meta = None
-        self._lib = None
+        self.reg = None
 
-    def setup_peer(self, eng):
-        """Allocate this rank's region (flags | exchange buffers | 3 H buffers), map every peer's region and
-        fill the peer fields of ``eng.st``.  Returns the three H tensors (views of the region)."""
-        import ctypes
-        lib = L.load()
-        self._lib = lib
-        st = eng.st
+    # kept for callers that address the region directly
+    @property
+    def bases(self):
+        return self.reg.bases
+
+    @property
+    def meta(self):
+        return self.reg.metas
+
+    def _layout(self, st):
         sz = 8 if st.c_dtype == L.F64 else 4
         hs_off = _up(st.n_pad * st.kp * sz, 128)
-        stride = _up(hs_off + 3 * st.kp * 8, 256)
+        slot = _up(hs_off + 3 * st.kp * 8, 256)          # one source rank: S [n_pad][kp] + 3 kp statistics
+        stride = _up(self.world * slot, 256)             # one parity: a slot per source rank
         x_off = L.PF_WORDS * 4
         h_bytes = _up(st.k * st.ldh * sz, 256)
         h_off = [_up(x_off + 2 * stride, 256) + i * h_bytes for i in range(3)]
         total = h_off[2] + h_bytes
-        ptr = ctypes.c_void_p()
-        L.check(lib.espm_peer_alloc(total, ctypes.byref(ptr)))
-        self.region = ptr.value
-        handle = ctypes.create_string_buffer(64)
-        L.check(lib.espm_peer_export(ctypes.c_void_p(self.region), handle))
-        mine = dict(handle=handle.raw, ldh=int(st.ldh), p_loc=int(st.p_loc), h_off=h_off, x_off=x_off, halo=int(st.halo))
-        metas = [None] * self.world
-        dist.all_gather_object(metas, mine, group=self.group)
-        bases = []
-        for r, m in enumerate(metas):
-            if r == self.rank:
-                bases.append(self.region)
-                continue
-            p = ctypes.c_void_p()
-            L.check(lib.espm_peer_open(m["handle"], ctypes.byref(p)))
-            self.opened.append(p.value)
-            bases.append(p.value)
-        self.bases, self.meta = bases, metas
+        return sz, hs_off, slot, stride, x_off, h_bytes, h_off, total
+
+    def _all_ok(self, ok):
+        """Collective AND of a per-rank success flag."""
+        oks = [None] * self.world
+        dist.all_gather_object(oks, bool(ok), group=self.group)
+        return all(oks)
+
+    def setup_peer(self, eng):
+        """Allocate (or reuse) this rank's region (flags | receive buffers | 3 H buffers), map every peer's region and
+        fill the peer fields of ``eng.st``.  Returns the three H tensors (views of the region), or None -- on EVERY
+        rank -- when any rank could not allocate, export or map (the caller then falls back to the NCCL exchange)."""
+        import ctypes
+        global _REGION
+        lib = L.load()
+        st = eng.st
+        sz, hs_off, slot, stride, x_off, h_bytes, h_off, total = self._layout(st)
+        key = (self.world, self.rank, int(total), int(st.ldh), int(st.p_loc), int(st.halo), tuple(h_off), int(x_off),
+               int(slot), eng.device.index, id(self.group))
+        reg = _REGION
+        if reg is not None and (reg.key != key or reg.region is None):
+            release_peer_memory()                    # another problem shape: collective free (every rank misses)
+            reg = None
+        if reg is None:
+            ptr = ctypes.c_void_p()
+            handle = ctypes.create_string_buffer(64)
+            mine = None
+            try:
+                L.check(lib.espm_peer_alloc(total, ctypes.byref(ptr)))
+                L.check(lib.espm_peer_export(ptr, handle))
+                mine = dict(handle=handle.raw, ldh=int(st.ldh), p_loc=int(st.p_loc), h_off=h_off, x_off=x_off,
+                            halo=int(st.halo))
+            except L.EspmError:
+                mine = None
+            metas = [None] * self.world
+            dist.all_gather_object(metas, mine, group=self.group)
+            opened, bases, ok = [], [], all(m is not None for m in metas)
+            if ok:
+                try:
+                    for r, m in enumerate(metas):
+                        if r == self.rank:
+                            bases.append(ptr.value)
+                            continue
+                        q = ctypes.c_void_p()
+                        L.check(lib.espm_peer_open(m["handle"], ctypes.byref(q)))
+                        opened.append(q.value)
+                        bases.append(q.value)
+                except L.EspmError:
+                    ok = False
+            if not self._all_ok(ok):
+                # some rank cannot reach a peer (other host, no P2P): nobody uses peer memory
+                for q in opened:
+                    lib.espm_peer_close(ctypes.c_void_p(q))
+                dist.barrier(group=self.group)
+                if ptr.value:
+                    lib.espm_peer_free(ptr)
+                return None
+            reg = _PeerRegion(key, ptr.value, total, bases, opened, metas, lib)
+            reg.group = self.group
+            _REGION = reg
+        self.reg = reg
         st.rank, st.world = self.rank, self.world
-        st.xchg_stride, st.xchg_hs_off = stride, hs_off
+        st.xchg_stride, st.xchg_slot, st.xchg_hs_off = stride, slot, hs_off
         for r in range(self.world):
-            st.peer_flags[r] = bases[r]
-            st.peer_xchg[r] = bases[r] + metas[r]["x_off"]
+            st.peer_flags[r] = reg.bases[r]
+            st.peer_xchg[r] = reg.bases[r] + reg.metas[r]["x_off"]
         st.flags |= L.FLAG_PEER | L.FLAG_FUSED_WREDUCE
         tdt = torch.float64 if st.c_dtype == L.F64 else torch.float32
-        raw = torch.as_tensor(_DevMem(self.region, total), device=eng.device)
+        raw = torch.as_tensor(_DevMem(reg.region, total), device=eng.device)
         H = []
         for i in range(3):
             t = raw[h_off[i]:h_off[i] + st.k * st.ldh * sz].view(tdt).view(st.k, st.ldh)
             t.fill_(1.0)
             H.append(t)
-        dist.barrier(group=self.group)          # every region is mapped and initialised before any kernel runs
+        # every region is mapped and initialised before any kernel of any rank writes into it
+        torch.cuda.current_stream(eng.device).synchronize()
+        dist.barrier(group=self.group)
         return H
+
+    @property
+    def seq(self):
+        return self.reg.seq_s, self.reg.seq_m
 
     def halo_targets(self, eng, ibuf):
         """(prev pointer, prev ldh, next pointer, next ldh) for pushing the boundary rows of H buffer ``ibuf``."""
@@ -238,25 +321,53 @@ class PeerShard(Shard):
             nl = m["ldh"]
         return pp, pl, npn, nl
 
-    def close(self):
-        """Collective: unmap the peers' regions and free this rank's (after every rank is done with them)."""
-        import ctypes
-        if self.region is None:
+    def close(self, seq_s=None, seq_m=None):
+        """End of a fit: every rank is done with the region (collective), which stays mapped for the next fit of the
+        same shape; ``release_peer_memory()`` frees it."""
+        if self.reg is None:
             return
+        if seq_s is not None:
+            self.reg.seq_s, self.reg.seq_m = int(seq_s), int(seq_m)
         torch.cuda.synchronize()
         dist.barrier(group=self.group)
-        for p in self.opened:
-            self._lib.espm_peer_close(ctypes.c_void_p(p))
-        self.opened = []
-        dist.barrier(group=self.group)
-        self._lib.espm_peer_free(ctypes.c_void_p(self.region))
-        self.region = None
+        self.reg = None
+
+
+def _peer_capable(group):
+    """Collective: True on every rank iff all ranks run on one host and no visible pair of their devices lacks peer
+    access.  (A pair that cannot be checked from here -- the peer's device is not visible to this process -- is
+    settled by ``PeerShard.setup_peer``, whose failure is collective as well.)"""
+    import socket
+    world = dist.get_world_size(group)
+    dev = torch.cuda.current_device()
+    try:
+        uuid = str(torch.cuda.get_device_properties(dev).uuid)
+    except Exception:
+        uuid = None
+    infos = [None] * world
+    dist.all_gather_object(infos, (socket.gethostname(), uuid), group=group)
+    ok = all(h == infos[0][0] for h, _ in infos)
+    if ok and uuid is not None:
+        local = {}
+        for i in range(torch.cuda.device_count()):
+            try:
+                local[str(torch.cuda.get_device_properties(i).uuid)] = i
+            except Exception:
+                pass
+        for _, u in infos:
+            j = local.get(u)
+            if j is not None and j != dev and not torch.cuda.can_device_access_peer(dev, j):
+                ok = False
+    oks = [None] * world
+    dist.all_gather_object(oks, ok, group=group)
+    return all(oks)
 
 
 def make_shard(group=None):
-    """PeerShard when the process group runs NCCL on one box (and ESPM_B200_PEER != 0), else Shard."""
+    """PeerShard when the process group runs NCCL, every rank sits on the same host with peer access between the
+    devices and ESPM_B200_PEER != 0; else Shard (NCCL collectives).  The decision is collective."""
     import os
-    if dist.get_backend(group) == "nccl" and os.environ.get("ESPM_B200_PEER", "1") != "0":
+    if dist.get_backend(group) == "nccl" and os.environ.get("ESPM_B200_PEER", "1") != "0" and _peer_capable(group):
         return PeerShard(group=group)
     return Shard(group=group)
 

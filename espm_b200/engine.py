@@ -197,7 +197,13 @@ class FitEngine:
         self._seq_s = self._seq_m = 0
         if self.peer:
             self.Hbuf = shard.setup_peer(self)       # H lives in CUDA-IPC memory the neighbours can write
-        else:
+            if self.Hbuf is None:                    # collective: some rank cannot map a peer -> NCCL exchange
+                from .dist import Shard
+                self.shard = shard = Shard(group=shard.group)
+                self.peer = False
+            else:
+                self._seq_s, self._seq_m = shard.seq  # the flag words persist across fits: keep counting
+        if not self.peer:
             self.Hbuf = [torch.ones(k, ldh, dtype=cdt, device=dev) for _ in range(3)]
         self.Wbuf = [zeros(self.m, k) for _ in range(2)]
         self.GWbuf = [zeros(n_pad, kp) for _ in range(2)]
@@ -519,7 +525,7 @@ class FitEngine:
         """Release peer memory (collective when sharded through peer memory); the engine is unusable after."""
         if self.peer and self.shard is not None:
             self.Hbuf = None
-            self.shard.close()
+            self.shard.close(self._seq_s, self._seq_m)
             self.peer = False
 
     def _sync_hstats(self):

@@ -191,14 +191,15 @@ typedef struct espm_state {
     uint32_t* bisect_mask;  /* 4 words: bit j set <=> max|f_j| > tol somewhere (lock-step trace) */
     uint32_t* dev_flags;    /* 8 words: [0] sticky ESPM_DEV_* error bits, [1] ESPM_DEV_GW_* of GW_next,
                              * [2] h_finish completion ticket, [3] grid-barrier counter of w_finish (start at 0),
-                             * [4] w_finish completion ticket */
+                             * [4] w_finish completion ticket, [5] w_finish "pushed" ticket (peer exchange) */
     double* scalars;        /* ESPM_NSCALARS doubles: the record being filled */
     double* coop_part;      /* ESPM_COOP_BLOCKS x (2*ESPM_MAX_K + 4) doubles: per-CTA partials of w_finish */
     /* ---- ESPM_FLAG_PEER: exchange between the pixel shards through CUDA-IPC peer memory over NVLink ----
      * No host-launched collective sits on the per-iteration path: the kernels signal and wait on flag words
      * (system-scope release/acquire) and move the few KiB that cross ranks with plain peer loads / stores.
-     *   - espm_w_finish publishes this rank's S and H' statistics in its exchange buffer, raises its S flag on
-     *     every rank, waits for all ranks and folds the peers' buffers in rank order (identical everywhere);
+     *   - espm_w_finish PUSHES this rank's S and H' statistics into slot [rank] of every rank's receive buffer
+     *     (remote stores), raises its S flag on every rank, waits for all flags and folds the slots of its own
+     *     (local) buffer in rank order (identical everywhere, no remote load on the path);
      *   - the H update pushes its first / last image row into the neighbours' halo columns (Laplacian);
      *   - espm_h_finish pushes the 128-bit bisection trace mask to every rank, espm_h_apply waits for all. */
     int32_t rank;           /* this shard */
@@ -207,11 +208,12 @@ typedef struct espm_state {
     uint32_t seq_m;         /* sequence number of the mask exchange (set before espm_h_finish, kept for espm_h_apply) */
     int32_t nb_prev_ldh;    /* row stride (elements) of the previous rank's H buffers */
     int32_t nb_next_ldh;
-    int64_t xchg_stride;    /* bytes between the two parities of an exchange buffer */
-    int64_t xchg_hs_off;    /* byte offset of the 3*kp statistics doubles inside one parity */
+    int64_t xchg_stride;    /* bytes between the two parities of a receive buffer (= world * xchg_slot, aligned) */
+    int64_t xchg_slot;      /* bytes of one source rank's slot {S [n_pad][kp], statistics} inside a parity */
+    int64_t xchg_hs_off;    /* byte offset of the 3*kp statistics doubles inside one slot */
     void* nb_prev_halo;     /* in the previous rank's H_next: where my FIRST image row goes (row kk at + kk*ldh) or NULL */
     void* nb_next_halo;     /* in the next rank's H_next: where my LAST image row goes, or NULL */
-    void* peer_xchg[ESPM_MAX_RANKS];       /* every rank's exchange buffer: 2 x {S [n_pad][kp], statistics} */
+    void* peer_xchg[ESPM_MAX_RANKS];       /* every rank's receive buffer: 2 parities x world slots x {S, statistics} */
     uint32_t* peer_flags[ESPM_MAX_RANKS];  /* every rank's flag block (ESPM_PF_WORDS words, zero at start) */
     /* ---- recorded bisection (simplex_H): espm_h_finish writes, espm_h_apply reads ----
      * [5][p_pad] words per pixel: words 0..3 = bit j set <=> iteration j of dicotomy.py:152-168 moved the
