@@ -82,7 +82,7 @@ class EspmState(ctypes.Structure):
         ("rank", _i32), ("world", _i32), ("seq_s", _u32), ("seq_m", _u32), ("nb_prev_ldh", _i32), ("nb_next_ldh", _i32),
         ("xchg_stride", _i64), ("xchg_slot", _i64), ("xchg_hs_off", _i64), ("nb_prev_halo", _vp), ("nb_next_halo", _vp),
         ("peer_xchg", _vp * MAX_RANKS), ("peer_flags", _vp * MAX_RANKS),
-        ("bisect_dec", _vp),
+        ("bisect_dec", _vp), ("bisect_anchor", _vp),
         ("gamma_h", _f64), ("gamma_w", _f64), ("x_total", _f64),
         ("x_colsum", _vp), ("x_rowsum", _vp), ("GG", _vp), ("gram_gw", _vp), ("gram_h", _vp), ("sigma_dev", _vp),
         ("ls_part", _vp),

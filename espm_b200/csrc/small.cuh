@@ -429,6 +429,152 @@ __device__ __forceinline__ End end_of(const KlEval<KP>& ev, double x) {
     return End{f > 0.0, f < 0.0, fabs(f) > ev.tol};
 }
 
+// ------------------------------------------------------------------------------------------------
+// Root-anchored evaluator of the KL simplex function  f(x) = sum_k max(n_k / (x + d_k), ls) - 1.
+//
+// The lock-step loop of the reference needs, per midpoint, only the sign of f and whether |f| > tol.  f is convex and
+// decreasing on the bracket (every t_k = x + d_k > 0 there), so both facts follow from WHERE the midpoint lies
+// relative to the root nu* of f, which is computed once per pixel:
+//   * Newton on g(x) = 1 / S(x) - 1, S = sum_k n_k / t_k.  g is concave and increasing (Cauchy-Schwarz:
+//     2 S'^2 <= S S''), so from the left end of the bracket the iterates increase monotonically to nu* without
+//     overshooting, and a single hyperbola is solved in one step; 4-6 fp64 iterations in practice.
+//   * sign:   f(x) <= 0  <=>  x >= nu*                                       (monotone)
+//   * size, left of the root  (e = nu* - x > 0):   D e <= f(x) <= D e + 0.52 F2 e^2     (tangent below a convex f;
+//                                                    Taylor with f'' <= 1.031 f''(nu*) while e <= 0.01 min_k t_k)
+//   * size, right of the root (e = x - nu* > 0):   D e - F2 e^2 / 2 <= |f(x)| <= D e   (f'' is decreasing), and
+//                                                    |f(x)| >= 0.4999 e / (b0 - nu*)    (chord to the initial right
+//                                                    end b0, where f <= -1/2 by construction, dicotomy.py:49)
+//     with D = |f'(nu*)|, F2 = f''(nu*).
+// A midpoint is classified from these bounds only when they decide it with a margin that covers the rounding of the
+// reference's own evaluation (|x - nu*| > mx, see below) and of ours (1e-9 relative on tol); every other midpoint --
+// the root within rounding distance, |f| within the bounds' gap of tol, no convergence, negative inputs -- goes
+// through KlEval, i.e. the fp32 screen and then the bit-faithful evaluation.  The anchor therefore never changes a
+// decision; it only avoids evaluating f where the answer is already certain.
+//   mx = 1e-12 / D + (8 + 2k) 2^-52 (max(|a0|, |b0|) + max_k |d_k|): beyond it |f| >= D |x - nu*| > 1e-12 (the
+//   reference's evaluation of f is accurate to a few k 2^-53) and the fp64 Newton iterate is that close to the true
+//   root (its last step was <= 2 ulps; each evaluation of S carries <= k/2 ulps of x of noise when x + d_k cancels).
+//   The size bounds additionally need D to be accurate to 1e-10, i.e. ulp(x) / min_k t_k small (`sized`).
+// ------------------------------------------------------------------------------------------------
+template <int KP>
+struct KlAnchorEval {
+    KlEval<KP> base;
+    double nu, D, F2, tmin, mx, chord, tol;
+    bool ok, sized;
+    __device__ __forceinline__ KlAnchorEval(const double (&num)[KP], const double (&den)[KP], int k, double ls, double tol_,
+                                            double a0, double b0)
+        : base(num, den, k, ls, tol_), tol(tol_) {
+        ok = sized = false;
+        nu = D = F2 = tmin = mx = chord = 0.0;
+        bool valid = (a0 > -1e300) && (b0 < 1e300) && (a0 < b0);
+        double dmax = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < KP; ++kk)
+            if (kk < k) {
+                valid = valid && (num[kk] >= 0.0) && (fabs(den[kk]) < 1e300);
+                dmax = fmax(dmax, fabs(den[kk]));
+            }
+        if (!valid) return;
+        double x = a0, S = 0.0, Dv = 0.0, F2v = 0.0, tm = 1e300;
+        bool conv = false;
+#pragma unroll 1
+        for (int it = 0; it < 24; ++it) {
+            S = 0.0;
+            Dv = 0.0;
+            F2v = 0.0;
+            tm = 1e300;
+#pragma unroll
+            for (int kk = 0; kk < KP; ++kk)
+                if (kk < k) {
+                    const double t = x + den[kk];
+                    const double r = Num<double>::rcp(t);
+                    const double q = num[kk] * r;
+                    if (q > ls) {             // clamped terms are constants: no slope, no curvature
+                        S += q;
+                        const double qr = q * r;
+                        Dv += qr;
+                        F2v = fma(qr, r, F2v);
+                        tm = fmin(tm, t);
+                    } else {
+                        S += ls;
+                    }
+                }
+            if (!(S > 0.0) || !(Dv > 0.0) || !(tm > 0.0)) return;     // NaN / outside the domain: no anchor
+            if (fabs(S - 1.0) <= 4e-15) {
+                conv = true;
+                break;
+            }
+            const double xn = x + S * (S - 1.0) * Num<double>::rcp(Dv);
+            if (!(xn > a0 - fabs(a0)) || !(xn < 1e300)) return;
+            // the step is within 2 ulps of x: converged as far as fp64 resolves the root (when x + d_k cancels, the
+            // residual cannot get smaller than D ulp(x); mx below covers that distance)
+            conv = fabs(xn - x) <= 4.5e-16 * fabs(x);
+            x = xn;
+            if (conv) break;
+        }
+        if (!conv || !(x > a0) || !(x < b0)) return;
+        nu = x;
+        D = Dv;
+        F2 = 2.0 * F2v;
+        tmin = tm;
+        // (the last evaluation was at the previous iterate when the loop ended on a 2-ulp step: D, F2, tmin move by
+        //  O(ulp(x) / tmin) relative, which `sized` bounds)
+        const double span = fmax(fabs(a0), fabs(b0)) + dmax;
+        mx = 1e-12 * Num<double>::rcp(Dv) + (double)(8 + 2 * k) * 2.3e-16 * span;
+        sized = 1e-15 * span <= 1e-10 * tm;     // else only the sign is taken from the anchor
+        chord = 0.4999 * Num<double>::rcp(b0 - x);
+        ok = true;
+    }
+    __device__ __forceinline__ double exact(double x) const { return base.exact(x); }
+    __device__ __forceinline__ Cls operator()(double x) const {
+        if (ok) {
+            const double d = x - nu, e = fabs(d);
+            if (e > mx) {
+                const double lin = D * e, hi = tol * (1.0 + 1e-9), lo = tol * (1.0 - 1e-9);
+                if (sized) {
+                    if (d < 0.0) {
+                        if (lin > hi) return Cls{false, true};
+                        if (e <= 0.01 * tmin && fma(0.52 * F2 * e, e, lin) < lo) return Cls{false, false};
+                    } else {
+                        if (lin < lo) return Cls{true, false};
+                        if (fma(-0.5 * F2 * e, e, lin) > hi || chord * e > hi) return Cls{true, true};
+                    }
+                }
+                // the sign is certain, the size class is not: evaluate like the reference
+                return Cls{d > 0.0, fabs(base.exact(x)) > tol};
+            }
+        }
+        return base(x);
+    }
+    __device__ __forceinline__ bool le0(double x) const {
+        if (ok && fabs(x - nu) > mx) return x > nu;
+        return base.le0(x);
+    }
+};
+// ends of the initial bracket: with a valid anchor a0 < nu* < b0 and |f| >= 1/2 there (dicotomy.py:29-49)
+template <int KP>
+__device__ __forceinline__ End end_of(const KlAnchorEval<KP>& ev, double x) {
+    if (ev.ok && ev.sized && fabs(x - ev.nu) > ev.mx && ev.D * fabs(x - ev.nu) > ev.tol * (1.0 + 1e-9) && x < ev.nu)
+        return End{true, false, true};
+    if (ev.ok && ev.sized && x - ev.nu > ev.mx && ev.chord * (x - ev.nu) > ev.tol * (1.0 + 1e-9))
+        return End{false, true, true};
+    return end_of(ev.base, x);
+}
+
+// replay-side view of the anchor (h_apply): only the sign decisions are needed
+template <int KP>
+struct KlAnchorReplay {
+    KlEval<KP> base;
+    double nu, mx, tol;
+    __device__ __forceinline__ KlAnchorReplay(const double (&num)[KP], const double (&den)[KP], int k, double ls, double tol_,
+                                              double nu_, double mx_)
+        : base(num, den, k, ls, tol_), nu(nu_), mx(mx_), tol(tol_) {}
+    __device__ __forceinline__ double exact(double x) const { return base.exact(x); }
+    __device__ __forceinline__ bool le0(double x) const {
+        if (fabs(x - nu) > mx) return x > nu;      // mx = +inf when the pixel has no anchor
+        return base.le0(x);
+    }
+};
+
 template <typename E>
 __device__ __forceinline__ void bisect_trace_rec(double a, double b, const E& ev, int maxit, Mask128& bad, Mask128& dec,
                                                  uint32_t& seen, uint32_t& err) {
@@ -646,9 +792,17 @@ __global__ void __launch_bounds__(PX_THREADS, 4) h_finish_kernel(const espm_stat
                     HL[kk] = h[kk];
                 }
                 // ---- ratio sums of the H pass (sum of channel splits in fixed order) ----
+                // (all splits are loaded before the first add: one L2 round trip instead of h_nsplit dependent ones)
                 const TC* nr = reinterpret_cast<const TC*>(st.numraw) + (size_t)kk * st.p_pad + j;
-                TC s = nr[0];
-                for (int sp = 1; sp < st.h_nsplit; ++sp) s += nr[(size_t)sp * KP * st.p_pad];
+                constexpr int SPU = 8;
+                TC sv[SPU];
+#pragma unroll
+                for (int sp = 0; sp < SPU; ++sp) sv[sp] = (sp < st.h_nsplit) ? nr[(size_t)sp * KP * st.p_pad] : TC(0);
+                TC s = sv[0];
+#pragma unroll
+                for (int sp = 1; sp < SPU; ++sp)
+                    if (sp < st.h_nsplit) s += sv[sp];
+                for (int sp = SPU; sp < st.h_nsplit; ++sp) s += nr[(size_t)sp * KP * st.p_pad];
                 if (!(Num<TC>::vabs(s) < Num<TC>::inf())) err |= ESPM_DEV_NONFINITE;
                 // ---- loss terms of the CURRENT iterate (measures.py:548, 577) ----
                 if (use_mu) logreg += st.mu[kk] * (double)Num<TC>::vlog(h[kk] + (TC)st.eps_reg);
@@ -762,8 +916,10 @@ __global__ void __launch_bounds__(PX_THREADS, 4) h_finish_kernel(const espm_stat
             } else {
                 double lo, hi;
                 simplex_bracket<double, KP>(numd, dend, k, lo, hi);
-                bisect_trace_rec(lo, hi, KlEval<KP>(numd, dend, k, st.log_shift, st.dicotomy_tol), st.maxit, bits, dec,
-                                 seen, err);
+                const KlAnchorEval<KP> ev(numd, dend, k, st.log_shift, st.dicotomy_tol, lo, hi);
+                bisect_trace_rec(lo, hi, ev, st.maxit, bits, dec, seen, err);
+                st.bisect_anchor[j] = ev.nu;
+                st.bisect_anchor[(size_t)st.p_pad + j] = ev.ok ? ev.mx : Num<double>::inf();
             }
             uint32_t* rec = st.bisect_dec + j;
 #pragma unroll
@@ -893,8 +1049,9 @@ __global__ void __launch_bounds__(PX_THREADS) h_apply_kernel(const espm_state st
         } else {
             double lo, hi;
             simplex_bracket<double, KP>(num, den, k, lo, hi);
-            const double nu = bisect_replay_rec(lo, hi, KlEval<KP>(num, den, k, st.log_shift, st.dicotomy_tol), its, dec,
-                                                seen);
+            const KlAnchorReplay<KP> ev(num, den, k, st.log_shift, st.dicotomy_tol, st.bisect_anchor[j],
+                                        st.bisect_anchor[(size_t)st.p_pad + j]);
+            const double nu = bisect_replay_rec(lo, hi, ev, its, dec, seen);
 #pragma unroll
             for (int kk = 0; kk < KP; ++kk)
                 hn[kk] = (kk < k) ? (TC)fmax(num[kk] / (den[kk] + nu), st.log_shift) : TC(0);

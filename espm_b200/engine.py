@@ -227,6 +227,8 @@ class FitEngine:
         self.mask = torch.zeros(4 * max(self.world, 1), dtype=torch.int32, device=dev)
         self.bisect_dec = torch.zeros(5 * p_pad if simplex_H else 1, dtype=torch.int32, device=dev)
         st.bisect_dec = self.bisect_dec.data_ptr()
+        self.bisect_anchor = torch.zeros(2 * p_pad if simplex_H else 2, dtype=torch.float64, device=dev)
+        st.bisect_anchor = self.bisect_anchor.data_ptr()
         # ---- alternative update rules ----
         self.gram = zeros(2, kp * kp, dtype=torch.float64)
         st.gram_gw, st.gram_h = self.gram[0].data_ptr(), self.gram[1].data_ptr()

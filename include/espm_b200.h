@@ -220,6 +220,10 @@ typedef struct espm_state {
      * upper end (b = new); word 4 = number of iterations the trace evaluated | 1<<8 if the bracket became
      * stationary.  The replay of the it* global iterations follows these bits instead of re-evaluating f. */
     uint32_t* bisect_dec;
+    /* [2][p_pad] doubles per pixel (KL simplex only): the root nu* of the pixel's simplex function found by
+     * espm_h_finish and the distance |x - nu*| beyond which the sign of f(x) is certain (+inf: no anchor); lets
+     * espm_h_apply decide the replayed iterations the trace has not seen without evaluating f. */
+    double* bisect_anchor;
     /* ---- alternative update rules (algo = "bmd" / "projected_gradient", l2 = True, linesearch) ---- */
     double gamma_h;         /* projected gradient: step 1/gamma_h of proj_grad_step_h (updates.py:378) */
     double gamma_w;         /* projected gradient: step 1/gamma_w of proj_grad_step_w (updates.py:357) */
