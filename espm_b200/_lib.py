@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIBPATH = os.path.join(HERE, "lib", "libespm_b200.so")
 
-F32, F64 = 0, 1
+F32, F64, U8, U16 = 0, 1, 2, 3
 TILE_PX = 128
 MAX_K = 16
 NSCALARS = 24
@@ -94,7 +94,7 @@ class EspmIngest(ctypes.Structure):
     _fields_ = [("row_nz", _vp), ("col_nz", _vp), ("flags", _vp), ("sum_part", _vp)]
 
 
-X_NAN, X_INF, X_NEGATIVE = 1, 2, 4
+X_NAN, X_INF, X_NEGATIVE, X_FRACTION = 1, 2, 4, 8
 
 
 class EspmError(RuntimeError):
@@ -110,6 +110,7 @@ _EXPORTS = {
     "espm_plan": (ctypes.c_int, [ctypes.POINTER(EspmState)]),
     "espm_plan_info": (ctypes.c_int, [ctypes.POINTER(EspmState), ctypes.POINTER(_i32)]),
     "espm_upload_2d": (ctypes.c_int, [_vp, _i64, _vp, _i64, _i64, _i64, _vp]),
+    "espm_x_prescan": (ctypes.c_int, [_vp, _i32, _i32, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "espm_retile_x": (ctypes.c_int, [ctypes.POINTER(EspmState), _vp, _i32, _i64, _i64, _i64, _f64,
                                      ctypes.POINTER(EspmIngest), _vp]),
     "espm_xt_fixup": (ctypes.c_int, [ctypes.POINTER(EspmState), _vp, _vp, _f64, _f64, _vp]),

@@ -18,8 +18,8 @@ OBJDIR = os.path.join(LIBDIR, "obj")
 LIBNAME = "libespm_b200.so"
 LIBPATH = os.path.join(LIBDIR, LIBNAME)
 
-SOURCES = ["api.cu", "xpass_f32f32.cu", "xpass_f32f64.cu", "xpass_f64f64.cu", "small_f32.cu", "small_f64.cu",
-           "ingest.cu"]
+SOURCES = ["api.cu", "xpass_f32f32.cu", "xpass_f32f64.cu", "xpass_f64f64.cu", "xpass_u8f32.cu", "xpass_u16f32.cu",
+           "small_f32.cu", "small_f64.cu", "ingest.cu"]
 HEADERS = ["common.cuh", "xpass.cuh", "xpass_inst.cuh", "small.cuh", "small_inst.cuh", "ingest.cuh", "ingest_decl.h",
            os.path.join("..", "..", "include", "espm_b200.h")]
 

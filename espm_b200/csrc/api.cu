@@ -34,12 +34,16 @@ static xpass_fn pick_xpass(const espm_state* st) {
     if (st->x_dtype == ESPM_F32 && st->c_dtype == ESPM_F32) return xpass_f32f32;
     if (st->x_dtype == ESPM_F32 && st->c_dtype == ESPM_F64) return xpass_f32f64;
     if (st->x_dtype == ESPM_F64 && st->c_dtype == ESPM_F64) return xpass_f64f64;
+    if (st->x_dtype == ESPM_U8 && st->c_dtype == ESPM_F32) return xpass_u8f32;
+    if (st->x_dtype == ESPM_U16 && st->c_dtype == ESPM_F32) return xpass_u16f32;
     return nullptr;
 }
 
 static int sizes_of(const espm_state* st, int safe, XPassSizes* o) {
     if (st->x_dtype == ESPM_F32 && st->c_dtype == ESPM_F32) return xpass_sizes<float, float>(st->kp, safe, o);
     if (st->x_dtype == ESPM_F32 && st->c_dtype == ESPM_F64) return xpass_sizes<float, double>(st->kp, safe, o);
+    if (st->x_dtype == ESPM_U8) return xpass_sizes<uint8_t, float>(st->kp, safe, o);
+    if (st->x_dtype == ESPM_U16) return xpass_sizes<uint16_t, float>(st->kp, safe, o);
     return xpass_sizes<double, double>(st->kp, safe, o);
 }
 
@@ -59,7 +63,8 @@ static int check_state(const espm_state* st) {
         return ESPM_ERR_BAD_ARG;
     }
     if (!pick_xpass(st)) {
-        set_error("unsupported dtype pair x=%d c=%d (f64 storage requires f64 arithmetic)", st->x_dtype, st->c_dtype);
+        set_error("unsupported dtype pair x=%d c=%d (f64 storage requires f64 arithmetic, uint8 / uint16 storage fp32)",
+                  st->x_dtype, st->c_dtype);
         return ESPM_ERR_UNSUPPORTED;
     }
     if (st->k < 1 || st->k > ESPM_MAX_K) {
@@ -300,6 +305,16 @@ int espm_upload_2d(void* dst, int64_t dpitch_bytes, const void* src_host, int64_
     ESPM_CUDA_CHECK(cudaMemcpy2DAsync(dst, (size_t)dpitch_bytes, src_host, (size_t)spitch_bytes, (size_t)width_bytes,
                                       (size_t)height, cudaMemcpyHostToDevice, (cudaStream_t)stream));
     return ESPM_OK;
+}
+
+int espm_x_prescan(const void* src, int32_t src_dtype, int32_t n, int64_t p_loc, int64_t stride_c, int64_t stride_p,
+                   int64_t j0, uint32_t* out4, int32_t* row_nz, int32_t* col_nz, void* stream) {
+    if (!src || !out4 || !row_nz || !col_nz || n < 1 || p_loc < 1 || (src_dtype != ESPM_F32 && src_dtype != ESPM_F64)) {
+        set_error("espm_x_prescan: bad arguments");
+        return ESPM_ERR_BAD_ARG;
+    }
+    return prescan_launch(src, src_dtype, n, (long long)p_loc, stride_c, stride_p, j0, out4, row_nz, col_nz,
+                          (cudaStream_t)stream);
 }
 
 int espm_retile_x(const espm_state* st, const void* src, int32_t src_dtype, int64_t stride_c, int64_t stride_p,

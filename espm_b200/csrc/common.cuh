@@ -246,15 +246,19 @@ __device__ __forceinline__ T warp_max(T v) {
     return v;
 }
 
-// Geometry of the X-pass kernels for a (storage, compute) type pair.
+// Geometry of the X-pass kernels for a (storage, compute) type pair.  A pipeline stage always holds CS = 32 channels
+// (16 for f64 storage) x 128 pixels, i.e. ONE contiguous bulk copy of 16 KiB (f32 / f64), 8 KiB (uint16) or 4 KiB
+// (uint8): compact count storage changes the bytes per stage, not the work distribution of the consumer warps.
 template <typename TX, typename TC>
 struct PassGeom {
     static constexpr int PPL = (sizeof(TC) == 8) ? 2 : 4;          // pixels per lane
     static constexpr int HALVES = 4 / PPL;                         // warps covering one 128-px row
     static constexpr int NSLOT = N_CONSUMER_WARPS / HALVES;        // channel rows processed at once
-    static constexpr int CS = STAGE_BYTES / (TILE_PX * (int)sizeof(TX));  // channels per stage
+    static constexpr int CS = (sizeof(TX) == 8) ? 16 : 32;         // channels per stage
+    static constexpr int X_BYTES = CS * TILE_PX * (int)sizeof(TX); // bytes of X per stage (<= STAGE_BYTES)
     static constexpr int CPW = CS / NSLOT;                         // channels per warp per stage
 };
+static_assert(PassGeom<float, float>::X_BYTES == STAGE_BYTES && PassGeom<double, double>::X_BYTES == STAGE_BYTES, "stage size");
 
 // host-side helpers implemented in api.cu
 int plan_stage_channels(int x_dtype);

@@ -23,12 +23,46 @@ int retile_launch(const espm_state* st, const void* src, int src_dtype, long lon
         return retile_launch_t<double, float>(st, src, stride_c, stride_p, j0, scale, io, s);
     if (src_dtype == ESPM_F32 && st->x_dtype == ESPM_F64)
         return retile_launch_t<float, double>(st, src, stride_c, stride_p, j0, scale, io, s);
+    // compact count storage: the caller has established (espm_x_prescan) that every entry is an integer in range
+    if (st->x_dtype == ESPM_U8 || st->x_dtype == ESPM_U16) {
+        if (scale != 1.0) {
+            set_error("retile: compact storage cannot be scaled (scale=%g)", scale);
+            return ESPM_ERR_BAD_ARG;
+        }
+        if (src_dtype == ESPM_F32 && st->x_dtype == ESPM_U8)
+            return retile_launch_t<float, uint8_t>(st, src, stride_c, stride_p, j0, scale, io, s);
+        if (src_dtype == ESPM_F32 && st->x_dtype == ESPM_U16)
+            return retile_launch_t<float, uint16_t>(st, src, stride_c, stride_p, j0, scale, io, s);
+        if (src_dtype == ESPM_F64 && st->x_dtype == ESPM_U8)
+            return retile_launch_t<double, uint8_t>(st, src, stride_c, stride_p, j0, scale, io, s);
+        if (src_dtype == ESPM_F64 && st->x_dtype == ESPM_U16)
+            return retile_launch_t<double, uint16_t>(st, src, stride_c, stride_p, j0, scale, io, s);
+    }
     set_error("retile: unsupported dtype combination %d -> %d", src_dtype, st->x_dtype);
     return ESPM_ERR_BAD_ARG;
 }
 
+int prescan_launch(const void* src, int src_dtype, int n, long long p_loc, long long stride_c, long long stride_p,
+                   long long j0, uint32_t* out4, int32_t* row_nz, int32_t* col_nz, cudaStream_t s) {
+    const int px_fast = (stride_p == 1 || stride_c != 1) ? 1 : 0;     // which axis is contiguous (see retile_kernel)
+    const long long n_fast = px_fast ? p_loc : n, n_slow = px_fast ? n : p_loc;
+    dim3 grid((unsigned)((n_fast + 255) / 256), (unsigned)((n_slow + 63) / 64));
+    if (src_dtype == ESPM_F32)
+        prescan_kernel<float><<<grid, 256, 0, s>>>((const float*)src, stride_c, stride_p, j0, n, p_loc, px_fast, out4,
+                                                   row_nz, col_nz);
+    else
+        prescan_kernel<double><<<grid, 256, 0, s>>>((const double*)src, stride_c, stride_p, j0, n, p_loc, px_fast, out4,
+                                                    row_nz, col_nz);
+    ESPM_CUDA_CHECK(cudaGetLastError());
+    return ESPM_OK;
+}
+
 int xt_fixup_launch(const espm_state* st, const int32_t* row_zero, const int32_t* col_zero, double eps, double scale,
                     cudaStream_t s) {
+    if (st->x_dtype != ESPM_F32 && st->x_dtype != ESPM_F64) {
+        set_error("xt_fixup: compact storage holds unpatched integer counts only");
+        return ESPM_ERR_UNSUPPORTED;
+    }
     dim3 grid(st->n_tiles, st->n_pad / 32);
     if (st->x_dtype == ESPM_F32)
         xt_fixup_kernel<float><<<grid, 256, 0, s>>>((float*)st->Xt, row_zero, col_zero, st->n, st->n_pad, st->p_loc, eps,
@@ -44,6 +78,12 @@ int xt_const_launch(const espm_state* st, double* part, cudaStream_t s) {
     if (st->x_dtype == ESPM_F32)
         xt_const_kernel<float><<<st->n_tiles, 256, 0, s>>>((const float*)st->Xt, st->n, st->n_pad, st->p_loc,
                                                           st->log_shift, part);
+    else if (st->x_dtype == ESPM_U8)
+        xt_const_kernel<uint8_t><<<st->n_tiles, 256, 0, s>>>((const uint8_t*)st->Xt, st->n, st->n_pad, st->p_loc,
+                                                            st->log_shift, part);
+    else if (st->x_dtype == ESPM_U16)
+        xt_const_kernel<uint16_t><<<st->n_tiles, 256, 0, s>>>((const uint16_t*)st->Xt, st->n, st->n_pad, st->p_loc,
+                                                             st->log_shift, part);
     else
         xt_const_kernel<double><<<st->n_tiles, 256, 0, s>>>((const double*)st->Xt, st->n, st->n_pad, st->p_loc,
                                                            st->log_shift, part);
@@ -52,7 +92,11 @@ int xt_const_launch(const espm_state* st, double* part, cudaStream_t s) {
 }
 
 int x_sums_launch(const espm_state* st, void* colsum, double* rowsum_part, cudaStream_t s) {
-    if (st->x_dtype == ESPM_F32 && st->c_dtype == ESPM_F32)
+    if (st->x_dtype == ESPM_U8)
+        x_sums_kernel<uint8_t, float><<<st->n_tiles, 128, 0, s>>>((const uint8_t*)st->Xt, st->n_pad, (float*)colsum, rowsum_part);
+    else if (st->x_dtype == ESPM_U16)
+        x_sums_kernel<uint16_t, float><<<st->n_tiles, 128, 0, s>>>((const uint16_t*)st->Xt, st->n_pad, (float*)colsum, rowsum_part);
+    else if (st->x_dtype == ESPM_F32 && st->c_dtype == ESPM_F32)
         x_sums_kernel<float, float><<<st->n_tiles, 128, 0, s>>>((const float*)st->Xt, st->n_pad, (float*)colsum, rowsum_part);
     else if (st->x_dtype == ESPM_F32)
         x_sums_kernel<float, double><<<st->n_tiles, 128, 0, s>>>((const float*)st->Xt, st->n_pad, (double*)colsum, rowsum_part);

@@ -97,6 +97,50 @@ __global__ void __launch_bounds__(256) retile_kernel(const TS* __restrict__ src,
     }
 }
 
+// Pre-scan of the raw X: NaN / inf / negative / fractional flags, the largest entry, and the non-zero marks of channels
+// and pixels.  A CTA covers 256 "fast" indices (the contiguous axis: pixels, or channels in the hyperspy layout) times
+// 64 "slow" ones; grid = (ceil(fast / 256), ceil(slow / 64)).  Marks are idempotent stores of 1, the maximum is an
+// atomicMax on the bit pattern of a non-negative float: deterministic whatever the block order.
+template <typename TS>
+__global__ void __launch_bounds__(256) prescan_kernel(const TS* __restrict__ src, long long stride_c, long long stride_p,
+                                                      long long j0, int n, long long p_loc, int px_fast,
+                                                      uint32_t* __restrict__ out4, int32_t* __restrict__ row_nz,
+                                                      int32_t* __restrict__ col_nz) {
+    const long long n_fast = px_fast ? p_loc : n, n_slow = px_fast ? n : p_loc;
+    const long long f = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long s0 = (long long)blockIdx.y * 64;
+    uint32_t flags = 0u;
+    float vmax = 0.f;
+    bool fast_any = false;
+    for (int i = 0; i < 64; ++i) {
+        const long long sl = s0 + i;
+        bool nz = false;
+        if (f < n_fast && sl < n_slow) {
+            const long long c = px_fast ? sl : f, j = px_fast ? f : sl;
+            const TS raw = src[c * stride_c + (j0 + j) * stride_p];
+            const double v = (double)raw;
+            if (v != v) flags |= ESPM_X_NAN;
+            else if (v > 1.7976931348623157e308 || v < -1.7976931348623157e308) flags |= ESPM_X_INF;
+            else {
+                if (v < 0.0) flags |= ESPM_X_NEGATIVE;
+                if (v != floor(v)) flags |= ESPM_X_FRACTION;
+                vmax = fmaxf(vmax, v > 3.0e38 ? 3.0e38f : __double2float_ru(v));
+            }
+            nz = raw != TS(0);
+        }
+        fast_any |= nz;
+        // the slow index is common to the warp: one mark per (warp, slow index) when any lane saw a non-zero
+        if (__any_sync(0xffffffffu, nz) && (threadIdx.x & 31) == 0 && sl < n_slow) (px_fast ? row_nz : col_nz)[sl] = 1;
+    }
+    if (fast_any && f < n_fast) (px_fast ? col_nz : row_nz)[f] = 1;
+    flags = __reduce_or_sync(0xffffffffu, flags);
+    vmax = warp_max(vmax);
+    if ((threadIdx.x & 31) == 0) {
+        if (flags) atomicOr(&out4[0], flags);
+        atomicMax(&out4[1], __float_as_uint(vmax));
+    }
+}
+
 // Xt <- (zero row or zero column ? eps : Xt) * scale, on the real entries only.  grid = (n_tiles, n_pad/32).
 template <typename TX>
 __global__ void __launch_bounds__(256) xt_fixup_kernel(TX* __restrict__ Xt, const int32_t* __restrict__ row_zero,

@@ -14,6 +14,8 @@ struct IngestOut {
 };
 int retile_launch(const espm_state* st, const void* src, int src_dtype, long long stride_c, long long stride_p,
                   long long j0, double scale, const IngestOut& io, cudaStream_t s);
+int prescan_launch(const void* src, int src_dtype, int n, long long p_loc, long long stride_c, long long stride_p,
+                   long long j0, uint32_t* out4, int32_t* row_nz, int32_t* col_nz, cudaStream_t s);
 int xt_fixup_launch(const espm_state* st, const int32_t* row_zero, const int32_t* col_zero, double eps, double scale,
                     cudaStream_t s);
 int xt_const_launch(const espm_state* st, double* part, cudaStream_t s);

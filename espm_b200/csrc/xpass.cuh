@@ -1,7 +1,7 @@
 // The two kernels that stream X from HBM: the H pass and the W pass.
 //
 // Both are warp-specialised persistent kernels: one producer warp issues TMA bulk copies
-// (cp.async.bulk, SASS UBLKCP) of 16 KiB X chunks + the matching GW rows (+ the H tile in the W pass)
+// (cp.async.bulk, SASS UBLKCP) of 16 KiB X chunks (8 / 4 KiB for uint16 / uint8 count storage) + the matching GW rows (+ the H tile in the W pass)
 // into a ring of shared-memory stages guarded by mbarriers; eight consumer warps read the stages with
 // 128-bit LDS, rebuild y = GW.H in registers (never materialised), form x/y and contract it on the fly.
 //
@@ -48,7 +48,7 @@ constexpr int XMODE_KL = 0, XMODE_FROB = 1, XMODE_KL_FROB = 2;
 template <typename TX, typename TC, int KP, bool SAFE>
 struct XPassSmem {
     using G = PassGeom<TX, TC>;
-    static constexpr int X_BYTES = STAGE_BYTES;
+    static constexpr int X_BYTES = G::X_BYTES;
     static constexpr int GW_BYTES = G::CS * KP * (int)sizeof(TC);
     static constexpr int GW_BYTES_AL = (GW_BYTES + 127) / 128 * 128;
     static constexpr int HROW_BYTES = TILE_PX * (int)sizeof(TC);
@@ -62,7 +62,7 @@ struct XPassSmem {
     static constexpr int WACC_BYTES = G::HALVES * G::CS * KP * (int)sizeof(TC);           // W pass flush / accumulator
     static constexpr int WTAIL_BYTES = GW_BYTES_AL + WACC_BYTES;                          // + GW rows of the channel block
     // the W pass keeps CPW x KP ratio sums per lane in registers when they fit, else in shared memory
-    static constexpr bool FAST32 = !SAFE && sizeof(TX) == 4 && sizeof(TC) == 4;
+    static constexpr bool FAST32 = !SAFE && sizeof(TX) <= 4 && sizeof(TC) == 4;   // f32 / uint16 / uint8 storage
     static constexpr int ACC_WORDS = G::CPW * KP * (FAST32 ? 2 : (int)sizeof(TC) / 4);
     static constexpr bool ACC_REG = ACC_WORDS <= 64;
     // CTAs per SM the kernels are compiled for (register budget: 96 regs/thread at 2, 168 at 1)
@@ -81,6 +81,9 @@ __device__ __forceinline__ void lds_vec(T (&dst)[N], const void* src) {
     } else if constexpr (BYTES == 8) {
         uint2 v = *reinterpret_cast<const uint2*>(src);
         memcpy(dst, &v, 8);
+    } else if constexpr (BYTES == 4) {
+        uint32_t v = *reinterpret_cast<const uint32_t*>(src);
+        memcpy(dst, &v, 4);
     } else {
         const T* s = reinterpret_cast<const T*>(src);
 #pragma unroll
@@ -138,6 +141,41 @@ __device__ __forceinline__ float lg2_ftz(float y) {
 }
 __device__ __forceinline__ float2 dup2(float v) { return make_float2(v, v); }
 
+// The 4 pixels of this lane in channel row `c` of a stage, as two packed pixel pairs (fp32 fast path).
+//   float    one LDS.128
+//   uint16   one LDS.64;  uint8  one LDS.32.  Counts become floats WITHOUT the conversion unit (I2F shares the XU pipe
+//            with MUFU, the busiest pipe of the H pass): PRMT drops the integer into the mantissa of 2^23
+//            (0x4B000000 | v  ==  8388608.0f + v, exact for v < 2^23) and one packed FADD removes the 2^23 again:
+//            1 PRMT per element + 1 FADD2 per pair.
+template <typename TX>
+__device__ __forceinline__ void load_x4(const unsigned char* xs, int c, int lane_px, float2 (&x2)[2]) {
+    const unsigned char* p = xs + ((size_t)c * TILE_PX + lane_px) * sizeof(TX);
+    if constexpr (sizeof(TX) == 4) {
+        const float4 xv = *reinterpret_cast<const float4*>(p);
+        x2[0] = make_float2(xv.x, xv.y);
+        x2[1] = make_float2(xv.z, xv.w);
+    } else {
+        constexpr uint32_t MAGIC = 0x4B000000u;
+        uint32_t m[4];
+        if constexpr (sizeof(TX) == 1) {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(p);
+            m[0] = __byte_perm(w, MAGIC, 0x7440);
+            m[1] = __byte_perm(w, MAGIC, 0x7441);
+            m[2] = __byte_perm(w, MAGIC, 0x7442);
+            m[3] = __byte_perm(w, MAGIC, 0x7443);
+        } else {
+            const uint2 w = *reinterpret_cast<const uint2*>(p);
+            m[0] = __byte_perm(w.x, MAGIC, 0x7410);
+            m[1] = __byte_perm(w.x, MAGIC, 0x7432);
+            m[2] = __byte_perm(w.y, MAGIC, 0x7410);
+            m[3] = __byte_perm(w.y, MAGIC, 0x7432);
+        }
+        const float2 off = make_float2(-8388608.0f, -8388608.0f);
+        x2[0] = __fadd2_rn(make_float2(__uint_as_float(m[0]), __uint_as_float(m[1])), off);
+        x2[1] = __fadd2_rn(make_float2(__uint_as_float(m[2]), __uint_as_float(m[3])), off);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Ring of pipeline stages: one elected producer lane fills it, the consumer warps drain it.
 // ------------------------------------------------------------------------------------------------
@@ -189,7 +227,7 @@ h_pass_kernel(const XPassArgs a) {
     using G = PassGeom<TX, TC>;
     using S = XPassSmem<TX, TC, KP, SAFE>;
     constexpr int PPL = G::PPL;
-    constexpr bool FAST32 = MODE == XMODE_KL && !SAFE && sizeof(TX) == 4 && sizeof(TC) == 4;
+    constexpr bool FAST32 = MODE == XMODE_KL && S::FAST32;
     constexpr bool FAST64 = MODE == XMODE_KL && !SAFE && sizeof(TC) == 8;   // table log2, branch-free loss terms
     extern __shared__ __align__(128) unsigned char smem[];
     Ring<S::H_STRIDE> ring(smem, a.depth, S::BAR_BYTES + S::MISC_BYTES);
@@ -276,10 +314,10 @@ h_pass_kernel(const XPassArgs a) {
 #pragma unroll
                 for (int ci = 0; ci < G::CPW; ++ci) {
                     const int c = slot + ci * G::NSLOT;
-                    const float4 xv = *reinterpret_cast<const float4*>(xs + ((size_t)c * TILE_PX + lane_px) * sizeof(float));
+                    float2 x2[2];
+                    load_x4<TX>(xs, c, lane_px, x2);
                     float gw[KP];
                     lds_gw<float, KP>(gw, gs + (size_t)c * KP * sizeof(float));
-                    const float2 x2[2] = {make_float2(xv.x, xv.y), make_float2(xv.z, xv.w)};
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
                         float2 y = __ffma2_rn(dup2(gw[0]), h2[0][j], ysh);
@@ -606,10 +644,10 @@ w_pass_kernel(const XPassArgs a) {
 #pragma unroll
             for (int ci = 0; ci < CPW; ++ci) {
                 const int c = slot + ci * G::NSLOT;
-                const float4 xv = *reinterpret_cast<const float4*>(xs + ((size_t)c * TILE_PX + lane_px) * sizeof(float));
+                float2 x2[2];
+                load_x4<TX>(xs, c, lane_px, x2);
                 float gw[KP];
                 lds_gw<float, KP>(gw, gs + (size_t)c * KP * sizeof(float));
-                const float2 x2[2] = {make_float2(xv.x, xv.y), make_float2(xv.z, xv.w)};
                 float2 tloc[KP];
                 float2 (&t2)[KP] = ACC_REG ? acc2[ACC_REG ? ci : 0] : tloc;
                 if constexpr (!ACC_REG) {

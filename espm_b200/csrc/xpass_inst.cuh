@@ -104,5 +104,8 @@ static int xpass_sizes(int kp, int safe, XPassSizes* o) {
 int xpass_f32f32(const XPassLaunch& l, const XPassArgs* a, int* occ_out, cudaStream_t stream);
 int xpass_f32f64(const XPassLaunch& l, const XPassArgs* a, int* occ_out, cudaStream_t stream);
 int xpass_f64f64(const XPassLaunch& l, const XPassArgs* a, int* occ_out, cudaStream_t stream);
+// compact count storage: uint8 / uint16 X with fp32 arithmetic
+int xpass_u8f32(const XPassLaunch& l, const XPassArgs* a, int* occ_out, cudaStream_t stream);
+int xpass_u16f32(const XPassLaunch& l, const XPassArgs* a, int* occ_out, cudaStream_t stream);
 
 }  // namespace espm

@@ -34,9 +34,14 @@ extern "C" {
 
 #define ESPM_F32 0
 #define ESPM_F64 1
+/* compact storage of count data (x dtype only): X holds non-negative integers (Poisson counts, datasets/base.py:68)
+ * below 256 / 65536; the kernels convert on the fly and compute in fp32.  4x / 2x fewer bytes per pass. */
+#define ESPM_U8  2
+#define ESPM_U16 3
 
 #define ESPM_TILE_PX 128          /* pixels per tile of Xt */
-#define ESPM_STAGE_BYTES 16384    /* bytes of X per pipeline stage (one bulk copy) */
+#define ESPM_STAGE_BYTES 16384    /* bytes of X per pipeline stage (one bulk copy) for f32 / f64 storage; a stage is
+                                   * always 32 (f64: 16) channels x 128 pixels, i.e. 8 / 4 KiB for uint16 / uint8 */
 #define ESPM_MAX_K 16             /* largest supported n_components */
 #define ESPM_COOP_BLOCKS 32        /* CTAs of the cooperative w_finish kernel */
 #define ESPM_MAX_RANKS 16          /* largest number of pixel shards (GPUs of one NVLink domain) */
@@ -128,7 +133,7 @@ typedef struct espm_state {
     int32_t row0;       /* first global image row owned by this rank */
     int32_t halo;       /* elements available before/after the owned pixels in every H row (>= ny) */
     int32_t ldh;        /* row stride of the H buffers, in elements */
-    int32_t x_dtype;    /* ESPM_F32 / ESPM_F64: storage of Xt */
+    int32_t x_dtype;    /* ESPM_F32 / ESPM_F64 / ESPM_U8 / ESPM_U16: storage of Xt */
     int32_t c_dtype;    /* ESPM_F32 / ESPM_F64: arithmetic, and storage of every other array */
     uint32_t flags;     /* ESPM_FLAG_* */
     int32_t n_simplex_rows;
@@ -272,6 +277,7 @@ int espm_plan_info(const espm_state* st, int32_t* info8);
 #define ESPM_X_NAN       (1u << 0)
 #define ESPM_X_INF       (1u << 1)
 #define ESPM_X_NEGATIVE  (1u << 2)
+#define ESPM_X_FRACTION  (1u << 3)   /* espm_x_prescan: some entry is not an integer */
 typedef struct espm_ingest {
     int32_t* row_nz;
     int32_t* col_nz;
@@ -282,6 +288,13 @@ typedef struct espm_ingest {
  * Lets a rank upload its pixel slab X[:, j0:j1] of a C-ordered host image without a host-side copy. */
 int espm_upload_2d(void* dst, int64_t dpitch_bytes, const void* src_host, int64_t spitch_bytes, int64_t width_bytes,
                    int64_t height, void* stream);
+/* Pre-scan of the uploaded raw X (before espm_plan: the storage type decides the layout): which compact storage would
+ * hold it exactly, and whether remove_zeros_lines (base.py:519-528) would have to patch it.
+ *   src, src_dtype (ESPM_F32 / ESPM_F64), strides, j0 as in espm_retile_x; n channels, p_loc pixels.
+ *   out4 (device, zero-filled by the caller): [0] ESPM_X_* bits, [1] float bits of the largest finite entry
+ *   row_nz[n], col_nz[p_loc] (device, zero-filled): set to 1 where a channel / pixel has a non-zero entry. */
+int espm_x_prescan(const void* src, int32_t src_dtype, int32_t n, int64_t p_loc, int64_t stride_c, int64_t stride_p,
+                   int64_t j0, uint32_t* out4, int32_t* row_nz, int32_t* col_nz, void* stream);
 int espm_retile_x(const espm_state* st, const void* src, int32_t src_dtype, int64_t stride_c,
                   int64_t stride_p, int64_t j0, double scale, const espm_ingest* stats, void* stream);
 int espm_xt_fixup(const espm_state* st, const int32_t* row_zero, const int32_t* col_zero, double eps,

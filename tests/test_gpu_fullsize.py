@@ -92,6 +92,8 @@ def test_one_iteration_at_full_size(cfg):
     eng = FitEngine(X, G, W0, H0, shape_2d=(nx, ny), lambda_L=lam, mu=mu, epsilon_reg=eps, simplex_H=True,
                     simplex_W=False, tol=0.0, max_records=16, x_local=True)
     eng.evaluate(0)
+    num_all = eng.num[:k, :nx * ny].double().cpu()          # what h_finish assembled for THIS update (num, den of
+    den_all = eng.den[:k, :nx * ny].double().cpu()          # updates.py:132-142), before the next pass overwrites it
     eng.advance(1)
     eng.evaluate(1)
     recs = eng.read_records(0, 2)
@@ -120,7 +122,21 @@ def test_one_iteration_at_full_size(cfg):
     nu, own = _replay(num, den, its)
     assert own <= its            # the global count is the slowest pixel's
     ref_HJ = np.maximum(num / (den + nu), LS)
-    assert rel_err(H1[:, J], ref_HJ) < tol
+    if dtype == np.float64:
+        assert rel_err(H1[:, J], ref_HJ) < tol
+    else:
+        # fp32: (1) the streamed contraction -- num, den as h_finish assembled them -- against fp64: 1e-6;
+        # (2) the update GIVEN those inputs (bracket, lock-step replay, quotient) against an fp64 evaluation: 1e-6;
+        # (3) end to end: 1e-5 (north star) on 99.9 % of the entries.  The worst entries sit at ~dicotomy_tol: the
+        # reference stops the bisection when max |f| <= 1e-5 (dicotomy.py:152), nu is then only determined up to the last
+        # bracket step, and a sign decision with |f(new)| below the fp32 rounding of num / den moves it by that step.
+        num_dev, den_dev = num_all.numpy()[:, J], den_all.numpy()[:, J]
+        assert rel_err(num_dev, num) < 1e-6 and rel_err(den_dev, den) < 1e-6
+        nu_dev, _ = _replay(num_dev.copy(), den_dev.copy(), its)
+        assert rel_err(H1[:, J], np.maximum(num_dev / (den_dev + nu_dev), LS)) < 1e-6
+        rel = np.abs(H1[:, J] - ref_HJ) / ref_HJ
+        assert np.quantile(rel, 0.999) < tol
+        assert rel.max() < 2.5 * TOL
 
     # ---- the GLOBAL lock-step count (dicotomy.py:152) over ALL pixels: independent fp64 evaluation (torch on the GPU)
     # of num / den from the same (fp32-rounded) inputs, then the reference's vectorised bisection.  This pins the count
