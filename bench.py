@@ -171,6 +171,8 @@ def main():
     ap.add_argument("--algo", default="log_surrogate", choices=["log_surrogate", "l2_surrogate"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-compact", action="store_true",
+                    help="skip the secondary measurement with uint8 / uint16 count storage of X")
     ap.add_argument("--no-selfcheck", action="store_true",
                     help="N > 1: skip the comparison with an unsharded run of the same image on rank 0")
     ap.add_argument("--cpu-rows", type=int, default=48, help="image rows of the CPU-baseline crop")
@@ -228,6 +230,8 @@ def main():
     import torch.distributed as dist
     from espm_b200 import _lib as L
     from espm_b200.engine import FitEngine
+    import espm_b200
+    espm_b200.config.x_storage = "dense"      # the headline metric is quoted on dense fp32 / fp64 storage of X
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     shard = None
@@ -343,13 +347,67 @@ def main():
                                            and check["vs_unsharded"]["bisect_its_equal"])
         eng1.close()
         del eng1
+    # ------------------------------------------------------------------ compact count storage (separate metric)
+    # X holds Poisson counts: the same iterations with Xt stored as uint8 / uint16 (espm_b200.config.x_storage =
+    # "auto", what a user gets by default).  Reported beside the dense line, against its OWN algorithmic bytes.
+    eng.close()
+    del eng
+    compact = None
+    if not args.no_compact and args.dtype == "f32":
+        espm_b200.config.x_storage = "auto"
+        shard_c = None
+        if world > 1 and not replicas:
+            shard_c = make_shard()
+        engc = FitEngine(X_loc, G, W0, H0, shape_2d=(nx, ny), max_records=W + K + 16, shard=shard_c, x_local=True,
+                         tol=0.0, **wl["kw"])
+        espm_b200.config.x_storage = "dense"
+        if engc.x_storage != "dense":
+            engc.evaluate(0)
+            for i in range(1, W + 1):
+                engc.advance(i)
+                engc.evaluate(i)
+            barrier()
+            engc.profile = {}
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for i in range(W + 1, W + K + 1):
+                engc.advance(i)
+                engc.evaluate(i)
+            c1.record()
+            barrier()
+            t_c = torch.tensor([c0.elapsed_time(c1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t_c, op=dist.ReduceOp.MAX)
+            ms_c = float(t_c.item())
+            pc = engc.profile
+            engc.profile = None
+            hc = float(np.mean([a.elapsed_time(b) for a, b in pc["h_pass"]]))
+            wc = float(np.mean([a.elapsed_time(b) for a, b in pc["w_pass"]]))
+            rc = engc.read_records(W + K, W + K + 1)[0]
+            Wc = engc.get_W().astype(np.float64)
+            itemsize = 1 if engc.x_storage == "uint8" else 2
+            bl = n * p * itemsize * (world if replicas else 1) / world
+            compact = {"storage": engc.x_storage, "value": K / (ms_c * 1e-3) * (world if replicas else 1),
+                       "unit": "it/s", "ms_per_step": ms_c / K, "h_pass_ms": hc, "w_pass_ms": wc,
+                       "bytes_per_launch": bl, "h_pass_gbs": bl / (hc * 1e-3) / 1e9, "w_pass_gbs": bl / (wc * 1e-3) / 1e9,
+                       "roofline": {"bound": "hbm", "achieved": bl / (max(hc, wc) * 1e-3) / 1e9, "peak": peak,
+                                    "unit": "GB/s", "frac": bl / (max(hc, wc) * 1e-3) / 1e9 / peak,
+                                    "note": "with 1 byte per entry the H pass is bound by the MUFU (XU) pipe -- one "
+                                            "rcp and one lg2 per entry -- not by HBM"},
+                       "speedup_vs_dense": (K / (ms_c * 1e-3)) / (K / (ms * 1e-3)),
+                       "kl_raw": float(rc[L.S_SUMY] - rc[L.S_XLOGY]),
+                       "kl_raw_rel_diff_vs_dense": abs(float(rc[L.S_SUMY] - rc[L.S_XLOGY]) - check["kl_raw"]) / abs(check["kl_raw"]),
+                       "W_max_rel_diff_vs_dense": float(np.max(np.abs(Wc - W_end) / np.maximum(np.abs(W_end), 1e-300))),
+                       "bisect_its_H": float(rc[L.S_BISECT_ITS_H])}
+        else:
+            compact = {"storage": "dense", "reason": engc.x_storage_reason}
+        engc.close()
+        del engc
+
     # ------------------------------------------------------------------ end to end through the public API
     e2e = None
     if not args.no_e2e:
-        import espm_b200
         from espm_b200 import SmoothNMF
-        eng.close()
-        del eng
         torch.cuda.empty_cache()
         # the user's host buffer: the whole image in pinned host memory (every rank reads its own rows)
         X_host = torch.empty((n, p), dtype=tdt, pin_memory=True)
@@ -400,8 +458,6 @@ def main():
                "best": K / min(walls) * (world if replicas else 1),
                "final_loss": float(est.losses_[-1])}
 
-    if args.no_e2e:
-        eng.close()
     if world > 1 and not replicas:
         from espm_b200.dist import release_peer_memory
         release_peer_memory()          # collective: the peer region is cached across fits until here
@@ -423,7 +479,7 @@ def main():
     line = {"metric": "smoothnmf_iterations_per_s", "value": value, "unit": "it/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak" if replicas else "strong", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic", "config": config, "roofline": roofline, "cpu_baseline": cpu,
-            "e2e": e2e, "gpu_launches": n_launches, "clocks": clocks,
+            "e2e": e2e, "compact": compact, "gpu_launches": n_launches, "clocks": clocks,
             "check": check}
     print(json.dumps(line))
     if world > 1:

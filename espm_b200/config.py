@@ -6,6 +6,11 @@ distributed : "auto" | True | False
 device_init : bool
     When neither W nor H is passed to ``fit_transform``, run the randomized SVD of scikit-learn's NNDSVD
     initialisation on the device (init_device.py) instead of on the host.  Unsharded fits with n < p only.
+x_storage : "auto" | "dense" | "uint8" | "uint16"
+    Storage of X on the device.  "auto" keeps count data (integers below 256 / 65536, fp32 arithmetic, nothing for
+    remove_zeros_lines / normalize to patch) as uint8 / uint16 and streams 4x / 2x fewer bytes per pass; "dense" always
+    stores the uploaded floating-point values (what BASELINE.json's fp32 / fp64 roofline figures are quoted on).
 """
 distributed = "auto"
+x_storage = "auto"
 device_init = True

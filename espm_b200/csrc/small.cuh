@@ -460,8 +460,11 @@ struct KlAnchorEval {
     KlEval<KP> base;
     double nu, D, F2, tmin, mx, chord, tol;
     bool ok, sized;
+    // `warm`: a guess of the root (the pixel's root of the previous NMF iteration) or NaN.  From any point of the domain
+    // the iteration is safe: right of the root the tangent of the concave g lands left of it, from there on the
+    // iterates increase monotonically.
     __device__ __forceinline__ KlAnchorEval(const double (&num)[KP], const double (&den)[KP], int k, double ls, double tol_,
-                                            double a0, double b0)
+                                            double a0, double b0, double warm)
         : base(num, den, k, ls, tol_), tol(tol_) {
         ok = sized = false;
         nu = D = F2 = tmin = mx = chord = 0.0;
@@ -474,7 +477,7 @@ struct KlAnchorEval {
                 dmax = fmax(dmax, fabs(den[kk]));
             }
         if (!valid) return;
-        double x = a0, S = 0.0, Dv = 0.0, F2v = 0.0, tm = 1e300;
+        double x = (warm > a0 && warm < b0) ? warm : a0, S = 0.0, Dv = 0.0, F2v = 0.0, tm = 1e300;
         bool conv = false;
 #pragma unroll 1
         for (int it = 0; it < 24; ++it) {
@@ -504,7 +507,12 @@ struct KlAnchorEval {
                 break;
             }
             const double xn = x + S * (S - 1.0) * Num<double>::rcp(Dv);
-            if (!(xn > a0 - fabs(a0)) || !(xn < 1e300)) return;
+            if (!(xn < 1e300)) return;
+            if (!(xn > a0)) {                 // a warm start far right of the root overshot the domain: restart at a0
+                if (x == a0) return;
+                x = a0;
+                continue;
+            }
             // the step is within 2 ulps of x: converged as far as fp64 resolves the root (when x + d_k cancels, the
             // residual cannot get smaller than D ulp(x); mx below covers that distance)
             conv = fabs(xn - x) <= 4.5e-16 * fabs(x);
@@ -916,7 +924,10 @@ __global__ void __launch_bounds__(PX_THREADS, 4) h_finish_kernel(const espm_stat
             } else {
                 double lo, hi;
                 simplex_bracket<double, KP>(numd, dend, k, lo, hi);
-                const KlAnchorEval<KP> ev(numd, dend, k, st.log_shift, st.dicotomy_tol, lo, hi);
+                // warm start of the root search: this pixel's root of the previous iteration (valid when its margin is)
+                const double prev_mx = st.bisect_anchor[(size_t)st.p_pad + j];
+                const double warm = (prev_mx > 0.0 && prev_mx < 1e300) ? st.bisect_anchor[j] : __longlong_as_double(-1LL);
+                const KlAnchorEval<KP> ev(numd, dend, k, st.log_shift, st.dicotomy_tol, lo, hi, warm);
                 bisect_trace_rec(lo, hi, ev, st.maxit, bits, dec, seen, err);
                 st.bisect_anchor[j] = ev.nu;
                 st.bisect_anchor[(size_t)st.p_pad + j] = ev.ok ? ev.mx : Num<double>::inf();

@@ -55,6 +55,10 @@ class Shard:
         dist.all_reduce(v, op=dist.ReduceOp.MAX, group=self.group)
         return v.to(dev)[0]
 
+    def allreduce_max_int(self, t):
+        """In-place elementwise maximum over the ranks of an integer tensor (marks: OR)."""
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+
     def allreduce_hstats(self, hstats, kp):
         """hstats = {rowsum[kp], rowsum(max(.,ls))[kp], rowmax[kp]} (float64)."""
         dist.all_reduce(hstats[:2 * kp], op=dist.ReduceOp.SUM, group=self.group)

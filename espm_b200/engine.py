@@ -36,6 +36,9 @@ def _torch_dtype(code):
     return torch.float64 if code == L.F64 else torch.float32
 
 
+_X_ITEMSIZE = {L.F32: 4, L.F64: 8, L.U8: 1, L.U16: 2}
+
+
 def _code_of(dtype):
     if isinstance(dtype, torch.dtype):
         dtype = {torch.float32: np.float32, torch.float64: np.float64}.get(dtype, None)
@@ -122,6 +125,12 @@ class FitEngine:
         self.j0, self.j1, self.row0 = j0, j1, row0
         p_loc = j1 - j0
         self.p_loc = p_loc
+
+        # ---- H2D copy of this rank's slab, then the storage type of Xt (it decides the launch plan) ----
+        self.src_code = x_code                       # dtype of the uploaded raw X
+        self._stage_x(X)
+        x_code = self._choose_storage(x_code, c_code, x_scale, ingest)
+        self.x_code = x_code
 
         st = L.EspmState()
         self.st = st
@@ -287,7 +296,7 @@ class FitEngine:
         self.const_KL = None
         self.norm_factor = None
         self.n_zero_rows = self.n_zero_cols = 0
-        self._upload_x(X, x_scale, ingest)
+        self._retile_x(x_scale, ingest)
         self.x_colsum = self.x_rowsum = None
         if st.flags & L.FLAG_BMD:
             self.compute_x_sums()
@@ -344,18 +353,16 @@ class FitEngine:
         self.profile.setdefault(name, []).append((e0, e1))
 
     # ------------------------------------------------------------------ uploads
-    def _upload_x(self, X, scale, ingest=None):
-        """H2D copy of this rank's pixel slab and re-tiling into the tile-major layout (base.py:262)."""
+    def _stage_x(self, X):
+        """H2D copy of this rank's pixel slab (base.py:262 copies X on the host; here the only touch of the host
+        buffer is this DMA).  Leaves ``self._xraw = (device tensor, channel stride, pixel stride)``."""
         if isinstance(X, np.ndarray) and not X.flags.writeable:
             # read-only inputs (memmaps, sklearn's checks) are only ever read; silence torch's notice
             import warnings
             with warnings.catch_warnings():
                 warnings.simplefilter("ignore", UserWarning)
                 X = torch.from_numpy(X)
-        st = self.st
-        xdt = _torch_dtype(self.x_code)
-        self.Xt = torch.empty(st.n_tiles * st.n_pad * L.TILE_PX, dtype=xdt, device=self.device)
-        st.Xt = self.Xt.data_ptr()
+        xdt = _torch_dtype(self.src_code)
         j0, j1 = self.j0, self.j1
         if self.x_local:
             if X.shape[1] != j1 - j0:
@@ -392,13 +399,72 @@ class FitEngine:
                 else:
                     d = torch.from_numpy(np.ascontiguousarray(slab)).to(self.device)
                 sc, sp = slab.shape[1], 1
+        self._xraw = (d, sc, sp)
+
+    def _choose_storage(self, src_code, c_code, scale, ingest):
+        """Storage type of Xt.  EDXS spectrum images are Poisson counts (datasets/base.py:68): non-negative integers,
+        ~3/4 of them zero.  When the arithmetic is fp32 and the uploaded slab holds only integers below 256 / 65536
+        that need no patching (no all-zero channel or pixel for remove_zeros_lines, no ``normalize``, no scale), Xt
+        keeps them as uint8 / uint16 and the X passes stream 4x / 2x fewer bytes.  One
+        device pass over the uploaded slab decides; pixel-sharded fits take the widest type any rank needs."""
+        from . import config
+        mode = getattr(config, "x_storage", "auto")
+        if mode not in ("auto", "dense", "uint8", "uint16"):
+            raise ValueError("espm_b200.config.x_storage must be 'auto', 'dense', 'uint8' or 'uint16'")
+        self.x_storage_reason = "dense storage requested" if mode == "dense" else None
+        if (mode == "dense" or c_code != L.F32 or src_code not in (L.F32, L.F64) or float(scale) != 1.0
+                or (ingest is not None and ingest.get("normalize") is not None)):
+            if self.x_storage_reason is None:
+                self.x_storage_reason = "fp64 arithmetic, scaling or normalisation"
+            want = 2
+        else:
+            d, sc, sp = self._xraw
+            dev = self.device
+            out4 = torch.zeros(4, dtype=torch.int32, device=dev)
+            row_nz = torch.zeros(self.n, dtype=torch.int32, device=dev)
+            col_nz = torch.zeros(self.p_loc, dtype=torch.int32, device=dev)
+            L.check(self.lib.espm_x_prescan(ctypes.c_void_p(d.data_ptr()), src_code, self.n, self.p_loc, sc, sp, 0,
+                                            ctypes.c_void_p(out4.data_ptr()), ctypes.c_void_p(row_nz.data_ptr()),
+                                            ctypes.c_void_p(col_nz.data_ptr()), self.stream))
+            if self.shard is not None:
+                self.shard.allreduce_max_int(row_nz)       # a channel is an all-zero line only if it is on every rank
+            info = torch.cat([out4[:2], row_nz.sum().reshape(1).to(torch.int32),
+                              col_nz.sum().reshape(1).to(torch.int32)]).cpu().numpy()
+            flags = int(info[0]) & 0xffffffff
+            vmax = float(np.array([info[1]], dtype=np.int32).view(np.float32)[0])
+            patched = ingest is not None and (int(info[2]) < self.n or int(info[3]) < self.p_loc)
+            if flags & (L.X_NAN | L.X_INF | L.X_NEGATIVE | L.X_FRACTION) or patched:
+                want = 2                                   # (errors are raised by the ingest pass, with its messages)
+                self.x_storage_reason = "non-integer / negative entries or all-zero lines"
+            elif vmax <= 255.0 and mode in ("auto", "uint8"):
+                want = 0
+            elif vmax <= 65535.0:
+                want = 1
+            else:
+                want = 2
+                self.x_storage_reason = "entries above 65535"
+        if self.shard is not None:
+            want = int(self.shard.allreduce_max_scalar(torch.tensor(float(want), dtype=torch.float64)))
+        self.x_storage = ("uint8", "uint16", "dense")[want]
+        return (L.U8, L.U16, src_code)[want]
+
+    def _retile_x(self, scale, ingest=None):
+        """Re-tiling of the staged slab into the tile-major layout (base.py:262) + the device prologue."""
+        st = self.st
+        d, sc, sp = self._xraw
+        self.Xt = torch.empty(st.n_tiles * st.n_pad * L.TILE_PX * _X_ITEMSIZE[self.x_code], dtype=torch.uint8,
+                              device=self.device)
+        if self.x_code in (L.F32, L.F64):
+            self.Xt = self.Xt.view(_torch_dtype(self.x_code))
+        st.Xt = self.Xt.data_ptr()
         src = ctypes.c_void_p(d.data_ptr())
         if ingest is None:
-            L.check(self.lib.espm_retile_x(ctypes.byref(st), src, self.x_code, sc, sp, 0, float(scale), None,
+            L.check(self.lib.espm_retile_x(ctypes.byref(st), src, self.src_code, sc, sp, 0, float(scale), None,
                                            self.stream))
             torch.cuda.current_stream(self.device).synchronize()
-            return
-        self._ingest(src, sc, sp, float(ingest.get("eps", st.log_shift)), ingest.get("normalize"))
+        else:
+            self._ingest(src, sc, sp, float(ingest.get("eps", st.log_shift)), ingest.get("normalize"))
+        self._xraw = None
 
     def _ingest(self, src, sc, sp, eps, normalize_nc):
         """Device-side prologue of the fit (see ``ingest`` in __init__)."""
@@ -409,7 +475,7 @@ class FitEngine:
         xflags = torch.zeros(1, dtype=i32, device=dev)
         sum_part = torch.zeros(st.n_tiles * (st.n_pad // 32), dtype=torch.float64, device=dev)
         io = L.EspmIngest(row_nz.data_ptr(), col_nz.data_ptr(), xflags.data_ptr(), sum_part.data_ptr())
-        L.check(self.lib.espm_retile_x(ctypes.byref(st), src, self.x_code, sc, sp, 0, 1.0, ctypes.byref(io),
+        L.check(self.lib.espm_retile_x(ctypes.byref(st), src, self.src_code, sc, sp, 0, 1.0, ctypes.byref(io),
                                        self.stream))
         scal = torch.zeros(2, dtype=torch.float64, device=dev)
         L.check(self.lib.espm_reduce_sum(sum_part.data_ptr(), sum_part.numel(), scal.data_ptr(), self.stream))
@@ -424,7 +490,7 @@ class FitEngine:
             raise ValueError("Input X contains NaN.")
         if flags & L.X_INF:
             raise ValueError("Input X contains infinity or a value too large for dtype('%s')."
-                             % np.dtype(_np_dtype(self.x_code)).name)
+                             % np.dtype(_np_dtype(self.src_code)).name)
         if flags & L.X_NEGATIVE:
             raise ValueError("Negative values in data")            # base.py:528
         total = float(info[1])
@@ -671,15 +737,17 @@ class FitEngine:
         st = self.st
         D = torch.as_tensor(np.ascontiguousarray(true_D), dtype=self.cdt).to(self.device)
         Ht = torch.as_tensor(np.ascontiguousarray(true_H[:, self.j0:self.j1]), dtype=self.cdt).to(self.device)
-        xdt = _torch_dtype(self.x_code)
+        # X_true is not integer-valued: dense storage in the arithmetic type, whatever the storage of X
+        self.truth_code = self.c_code
+        xdt = _torch_dtype(self.truth_code)
         dense = (D @ Ht).to(xdt)                 # once per fit (setup, not the per-iteration path)
-        self.Xt_true = torch.empty_like(self.Xt)
-        keep = st.Xt
-        st.Xt = self.Xt_true.data_ptr()
-        L.check(self.lib.espm_retile_x(ctypes.byref(st), ctypes.c_void_p(dense.data_ptr()), self.x_code,
+        self.Xt_true = torch.empty(st.n_tiles * st.n_pad * L.TILE_PX, dtype=xdt, device=self.device)
+        keep = (st.Xt, st.x_dtype)
+        st.Xt, st.x_dtype = self.Xt_true.data_ptr(), self.truth_code
+        L.check(self.lib.espm_retile_x(ctypes.byref(st), ctypes.c_void_p(dense.data_ptr()), self.truth_code,
                                        dense.stride(0), 1, 0, 1.0, None, self.stream))
         torch.cuda.current_stream(self.device).synchronize()
-        st.Xt = keep
+        st.Xt, st.x_dtype = keep
         del dense
         self.H_tmp = torch.ones(self.k, self.ldh, dtype=self.cdt, device=self.device)
         self.hstats_tmp = torch.zeros(3 * st.kp, dtype=torch.float64, device=self.device)
@@ -688,9 +756,10 @@ class FitEngine:
         """Loss terms of (W_cur, H) against X into scalar record ``slot`` without touching the iteration state
         (the ``self.loss(W, H, X=...)`` calls of the reference): h_pass + h_finish with ESPM_FLAG_EVAL_ONLY."""
         st = self.st
-        keep = (st.Xt, st.H_cur, st.hstats_cur, st.flags)
+        keep = (st.Xt, st.H_cur, st.hstats_cur, st.flags, st.x_dtype)
         if xt_ptr is not None:
             st.Xt = xt_ptr
+            st.x_dtype = self.truth_code         # the truth image is stored dense (enable_truth)
         if h_ptr is not None:
             st.H_cur, st.hstats_cur = h_ptr, hstats_ptr
         st.flags = (st.flags & ~L.FLAG_HAVE_HPREV) | L.FLAG_EVAL_ONLY
@@ -699,7 +768,7 @@ class FitEngine:
             L.check(self.lib.espm_gram(ctypes.byref(st), 0, self.stream))
         self._call(self.lib.espm_h_pass)
         self._call(self.lib.espm_h_finish)
-        st.Xt, st.H_cur, st.hstats_cur, st.flags = keep
+        st.Xt, st.H_cur, st.hstats_cur, st.flags, st.x_dtype = keep
         self._bind()
 
     def truth_loss(self, slot, H_t=None):

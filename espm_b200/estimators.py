@@ -296,6 +296,7 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
                         clamp_init=True,
                         ingest=dict(eps=self.log_shift, normalize=self.n_components if self.normalize else None))
         self._engine = eng
+        self.x_storage_ = eng.x_storage      # "dense" | "uint8" | "uint16": how X is held on the device (config.x_storage)
         if device_init:
             from .init_device import initialize_nmf_device
             _, W0, H0 = initialize_factors(

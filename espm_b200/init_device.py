@@ -35,8 +35,14 @@ class _DeviceX:
     def __init__(self, eng):
         st = eng.st
         self.n, self.p, self.n_pad, self.n_tiles = eng.n, eng.p_loc, st.n_pad, st.n_tiles
-        self.T3 = eng.Xt.view(st.n_tiles, st.n_pad, L.TILE_PX)
-        self.dtype = eng.Xt.dtype
+        self.dtype = torch.float64 if eng.c_code == L.F64 else torch.float32
+        if eng.x_code == L.U8:          # compact count storage: a dense copy for the 16 GEMMs of the initialisation
+            self.T3 = eng.Xt.view(st.n_tiles, st.n_pad, L.TILE_PX).to(self.dtype)
+        elif eng.x_code == L.U16:
+            t = eng.Xt.view(torch.int16).view(st.n_tiles, st.n_pad, L.TILE_PX).to(self.dtype)
+            self.T3 = torch.where(t < 0, t + 65536.0, t)
+        else:
+            self.T3 = eng.Xt.view(st.n_tiles, st.n_pad, L.TILE_PX)
         self.device = eng.Xt.device
 
     def mean(self):
@@ -130,7 +136,7 @@ def initialize_nmf_device(eng, n_components, init=None, random_state=None):
         raise ValueError("init = '{}' can only be used when n_components <= min(n_samples, n_features)".format(init))
     if init is None:
         init = "nndsvda" if n_components <= min(n, p) else "random"
-    np_dtype = np.float32 if eng.Xt.dtype == torch.float32 else np.float64
+    np_dtype = np.float64 if eng.c_code == L.F64 else np.float32
     if init == "random":
         avg = np_dtype(np.sqrt(_DeviceX(eng).mean() / n_components))
         rng = check_random_state(random_state)

@@ -74,12 +74,25 @@ def _lockstep_count_torch(num, den):
     return it
 
 
-@pytest.mark.parametrize("cfg", ["C2-f64", "C3-f32"])
-def test_one_iteration_at_full_size(cfg):
+@pytest.fixture
+def x_storage():
+    """Sets espm_b200.config.x_storage for one test and restores it."""
+    import espm_b200
+    keep = espm_b200.config.x_storage
+
+    def set_mode(mode):
+        espm_b200.config.x_storage = mode
+    yield set_mode
+    espm_b200.config.x_storage = keep
+
+
+@pytest.mark.parametrize("cfg", ["C2-f64", "C3-f32", "C3-f32-dense"])
+def test_one_iteration_at_full_size(cfg, x_storage):
     import torch
     from espm_b200 import _lib as L
     from espm_b200.engine import FitEngine
     from oracle import smooth_nmf_oracle as orc
+    x_storage("dense" if cfg.endswith("dense") else "auto")
     if cfg == "C2-f64":
         nx = ny = 256
         n, k, n_el, dtype, tol = 2048, 3, 9, np.float64, 1e-10
@@ -91,6 +104,8 @@ def test_one_iteration_at_full_size(cfg):
     p = nx * ny
     eng = FitEngine(X, G, W0, H0, shape_2d=(nx, ny), lambda_L=lam, mu=mu, epsilon_reg=eps, simplex_H=True,
                     simplex_W=False, tol=0.0, max_records=16, x_local=True)
+    # the synthetic image holds Poisson counts below 256: uint8 storage unless dense storage / fp64 was asked for
+    assert eng.x_storage == ("uint8" if cfg == "C3-f32" else "dense")
     eng.evaluate(0)
     num_all = eng.num[:k, :nx * ny].double().cpu()          # what h_finish assembled for THIS update (num, den of
     den_all = eng.den[:k, :nx * ny].double().cpu()          # updates.py:132-142), before the next pass overwrites it
