@@ -51,6 +51,7 @@ DEV_PEER_TIMEOUT = 1 << 5
 # scalar record slots
 S_XLOGY, S_SUMY, S_LOGREG, S_LAPL, S_REL_H, S_REL_W, S_BISECT_ITS_H, S_BISECT_ITS_W, S_DEV_FLAGS, \
     S_MEAN_H, S_MEAN_W, S_GW_FLAGS, S_GAMMA, S_LS_D = range(14)
+S_STAMP = 23
 
 _i32, _u32, _i64, _f64, _vp = ctypes.c_int32, ctypes.c_uint32, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
 
@@ -85,7 +86,7 @@ class EspmState(ctypes.Structure):
         ("bisect_dec", _vp), ("bisect_anchor", _vp),
         ("gamma_h", _f64), ("gamma_w", _f64), ("x_total", _f64),
         ("x_colsum", _vp), ("x_rowsum", _vp), ("GG", _vp), ("gram_gw", _vp), ("gram_h", _vp), ("sigma_dev", _vp),
-        ("ls_part", _vp),
+        ("ls_part", _vp), ("rec_stamp", _f64),
     ]
 
 

@@ -1198,6 +1198,9 @@ __device__ __forceinline__ void h_scalars_block(const espm_state& st) {
             (st.flags & ESPM_FLAG_SIMPLEX_H) ? (double)first_clear_bit(st.bisect_mask, st.maxit) : 0.0;
         rec[ESPM_S_DEV_FLAGS] = (double)st.dev_flags[0];
         rec[ESPM_S_MEAN_H] = meanh / ((double)st.k * (double)st.p_total);
+        // the record is complete (rel_W etc. were written by earlier kernels of the stream): stamp it
+        __threadfence_system();
+        *reinterpret_cast<volatile double*>(rec + ESPM_S_STAMP) = st.rec_stamp;
     }
 }
 

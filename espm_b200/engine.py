@@ -256,7 +256,13 @@ class FitEngine:
         self.dev_flags = torch.zeros(8, dtype=torch.int32, device=dev)
         self.coop_part = zeros(L.COOP_BLOCKS * (2 * L.MAX_K + 4), dtype=torch.float64)
         self.max_records = int(max_records)
-        self.records = zeros(self.max_records, L.NSCALARS, dtype=torch.float64)
+        # The scalar records live in PINNED HOST memory that the kernels write directly (unified addressing: the host
+        # pointer is valid on the device): a record needs no D2H copy and no stream synchronisation -- its last word is
+        # a stamp the host can poll (wait_record), so the loop with stop tests runs one iteration ahead of the host.
+        self.records = torch.zeros(self.max_records, L.NSCALARS, dtype=torch.float64).pin_memory()
+        self.rec_np = self.records.numpy()
+        self._stamp = 0
+        self._stamps = {}
         st.numraw, st.num, st.den = self.numraw.data_ptr(), self.num.data_ptr(), self.den.data_ptr()
         st.s_part, st.s_sum = self.s_part.data_ptr(), self.s_sum.data_ptr()
         # tile-major copy of H_next read by the W pass; pad pixels stay 1 (y > 0), pad rows are never read
@@ -335,6 +341,12 @@ class FitEngine:
         if not 0 <= slot < self.max_records:
             raise IndexError("scalar record slot %d out of range" % slot)
         self.st.scalars = self.records.data_ptr() + slot * L.NSCALARS * 8
+
+    def _stamp_next(self, slot):
+        """The coming espm_h_finish completes record ``slot``: give it a fresh stamp."""
+        self._stamp += 1
+        self.st.rec_stamp = float(self._stamp)
+        self._stamps[slot] = self._stamp
 
     def _call(self, fn, name=None):
         """Launch one C-ABI entry point on the current stream.  With ``self.profile`` set to a dict,
@@ -608,6 +620,7 @@ class FitEngine:
     def evaluate(self, slot):
         """Phase A on (W_cur, H_cur): fills scalar record ``slot`` (loss parts, rel_H, flags)."""
         self._set_record(slot)
+        self._stamp_next(slot)
         self._eval_slot = slot
         self._seq_m += 1
         self.st.seq_m = self._seq_m                          # mask exchange of this evaluation (peer mode)
@@ -696,11 +709,29 @@ class FitEngine:
 
     # ------------------------------------------------------------------ read-back
     def read_records(self, lo, hi):
-        """Synchronous D2H read of scalar records [lo, hi) -> float64 array (hi-lo, NSCALARS)."""
-        rec = self.records[lo:hi].cpu().numpy()
+        """Scalar records [lo, hi) -> float64 array (hi-lo, NSCALARS), after everything enqueued so far has run."""
+        torch.cuda.current_stream(self.device).synchronize()
+        rec = self.rec_np[lo:hi].copy()
         if self.shard is not None:
             rec = self.shard.combine_records(rec)
         return rec
+
+    def wait_record(self, slot, timeout=2.0):
+        """Record ``slot`` as soon as the espm_h_finish that completes it has stamped it -- WITHOUT synchronising the
+        stream, so kernels enqueued after that evaluation keep running while the host looks at the scalars."""
+        if self.shard is not None:
+            return self.read_records(slot, slot + 1)[0]
+        want = float(self._stamps[slot])
+        row = self.rec_np[slot]
+        import time
+        t0 = time.perf_counter()
+        while row[L.S_STAMP] != want:
+            if time.perf_counter() - t0 > timeout:
+                torch.cuda.current_stream(self.device).synchronize()     # surfaces a kernel fault, if that is the reason
+                if row[L.S_STAMP] != want:
+                    raise L.EspmError("scalar record %d was never completed (stamp %r, expected %r)"
+                                      % (slot, row[L.S_STAMP], want))
+        return row.copy()
 
     def loss_parts(self, rec, const_KL, numel):
         """(kl, log_reg, lapl) of base.py:203-205 + smooth_nmf.py:461-469 from one scalar record."""
@@ -764,6 +795,7 @@ class FitEngine:
             st.H_cur, st.hstats_cur = h_ptr, hstats_ptr
         st.flags = (st.flags & ~L.FLAG_HAVE_HPREV) | L.FLAG_EVAL_ONLY
         self._set_record(slot)
+        self._stamp_next(slot)
         if st.flags & L.FLAG_L2_H:
             L.check(self.lib.espm_gram(ctypes.byref(st), 0, self.stream))
         self._call(self.lib.espm_h_pass)
@@ -835,8 +867,8 @@ class FitEngine:
 
     def gw_flags_init(self):
         """ESPM_DEV_GW_* bits of the initial G W (one small D2H)."""
-        rec = self.records[self.max_records - 1].cpu().numpy()
-        return int(rec[L.S_GW_FLAGS])
+        torch.cuda.current_stream(self.device).synchronize()
+        return int(self.rec_np[self.max_records - 1][L.S_GW_FLAGS])
 
     def set_flag(self, flag, on=True):
         if on:

@@ -429,54 +429,95 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
         print("exits because max_iteration was reached")
 
     def _run_checked(self, eng, max_iter, algo_start):
-        """The reference's while-loop with its ordered stop tests (base.py:313-393)."""
+        """The reference's while-loop with its ordered stop tests (base.py:313-393).
+
+        The device runs ONE ITERATION AHEAD of the host: the scalar record of iterate t is written by the kernels into
+        pinned host memory and stamped (engine.wait_record), so the host enqueues iteration t+1 before it looks at
+        record t and the stream never drains between iterations.  When a stop test fires at t the speculative
+        iteration is undone (engine.rollback: every kernel writes only the `next` buffer set).  Anything that feeds
+        host results back into the next iteration -- physical-model G refresh, ground-truth tracking, the projected-
+        gradient line search -- or changes device state that rollback cannot restore (the gamma_ line search) runs
+        without speculation, as before."""
         eng.evaluate(0)
-        rec = eng.read_records(0, 1)[0]
+        rec = eng.wait_record(0)
         if int(rec[L.S_DEV_FLAGS]) & L.DEV_NONFINITE and not eng.clamped:
             eng.enable_clamp()
             eng.evaluate(0)
-            rec = eng.read_records(0, 1)[0]
+            rec = eng.wait_record(0)
         self._check_flags(rec)
         eval_init = self._loss_from_record(rec)                        # base.py:295
         self._eval_init = eval_init
         self._final_rec = rec
         eval_before = np.inf
+        speculate = (self.physics_model_ is None and not self._track and not self.linesearch and not eng.pg_ls)
+        ahead = False                      # is iteration n_iter_ + 1 already enqueued?
         while True:
             it = self.n_iter_ + 1
-            eng.advance(it)
-            if self._track:
-                self._track_truth(eng)
-            eng.evaluate(it)
-            rec = eng.read_records(it, it + 1)[0]
+            if not ahead:
+                eng.advance(it)
+                if self._track:
+                    self._track_truth(eng)
+                eng.evaluate(it)
+            ahead = speculate and it < max_iter
+            if ahead:                      # iteration it + 1, before the host has seen record `it`
+                eng.advance(it + 1)
+                eng.evaluate(it + 1)
+            rec = eng.wait_record(it)
             if int(rec[L.S_DEV_FLAGS]) & L.DEV_NONFINITE and not eng.clamped:
-                # x / 0 in this H pass: redo it like the reference's NaN fallback (updates.py:129-131)
+                # x / 0 in this iteration: redo it like the reference's NaN fallback (updates.py:129-131, 54-56) -- the
+                # W pass of advance(it) when the ratio sums of W were hit, then the H pass of evaluate(it)
+                if ahead:
+                    eng.rollback()
+                    ahead = False
                 rel_w = rec[L.S_REL_W]
                 eng.enable_clamp()
+                if not np.isfinite(rel_w):
+                    eng.rollback()
+                    eng.advance(it)
+                    rel_w = None
                 eng.evaluate(it)
-                rec = eng.read_records(it, it + 1)[0]
+                rec = eng.wait_record(it)
+                if rel_w is not None:
+                    rec[L.S_REL_W] = rel_w
+            gwf = int(rec[L.S_GW_FLAGS])
+            if gwf & L.DEV_GW_BELOW_LS and not (eng.st.flags & L.FLAG_LOSS_DUAL):
+                # an entry of G W fell below log_shift during the fit: from here on the loss clamps it separately
+                # (measures.py:493) while the updates do not
+                if ahead:
+                    eng.rollback()
+                    ahead = False
+                eng.set_flag(L.FLAG_LOSS_DUAL)
+                eng.evaluate(it)
+                rel_w = rec[L.S_REL_W]
+                rec = eng.wait_record(it)
                 rec[L.S_REL_W] = rel_w
             self._check_flags(rec)
             eval_after = self._append(rec)                             # base.py:320-351
             self.n_iter_ = it
             self._final_rec = rec
             rel_W, rel_H = rec[L.S_REL_W], rec[L.S_REL_H]
+            stop = False
             if self.n_iter_ >= max_iter:                               # base.py:354-378
                 print("exits because max_iteration was reached")
-                break
-            if not self.no_stop_criterion:
+                stop = True
+            elif not self.no_stop_criterion:
                 if max(rel_H, rel_W) < self.tol:
                     print("exits because of relative change rel_A {} and rel_P {} < tol ".format(rel_H, rel_W))
-                    break
+                    stop = True
                 elif abs((eval_before - eval_after) / eval_init) < self.tol:
                     print("exits because of relative change < tol: {}".format((eval_before - eval_after) / eval_init))
-                    break
+                    stop = True
                 elif np.isnan(eval_after):
                     print("exit because of the presence of NaN")
-                    break
+                    stop = True
                 elif (eval_before - eval_after) < 0:
                     print("exit because of negative decrease {}: {}, {}".format(
                         (eval_before - eval_after), eval_before, eval_after))
-                    break
+                    stop = True
+            if stop:
+                if ahead:
+                    eng.rollback()         # the iterate of the stop test is the result; drop the speculative one
+                break
             if self.verbose > 0 and np.mod(self.n_iter_, self.eval_print) == 0:
                 print(f"It {self.n_iter_} / {max_iter}: loss {eval_after:3e},  "
                       f"{self.n_iter_ / (time.time() - algo_start + _LOG_SHIFT):0.3f} it/s")

@@ -111,7 +111,10 @@ enum {
     ESPM_S_MEAN_W = 10,
     ESPM_S_GW_FLAGS = 11, /* ESPM_DEV_GW_* bits of the GW produced for the NEXT H pass */
     ESPM_S_GAMMA = 12,    /* line search: gamma_ after this iteration's update (smooth_nmf.py:378-382) */
-    ESPM_S_LS_D = 13      /* line search: diff_surrogate(H_old, H_new) (surrogates.py:116-149) */
+    ESPM_S_LS_D = 13,     /* line search: diff_surrogate(H_old, H_new) (surrogates.py:116-149) */
+    ESPM_S_STAMP = 23     /* espm_state.rec_stamp of the espm_h_finish that completed this record: written LAST, after a
+                           * system-scope fence, so a host that sees the stamp in (pinned, device-mapped) memory sees
+                           * the whole record without synchronising the stream */
 };
 
 /*
@@ -197,7 +200,8 @@ typedef struct espm_state {
     uint32_t* dev_flags;    /* 8 words: [0] sticky ESPM_DEV_* error bits, [1] ESPM_DEV_GW_* of GW_next,
                              * [2] h_finish completion ticket, [3] grid-barrier counter of w_finish (start at 0),
                              * [4] w_finish completion ticket, [5] w_finish "pushed" ticket (peer exchange) */
-    double* scalars;        /* ESPM_NSCALARS doubles: the record being filled */
+    double* scalars;        /* ESPM_NSCALARS doubles: the record being filled.  Only ever WRITTEN by the kernels: it may
+                             * live in pinned host memory (the host then polls ESPM_S_STAMP instead of synchronising) */
     double* coop_part;      /* ESPM_COOP_BLOCKS x (2*ESPM_MAX_K + 4) doubles: per-CTA partials of w_finish */
     /* ---- ESPM_FLAG_PEER: exchange between the pixel shards through CUDA-IPC peer memory over NVLink ----
      * No host-launched collective sits on the per-iteration path: the kernels signal and wait on flag words
@@ -241,6 +245,7 @@ typedef struct espm_state {
     double* sigma_dev;      /* line search: device-resident gamma_ read by espm_h_finish / espm_h_apply and updated by
                              * espm_linesearch; NULL: the kernels use `sigma` */
     double* ls_part;        /* px_blocks x (4 + kp) partial sums of espm_linesearch */
+    double rec_stamp;       /* value espm_h_finish leaves in ESPM_S_STAMP of the record it completes (> 0, increasing) */
 } espm_state;
 
 /* library / device */
