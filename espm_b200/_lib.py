@@ -87,6 +87,17 @@ class EspmState(ctypes.Structure):
         ("gamma_h", _f64), ("gamma_w", _f64), ("x_total", _f64),
         ("x_colsum", _vp), ("x_rowsum", _vp), ("GG", _vp), ("gram_gw", _vp), ("gram_h", _vp), ("sigma_dev", _vp),
         ("ls_part", _vp), ("rec_stamp", _f64),
+        ("peer_rec", _vp * MAX_RANKS), ("rec_slot", _i32), ("rec_cap", _i32),
+    ]
+
+
+class EspmLoop(ctypes.Structure):
+    """Mirror of ``struct espm_loop`` (espm_run_iterations)."""
+    _fields_ = [
+        ("H", _vp * 3), ("W", _vp * 2), ("GW", _vp * 2), ("GWc", _vp * 2), ("gwstats", _vp * 2), ("hstats", _vp * 2),
+        ("nb_prev_halo", _vp * 3), ("nb_next_halo", _vp * 3), ("records", _vp), ("ev", _vp),
+        ("ih", _i32 * 3), ("iw", _i32 * 2), ("ihs", _i32 * 2), ("have_prev", _i32),
+        ("seq_s", _u32), ("seq_m", _u32), ("stamp", _f64), ("launches", _i64),
     ]
 
 
@@ -128,11 +139,14 @@ _EXPORTS = {
     "espm_w_pass": (ctypes.c_int, [ctypes.POINTER(EspmState), _vp]),
     "espm_w_reduce": (ctypes.c_int, [ctypes.POINTER(EspmState), _vp]),
     "espm_w_finish": (ctypes.c_int, [ctypes.POINTER(EspmState), _vp]),
+    "espm_run_iterations": (ctypes.c_int, [ctypes.POINTER(EspmState), ctypes.POINTER(EspmLoop), _i32, _i32, _vp]),
     "espm_peer_alloc": (ctypes.c_int, [_i64, ctypes.POINTER(_vp)]),
     "espm_peer_export": (ctypes.c_int, [_vp, ctypes.c_char_p]),
     "espm_peer_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(_vp)]),
     "espm_peer_close": (ctypes.c_int, [_vp]),
     "espm_peer_free": (ctypes.c_int, [_vp]),
+    "espm_host_register": (ctypes.c_int, [_vp, _i64, ctypes.POINTER(_vp)]),
+    "espm_host_unregister": (ctypes.c_int, [_vp]),
     "espm_dichotomy_simplex": (ctypes.c_int, [_i32, _i32, _i64, _vp, _vp, _f64, _f64, _i32, _vp, _vp, _vp, _vp, _vp]),
     "espm_gram": (ctypes.c_int, [ctypes.POINTER(EspmState), _i32, _vp]),
     "espm_x_sums": (ctypes.c_int, [ctypes.POINTER(EspmState), _vp, _vp, _vp]),

@@ -434,6 +434,86 @@ int espm_w_pass(const espm_state* st, void* stream) {
     return pick_xpass(st)(l, &a, nullptr, (cudaStream_t)stream);
 }
 
+static void loop_bind(espm_state* st, const espm_loop* lp) {
+    const int hp = lp->ih[0], hc = lp->ih[1], hn = lp->ih[2];
+    const int wc = lp->iw[0], wn = lp->iw[1], sc = lp->ihs[0], sn = lp->ihs[1];
+    st->H_prev = lp->H[hp];
+    st->H_cur = lp->H[hc];
+    st->H_next = lp->H[hn];
+    st->W_cur = lp->W[wc];
+    st->W_next = lp->W[wn];
+    st->GW_cur = lp->GW[wc];
+    st->GW_next = lp->GW[wn];
+    st->GWc_cur = lp->GWc[wc];
+    st->GWc_next = lp->GWc[wn];
+    st->gwstats_cur = lp->gwstats[wc];
+    st->gwstats_next = lp->gwstats[wn];
+    st->hstats_cur = lp->hstats[sc];
+    st->hstats_next = lp->hstats[sn];
+    if (lp->have_prev) st->flags |= ESPM_FLAG_HAVE_HPREV;
+    else st->flags &= ~ESPM_FLAG_HAVE_HPREV;
+    if (st->flags & ESPM_FLAG_PEER) {
+        st->nb_prev_halo = lp->nb_prev_halo[hn];
+        st->nb_next_halo = lp->nb_next_halo[hn];
+    }
+}
+
+int espm_run_iterations(espm_state* st, espm_loop* lp, int32_t first_slot, int32_t n_iters, void* stream) {
+    int rc = check_state(st);
+    if (rc) return rc;
+    if (!lp || !lp->records || n_iters < 0 || first_slot < 0) {
+        set_error("espm_run_iterations: bad arguments");
+        return ESPM_ERR_BAD_ARG;
+    }
+    if (st->flags & (ESPM_FLAG_L2 | ESPM_FLAG_L2_H | ESPM_FLAG_LINESEARCH | ESPM_FLAG_EVAL_ONLY)) {
+        set_error("espm_run_iterations: this fit needs host work between the launches (Gram matrices / line search)");
+        return ESPM_ERR_UNSUPPORTED;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    lp->launches = 0;
+    loop_bind(st, lp);
+    for (int32_t it = first_slot; it < first_slot + n_iters; ++it) {
+        void* const* ev = lp->ev ? lp->ev + (size_t)(it - first_slot) * 4 : nullptr;
+        // ---- advance: (W_cur, H_cur) -> (W_next, H_next), rel_W etc. to record `it`
+        st->scalars = lp->records + (size_t)it * ESPM_NSCALARS;
+        st->rec_slot = it;
+        if (st->flags & ESPM_FLAG_SIMPLEX_H) {
+            if ((rc = espm_h_apply(st, stream))) return rc;
+            ++lp->launches;
+        }
+        st->seq_s = ++lp->seq_s;
+        if (ev) ESPM_CUDA_CHECK(cudaEventRecord((cudaEvent_t)ev[0], s));
+        if ((rc = espm_w_pass(st, stream))) return rc;
+        if (ev) ESPM_CUDA_CHECK(cudaEventRecord((cudaEvent_t)ev[1], s));
+        if ((rc = espm_w_finish(st, stream))) return rc;
+        lp->launches += 2;
+        {   // rotate: next -> cur
+            const int hp = lp->ih[0], hc = lp->ih[1], hn = lp->ih[2];
+            lp->ih[0] = hc;
+            lp->ih[1] = hn;
+            lp->ih[2] = hp;
+            const int w0 = lp->iw[0];
+            lp->iw[0] = lp->iw[1];
+            lp->iw[1] = w0;
+            const int s0 = lp->ihs[0];
+            lp->ihs[0] = lp->ihs[1];
+            lp->ihs[1] = s0;
+            lp->have_prev = 1;
+            loop_bind(st, lp);
+        }
+        // ---- evaluate the new iterate: completes and stamps record `it`
+        lp->stamp += 1.0;
+        st->rec_stamp = lp->stamp;
+        st->seq_m = ++lp->seq_m;
+        if (ev) ESPM_CUDA_CHECK(cudaEventRecord((cudaEvent_t)ev[2], s));
+        if ((rc = espm_h_pass(st, stream))) return rc;
+        if (ev) ESPM_CUDA_CHECK(cudaEventRecord((cudaEvent_t)ev[3], s));
+        if ((rc = espm_h_finish(st, stream))) return rc;
+        lp->launches += 2;
+    }
+    return ESPM_OK;
+}
+
 int espm_peer_alloc(int64_t bytes, void** ptr_out) {
     if (!ptr_out || bytes <= 0) {
         set_error("espm_peer_alloc: bad arguments");
@@ -475,6 +555,24 @@ int espm_peer_close(void* ptr) {
 int espm_peer_free(void* ptr) {
     if (!ptr) return ESPM_OK;
     ESPM_CUDA_CHECK(cudaFree(ptr));
+    return ESPM_OK;
+}
+
+int espm_host_register(void* ptr, int64_t bytes, void** dev_ptr_out) {
+    if (!ptr || bytes <= 0 || !dev_ptr_out) {
+        set_error("espm_host_register: bad arguments");
+        return ESPM_ERR_BAD_ARG;
+    }
+    ESPM_CUDA_CHECK(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+    void* d = nullptr;
+    ESPM_CUDA_CHECK(cudaHostGetDevicePointer(&d, ptr, 0));
+    *dev_ptr_out = d;
+    return ESPM_OK;
+}
+
+int espm_host_unregister(void* ptr) {
+    if (!ptr) return ESPM_OK;
+    ESPM_CUDA_CHECK(cudaHostUnregister(ptr));
     return ESPM_OK;
 }
 

@@ -725,7 +725,7 @@ __device__ __forceinline__ void store_h_next(const espm_state& st, int j, int k,
 }
 
 template <typename TC>
-__device__ __forceinline__ void h_scalars_block(const espm_state& st);
+__device__ __forceinline__ void h_scalars_block(const espm_state& st, double* pub = nullptr);
 
 // ------------------------------------------------------------------------------------------------
 // h_finish: per-pixel assembly (updates.py:132-152) + loss regularisers + rel_H + bisection trace
@@ -980,8 +980,23 @@ __global__ void __launch_bounds__(PX_THREADS, 4) h_finish_kernel(const espm_stat
     __syncthreads();
     if (is_last) {
         __threadfence();
-        h_scalars_block<TC>(st);
+        __shared__ double pub[5];
+        h_scalars_block<TC>(st, pub);
         if (threadIdx.x == 0) st.dev_flags[2] = 0u;
+        if ((st.flags & ESPM_FLAG_PEER) && st.rec_cap > 0) {
+            // Pixel-sharded fit: the loss sums, rel_H and the error word of a record are per-shard quantities.  Every
+            // rank stores its share into slot [rank][rec_slot] of EVERY rank's record inbox -- pinned host memory of
+            // that rank's process, mapped into this one -- and stamps it; each host folds the `world` shares in rank
+            // order once all stamps are there.  No collective, no device-side wait.
+            __syncthreads();
+            if ((int)threadIdx.x < st.world && st.peer_rec[threadIdx.x]) {
+                double* dst = st.peer_rec[threadIdx.x] + ((size_t)st.rank * st.rec_cap + st.rec_slot) * 8;
+#pragma unroll
+                for (int i = 0; i < 5; ++i) dst[i] = pub[i];
+                __threadfence_system();
+                *reinterpret_cast<volatile double*>(dst + 7) = st.rec_stamp;
+            }
+        }
         if ((st.flags & ESPM_FLAG_PEER) && simplex && (int)threadIdx.x < st.world) {
             // publish this rank's complete trace mask on every rank (its own included), then raise the flag
             uint32_t* pf = st.peer_flags[threadIdx.x];
@@ -1150,8 +1165,10 @@ __global__ void __launch_bounds__(256) hstats_reduce_kernel(const espm_state st)
 // ------------------------------------------------------------------------------------------------
 // h_scalars: loss parts of the current iterate + rel_H + bisection count into the scalar record
 // ------------------------------------------------------------------------------------------------
+// `pub` (shared memory, 5 doubles, optional): this rank's share of the additive / max / OR fields, for the push to the
+// other ranks' record inboxes (pixel-sharded fits).
 template <typename TC>
-__device__ __forceinline__ void h_scalars_block(const espm_state& st) {
+__device__ __forceinline__ void h_scalars_block(const espm_state& st, double* pub) {
     __shared__ double sm[8][4];
     const int kp = st.kp, stride = px_part_stride(kp);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1198,6 +1215,13 @@ __device__ __forceinline__ void h_scalars_block(const espm_state& st) {
             (st.flags & ESPM_FLAG_SIMPLEX_H) ? (double)first_clear_bit(st.bisect_mask, st.maxit) : 0.0;
         rec[ESPM_S_DEV_FLAGS] = (double)st.dev_flags[0];
         rec[ESPM_S_MEAN_H] = meanh / ((double)st.k * (double)st.p_total);
+        if (pub) {
+            pub[0] = xl;
+            pub[1] = lr;
+            pub[2] = lp;
+            pub[3] = rh;
+            pub[4] = (double)st.dev_flags[0];
+        }
         // the record is complete (rel_W etc. were written by earlier kernels of the stream): stamp it
         __threadfence_system();
         *reinterpret_cast<volatile double*>(rec + ESPM_S_STAMP) = st.rec_stamp;

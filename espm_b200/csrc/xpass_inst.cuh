@@ -30,7 +30,24 @@ static int xpass_do(const XPassLaunch& l, const XPassArgs* a, int* occ_out, cuda
         set_error("the Frobenius X passes have no clamped (SAFE) instances");
         return ESPM_ERR_UNSUPPORTED;
     }
-    ESPM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, l.smem));
+    {
+        // the opt-in shared-memory size is a per-function attribute: set it when it changes, not on every launch
+        // (slot = kernel of this instantiation; one device per process is the rule, but the device is checked)
+        static int last_smem[8], last_dev[8];
+        static bool init = false;
+        if (!init) {
+            for (int i = 0; i < 8; ++i) last_smem[i] = last_dev[i] = -1;
+            init = true;
+        }
+        const int slot = (l.kind == XPASS_H ? 0 : 4) + (l.mode & 3);
+        int dev = 0;
+        ESPM_CUDA_CHECK(cudaGetDevice(&dev));
+        if (last_smem[slot] != l.smem || last_dev[slot] != dev) {
+            ESPM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, l.smem));
+            last_smem[slot] = l.smem;
+            last_dev[slot] = dev;
+        }
+    }
     if (occ_out) {
         ESPM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ_out, kern, XPASS_THREADS, l.smem));
         return ESPM_OK;

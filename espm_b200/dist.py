@@ -192,6 +192,85 @@ def release_peer_memory(group=None):
     if _REGION is not None and _REGION.region is not None:
         _REGION.free(_REGION.group)
     _REGION = None
+    release_record_inbox()
+
+
+# Record inboxes of the sharded fit (see espm_state.peer_rec): one POSIX shared-memory segment per rank, opened by every
+# process of the box and page-locked / device-mapped in each (espm_host_register), so that every GPU can store its share
+# of a scalar record straight into every host's memory.  Cached across fits like the peer region.
+_INBOX = None
+_INBOX_SEQ = 0
+
+
+class _RecordInbox:
+    WORDS = 8          # doubles per share: sum X log Y, log-reg, Laplacian, rel_H, device flags, -, -, stamp
+
+    def __init__(self, shard, cap):
+        import ctypes
+        import mmap
+        import os
+        global _INBOX_SEQ
+        self.world, self.rank, self.cap, self.group = shard.world, shard.rank, int(cap), shard.group
+        self.nbytes = self.world * self.cap * self.WORDS * 8
+        self.lib = L.load()
+        self.stamp = 0                     # record stamps continue across fits: a stale share never matches
+        _INBOX_SEQ += 1
+        path = "/dev/shm/espm_b200_inbox_%d_%d_%d" % (os.getpid(), self.rank, _INBOX_SEQ)
+        self.maps, self.dev_ptrs, self.registered = [], [], []
+        ok = True
+        try:
+            fd = os.open(path, os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
+            os.ftruncate(fd, self.nbytes)            # zero-filled
+            os.close(fd)
+        except OSError:
+            ok, path = False, None
+        paths = [None] * self.world
+        dist.all_gather_object(paths, path, group=self.group)
+        ok = ok and all(q is not None for q in paths)
+        if ok:
+            try:
+                for q in paths:
+                    fd = os.open(q, os.O_RDWR)
+                    m = mmap.mmap(fd, self.nbytes)
+                    os.close(fd)
+                    self.maps.append(m)
+                    arr = np.frombuffer(m, dtype=np.float64)
+                    d = ctypes.c_void_p()
+                    L.check(self.lib.espm_host_register(ctypes.c_void_p(arr.ctypes.data), self.nbytes, ctypes.byref(d)))
+                    self.registered.append(arr.ctypes.data)
+                    self.dev_ptrs.append(d.value)
+            except (OSError, L.EspmError, ValueError):
+                ok = False
+        oks = [None] * self.world
+        dist.all_gather_object(oks, ok, group=self.group)      # also: everybody has opened every segment
+        if path is not None:
+            try:
+                os.unlink(path)                      # the mappings keep the memory alive; nothing is left behind
+            except OSError:
+                pass
+        self.ok = all(oks)
+        if self.ok:
+            self.mine = np.frombuffer(self.maps[self.rank], dtype=np.float64).reshape(self.world, self.cap, self.WORDS)
+        else:
+            self.free()
+
+    def free(self):
+        import ctypes
+        for ptr in self.registered:
+            self.lib.espm_host_unregister(ctypes.c_void_p(ptr))
+        self.registered, self.dev_ptrs = [], []
+        self.mine = None
+        self.maps = []                     # (the mmap objects are closed by the garbage collector once unreferenced)
+
+
+def release_record_inbox():
+    """Collective: unmap the cached record inboxes."""
+    global _INBOX
+    if _INBOX is not None and _INBOX.ok:
+        torch.cuda.synchronize()
+        dist.barrier(group=_INBOX.group)
+        _INBOX.free()
+    _INBOX = None
 
 
 class PeerShard(Shard):
@@ -308,6 +387,27 @@ class PeerShard(Shard):
     @property
     def seq(self):
         return self.reg.seq_s, self.reg.seq_m
+
+    def setup_inbox(self, eng, n_slots):
+        """Record inboxes for ``n_slots`` record slots (cached; grown collectively when a fit needs more).  Returns the
+        inbox, or None when shared memory / host registration is not available on some rank (the records are then
+        gathered with a collective at read-back, as with the NCCL exchange)."""
+        global _INBOX
+        box = _INBOX
+        if box is not None and (not box.ok or box.cap < n_slots or box.world != self.world or box.rank != self.rank
+                                or box.group is not self.group):
+            release_record_inbox()
+            box = None
+        if box is None:
+            box = _RecordInbox(self, max(int(n_slots), 1024))
+            _INBOX = box
+        if not box.ok:
+            return None
+        st = eng.st
+        for r in range(self.world):
+            st.peer_rec[r] = box.dev_ptrs[r]
+        st.rec_cap = box.cap
+        return box
 
     def halo_targets(self, eng, ibuf):
         """(prev pointer, prev ldh, next pointer, next ldh) for pushing the boundary rows of H buffer ``ibuf``."""

@@ -212,6 +212,7 @@ class FitEngine:
                 self.peer = False
             else:
                 self._seq_s, self._seq_m = shard.seq  # the flag words persist across fits: keep counting
+        self.inbox = None
         if not self.peer:
             self.Hbuf = [torch.ones(k, ldh, dtype=cdt, device=dev) for _ in range(3)]
         self.Wbuf = [zeros(self.m, k) for _ in range(2)]
@@ -263,6 +264,11 @@ class FitEngine:
         self.rec_np = self.records.numpy()
         self._stamp = 0
         self._stamps = {}
+        if self.peer:
+            # sharded: every rank's share of a record lands in every host's inbox (dist._RecordInbox)
+            self.inbox = shard.setup_inbox(self, self.max_records)
+            if self.inbox is not None:
+                self._stamp = self.inbox.stamp
         st.numraw, st.num, st.den = self.numraw.data_ptr(), self.num.data_ptr(), self.den.data_ptr()
         st.s_part, st.s_sum = self.s_part.data_ptr(), self.s_sum.data_ptr()
         # tile-major copy of H_next read by the W pass; pad pixels stay 1 (y > 0), pad rows are never read
@@ -341,6 +347,7 @@ class FitEngine:
         if not 0 <= slot < self.max_records:
             raise IndexError("scalar record slot %d out of range" % slot)
         self.st.scalars = self.records.data_ptr() + slot * L.NSCALARS * 8
+        self.st.rec_slot = slot
 
     def _stamp_next(self, slot):
         """The coming espm_h_finish completes record ``slot``: give it a fresh stamp."""
@@ -605,6 +612,8 @@ class FitEngine:
         """Release peer memory (collective when sharded through peer memory); the engine is unusable after."""
         if self.peer and self.shard is not None:
             self.Hbuf = None
+            if self.inbox is not None:
+                self.inbox.stamp = self._stamp
             self.shard.close(self._seq_s, self._seq_m)
             self.peer = False
 
@@ -665,6 +674,55 @@ class FitEngine:
         self.have_prev = True
         self._bind()
 
+    # ------------------------------------------------------------------ the loop in native code
+    @property
+    def fast_loop(self):
+        """Can ``run_iterations`` be used?  Not when an iteration needs host work between its launches."""
+        st = self.st
+        return (not (st.flags & (L.FLAG_L2 | L.FLAG_L2_H | L.FLAG_LINESEARCH)) and not self.pg_ls
+                and (self.shard is None or self.peer) and self.profile is None)
+
+    def run_iterations(self, first, n, events=None):
+        """``for it in range(first, first + n): advance(it); evaluate(it)`` issued by ONE call into the library
+        (espm_run_iterations): the Python binding costs ~10 us per launch, more than the kernels of a small pixel shard
+        take.  ``events``: optional list of n 4-tuples of recorded-once torch.cuda.Event (w_pass start / end, h_pass
+        start / end) the native loop records around the two X passes."""
+        if n <= 0:
+            return
+        if first < 0 or first + n > self.max_records:
+            raise IndexError("scalar record slots %d..%d out of range" % (first, first + n - 1))
+        lp = L.EspmLoop()
+        sz = self.Hbuf[0].element_size()
+        for i in range(3):
+            lp.H[i] = self._hptr(i)
+            if self.peer:
+                pp, _, npn, _ = self.shard.halo_targets(self, i)
+                lp.nb_prev_halo[i], lp.nb_next_halo[i] = pp, npn
+        for i in range(2):
+            lp.W[i], lp.GW[i], lp.GWc[i] = self.Wbuf[i].data_ptr(), self.GWbuf[i].data_ptr(), self.GWcbuf[i].data_ptr()
+            lp.gwstats[i], lp.hstats[i] = self.gwstats[i].data_ptr(), self.hstats[i].data_ptr()
+        lp.records = self.records.data_ptr()
+        ev_arr = None
+        if events is not None:
+            ev_arr = (ctypes.c_void_p * (4 * n))(*[e.cuda_event for tup in events for e in tup])
+            lp.ev = ctypes.cast(ev_arr, ctypes.c_void_p)
+        for i in range(3):
+            lp.ih[i] = self.ih[i]
+        for i in range(2):
+            lp.iw[i], lp.ihs[i] = self.iw[i], self.ihs[i]
+        lp.have_prev = 1 if self.have_prev else 0
+        lp.seq_s, lp.seq_m, lp.stamp = self._seq_s, self._seq_m, float(self._stamp)
+        L.check(self.lib.espm_run_iterations(ctypes.byref(self.st), ctypes.byref(lp), first, n, self.stream))
+        self.ih, self.iw, self.ihs = list(lp.ih), list(lp.iw), list(lp.ihs)
+        self.have_prev = bool(lp.have_prev)
+        self._seq_s, self._seq_m = int(lp.seq_s), int(lp.seq_m)
+        for i in range(n):
+            self._stamps[first + i] = self._stamp + 1 + i
+        self._stamp = int(lp.stamp)
+        self._eval_slot = first + n - 1
+        self.n_launches += int(lp.launches)
+        del sz
+
     # ------------------------------------------------------------------ single steps (operator API)
     def step_h_only(self):
         """One H update from (W_cur, H_cur): returns (H_next local, scalar record)."""
@@ -711,14 +769,50 @@ class FitEngine:
     def read_records(self, lo, hi):
         """Scalar records [lo, hi) -> float64 array (hi-lo, NSCALARS), after everything enqueued so far has run."""
         torch.cuda.current_stream(self.device).synchronize()
+        if self.inbox is not None:
+            return np.stack([self._fold_record(slot, 10.0) for slot in range(lo, hi)])
         rec = self.rec_np[lo:hi].copy()
         if self.shard is not None:
             rec = self.shard.combine_records(rec)
         return rec
 
+    def _fold_record(self, slot, timeout):
+        """Sharded fit: record ``slot`` with the per-shard fields folded over the ranks' shares in this host's inbox
+        (sums in rank order, max, OR: identical on every rank).  Waits for the stamps of the evaluation that completes
+        the slot -- the local one and every rank's share -- without touching the stream."""
+        import time
+        row = self.rec_np[slot]
+        want = self._stamps.get(slot)
+        if want is None:                       # never evaluated (e.g. a W-only step): nothing to fold
+            return row.copy()
+        want = float(want)
+        shares = self.inbox.mine[:, slot, :]
+        t0 = time.perf_counter()
+        while row[L.S_STAMP] != want or not np.all(shares[:, 7] == want):
+            if time.perf_counter() - t0 > timeout:
+                torch.cuda.current_stream(self.device).synchronize()
+                if row[L.S_STAMP] != want or not np.all(shares[:, 7] == want):
+                    raise L.EspmError("scalar record %d was never completed by every rank (stamps %r / %r, expected %r)"
+                                      % (slot, row[L.S_STAMP], shares[:, 7].tolist(), want))
+        out = row.copy()
+        sh = shares.copy()
+        for col, s in ((0, L.S_XLOGY), (1, L.S_LOGREG), (2, L.S_LAPL)):
+            acc = 0.0
+            for r in range(sh.shape[0]):
+                acc += float(sh[r, col])
+            out[s] = acc
+        out[L.S_REL_H] = float(sh[:, 3].max())
+        flags = 0
+        for v in sh[:, 4]:
+            flags |= int(v)
+        out[L.S_DEV_FLAGS] = float(flags)
+        return out
+
     def wait_record(self, slot, timeout=2.0):
         """Record ``slot`` as soon as the espm_h_finish that completes it has stamped it -- WITHOUT synchronising the
         stream, so kernels enqueued after that evaluation keep running while the host looks at the scalars."""
+        if self.inbox is not None:
+            return self._fold_record(slot, timeout)
         if self.shard is not None:
             return self.read_records(slot, slot + 1)[0]
         want = float(self._stamps[slot])

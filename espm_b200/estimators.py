@@ -411,9 +411,12 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
     def _run_batch(self, eng, max_iter):
         """no_stop_criterion and nothing to print: enqueue every iteration, read the scalars once."""
         eng.evaluate(0)
-        for it in range(1, max_iter + 1):
-            eng.advance(it)
-            eng.evaluate(it)
+        if eng.fast_loop:
+            eng.run_iterations(1, max_iter)          # one call: the launches of every iteration are issued natively
+        else:
+            for it in range(1, max_iter + 1):
+                eng.advance(it)
+                eng.evaluate(it)
         recs = eng.read_records(0, max_iter + 1)
         if not eng.clamped and any(int(r[L.S_DEV_FLAGS]) & L.DEV_NONFINITE for r in recs):
             # x / 0 appeared mid-fit (a row of G W became zero): the reference then clamps GWH
@@ -451,17 +454,24 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
         eval_before = np.inf
         speculate = (self.physics_model_ is None and not self._track and not self.linesearch and not eng.pg_ls)
         ahead = False                      # is iteration n_iter_ + 1 already enqueued?
+        native = eng.fast_loop and not self._track
+
+        def step(i):
+            if native:
+                eng.run_iterations(i, 1)
+            else:
+                eng.advance(i)
+                if self._track:
+                    self._track_truth(eng)
+                eng.evaluate(i)
+
         while True:
             it = self.n_iter_ + 1
             if not ahead:
-                eng.advance(it)
-                if self._track:
-                    self._track_truth(eng)
-                eng.evaluate(it)
+                step(it)
             ahead = speculate and it < max_iter
             if ahead:                      # iteration it + 1, before the host has seen record `it`
-                eng.advance(it + 1)
-                eng.evaluate(it + 1)
+                step(it + 1)
             rec = eng.wait_record(it)
             if int(rec[L.S_DEV_FLAGS]) & L.DEV_NONFINITE and not eng.clamped:
                 # x / 0 in this iteration: redo it like the reference's NaN fallback (updates.py:129-131, 54-56) -- the

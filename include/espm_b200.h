@@ -246,6 +246,13 @@ typedef struct espm_state {
                              * espm_linesearch; NULL: the kernels use `sigma` */
     double* ls_part;        /* px_blocks x (4 + kp) partial sums of espm_linesearch */
     double rec_stamp;       /* value espm_h_finish leaves in ESPM_S_STAMP of the record it completes (> 0, increasing) */
+    /* ---- ESPM_FLAG_PEER: record inboxes.  peer_rec[r] = rank r's inbox (pinned host memory of r's process, mapped into
+     * this one with espm_host_register): [world][rec_cap][8] doubles.  espm_h_finish stores this rank's share
+     * {sum X log Y, log-reg, Laplacian, rel_H, device flags, -, -, stamp} of record `rec_slot` into [rank][rec_slot] of
+     * every inbox; the hosts fold the shares.  rec_cap == 0: no inboxes (the caller gathers the records itself). */
+    double* peer_rec[ESPM_MAX_RANKS];
+    int32_t rec_slot;
+    int32_t rec_cap;
 } espm_state;
 
 /* library / device */
@@ -348,6 +355,39 @@ int espm_w_reduce(const espm_state* st, void* stream);
  * cooperative kernel of ESPM_COOP_BLOCKS CTAs. */
 int espm_w_finish(const espm_state* st, void* stream);
 
+/*
+ * The iteration loop in native code.  One SmoothNMF iteration is five launches (espm_h_apply, espm_w_pass,
+ * espm_w_finish, then espm_h_pass, espm_h_finish for the new iterate) plus the rotation of the `prev / cur / next`
+ * buffer sets; issued one by one through a Python binding that costs more host time than the kernels take on a
+ * small pixel shard.  espm_run_iterations does the launches and the rotation for `n_iters` iterations in one call:
+ *   for it = first_slot .. first_slot + n_iters - 1:
+ *       advance:  record `it` <- rel_W ...; [h_apply]; w_pass; w_finish; rotate          (base.py:316-318)
+ *       evaluate: h_pass; h_finish -> record `it` completed and stamped                   (base.py:320-324)
+ * `st` is left bound to the last iterate, `lp` carries the buffer sets and the counters (in / out).  Only for fits
+ * whose iteration needs nothing from the host in between (no NCCL exchange, no Gram matrices, no line search).
+ */
+typedef struct espm_loop {
+    void* H[3];              /* the three H buffers (pointers to local pixel 0) */
+    void* W[2];
+    void* GW[2];
+    void* GWc[2];
+    void* gwstats[2];
+    void* hstats[2];
+    void* nb_prev_halo[3];   /* ESPM_FLAG_PEER: halo targets in the neighbours' copy of H buffer i, or NULL */
+    void* nb_next_halo[3];
+    double* records;         /* base of the scalar records (ESPM_NSCALARS doubles per slot) */
+    void* const* ev;         /* optional: 4 cudaEvent_t per iteration, recorded before / after h_pass and w_pass
+                              * ({w0, w1, h0, h1}); NULL: none */
+    int32_t ih[3];           /* indices of the (prev, cur, next) H buffers            in / out */
+    int32_t iw[2];           /* (cur, next) of W / GW / GWc / gwstats                 in / out */
+    int32_t ihs[2];          /* (cur, next) of hstats                                 in / out */
+    int32_t have_prev;       /* H_prev is valid                                       in / out */
+    uint32_t seq_s, seq_m;   /* exchange sequence numbers                             in / out */
+    double stamp;            /* last record stamp handed out                          in / out */
+    int64_t launches;        /* kernels launched by the call                          out */
+} espm_loop;
+int espm_run_iterations(espm_state* st, espm_loop* lp, int32_t first_slot, int32_t n_iters, void* stream);
+
 /* Peer memory for ESPM_FLAG_PEER: cudaMalloc'ed (zero-filled) regions that other processes of the same
  * box map through CUDA IPC.  handle64 is the 64-byte cudaIpcMemHandle_t. */
 int espm_peer_alloc(int64_t bytes, void** ptr_out);
@@ -355,6 +395,10 @@ int espm_peer_export(void* ptr, unsigned char* handle64);
 int espm_peer_open(const unsigned char* handle64, void** ptr_out);
 int espm_peer_close(void* ptr);
 int espm_peer_free(void* ptr);
+/* Page-lock `bytes` of host memory at `ptr` (e.g. a POSIX shared-memory mapping every process of the box has opened) and
+ * map it into the device address space; *dev_ptr_out is the address kernels use.  espm_host_unregister undoes it. */
+int espm_host_register(void* ptr, int64_t bytes, void** dev_ptr_out);
+int espm_host_unregister(void* ptr);
 
 /* Standalone operator used by the unit-level API: nu = dichotomy_simplex(num, den) (dicotomy.py:4-55).
  * num/den: k x p (c dtype, row stride p), nu_out: p.  its_out (device int32) receives it*. */
