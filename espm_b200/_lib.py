@@ -38,6 +38,7 @@ FLAG_L2 = 1 << 16
 FLAG_L2_H = 1 << 17
 FLAG_LINESEARCH = 1 << 18
 FLAG_EVAL_ONLY = 1 << 19
+FLAG_LS_PARTIAL = 1 << 20
 COOP_BLOCKS = 32
 
 # device error word
@@ -47,6 +48,7 @@ DEV_NEGATIVE = 1 << 2
 DEV_GW_BELOW_LS = 1 << 3
 DEV_GW_ZERO_ROW = 1 << 4
 DEV_PEER_TIMEOUT = 1 << 5
+DEV_NONFINITE_W = 1 << 6
 
 # scalar record slots
 S_XLOGY, S_SUMY, S_LOGREG, S_LAPL, S_REL_H, S_REL_W, S_BISECT_ITS_H, S_BISECT_ITS_W, S_DEV_FLAGS, \

@@ -458,16 +458,19 @@ __device__ __forceinline__ End end_of(const KlEval<KP>& ev, double x) {
 template <int KP>
 struct KlAnchorEval {
     KlEval<KP> base;
-    double nu, D, F2, tmin, mx, chord, tol;
-    bool ok, sized;
+    double nu, mx, tol;
+    double eLlo, eLhi, eRlo, eRhi;     // |x - nu*| below / above which |f(x)| <= tol / > tol is certain, per side
+    bool ok;
     // `warm`: a guess of the root (the pixel's root of the previous NMF iteration) or NaN.  From any point of the domain
     // the iteration is safe: right of the root the tangent of the concave g lands left of it, from there on the
     // iterates increase monotonically.
     __device__ __forceinline__ KlAnchorEval(const double (&num)[KP], const double (&den)[KP], int k, double ls, double tol_,
                                             double a0, double b0, double warm)
         : base(num, den, k, ls, tol_), tol(tol_) {
-        ok = sized = false;
-        nu = D = F2 = tmin = mx = chord = 0.0;
+        ok = false;
+        nu = mx = 0.0;
+        eLlo = eRlo = 0.0;
+        eLhi = eRhi = Num<double>::inf();
         bool valid = (a0 > -1e300) && (b0 < 1e300) && (a0 < b0);
         double dmax = 0.0;
 #pragma unroll
@@ -521,34 +524,37 @@ struct KlAnchorEval {
         }
         if (!conv || !(x > a0) || !(x < b0)) return;
         nu = x;
-        D = Dv;
-        F2 = 2.0 * F2v;
-        tmin = tm;
+        const double D = Dv, F2 = 2.0 * F2v, invD = Num<double>::rcp(Dv);
         // (the last evaluation was at the previous iterate when the loop ended on a 2-ulp step: D, F2, tmin move by
         //  O(ulp(x) / tmin) relative, which `sized` bounds)
         const double span = fmax(fabs(a0), fabs(b0)) + dmax;
-        mx = 1e-12 * Num<double>::rcp(Dv) + (double)(8 + 2 * k) * 2.3e-16 * span;
-        sized = 1e-15 * span <= 1e-10 * tm;     // else only the sign is taken from the anchor
-        chord = 0.4999 * Num<double>::rcp(b0 - x);
+        mx = 1e-12 * invD + (double)(8 + 2 * k) * 2.3e-16 * span;
         ok = true;
+        if (1e-15 * span <= 1e-10 * tm) {       // D is accurate to 1e-10: the size bounds can be used (else sign only)
+            // |f| is monotone in the distance e from the root on either side, so every bound turns into a threshold on e:
+            const double hi = tol * (1.0 + 1e-9), lo = tol * (1.0 - 1e-9);
+            eLhi = hi * invD;                                                    // left:  f >= D e
+            eLlo = fmin(0.01 * tm, lo * Num<double>::rcp(D + 0.52 * F2 * lo * invD)); //  f <= D e + 0.52 F2 e^2, e <= 0.01 tmin
+            eRlo = lo * invD;                                                    // right: |f| <= D e
+            const double q = F2 * hi * invD * invD;                              //        |f| >= D e - F2 e^2 / 2:
+            const double chord_e = hi * (b0 - x) * (1.0 / 0.4999);               //        |f| >= 0.4999 e / (b0 - nu*)
+            // for q < 1/4: D e - F2 e^2 / 2 >= (D - F2 hi / D) e > hi on (hi / (D (1 - q)), 2 hi / D], and beyond that
+            // |f(e)| >= |f(2 hi / D)| >= 2 hi (1 - q) > hi
+            eRhi = q < 0.25 ? fmin(chord_e, hi * invD * Num<double>::rcp(1.0 - q)) : chord_e;
+            eLhi = fmax(eLhi, mx);
+            eRhi = fmax(eRhi, mx);
+        }
     }
     __device__ __forceinline__ double exact(double x) const { return base.exact(x); }
     __device__ __forceinline__ Cls operator()(double x) const {
         if (ok) {
             const double d = x - nu, e = fabs(d);
             if (e > mx) {
-                const double lin = D * e, hi = tol * (1.0 + 1e-9), lo = tol * (1.0 - 1e-9);
-                if (sized) {
-                    if (d < 0.0) {
-                        if (lin > hi) return Cls{false, true};
-                        if (e <= 0.01 * tmin && fma(0.52 * F2 * e, e, lin) < lo) return Cls{false, false};
-                    } else {
-                        if (lin < lo) return Cls{true, false};
-                        if (fma(-0.5 * F2 * e, e, lin) > hi || chord * e > hi) return Cls{true, true};
-                    }
-                }
+                const bool right = d > 0.0;
+                if (e > (right ? eRhi : eLhi)) return Cls{right, true};
+                if (e < (right ? eRlo : eLlo)) return Cls{right, false};
                 // the sign is certain, the size class is not: evaluate like the reference
-                return Cls{d > 0.0, fabs(base.exact(x)) > tol};
+                return Cls{right, fabs(base.exact(x)) > tol};
             }
         }
         return base(x);
@@ -561,10 +567,10 @@ struct KlAnchorEval {
 // ends of the initial bracket: with a valid anchor a0 < nu* < b0 and |f| >= 1/2 there (dicotomy.py:29-49)
 template <int KP>
 __device__ __forceinline__ End end_of(const KlAnchorEval<KP>& ev, double x) {
-    if (ev.ok && ev.sized && fabs(x - ev.nu) > ev.mx && ev.D * fabs(x - ev.nu) > ev.tol * (1.0 + 1e-9) && x < ev.nu)
-        return End{true, false, true};
-    if (ev.ok && ev.sized && x - ev.nu > ev.mx && ev.chord * (x - ev.nu) > ev.tol * (1.0 + 1e-9))
-        return End{false, true, true};
+    if (ev.ok) {
+        const double d = x - ev.nu, e = fabs(d);
+        if (e > ev.mx && e > (d > 0.0 ? ev.eRhi : ev.eLhi)) return End{d < 0.0, d > 0.0, true};
+    }
     return end_of(ev.base, x);
 }
 
@@ -997,7 +1003,7 @@ __global__ void __launch_bounds__(PX_THREADS, 4) h_finish_kernel(const espm_stat
                 *reinterpret_cast<volatile double*>(dst + 7) = st.rec_stamp;
             }
         }
-        if ((st.flags & ESPM_FLAG_PEER) && simplex && (int)threadIdx.x < st.world) {
+        if ((st.flags & ESPM_FLAG_PEER) && simplex && !(st.flags & ESPM_FLAG_EVAL_ONLY) && (int)threadIdx.x < st.world) {
             // publish this rank's complete trace mask on every rank (its own included), then raise the flag
             uint32_t* pf = st.peer_flags[threadIdx.x];
 #pragma unroll
@@ -1006,7 +1012,7 @@ __global__ void __launch_bounds__(PX_THREADS, 4) h_finish_kernel(const espm_stat
             st_release_sys(pf + ESPM_PF_MFLAG + st.rank, st.seq_m);
         }
     }
-    if (st.flags & ESPM_FLAG_PEER) __threadfence_system();   // halo rows pushed by store_h_next (no simplex)
+    if ((st.flags & ESPM_FLAG_PEER) && !simplex) __threadfence_system();   // halo rows pushed by store_h_next
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1602,7 +1608,8 @@ __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_sta
         }
     }
     // x / 0 in the W pass (updates.py:53-56): the caller redoes the step with ESPM_FLAG_CLAMP_Y
-    if (__any_sync(0xffffffffu, nonfinite) && lane == 0) atomicOr(&st.dev_flags[0], ESPM_DEV_NONFINITE);
+    if (__any_sync(0xffffffffu, nonfinite) && lane == 0)
+        atomicOr(&st.dev_flags[0], ESPM_DEV_NONFINITE | ESPM_DEV_NONFINITE_W);
     grid_barrier(bar, gridDim.x);
 
     if (threadIdx.x == 0) {
@@ -2008,6 +2015,12 @@ __global__ void __launch_bounds__(PX_THREADS) linesearch_kernel(const espm_state
         if (lane == 0) tot[v] = r;
     }
     __syncthreads();
+    if (st.flags & ESPM_FLAG_LS_PARTIAL) {
+        // sharded: the sums of this rank only; the caller adds the ranks (max for the row maxima) and decides
+        if ((int)threadIdx.x < NV + KP) st.ls_part[(size_t)gridDim.x * NV + threadIdx.x] = tot[threadIdx.x];
+        if (threadIdx.x == 0) st.dev_flags[4] = 0u;
+        return;
+    }
     if (threadIdx.x == 0 && (st.flags & ESPM_FLAG_PG)) {
         st.scalars[ESPM_S_LS_D] = tot[0];
         st.scalars[ESPM_S_GAMMA] = tot[1];

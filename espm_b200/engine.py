@@ -162,8 +162,6 @@ class FitEngine:
             flags &= ~L.FLAG_SIMPLEX_W           # those W branches have no simplex projection (updates.py:29-48)
         self.pg_ls = False
         if linesearch:
-            if shard is not None:
-                raise NotImplementedError("espm_b200: linesearch is not available for pixel-sharded fits")
             if flags & L.FLAG_PG:
                 self.pg_ls = True                # quadratic-surrogate line search (smooth_nmf.py:383-401, 438-447)
             else:
@@ -245,11 +243,13 @@ class FitEngine:
         self.sigma_dev = None
         if st.flags & L.FLAG_LINESEARCH:
             self.sigma_dev = torch.full((1,), float(sigma), dtype=torch.float64, device=dev)
-            self.ls_part = zeros(st.px_blocks, 4 + kp, dtype=torch.float64)
+            self.ls_part = zeros(st.px_blocks + 3, 4 + kp, dtype=torch.float64)
             st.sigma_dev, st.ls_part = self.sigma_dev.data_ptr(), self.ls_part.data_ptr()
         if self.pg_ls:
-            self.ls_part = zeros(st.px_blocks, 4 + kp, dtype=torch.float64)
+            self.ls_part = zeros(st.px_blocks + 3, 4 + kp, dtype=torch.float64)
             st.ls_part = self.ls_part.data_ptr()
+        if shard is not None and (self.pg_ls or (st.flags & L.FLAG_LINESEARCH)):
+            st.flags |= L.FLAG_LS_PARTIAL        # the sums of the line search are combined over the ranks on the host
         self._eval_slot = 0
         self._pg_w_pending = None
         if gamma_pg is not None:
@@ -653,6 +653,8 @@ class FitEngine:
             self._set_record(slot)
         if st.flags & L.FLAG_LINESEARCH:
             self._call(self.lib.espm_linesearch, "linesearch")   # smooth_nmf.py:376-382, gamma_ stays on the device
+            if self.shard is not None:
+                self._ls_decide(slot)
         if st.flags & L.FLAG_L2:
             L.check(self.lib.espm_gram(ctypes.byref(st), 1, self.stream))        # H' H'^T, updates.py:31
             if self.shard is not None:
@@ -857,8 +859,6 @@ class FitEngine:
     def enable_truth(self, true_D, true_H):
         """Keep X_true = true_D @ true_H on the device in the same tile-major layout as X, so that
         ``loss(W, H, X=true_DH)`` (base.py:345) is one more H pass."""
-        if self.shard is not None:
-            raise NotImplementedError("espm_b200: ground-truth tracking is not available for pixel-sharded fits")
         st = self.st
         D = torch.as_tensor(np.ascontiguousarray(true_D), dtype=self.cdt).to(self.device)
         Ht = torch.as_tensor(np.ascontiguousarray(true_H[:, self.j0:self.j1]), dtype=self.cdt).to(self.device)
@@ -910,6 +910,10 @@ class FitEngine:
             st.H_next, st.hstats_next = h_ptr, hs_ptr
             self._call(self.lib.espm_h_stats)                  # row statistics of H_t (sum Y of the loss)
             st.H_next, st.hstats_next = keep
+            if self.shard is not None:         # global statistics and the neighbours' rows of H_t (Laplacian term)
+                self.shard.allreduce_hstats(self.hstats_tmp, st.kp)
+                if self.ny > 0:
+                    self.shard.exchange_halo(self.H_tmp, self.halo, self.p_loc, self.ny)
         self._eval_only(slot, xt_ptr=self.Xt_true.data_ptr(), h_ptr=h_ptr, hstats_ptr=hs_ptr)
 
     # ------------------------------------------------------------------ projected-gradient line search
@@ -917,6 +921,31 @@ class FitEngine:
         """loss(W, H, average=False) (smooth_nmf.py:457-475) from a scalar record."""
         kl = 0.5 * rec[L.S_XLOGY] if self.st.flags & L.FLAG_L2 else rec[L.S_SUMY] - rec[L.S_XLOGY] + self.const_KL
         return kl + rec[L.S_LOGREG] + 0.5 * self.st.lambda_L * rec[L.S_LAPL]
+
+    def _ls_totals(self):
+        """Pixel-sharded line search: this rank's sums left by espm_linesearch (ESPM_FLAG_LS_PARTIAL), combined over the
+        ranks -- sums for the first 4 + kp values, maxima for the kp row maxima of H'."""
+        st = self.st
+        nv = 4 + st.kp
+        tot = self.ls_part.view(-1)[st.px_blocks * nv: st.px_blocks * nv + nv + st.kp].clone()
+        self.shard.allreduce_sum(tot[:nv])
+        self.shard.allreduce_max_int(tot[nv:])
+        return tot.cpu().numpy(), nv
+
+    def _ls_decide(self, slot):
+        """smooth_nmf.py:376-382 for a sharded fit: d = diff_surrogate(H_old, H_new) from the global sums, then
+        gamma_ /= 1.05 if d > 0 else gamma_ *= 1.5 (what the kernel does itself on one GPU)."""
+        st = self.st
+        t, nv = self._ls_totals()
+        sigma = float(self.sigma_dev.item())
+        if st.flags & L.FLAG_HQ:
+            t3 = t[3]
+        else:
+            t3 = sum(t[nv + kk] * t[4 + kk] for kk in range(st.k))
+        d = 0.5 * (2.0 * t[1] - t[0] + sigma * t3) - 0.5 * t[2]
+        g = sigma / 1.05 if d > 0.0 else sigma * 1.5
+        self.sigma_dev.fill_(g)
+        self.rec_np[slot, L.S_GAMMA], self.rec_np[slot, L.S_LS_D] = g, d
 
     def _pg_ls_h(self):
         """smooth_nmf.py:383-401 for (H_cur -> H_next): d = f(Ht) + <H - Ht, grad f(Ht)> + gamma |H - Ht|^2 - f(H)."""
@@ -926,9 +955,13 @@ class FitEngine:
         self._set_record(a1)
         self._call(self.lib.espm_linesearch)                   # sums of the quadratic surrogate (den = gradH(Ht))
         self._call(self.lib.espm_h_stats)                      # row statistics of H_next for sum Y
+        self._sync_hstats()                                    # (global ones when the pixels are sharded)
         self._eval_only(a2, h_ptr=st.H_next, hstats_ptr=st.hstats_next)
         r1 = self.read_records(a1, a1 + 1)[0]
         r2 = self.read_records(a2, a2 + 1)[0]
+        if self.shard is not None:             # the two sums of the quadratic surrogate over all ranks
+            t, _ = self._ls_totals()
+            r1[L.S_LS_D], r1[L.S_GAMMA] = t[0], t[1]
         f_xt, f_x = self._unaveraged(rec0), self._unaveraged(r2)
         d = f_xt + r1[L.S_LS_D] + st.gamma_h * r1[L.S_GAMMA] - f_x
         st.gamma_h = st.gamma_h / 1.05 if d > 0 else st.gamma_h * 1.5

@@ -11,8 +11,8 @@ On the device: every ``algo`` of the reference (``"log_surrogate"``, ``"l2_surro
 per phase), ``lambda_L`` with ``shape_2d`` (5-point Laplacian) or without (identity), ``fixed_H`` / ``fixed_W``,
 ``normalize``, ``linesearch``, ground-truth tracking (``true_D`` / ``true_H``), ``G`` as ``None`` / ndarray / physical
 model, ``hspy_comp``; the NNDSVD initialisation of a call without ``W`` and ``H`` runs its randomized SVD on the device
-too (``init_device.py``).  Pixel-sharded fits (one process per GPU) support every algorithm and loss; ``linesearch`` and
-truth tracking raise ``NotImplementedError`` there.
+too (``init_device.py``).  Pixel-sharded fits (one process per GPU) support every algorithm, loss and option, including
+``linesearch`` and ground-truth tracking.
 """
 import sys
 import time
@@ -22,6 +22,7 @@ from sklearn.base import BaseEstimator, TransformerMixin
 from sklearn.utils.validation import check_is_fitted, validate_data
 
 from . import _lib as L
+from . import config
 from .conf import dicotomy_tol as _DICOTOMY_TOL
 from .conf import log_shift as _LOG_SHIFT
 from .conf import sigmaL as _SIGMA_L
@@ -411,7 +412,7 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
     def _run_batch(self, eng, max_iter):
         """no_stop_criterion and nothing to print: enqueue every iteration, read the scalars once."""
         eng.evaluate(0)
-        if eng.fast_loop:
+        if eng.fast_loop and config.native_loop:
             eng.run_iterations(1, max_iter)          # one call: the launches of every iteration are issued natively
         else:
             for it in range(1, max_iter + 1):
@@ -452,9 +453,10 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
         self._eval_init = eval_init
         self._final_rec = rec
         eval_before = np.inf
-        speculate = (self.physics_model_ is None and not self._track and not self.linesearch and not eng.pg_ls)
+        speculate = (self.physics_model_ is None and not self._track and not self.linesearch and not eng.pg_ls
+                     and config.speculate)
         ahead = False                      # is iteration n_iter_ + 1 already enqueued?
-        native = eng.fast_loop and not self._track
+        native = eng.fast_loop and not self._track and config.native_loop
 
         def step(i):
             if native:
@@ -481,7 +483,7 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
                     ahead = False
                 rel_w = rec[L.S_REL_W]
                 eng.enable_clamp()
-                if not np.isfinite(rel_w):
+                if int(rec[L.S_DEV_FLAGS]) & L.DEV_NONFINITE_W:
                     eng.rollback()
                     eng.advance(it)
                     rel_w = None

@@ -86,6 +86,9 @@ typedef enum espm_status {
                                           * through the operator-level API, like in the reference */
 #define ESPM_FLAG_EVAL_ONLY   (1u << 19) /* espm_h_finish only evaluates the loss terms of (W_cur, H_cur): no update, no
                                           * bisection, H_next / Ht untouched (loss(W, H, X=...) calls of the reference) */
+#define ESPM_FLAG_LS_PARTIAL  (1u << 20) /* pixel-sharded fit: espm_linesearch only leaves this rank's sums (4 + kp values,
+                                          * then the kp row maxima of H') in row `px_blocks` of ls_part; the caller
+                                          * combines the ranks and takes the gamma_ decision */
 #define ESPM_FLAG_LINESEARCH  (1u << 18) /* smooth_nmf.py:376-386: gamma_ adapts from diff_surrogate; see sigma_dev */
 
 /* bits of the device-side error word (espm_state.dev_flags[0]) */
@@ -94,6 +97,7 @@ typedef enum espm_status {
 #define ESPM_DEV_NEGATIVE     (1u << 2)  /* negative num/denum (updates.py:148-149, dicotomy.py:17-19) */
 #define ESPM_DEV_GW_BELOW_LS  (1u << 3)  /* some GW entry < log_shift: loss needs ESPM_FLAG_LOSS_DUAL */
 #define ESPM_DEV_GW_ZERO_ROW  (1u << 4)  /* some row of GW is all zero: updates need ESPM_FLAG_CLAMP_Y */
+#define ESPM_DEV_NONFINITE_W  (1u << 6)  /* (with ESPM_DEV_NONFINITE) the non-finite sums came from the W pass (updates.py:53-56) */
 #define ESPM_DEV_PEER_TIMEOUT (1u << 5)  /* a peer rank did not signal within ~1 s: results of this fit are invalid */
 
 /* layout of one scalar record (doubles), written by espm_h_scalars / espm_w_finish */

@@ -38,8 +38,17 @@ def anchor(num, den, a0, b0):
         return None
     span = max(abs(a0), abs(b0)) + np.max(np.abs(den))
     mx = 1e-12 / D + (8 + 2 * len(num)) * 2.3e-16 * span
-    return dict(nu=x, D=D, F2=2 * F2, tmin=tm, mx=mx, chord=0.4999 / (b0 - x), its=it,
-                sized=1e-15 * span <= 1e-10 * tm)
+    an = dict(nu=x, mx=mx, its=it, eLlo=0.0, eRlo=0.0, eLhi=np.inf, eRhi=np.inf)
+    F2 = 2 * F2
+    if 1e-15 * span <= 1e-10 * tm:
+        hi, lo = TOL * (1 + 1e-9), TOL * (1 - 1e-9)
+        an["eLhi"] = max(hi / D, mx)
+        an["eLlo"] = min(0.01 * tm, lo / (D + 0.52 * F2 * lo / D))
+        an["eRlo"] = lo / D
+        q = F2 * hi / D / D
+        chord_e = hi * (b0 - x) / 0.4999
+        an["eRhi"] = max(min(chord_e, hi / D / (1 - q)) if q < 0.25 else chord_e, mx)
+    return an
 
 
 def classify(an, x):
@@ -48,20 +57,12 @@ def classify(an, x):
     e = abs(d)
     if e <= an["mx"]:
         return None
-    lin, hi, lo = an["D"] * e, TOL * (1 + 1e-9), TOL * (1 - 1e-9)
-    if not an["sized"]:
-        return (d > 0, None)
-    if d < 0:
-        if lin > hi:
-            return (False, True)
-        if e <= 0.01 * an["tmin"] and lin + 0.52 * an["F2"] * e * e < lo:
-            return (False, False)
-    else:
-        if lin < lo:
-            return (True, False)
-        if lin - 0.5 * an["F2"] * e * e > hi or an["chord"] * e > hi:
-            return (True, True)
-    return (d > 0, None)
+    right = d > 0
+    if e > (an["eRhi"] if right else an["eLhi"]):
+        return (right, True)
+    if e < (an["eRlo"] if right else an["eLlo"]):
+        return (right, False)
+    return (right, None)
 
 
 def run(rng, k, kind):

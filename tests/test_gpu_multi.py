@@ -52,8 +52,20 @@ CASES = {
     "l2_frobenius": dict(simplex_H=True, simplex_W=False, lambda_L=0.8, algo="l2_surrogate", l2=True),
     "proj_grad": dict(simplex_H=True, simplex_W=False, lambda_L=0.4, mu=0.02, algo="projected_gradient",
                       gamma=[3000.0, 4.0e5]),      # a stable step size: the trajectory is not chaotic
+    # smooth_nmf.py:376-382: gamma_ adapts from diff_surrogate over ALL pixels (sums combined over the ranks)
+    "linesearch": dict(simplex_H=True, simplex_W=False, lambda_L=0.6, linesearch=True),
+    # base.py:335-347: per-iteration loss against true_D @ true_H (each rank holds its slab of the truth image)
+    "truth": dict(simplex_H=True, simplex_W=False, lambda_L=0.5, mu=0.02, track=True),
+    "truth_free": dict(simplex_H=False, simplex_W=False, mu=0.05, track=True),      # rescaled_DH before the truth loss
 }
 NX, NY = 37, 29          # 37 rows do not divide evenly: ragged shards
+
+
+def _truth():
+    rng = np.random.default_rng(77)
+    D = rng.uniform(0.05, 1.0, size=(300, 3))
+    Ht = rng.uniform(0.05, 1.0, size=(3, NX * NY))
+    return D, Ht / Ht.sum(0, keepdims=True)
 
 
 def _data(tag):
@@ -85,10 +97,15 @@ def _worker(rank, world, port, out_dir, peer):
         res = {}
         for tag, kw in CASES.items():
             X, G, W0, H0 = _data(tag)
+            kw = dict(kw)
+            if kw.pop("track", False):
+                kw["true_D"], kw["true_H"] = _truth()
             est = SmoothNMF(n_components=3, G=G, shape_2d=(NX, NY), tol=0, no_stop_criterion=True, max_iter=8,
                             verbose=0, **kw)
             with contextlib.redirect_stdout(io.StringIO()):
                 est.fit_transform(X, W=W0.copy(), H=H0.copy())
+            if "true_D" in kw:
+                res[tag + "__true_losses"] = np.array(est.true_losses_)
             res[tag + "__W"] = est.W_
             res[tag + "__H"] = est.H_
             res[tag + "__losses"] = np.array(est.losses_)
@@ -117,8 +134,13 @@ def test_sharded_fit_matches_oracle(tmp_path, peer, world):
     res = [dict(np.load(tmp_path / ("rank%d.npz" % r))) for r in range(world)]
     for tag, kw in CASES.items():
         X, G, W0, H0 = _data(tag)
+        kw = dict(kw)
+        if kw.pop("track", False):
+            kw["true_D"], kw["true_H"] = _truth()
         ref = orc.fit(X, G, W0, H0, shape_2d=(NX, NY), tol=0, no_stop_criterion=True, max_iter=8, **kw)
         for r in res:
+            if "true_D" in kw:
+                assert rel_err(r[tag + "__true_losses"], ref["true_losses"]) < 1e-8, tag
             assert rel_err(r[tag + "__losses"], ref["losses"]) < 1e-9, tag
             assert rel_err(r[tag + "__W"], ref["W"]) < 1e-8, tag
             assert rel_err(r[tag + "__H"], ref["H"]) < 1e-8, tag
