@@ -37,8 +37,9 @@ WORKLOADS = {
     # configs[3]: 1024x1024 px x 4096 ch (17.2 GB fp32), 5 phases + Laplacian; --algo l2_surrogate for the "L2" reading
     "C4": dict(nx=1024, ny=1024, n=4096, k=5, n_elements=25,
                kw=dict(simplex_H=True, simplex_W=False, lambda_L=2.0, mu=0.05)),
-    # configs[4]: free NMF (G=None), simplex_W, 8 components; independent images = replicas (one image per rank)
-    "C5": dict(nx=512, ny=512, n=2048, k=8, n_elements=25, identity=True,
+    # configs[4]: free NMF (G=None), simplex_W, 8 components, a batch of 16 INDEPENDENT images: replicas only -- the
+    # images are dealt to the ranks (16 / N each), every image iterates on its own CUDA stream, no communication
+    "C5": dict(nx=512, ny=512, n=2048, k=8, n_elements=25, identity=True, n_images=16,
                kw=dict(simplex_H=False, simplex_W=True)),
 }
 
@@ -159,6 +160,150 @@ def cpu_baseline(prob, wl, X_crop, rows_crop, steps, seed):
     return its_crop * p_crop / (nx * ny), its_crop, dt
 
 
+def run_image_batch(args, wl, prob, rank, world, local_rank, W, K, config):
+    """BASELINE config C5: a batch of independent spectrum images (free NMF, G=None, simplex_W) dealt to the ranks.
+    One "step" = one iteration of EVERY image of the batch; value = image-iterations / s over all ranks.  The images
+    of a rank run on separate CUDA streams (the k x p / m x k kernels of one image overlap the X passes of another)."""
+    import torch
+    import torch.distributed as dist
+    import espm_b200
+    from espm_b200 import _lib as L
+    from espm_b200 import synth
+    from espm_b200.engine import FitEngine
+    espm_b200.config.x_storage = "dense"
+    nx, ny, n, k, n_img = wl["nx"], wl["ny"], wl["n"], wl["k"], wl["n_images"]
+    p = nx * ny
+    if n_img % world:
+        raise SystemExit("C5: %d images do not divide over %d ranks" % (n_img, world))
+    per = n_img // world
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    np_dtype = np.float32 if args.dtype == "f32" else np.float64
+    tdt = torch.float32 if args.dtype == "f32" else torch.float64
+    W0, H0 = synth.init_factors(n, k, p, args.seed, dtype=np_dtype)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    engines, streams = [], []
+    for i in range(per):
+        st = torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            X = synth.poisson_X_torch(prob, 0, p, args.seed + 1 + rank * per + i, dev, tdt)
+            eng = FitEngine(X, None, W0, H0, shape_2d=(nx, ny), max_records=W + K + 16, x_local=True, tol=0.0, **wl["kw"])
+            del X
+            eng.evaluate(0)
+            eng.run_iterations(1, W)
+        engines.append(eng)
+        streams.append(st)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    evs = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(4)) for _ in range(K)]
+    for tup in evs:
+        for e in tup:
+            e.record()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    main = torch.cuda.current_stream()
+    launches = 0
+    e0.record()
+    for i, (eng, st) in enumerate(zip(engines, streams)):
+        st.wait_event(e0)
+        with torch.cuda.stream(st):
+            l0 = eng.n_launches
+            eng.run_iterations(W + 1, K, events=evs if i == 0 else None)
+            launches += eng.n_launches - l0
+        main.wait_stream(st)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    t_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms = float(t_ms.item())
+    value = n_img * K / (ms * 1e-3)
+    # the dominant kernel timed ALONE (one image, nothing else on the device): the roofline of the kernel itself
+    solo = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(4)) for _ in range(6)]
+    for tup in solo:
+        for e in tup:
+            e.record()
+    with torch.cuda.stream(streams[0]):
+        engines[0].run_iterations(W + K + 1, 6, events=solo)
+    torch.cuda.synchronize()
+    h_ms = float(np.mean([t[2].elapsed_time(t[3]) for t in solo]))
+    w_ms = float(np.mean([t[0].elapsed_time(t[1]) for t in solo]))
+    rec = engines[0].read_records(W + K, W + K + 1)[0]
+    peak, peak_src = load_peaks()
+    bl = n * p * np_dtype().itemsize
+    dom_ms = max(h_ms, w_ms)
+    line = {"metric": "smoothnmf_iterations_per_s", "value": value, "unit": "it/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic", "config": dict(config, batch="%d independent images, %d per rank, "
+                                                                     "one CUDA stream per image; value counts image-iterations" % (n_img, per)),
+            "roofline": {"bound": "hbm", "kernel": "h_pass" if h_ms >= w_ms else "w_pass",
+                         "achieved": bl / (dom_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": bl / (dom_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                         "bytes_per_launch": bl, "h_pass_ms": h_ms, "w_pass_ms": w_ms,
+                         "iteration_frac": (2 * bl * per * K / (ms * 1e-3) / 1e9) / peak,
+                         "note": "kernel durations from one image iterating alone; iteration_frac = bytes of X all "
+                                 "images of a rank stream per second / peak"},
+            "cpu_baseline": None, "e2e": None, "gpu_launches": launches, "clocks": clocks,
+            "check": {"kl_raw_image0": float(rec[L.S_SUMY] - rec[L.S_XLOGY]), "bisect_its_W": float(rec[L.S_BISECT_ITS_W]),
+                      "dev_flags": float(rec[L.S_DEV_FLAGS])}}
+    if not args.no_e2e:
+        # end to end through the public API: the first (at most two) images of this rank, one fit after the other
+        from espm_b200 import SmoothNMF
+        import contextlib
+        import io
+        for eng in engines:
+            eng.close()
+        del engines
+        torch.cuda.empty_cache()
+        n_e = min(per, 2)
+        hosts = []
+        for i in range(n_e):
+            Xh = torch.empty((n, p), dtype=tdt, pin_memory=True)
+            Xh.copy_(synth.poisson_X_torch(prob, 0, p, args.seed + 1 + rank * per + i, dev, tdt))
+            hosts.append(Xh)
+        espm_b200.config.distributed = False
+        est = SmoothNMF(n_components=k, G=None, shape_2d=(nx, ny), tol=0.0, no_stop_criterion=True, max_iter=K,
+                        verbose=0, **wl["kw"])
+        with contextlib.redirect_stdout(io.StringIO()):
+            SmoothNMF(n_components=k, G=None, shape_2d=(nx, ny), tol=0.0, no_stop_criterion=True, max_iter=W,
+                      verbose=0, **wl["kw"]).fit_transform(hosts[0].numpy(), W=W0.copy(), H=H0.copy())
+        walls = []
+        for _ in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            with contextlib.redirect_stdout(io.StringIO()):
+                for Xh in hosts:
+                    est.fit_transform(Xh.numpy(), W=W0.copy(), H=H0.copy())
+            torch.cuda.synchronize()
+            t_e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+            walls.append(float(t_e.item()))
+        dt = sorted(walls)[1]
+        line["e2e"] = {"value": n_e * world * K / dt, "unit": "it/s",
+                       "h2d_bytes_per_step": n_e * world * (bl + W0.nbytes + H0.nbytes) / K,
+                       "d2h_bytes_per_step": n_e * world * (W0.nbytes + H0.nbytes + (K + 1) * L.NSCALARS * 8) / K,
+                       "what": "SmoothNMF.fit_transform on %d image(s) per rank in turn (pinned host buffers), "
+                               "max_iter=%d; median of 3 rounds %.3f s" % (n_e, K, dt)}
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -226,6 +371,8 @@ def main():
         return 0
 
     # ------------------------------------------------------------------ our arm (GPU)
+    if wl.get("n_images"):
+        return run_image_batch(args, wl, prob, rank, world, local_rank, W, K, config)
     import torch
     import torch.distributed as dist
     from espm_b200 import _lib as L
