@@ -136,28 +136,60 @@ class ClockSampler(threading.Thread):
                 "sm_mhz_min": sm[0], "source": self.source}
 
 
-def cpu_baseline(prob, wl, X_crop, rows_crop, steps, seed):
-    """The reference algorithm (oracle port, NumPy + BLAS threads) on a crop of the same image.
-    Every operation of the reference is linear in the pixel count, so it/s scales as p_crop / p."""
-    from oracle import smooth_nmf_oracle as orc
+def cpu_baseline(prob, wl, rows, steps, seed, np_dtype, threads=None):
+    """The reference's CPU implementation of the fit loop on the host cores: the UNMODIFIED
+    reference imported from /root/reference where that tree exists (kind "reference"), else its NumPy restatement
+    oracle/smooth_nmf_oracle.py (kind "port": same operation order, same n x p temporaries, same BLAS contractions).
+    Same synthetic image, same fixed W0 / H0, same parameters and dtypes as the GPU arm; `rows` image rows of it
+    (all of them, or a crop scaled by p_crop / p: every reference operation is linear in the pixel count).
+    Returns (it/s scaled to the full image, it/s on the sample, seconds, kind, BLAS threads)."""
     from espm_b200 import synth
-    try:
-        # torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm is meant to use every host core
-        from threadpoolctl import threadpool_limits
-        threadpool_limits(limits=os.cpu_count())
-    except Exception:
-        pass
+    from oracle import ref_import
+    from threadpoolctl import threadpool_info, threadpool_limits
     nx, ny, k = wl["nx"], wl["ny"], wl["k"]
-    p_crop = rows_crop * ny
-    W0, H0 = synth.init_factors(prob["G_full"].shape[1], k, nx * ny, seed)
+    p_crop = rows * ny
+    identity = bool(wl.get("identity"))
+    G = None if identity else prob["G_full"].astype(np_dtype)
+    m = wl["n"] if identity else prob["G_full"].shape[1]
+    W0, H0 = synth.init_factors(m, k, nx * ny, seed, dtype=np_dtype)
+    H0 = np.ascontiguousarray(H0[:, :p_crop])
+    X = synth.poisson_X_numpy(prob, 0, p_crop, seed, dtype=np_dtype)
     kw = dict(wl["kw"])
-    kw.update(tol=0, no_stop_criterion=True, shape_2d=(rows_crop, ny))
-    orc.fit(X_crop, prob["G_full"], W0, H0[:, :p_crop], max_iter=1, **kw)       # warm-up (BLAS threads, pages)
-    t0 = time.perf_counter()
-    orc.fit(X_crop, prob["G_full"], W0, H0[:, :p_crop], max_iter=steps, **kw)
-    dt = time.perf_counter() - t0
-    its_crop = steps / dt
-    return its_crop * p_crop / (nx * ny), its_crop, dt
+    kw.update(tol=0, no_stop_criterion=True, shape_2d=(rows, ny))
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm is meant to use every host core
+    limit = os.cpu_count() if threads is None else threads
+    with threadpool_limits(limits=limit):
+        blas = max([t.get("num_threads", 1) for t in threadpool_info() if t.get("user_api") == "blas"] or [1])
+        if ref_import.reference_available():
+            import contextlib
+            import io
+            kind = "reference"
+            ref = ref_import.load_reference()
+
+            def run(iters):
+                est = ref.SmoothNMF(n_components=k, G=G, max_iter=iters, verbose=0, **kw)
+                with contextlib.redirect_stdout(io.StringIO()):
+                    est.fit_transform(X, W=W0.copy(), H=H0.copy())
+        else:
+            from oracle import smooth_nmf_oracle as orc
+            kind = "port"
+
+            def run(iters):
+                orc.fit(X, G, W0, H0, max_iter=iters, **kw)
+        run(1)                                    # warm-up (BLAS threads, page faults)
+        t0 = time.perf_counter()
+        run(steps)
+        dt = time.perf_counter() - t0
+    its = steps / dt
+    return its * p_crop / (nx * ny), its, dt, kind, blas
+
+
+def host_ram_gb():
+    try:
+        import psutil
+        return psutil.virtual_memory().total / 2 ** 30
+    except Exception:
+        return 0.0
 
 
 def run_image_batch(args, wl, prob, rank, world, local_rank, W, K, config):
@@ -320,7 +352,10 @@ def main():
                     help="skip the secondary measurement with uint8 / uint16 count storage of X")
     ap.add_argument("--no-selfcheck", action="store_true",
                     help="N > 1: skip the comparison with an unsharded run of the same image on rank 0")
-    ap.add_argument("--cpu-rows", type=int, default=48, help="image rows of the CPU-baseline crop")
+    ap.add_argument("--cpu-rows", type=int, default=0,
+                    help="image rows of the CPU-baseline crop (0: the reference arm takes the whole image when the host "
+                         "has the memory, the in-line cpu_baseline of the GPU arm 48 rows)")
+    ap.add_argument("--no-single-thread", action="store_true", help="reference arm: skip the OPENBLAS_NUM_THREADS=1 row")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     wl["kw"] = dict(wl["kw"])
@@ -351,20 +386,35 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        rows = min(args.cpu_rows, nx)
-        X_crop = synth.poisson_X_numpy(prob, 0, rows * ny, args.seed, dtype=np_dtype)
-        steps = max(1, min(K, 20))
-        val, its_crop, dt = cpu_baseline(prob, wl, X_crop, rows, steps, args.seed)
+        # the whole image when the host has the memory for the reference's n x p temporaries
+        # (4 of them live at once: 8.6 GB fp32 / 17 GB fp64 at C3), else a crop scaled linearly in p
+        full_gb = 6.0 * n * p * np_dtype().itemsize / 2 ** 30
+        rows = nx if (args.cpu_rows <= 0 and host_ram_gb() >= max(64.0, 2 * full_gb)) else min(max(args.cpu_rows, 1), nx)
+        if args.cpu_rows <= 0 and rows == nx and args.workload in ("C4", "C5"):
+            rows = min(48, nx)                       # always crop-and-scale
+        steps = max(1, min(K, 5 if rows == nx else 20))
+        val, its_crop, dt, kind, blas = cpu_baseline(prob, wl, rows, steps, args.seed, np_dtype)
+        one = None
+        if not args.no_single_thread:
+            r1 = min(rows, 16)
+            v1, i1, d1, _, _ = cpu_baseline(prob, wl, r1, 3, args.seed, np_dtype, threads=1)
+            one = {"value": v1, "unit": "it/s", "blas_threads": 1,
+                   "sample": "%d image rows, 3 iterations in %.1f s, scaled by p_crop/p" % (r1, d1)}
         cores = os.cpu_count()
+        sample = ("the whole image (%d px x %d ch), %d iterations in %.1f s" % (p, n, steps, dt) if rows == nx else
+                  "the first %d of %d image rows (%d px x %d ch), %d iterations in %.1f s = %.3f it/s on the crop, "
+                  "scaled by p_crop/p (every reference op is linear in p)" % (rows, nx, rows * ny, n, steps, dt, its_crop))
+        what = ("the unmodified reference (espm.estimators.SmoothNMF imported from /root/reference)" if kind == "reference"
+                else "oracle port of the reference (the reference tree is not on this box)")
         line = {"impl": "reference", "metric": "smoothnmf_iterations_per_s", "value": val, "unit": "it/s",
                 "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": 1e3 / val,
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype,
                 "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": val, "unit": "it/s", "cores": cores, "kind": "port",
-                                 "sample": "oracle port of the reference (NumPy/OpenBLAS, all host threads) on the first "
-                                           "%d of %d image rows (%d px x %d ch), %d iterations in %.1f s = %.3f it/s on the "
-                                           "crop, scaled by p_crop/p (every reference op is linear in p)" % (
-                                               rows, nx, rows * ny, n, steps, dt, its_crop)},
+                "cpu_baseline": {"value": val, "unit": "it/s", "cores": cores, "kind": kind, "blas_threads": blas,
+                                 "host_ram_gb": round(host_ram_gb(), 1),
+                                 "sample": "%s, NumPy/OpenBLAS with %d BLAS threads on %d cores, %s inputs: %s" % (
+                                     what, blas, cores, args.dtype, sample),
+                                 "single_thread": one},
                 "e2e": {"value": val, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -635,13 +685,13 @@ def main():
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        rows = min(args.cpu_rows, nx)
-        X_crop = synth.poisson_X_numpy(prob, 0, rows * ny, args.seed, dtype=np_dtype)
-        val, its_crop, dtc = cpu_baseline(prob, wl, X_crop, rows, 12, args.seed)
-        cpu = {"value": val, "unit": "it/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": "oracle port of the reference (NumPy/OpenBLAS, all host threads) on the first %d of %d image "
-                         "rows (%d px x %d ch), 12 iterations in %.1f s = %.3f it/s on the crop, scaled by p_crop/p" % (
-                             rows, nx, rows * ny, n, dtc, its_crop)}
+        rows = min(args.cpu_rows if args.cpu_rows > 0 else 48, nx)
+        val, its_crop, dtc, kind, blas = cpu_baseline(prob, wl, rows, 12, args.seed, np_dtype)
+        cpu = {"value": val, "unit": "it/s", "cores": os.cpu_count(), "kind": kind, "blas_threads": blas,
+               "sample": "%s (NumPy/OpenBLAS, %d BLAS threads, %s inputs) on the first %d of %d image rows (%d px x %d ch), "
+                         "12 iterations in %.1f s = %.3f it/s on the crop, scaled by p_crop/p" % (
+                             "the unmodified reference" if kind == "reference" else "oracle port of the reference", blas,
+                             args.dtype, rows, nx, rows * ny, n, dtc, its_crop)}
 
     line = {"metric": "smoothnmf_iterations_per_s", "value": value, "unit": "it/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak" if replicas else "strong", "vs_baseline": None,

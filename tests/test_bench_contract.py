@@ -27,7 +27,12 @@ def test_reference_arm_json_line():
     assert d["higher_is_better"] is True and d["value"] > 0 and d["vs_baseline"] is None
     assert d["config"]["workload"].startswith("C1:")
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] == os.cpu_count() and cb["value"] == d["value"] and cb["sample"]
+    # the unmodified reference where its tree is present (this container), else the oracle port (the GPU box)
+    sys.path.insert(0, ROOT)
+    from oracle import ref_import
+    assert cb["kind"] == ("reference" if ref_import.reference_available() else "port")
+    assert cb["cores"] == os.cpu_count() and cb["value"] == d["value"] and cb["sample"] and cb["blas_threads"] >= 1
+    assert cb["single_thread"]["blas_threads"] == 1 and cb["single_thread"]["value"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0
 
