@@ -15,7 +15,7 @@ MAX_K = 16
 NSCALARS = 24
 MAXIT_DICHOTOMY = 100
 MAX_RANKS = 16
-PF_SFLAG, PF_MFLAG, PF_MASK, PF_WORDS = 0, 16, 32, 128
+PF_SFLAG, PF_MFLAG, PF_MASK, PF_TFLAG, PF_WORDS = 0, 16, 32, 128, 640
 
 # espm_state.flags
 FLAG_SIMPLEX_H = 1 << 0
@@ -39,6 +39,8 @@ FLAG_L2_H = 1 << 17
 FLAG_LINESEARCH = 1 << 18
 FLAG_EVAL_ONLY = 1 << 19
 FLAG_LS_PARTIAL = 1 << 20
+FLAG_NO_HSPEC = 1 << 21
+FLAG_TIMING = 1 << 22
 COOP_BLOCKS = 32
 
 # device error word
@@ -53,6 +55,7 @@ DEV_NONFINITE_W = 1 << 6
 # scalar record slots
 S_XLOGY, S_SUMY, S_LOGREG, S_LAPL, S_REL_H, S_REL_W, S_BISECT_ITS_H, S_BISECT_ITS_W, S_DEV_FLAGS, \
     S_MEAN_H, S_MEAN_W, S_GW_FLAGS, S_GAMMA, S_LS_D = range(14)
+S_T0 = 14
 S_STAMP = 23
 
 _i32, _u32, _i64, _f64, _vp = ctypes.c_int32, ctypes.c_uint32, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p

@@ -15,11 +15,15 @@ native_loop : bool
 speculate : bool
     In the loop with stop tests, enqueue iteration t+1 before the host has looked at the scalars of iteration t (and
     roll it back when a stop test fires).  Both switches exist for A/B measurements and debugging.
+speculate_h : bool
+    simplex_H: espm_h_finish applies the lock-step bisection count of the previous H update right after its trace and
+    espm_h_apply only confirms it (and redoes the replay when the count changed).  Results are identical either way.
 """
 import os as _os
 
 distributed = "auto"
 native_loop = _os.environ.get("ESPM_B200_NATIVE_LOOP", "1") != "0"
 speculate = _os.environ.get("ESPM_B200_SPECULATE", "1") != "0"
+speculate_h = _os.environ.get("ESPM_B200_SPECULATE_H", "1") != "0"
 x_storage = "auto"
 device_init = True

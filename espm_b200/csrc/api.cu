@@ -232,6 +232,10 @@ int espm_plan(espm_state* st) {
             }
             if (eff >= 0.95) break;
         }
+        if (const char* e = getenv("ESPM_B200_HSPLIT")) {     // experiments
+            const int v = atoi(e);
+            if (v >= 1 && v <= NS) best = v;
+        }
         st->h_nsplit = best;
         const long long items = (long long)st->n_tiles * best;
         st->h_grid = (int)(items < cap_h ? items : cap_h);
@@ -482,9 +486,9 @@ int espm_run_iterations(espm_state* st, espm_loop* lp, int32_t first_slot, int32
             ++lp->launches;
         }
         st->seq_s = ++lp->seq_s;
-        if (ev) ESPM_CUDA_CHECK(cudaEventRecord((cudaEvent_t)ev[0], s));
+        if (ev && ev[0]) ESPM_CUDA_CHECK(cudaEventRecord((cudaEvent_t)ev[0], s));
         if ((rc = espm_w_pass(st, stream))) return rc;
-        if (ev) ESPM_CUDA_CHECK(cudaEventRecord((cudaEvent_t)ev[1], s));
+        if (ev && ev[1]) ESPM_CUDA_CHECK(cudaEventRecord((cudaEvent_t)ev[1], s));
         if ((rc = espm_w_finish(st, stream))) return rc;
         lp->launches += 2;
         {   // rotate: next -> cur
@@ -505,9 +509,9 @@ int espm_run_iterations(espm_state* st, espm_loop* lp, int32_t first_slot, int32
         lp->stamp += 1.0;
         st->rec_stamp = lp->stamp;
         st->seq_m = ++lp->seq_m;
-        if (ev) ESPM_CUDA_CHECK(cudaEventRecord((cudaEvent_t)ev[2], s));
+        if (ev && ev[2]) ESPM_CUDA_CHECK(cudaEventRecord((cudaEvent_t)ev[2], s));
         if ((rc = espm_h_pass(st, stream))) return rc;
-        if (ev) ESPM_CUDA_CHECK(cudaEventRecord((cudaEvent_t)ev[3], s));
+        if (ev && ev[3]) ESPM_CUDA_CHECK(cudaEventRecord((cudaEvent_t)ev[3], s));
         if ((rc = espm_h_finish(st, stream))) return rc;
         lp->launches += 2;
     }

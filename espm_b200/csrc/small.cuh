@@ -39,6 +39,15 @@ __device__ __forceinline__ void ldcg_row(T (&dst)[N], const T* src) {
 }
 constexpr int PX_WARPS = PX_THREADS / 32;
 
+// ESPM_FLAG_TIMING: one thread leaves a %globaltimer stamp in the record (diagnostics only)
+__device__ __forceinline__ void time_stamp(const espm_state& st, int which) {
+    if (st.flags & ESPM_FLAG_TIMING) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        st.scalars[ESPM_S_T0 + which] = (double)t;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Peer exchange primitives (ESPM_FLAG_PEER): system-scope flags in CUDA-IPC memory over NVLink.
 // ------------------------------------------------------------------------------------------------
@@ -700,6 +709,26 @@ __device__ __forceinline__ void block_reduce_vals(const double (&vals)[NV], int 
     }
 }
 
+// H' of one pixel from the multiplier nu of its simplex constraint (updates.py:152, 289, 387): ONE definition, used by the
+// speculative replay inside h_finish and by h_apply, so that both produce the same bits.
+template <typename TC, int KP>
+__device__ __forceinline__ void h_from_nu(const espm_state& st, const double (&num)[KP], const double (&den)[KP], int k,
+                                          double nu, double sigma, TC (&hn)[KP]) {
+    if (st.flags & ESPM_FLAG_PG) {                                         // updates.py:381-387
+#pragma unroll
+        for (int kk = 0; kk < KP; ++kk) hn[kk] = (kk < k) ? (TC)fmax(num[kk] + nu, st.log_shift) : TC(0);
+    } else if ((st.flags & ESPM_FLAG_HQ) && (st.flags & ESPM_FLAG_LAPLACIAN)) {   // updates.py:286-289
+        const double a = st.lambda_L * sigma;
+#pragma unroll
+        for (int kk = 0; kk < KP; ++kk)
+            hn[kk] = (kk < k) ? (TC)fmax(hq_root(num[kk], den[kk] + nu, a), st.log_shift) : TC(0);
+    } else {
+#pragma unroll
+        for (int kk = 0; kk < KP; ++kk)
+            hn[kk] = (kk < k) ? (TC)fmax(num[kk] / (den[kk] + nu), st.log_shift) : TC(0);
+    }
+}
+
 template <typename TC, int KP>
 __device__ __forceinline__ void store_h_next(const espm_state& st, int j, int k, const TC (&hn)[KP],
                                              double (&vals)[3 + 3 * KP]) {
@@ -731,7 +760,7 @@ __device__ __forceinline__ void store_h_next(const espm_state& st, int j, int k,
 }
 
 template <typename TC>
-__device__ __forceinline__ void h_scalars_block(const espm_state& st, double* pub = nullptr);
+__device__ __forceinline__ void h_scalars_block(const espm_state& st, double* share);
 
 // ------------------------------------------------------------------------------------------------
 // h_finish: per-pixel assembly (updates.py:132-152) + loss regularisers + rel_H + bisection trace
@@ -740,6 +769,7 @@ template <typename TC, int KP>
 __global__ void __launch_bounds__(PX_THREADS, 4) h_finish_kernel(const espm_state st) {
     pdl_wait();
     pdl_trigger();
+    if (blockIdx.x == 0 && threadIdx.x == 0) time_stamp(st, 6);
     const int j = blockIdx.x * PX_THREADS + threadIdx.x;
     const bool active = j < st.p_loc;
     const int k = st.k;
@@ -757,6 +787,12 @@ __global__ void __launch_bounds__(PX_THREADS, 4) h_finish_kernel(const espm_stat
     const bool pg = st.flags & ESPM_FLAG_PG;   // proj_grad_step_h (updates.py:369-391)
     const bool l2h = st.flags & ESPM_FLAG_L2_H;  // Frobenius H step / gradient (updates.py:109-118, 330-332)
     const double sigma = st.sigma_dev ? *st.sigma_dev : st.sigma;   // gamma_ (device-resident under line search)
+    // Speculative replay (simplex_H): the lock-step count it* of the bisection is a GLOBAL quantity -- known only once every
+    // pixel (of every rank) has been traced -- but it hardly ever changes from one NMF iteration to the next.  dev_flags[6]
+    // holds it* + 1 of the previous H update (0: none yet); this kernel replays that many iterations right after its
+    // trace and writes H' (and its statistics) itself.  h_apply then only has to CONFIRM the count; it redoes the replay
+    // when the guess was wrong.  dev_flags[7] tells h_apply which count was applied.
+    const uint32_t spec = (simplex && !(st.flags & (ESPM_FLAG_EVAL_ONLY | ESPM_FLAG_NO_HSPEC))) ? st.dev_flags[6] : 0u;
 
     constexpr int NV = 3 + 3 * KP;
     double vals[NV];
@@ -916,17 +952,21 @@ __global__ void __launch_bounds__(PX_THREADS, 4) h_finish_kernel(const espm_stat
             Mask128 dec;
             dec.clear();
             uint32_t seen = 0u;
+            double nu_spec = 0.0;
+            const int its_spec = (int)spec - 1;
             if (pg) {     // dicotomy.py:83-108 on new_H
                 const PgEval<KP> ev(numd, k, st.log_shift, st.dicotomy_tol);
                 double lo, hi;
                 ev.bracket(lo, hi);
                 bisect_trace_rec(lo, hi, ev, st.maxit, bits, dec, seen, err);
+                if (spec) nu_spec = bisect_replay_rec(lo, hi, ev, its_spec, dec, seen);
             } else if (quad) {   // dicotomy.py:57-81 on (a, b, minus_c)
                 const double qa = st.lambda_L * sigma;
                 double lo, hi;
                 acc_bracket<KP>(numd, dend, k, qa, lo, hi);
-                bisect_trace_rec(lo, hi, AccEval<KP>(numd, dend, k, qa, st.log_shift, st.dicotomy_tol), st.maxit, bits,
-                                 dec, seen, err);
+                const AccEval<KP> ev(numd, dend, k, qa, st.log_shift, st.dicotomy_tol);
+                bisect_trace_rec(lo, hi, ev, st.maxit, bits, dec, seen, err);
+                if (spec) nu_spec = bisect_replay_rec(lo, hi, ev, its_spec, dec, seen);
             } else {
                 double lo, hi;
                 simplex_bracket<double, KP>(numd, dend, k, lo, hi);
@@ -937,11 +977,17 @@ __global__ void __launch_bounds__(PX_THREADS, 4) h_finish_kernel(const espm_stat
                 bisect_trace_rec(lo, hi, ev, st.maxit, bits, dec, seen, err);
                 st.bisect_anchor[j] = ev.nu;
                 st.bisect_anchor[(size_t)st.p_pad + j] = ev.ok ? ev.mx : Num<double>::inf();
+                if (spec) nu_spec = bisect_replay_rec(lo, hi, ev, its_spec, dec, seen);
             }
             uint32_t* rec = st.bisect_dec + j;
 #pragma unroll
             for (int w = 0; w < 4; ++w) rec[(size_t)w * st.p_pad] = dec.w[w];
             rec[(size_t)4 * st.p_pad] = seen;
+            if (spec) {
+                TC hn[KP];
+                h_from_nu<TC, KP>(st, numd, dend, k, nu_spec, sigma, hn);
+                store_h_next<TC, KP>(st, j, k, hn, vals);
+            }
         } else {
             if (pg) {   // keep new_H / grad readable (gradH, proj_grad_step_h of the operator-level API)
 #pragma unroll
@@ -963,7 +1009,7 @@ __global__ void __launch_bounds__(PX_THREADS, 4) h_finish_kernel(const espm_stat
             store_h_next<TC, KP>(st, j, k, hn, vals);
         }
     }
-    if ((st.flags & ESPM_FLAG_EVAL_ONLY) || simplex) {
+    if (((st.flags & ESPM_FLAG_EVAL_ONLY) || simplex) && !spec) {
         // only the loss partials and rel_H are ours: the H_next statistics in px_part come from another kernel
         // (evaluation only) or from the h_apply that follows (simplex_H), which writes the other columns
         const double v3[3] = {vals[0], vals[1], vals[2 + 2 * KP]};
@@ -986,33 +1032,38 @@ __global__ void __launch_bounds__(PX_THREADS, 4) h_finish_kernel(const espm_stat
     __syncthreads();
     if (is_last) {
         __threadfence();
-        __shared__ double pub[5];
-        h_scalars_block<TC>(st, pub);
-        if (threadIdx.x == 0) st.dev_flags[2] = 0u;
-        if ((st.flags & ESPM_FLAG_PEER) && st.rec_cap > 0) {
-            // Pixel-sharded fit: the loss sums, rel_H and the error word of a record are per-shard quantities.  Every
-            // rank stores its share into slot [rank][rec_slot] of EVERY rank's record inbox -- pinned host memory of
-            // that rank's process, mapped into this one -- and stamps it; each host folds the `world` shares in rank
-            // order once all stamps are there.  No collective, no device-side wait.
-            __syncthreads();
-            if ((int)threadIdx.x < st.world && st.peer_rec[threadIdx.x]) {
-                double* dst = st.peer_rec[threadIdx.x] + ((size_t)st.rank * st.rec_cap + st.rec_slot) * 8;
-#pragma unroll
-                for (int i = 0; i < 5; ++i) dst[i] = pub[i];
-                __threadfence_system();
-                *reinterpret_cast<volatile double*>(dst + 7) = st.rec_stamp;
-            }
-        }
         if ((st.flags & ESPM_FLAG_PEER) && simplex && !(st.flags & ESPM_FLAG_EVAL_ONLY) && (int)threadIdx.x < st.world) {
-            // publish this rank's complete trace mask on every rank (its own included), then raise the flag
+            // FIRST (the other ranks' h_apply waits for it): publish this rank's complete trace mask on every rank (its
+            // own included), then raise the flag
             uint32_t* pf = st.peer_flags[threadIdx.x];
 #pragma unroll
             for (int w = 0; w < 4; ++w) pf[ESPM_PF_MASK + 4 * st.rank + w] = __ldcg(st.bisect_mask + w);
-            __threadfence_system();
             st_release_sys(pf + ESPM_PF_MFLAG + st.rank, st.seq_m);
         }
+        // Pixel-sharded fit: the loss sums, rel_H and the error word of a record are per-shard quantities.  Every rank
+        // leaves its share in slot [rank][rec_slot] of its OWN record inbox -- pinned host memory that every rank's
+        // process has mapped -- and stamps it; each host folds the `world` shares in rank order once all stamps are
+        // there.  No collective, no device-side wait, no store that leaves this GPU's host.
+        double* share = nullptr;
+        if ((st.flags & ESPM_FLAG_PEER) && st.rec_cap > 0 && st.peer_rec[st.rank])
+            share = st.peer_rec[st.rank] + ((size_t)st.rank * st.rec_cap + st.rec_slot) * 8;
+        h_scalars_block<TC>(st, share);
+        if (threadIdx.x == 0) {
+            time_stamp(st, 7);
+            st.dev_flags[2] = 0u;
+            if (simplex && !(st.flags & ESPM_FLAG_EVAL_ONLY)) st.dev_flags[7] = spec;   // the count this trace was applied with
+        }
     }
-    if ((st.flags & ESPM_FLAG_PEER) && !simplex) __threadfence_system();   // halo rows pushed by store_h_next
+    // halo rows pushed by store_h_next (the CTAs that own the first / last image row of the shard): one system fence per
+    // CTA, by one thread after the barrier (fences are cumulative over what the barrier made visible to that thread)
+    if ((st.flags & ESPM_FLAG_PEER) && (!simplex || spec)) {
+        const int c0 = blockIdx.x * PX_THREADS, c1 = c0 + PX_THREADS;
+        const bool pushed = (st.nb_prev_halo && c0 < st.ny) || (st.nb_next_halo && c1 > st.p_loc - st.ny);
+        if (pushed) {
+            __syncthreads();
+            if (threadIdx.x == 0) __threadfence_system();
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1022,6 +1073,7 @@ template <typename TC, int KP>
 __global__ void __launch_bounds__(PX_THREADS) h_apply_kernel(const espm_state st) {
     pdl_wait();
     pdl_trigger();
+    if (blockIdx.x == 0 && threadIdx.x == 0) time_stamp(st, 0);
     const int j = blockIdx.x * PX_THREADS + threadIdx.x;
     const int k = st.k;
     const TC ls = (TC)st.log_shift;
@@ -1047,6 +1099,12 @@ __global__ void __launch_bounds__(PX_THREADS) h_apply_kernel(const espm_state st
     } else {
         its = first_clear_bit(st.bisect_mask, st.maxit);
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) time_stamp(st, 1);
+    // dev_flags[7]: the count (+ 1) the preceding h_finish has already applied speculatively; dev_flags[6]: the guess
+    // for the next H update.  Both are uniform over the grid (written by one thread of an EARLIER kernel / read by a
+    // LATER one), so the early exit below is taken by every CTA or by none.
+    if (blockIdx.x == 0 && threadIdx.x == 0) st.dev_flags[6] = (uint32_t)its + 1u;
+    if (st.dev_flags[7] == (uint32_t)its + 1u) return;      // H', Ht, the halos and the statistics are in place
     if (j < st.p_loc) {
         double num[KP], den[KP];
         TC hn[KP];
@@ -1062,32 +1120,26 @@ __global__ void __launch_bounds__(PX_THREADS) h_apply_kernel(const espm_state st
 #pragma unroll
         for (int w = 0; w < 4; ++w) dec.w[w] = rec[(size_t)w * st.p_pad];
         const uint32_t seen = rec[(size_t)4 * st.p_pad];
+        const double sigma = st.sigma_dev ? *st.sigma_dev : st.sigma;
+        double nu;
         if (st.flags & ESPM_FLAG_PG) {                                         // updates.py:381-387
             const PgEval<KP> ev(num, k, st.log_shift, st.dicotomy_tol);
             double lo, hi;
             ev.bracket(lo, hi);
-            const double nu = bisect_replay_rec(lo, hi, ev, its, dec, seen);
-#pragma unroll
-            for (int kk = 0; kk < KP; ++kk) hn[kk] = (kk < k) ? (TC)fmax(num[kk] + nu, st.log_shift) : TC(0);
+            nu = bisect_replay_rec(lo, hi, ev, its, dec, seen);
         } else if ((st.flags & ESPM_FLAG_HQ) && (st.flags & ESPM_FLAG_LAPLACIAN)) {   // updates.py:286-289
-            const double a = st.lambda_L * (st.sigma_dev ? *st.sigma_dev : st.sigma);
+            const double a = st.lambda_L * sigma;
             double lo, hi;
             acc_bracket<KP>(num, den, k, a, lo, hi);
-            const double nu = bisect_replay_rec(lo, hi, AccEval<KP>(num, den, k, a, st.log_shift, st.dicotomy_tol), its,
-                                                dec, seen);
-#pragma unroll
-            for (int kk = 0; kk < KP; ++kk)
-                hn[kk] = (kk < k) ? (TC)fmax(hq_root(num[kk], den[kk] + nu, a), st.log_shift) : TC(0);
+            nu = bisect_replay_rec(lo, hi, AccEval<KP>(num, den, k, a, st.log_shift, st.dicotomy_tol), its, dec, seen);
         } else {
             double lo, hi;
             simplex_bracket<double, KP>(num, den, k, lo, hi);
             const KlAnchorReplay<KP> ev(num, den, k, st.log_shift, st.dicotomy_tol, st.bisect_anchor[j],
                                         st.bisect_anchor[(size_t)st.p_pad + j]);
-            const double nu = bisect_replay_rec(lo, hi, ev, its, dec, seen);
-#pragma unroll
-            for (int kk = 0; kk < KP; ++kk)
-                hn[kk] = (kk < k) ? (TC)fmax(num[kk] / (den[kk] + nu), st.log_shift) : TC(0);
+            nu = bisect_replay_rec(lo, hi, ev, its, dec, seen);
         }
+        h_from_nu<TC, KP>(st, num, den, k, nu, sigma, hn);
         store_h_next<TC, KP>(st, j, k, hn, vals);
     }
     // only the H_next statistics are produced here; keep the loss partials written by h_finish
@@ -1096,7 +1148,14 @@ __global__ void __launch_bounds__(PX_THREADS) h_apply_kernel(const espm_state st
     __syncthreads();
     double* out = st.px_part + (size_t)blockIdx.x * NV;
     if (threadIdx.x < NV && threadIdx.x >= 2 && threadIdx.x != 2 + 2 * KP) out[threadIdx.x] = tmp[threadIdx.x];
-    if (st.flags & ESPM_FLAG_PEER) __threadfence_system();   // halo rows pushed by store_h_next
+    if (st.flags & ESPM_FLAG_PEER) {                         // halo rows pushed by store_h_next (see h_finish)
+        const int c0 = blockIdx.x * PX_THREADS, c1 = c0 + PX_THREADS;
+        const bool pushed = (st.nb_prev_halo && c0 < st.ny) || (st.nb_next_halo && c1 > st.p_loc - st.ny);
+        if (pushed) {
+            __syncthreads();
+            if (threadIdx.x == 0) __threadfence_system();
+        }
+    }
 }
 
 // h_stats: statistics of H_next only (initialisation, operator-level API).
@@ -1171,10 +1230,11 @@ __global__ void __launch_bounds__(256) hstats_reduce_kernel(const espm_state st)
 // ------------------------------------------------------------------------------------------------
 // h_scalars: loss parts of the current iterate + rel_H + bisection count into the scalar record
 // ------------------------------------------------------------------------------------------------
-// `pub` (shared memory, 5 doubles, optional): this rank's share of the additive / max / OR fields, for the push to the
-// other ranks' record inboxes (pixel-sharded fits).
+// `share` (optional): this rank's slot of its OWN record inbox (pixel-sharded fits; host memory every rank's process has
+// mapped): the additive / max / OR fields of the record that are per-shard quantities.  Written together with the record
+// under ONE system fence, stamped like the record.
 template <typename TC>
-__device__ __forceinline__ void h_scalars_block(const espm_state& st, double* pub) {
+__device__ __forceinline__ void h_scalars_block(const espm_state& st, double* share) {
     __shared__ double sm[8][4];
     const int kp = st.kp, stride = px_part_stride(kp);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1212,6 +1272,7 @@ __device__ __forceinline__ void h_scalars_block(const espm_state& st, double* pu
             meanh += hstats[kk];
         }
         double* rec = st.scalars;
+        const double flags = (double)st.dev_flags[0];
         rec[ESPM_S_XLOGY] = xl;
         rec[ESPM_S_SUMY] = sumy;
         rec[ESPM_S_LOGREG] = lr;
@@ -1219,24 +1280,25 @@ __device__ __forceinline__ void h_scalars_block(const espm_state& st, double* pu
         rec[ESPM_S_REL_H] = rh;
         rec[ESPM_S_BISECT_ITS_H] =
             (st.flags & ESPM_FLAG_SIMPLEX_H) ? (double)first_clear_bit(st.bisect_mask, st.maxit) : 0.0;
-        rec[ESPM_S_DEV_FLAGS] = (double)st.dev_flags[0];
+        rec[ESPM_S_DEV_FLAGS] = flags;
         rec[ESPM_S_MEAN_H] = meanh / ((double)st.k * (double)st.p_total);
-        if (pub) {
-            pub[0] = xl;
-            pub[1] = lr;
-            pub[2] = lp;
-            pub[3] = rh;
-            pub[4] = (double)st.dev_flags[0];
+        if (share) {
+            share[0] = xl;
+            share[1] = lr;
+            share[2] = lp;
+            share[3] = rh;
+            share[4] = flags;
         }
         // the record is complete (rel_W etc. were written by earlier kernels of the stream): stamp it
         __threadfence_system();
         *reinterpret_cast<volatile double*>(rec + ESPM_S_STAMP) = st.rec_stamp;
+        if (share) *reinterpret_cast<volatile double*>(share + 7) = st.rec_stamp;
     }
 }
 
 template <typename TC>
 __global__ void __launch_bounds__(256) h_scalars_kernel(const espm_state st) {
-    h_scalars_block<TC>(st);
+    h_scalars_block<TC>(st, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1387,6 +1449,7 @@ template <typename TC, int KP>
 __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_state st) {
     pdl_wait();      // results of the W pass (and of everything before it) are visible from here on
     pdl_trigger();   // lets the next H pass set up while we run
+    if (blockIdx.x == 0 && threadIdx.x == 0) time_stamp(st, 2);
     __shared__ double sm[8 * 2 * ESPM_MAX_K + 8];
     __shared__ int s_its;
     __shared__ uint32_t s_err;
@@ -1417,7 +1480,45 @@ __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_sta
     // ---- phase 0: fold the W-pass partial slots and the per-pixel statistics ----
     const bool peer = st.flags & ESPM_FLAG_PEER;
     const size_t recv_off = (size_t)(st.seq_s & 1u) * st.xchg_stride;   // parity of this exchange in every rank's buffer
-    if (peer) {
+    const bool w_bmd = st.flags & ESPM_FLAG_BMD, w_pg = st.flags & ESPM_FLAG_PG, w_l2 = st.flags & ESPM_FLAG_L2;
+    // "T path" (plain KL update with a real G, W' small enough for shared memory: the C2 / C3 / C4 case).  The W pass left
+    // partial sums of S = R H'^T; G^T is applied to the LOCAL S first, one CTA per row of G^T, while the last CTA folds the
+    // H' statistics; num / denum are only formed after the synchronisation point (phase B), from T = G^T S and the
+    // statistics.  Sharded (tx): the ranks exchange T_r = G^T S_r -- m x k values instead of n x k (108 floats instead
+    // of 8192 at C3; G^T sum_r S_r = sum_r G^T S_r) -- every CTA pushes the k values of its row into slot [rank] of every
+    // rank's receive buffer and raises ITS OWN flag word there (no ticket, no second fence); the wait for all
+    // world x gridDim flag words doubles as the grid barrier of the single-GPU path, and the slots are folded in rank
+    // order (identical W' on every rank, no broadcast).
+    const bool tp = fly && !ident && redundant_b && !(w_bmd || w_pg || w_l2) && m <= st.n_pad;
+    const bool tx = tp && peer;
+    const size_t my_slot_off = recv_off + (size_t)st.rank * st.xchg_slot;
+    // W-pass partial slots of every channel block (see w_pass_kernel), once per CTA: no 64-bit divisions per channel
+    __shared__ int cb_nr[256];
+    const int n_cb = st.n_pad / st.cs;
+    const bool cb_tab = fly && n_cb <= 256;
+    if (cb_tab) {
+        for (int cb = threadIdx.x; cb < n_cb; cb += W_COOP_THREADS) {
+            const int first = (int)(((long long)cb * st.n_tiles) / st.w_upc);
+            const int last = (int)((((long long)cb + 1) * st.n_tiles - 1) / st.w_upc);
+            cb_nr[cb] = last - first;
+        }
+        __syncthreads();
+    }
+    if (tp) {
+        if (blockIdx.x == gridDim.x - 1) {
+            reduce_hstats_block<KP>(st, hs_sm);
+            if ((int)threadIdx.x < 3 * KP) {
+                if (tx) {
+                    for (int r = 0; r < st.world; ++r)
+                        reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(st.peer_xchg[r]) + my_slot_off + st.xchg_hs_off)[threadIdx.x] =
+                            hs_sm[threadIdx.x];
+                } else {
+                    hstats[threadIdx.x] = hs_sm[threadIdx.x];
+                }
+            }
+            __syncthreads();
+        }
+    } else if (peer) {
         // Sharded: PUSH model.  Every rank folds its own partial slots and stores the result into slot [rank] of the
         // receive buffer of EVERY rank (its own included) -- remote stores over NVLink are fire-and-forget, so no
         // thread ever waits for a remote load.  The last CTA to finish pushing raises this rank's flag everywhere;
@@ -1474,7 +1575,6 @@ __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_sta
 
     // ---- phase A: num = W * (G^T S), den = colsum(G) (x) rowsum(H')   (updates.py:58-60) ----
     bool nonfinite = false;
-    const bool w_bmd = st.flags & ESPM_FLAG_BMD, w_pg = st.flags & ESPM_FLAG_PG, w_l2 = st.flags & ESPM_FLAG_L2;
     // num / denum of one entry from v = (G^T S)[mm][kk] and cs_h = colsum(G)[mm] * rowsum(H')[kk]; trow = (G^T G W)[mm][:]
     auto entry = [&](int mm, int kk, TC v, TC cs_h, const TC (&trow)[KP]) {
         const int i = mm * k + kk;
@@ -1506,7 +1606,7 @@ __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_sta
     const size_t s_total = (size_t)st.n_pad * KP;
     const TC* s_part = reinterpret_cast<const TC*>(st.s_part);
     auto load_srow = [&](int c, TC (&srow)[KP]) {
-        if (peer) {
+        if (peer && !tx) {
             // slots of the ranks in this rank's receive buffer (written by the peers, read through L2 only)
             const unsigned char* base = reinterpret_cast<const unsigned char*>(st.peer_xchg[st.rank]) + recv_off;
             ldcg_row<TC, KP>(srow, reinterpret_cast<const TC*>(base) + (size_t)c * KP);
@@ -1519,9 +1619,14 @@ __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_sta
             }
         } else if (fly) {
             const int cb = c / st.cs;
-            const int first = (int)(((long long)cb * st.n_tiles) / st.w_upc);
-            const int last = (int)((((long long)cb + 1) * st.n_tiles - 1) / st.w_upc);
-            const int nr = last - first;           // slots 0..nr hold partial sums of this channel block
+            int nr;                                // slots 0..nr hold partial sums of this channel block
+            if (cb_tab) {
+                nr = cb_nr[cb];
+            } else {
+                const int first = (int)(((long long)cb * st.n_tiles) / st.w_upc);
+                const int last = (int)((((long long)cb + 1) * st.n_tiles - 1) / st.w_upc);
+                nr = last - first;
+            }
             constexpr int RU = 6;                  // slots loaded at once (independent loads: one L2 round trip)
             TC t[RU][KP];
             lds_row<TC, KP>(srow, s_part + (size_t)c * KP);
@@ -1601,7 +1706,14 @@ __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_sta
                     TC v = accsm[lane];
                     for (int w = 1; w < NWARPS; ++w) v += accsm[w * KP + lane];
                     nonfinite |= !(Num<TC>::vabs(v) < Num<TC>::inf());
-                    entry(mm, lane, v, colsumG[mm] * (TC)hs[lane], trow);
+                    if (tx) {     // this rank's (G^T S)[mm][lane] into slot [rank] of every rank's receive buffer
+                        for (int r = 0; r < st.world; ++r)
+                            reinterpret_cast<TC*>(reinterpret_cast<unsigned char*>(st.peer_xchg[r]) + my_slot_off)[mm * KP + lane] = v;
+                    } else if (tp) {
+                        S[mm * KP + lane] = v;        // (s_sum is free in fused mode: it holds T = G^T S until phase B)
+                    } else {
+                        entry(mm, lane, v, colsumG[mm] * (TC)hs[lane], trow);
+                    }
                 }
             }
             __syncthreads();
@@ -1610,7 +1722,55 @@ __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_sta
     // x / 0 in the W pass (updates.py:53-56): the caller redoes the step with ESPM_FLAG_CLAMP_Y
     if (__any_sync(0xffffffffu, nonfinite) && lane == 0)
         atomicOr(&st.dev_flags[0], ESPM_DEV_NONFINITE | ESPM_DEV_NONFINITE_W);
-    grid_barrier(bar, gridDim.x);
+    if (tx) {
+        // every thread of this CTA is past its remote stores: threads 0..world-1 each raise this CTA's flag word on one
+        // rank.  st.release is cumulative over the stores the barrier ordered before it; the `world` releases run in
+        // parallel, so the CTA pays one round trip, and nothing waits for a ticket of the whole grid.
+        if (blockIdx.x == 0 && threadIdx.x == 0) time_stamp(st, 3);
+        __syncthreads();
+        if ((int)threadIdx.x < st.world)
+            st_release_sys(st.peer_flags[threadIdx.x] + ESPM_PF_TFLAG + 32 * st.rank + blockIdx.x, st.seq_s);
+        // wait for the flag words of every CTA of every rank (bounded, like wait_peer_flags)
+        {
+            const uint32_t* tf = st.peer_flags[st.rank] + ESPM_PF_TFLAG;
+            for (int w = threadIdx.x; w < 32 * st.world; w += W_COOP_THREADS) {
+                if ((w & 31) >= (int)gridDim.x) continue;
+                const long long t0 = clock64();
+                while ((int32_t)(ld_acquire_sys(tf + w) - st.seq_s) < 0) {
+                    if (clock64() - t0 > (1ll << 31)) {
+                        atomicOr(st.dev_flags, ESPM_DEV_PEER_TIMEOUT);
+                        break;
+                    }
+                    __nanosleep(32);
+                }
+            }
+            __syncthreads();
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) time_stamp(st, 4);
+        // global H' statistics: every CTA folds the ranks' slots for itself (rank order)
+        if ((int)threadIdx.x < 3 * KP) {
+            const bool is_max = (int)threadIdx.x >= 2 * KP;
+            const unsigned char* base = reinterpret_cast<const unsigned char*>(st.peer_xchg[st.rank]) + recv_off + st.xchg_hs_off;
+            double v = 0.0;
+            for (int r = 0; r < st.world; ++r) {
+                const double u = __ldcg(reinterpret_cast<const double*>(base + (size_t)r * st.xchg_slot) + threadIdx.x);
+                v = (r == 0) ? u : (is_max ? (u > v ? u : v) : v + u);
+            }
+            hs_sm[threadIdx.x] = v;
+            if (blockIdx.x == gridDim.x - 1) hstats[threadIdx.x] = v;
+        }
+        __syncthreads();
+    } else if (tp) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) time_stamp(st, 3);
+        grid_barrier(bar, gridDim.x);
+        if (blockIdx.x == 0 && threadIdx.x == 0) time_stamp(st, 4);
+        if ((int)threadIdx.x < 3 * KP) hs_sm[threadIdx.x] = __ldcg(hstats + threadIdx.x);   // written by the last CTA
+        __syncthreads();
+    } else {
+        if (blockIdx.x == 0 && threadIdx.x == 0) time_stamp(st, 3);
+        grid_barrier(bar, gridDim.x);
+        if (blockIdx.x == 0 && threadIdx.x == 0) time_stamp(st, 4);
+    }
 
     if (threadIdx.x == 0) {
         s_its = 0;
@@ -1758,10 +1918,34 @@ __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_sta
         __syncthreads();
         return t;
     };
+    // T-exchange path: num / denum of entry i from the ranks' slots of G^T S (rank order) and the global H' statistics
+    auto w_entry_tx = [&](int i) {
+        const int mm = i / k, kk = i - mm * k;
+        TC gs;
+        if (tx) {
+            const unsigned char* base = reinterpret_cast<const unsigned char*>(st.peer_xchg[st.rank]) + recv_off;
+            gs = __ldcg(reinterpret_cast<const TC*>(base) + mm * KP + kk);
+            for (int r = 1; r < st.world; ++r)
+                gs += __ldcg(reinterpret_cast<const TC*>(base + (size_t)r * st.xchg_slot) + mm * KP + kk);
+        } else {
+            gs = __ldcg(S + mm * KP + kk);
+        }
+        const TC nv = W[i] * gs, dv = colsumG[mm] * (TC)hs_sm[kk];      // updates.py:59-60
+        if (blockIdx.x == 0) {
+            wnum[i] = nv;
+            wden[i] = dv;
+        }
+        TC v = Num<TC>::vmax(nv / dv, ls);
+        if (st.flags & ESPM_FLAG_FIXED_W) {
+            const TC f = fw[i];
+            if (f >= TC(0)) v = f;
+        }
+        return v;
+    };
     if (redundant_b) {
         double wsum = 0.0;
         for (int i = threadIdx.x; i < m * k; i += W_COOP_THREADS) {
-            const TC v = w_entry(i);
+            const TC v = tp ? w_entry_tx(i) : w_entry(i);
             if (blockIdx.x == 0) Wn[i] = v;
             wsm[i] = v;
             wsum += (double)v;
@@ -1889,6 +2073,7 @@ __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_sta
             gwstats[threadIdx.x] = (TC)a;
         }
         if (threadIdx.x == 0) {
+            time_stamp(st, 5);
             uint32_t f = 0u;
             for (int b = 0; b < (int)gridDim.x; ++b)
                 f |= (uint32_t)__ldcg(st.coop_part + (size_t)b * W_COOP_STRIDE + 2 * ESPM_MAX_K);

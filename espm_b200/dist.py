@@ -250,7 +250,10 @@ class _RecordInbox:
                 pass
         self.ok = all(oks)
         if self.ok:
-            self.mine = np.frombuffer(self.maps[self.rank], dtype=np.float64).reshape(self.world, self.cap, self.WORDS)
+            # views[r][r, slot, :] is rank r's share of record `slot`: every GPU writes only into its OWN host's inbox
+            # (slot row [rank]), every host reads the shares out of the inboxes it has mapped
+            self.views = [np.frombuffer(m, dtype=np.float64).reshape(self.world, self.cap, self.WORDS) for m in self.maps]
+            self.mine = self.views[self.rank]
         else:
             self.free()
 
@@ -260,6 +263,7 @@ class _RecordInbox:
             self.lib.espm_host_unregister(ctypes.c_void_p(ptr))
         self.registered, self.dev_ptrs = [], []
         self.mine = None
+        self.views = []
         self.maps = []                     # (the mmap objects are closed by the garbage collector once unreferenced)
 
 

@@ -185,6 +185,9 @@ class FitEngine:
         st.lambda_L, st.sigma, st.eps_reg = float(lambda_L), float(sigma), float(epsilon_reg)
         st.log_shift, st.dicotomy_tol, st.dicotomy_tol_w, st.tol = (
             float(log_shift), float(dicotomy_tol), float(dicotomy_tol_w), float(tol))
+        from . import config as _config
+        if not getattr(_config, "speculate_h", True):
+            flags |= L.FLAG_NO_HSPEC
         st.flags = flags
         L.check(self.lib.espm_plan(ctypes.byref(st)))
 
@@ -687,8 +690,10 @@ class FitEngine:
     def run_iterations(self, first, n, events=None):
         """``for it in range(first, first + n): advance(it); evaluate(it)`` issued by ONE call into the library
         (espm_run_iterations): the Python binding costs ~10 us per launch, more than the kernels of a small pixel shard
-        take.  ``events``: optional list of n 4-tuples of recorded-once torch.cuda.Event (w_pass start / end, h_pass
-        start / end) the native loop records around the two X passes."""
+        take.  ``events``: optional list of n entries, each None or a 4-tuple of recorded-once torch.cuda.Event (w_pass
+        start / end, h_pass start / end) the native loop records around the two X passes of that iteration.  (An event
+        between two kernels costs their programmatic-dependent-launch overlap, ~4 us per event: sample, don't record
+        every iteration.)"""
         if n <= 0:
             return
         if first < 0 or first + n > self.max_records:
@@ -706,7 +711,8 @@ class FitEngine:
         lp.records = self.records.data_ptr()
         ev_arr = None
         if events is not None:
-            ev_arr = (ctypes.c_void_p * (4 * n))(*[e.cuda_event for tup in events for e in tup])
+            ev_arr = (ctypes.c_void_p * (4 * n))(*[(None if tup is None else tup[i].cuda_event)
+                                                   for tup in events for i in range(4)])
             lp.ev = ctypes.cast(ev_arr, ctypes.c_void_p)
         for i in range(3):
             lp.ih[i] = self.ih[i]
@@ -788,14 +794,19 @@ class FitEngine:
         if want is None:                       # never evaluated (e.g. a W-only step): nothing to fold
             return row.copy()
         want = float(want)
-        shares = self.inbox.mine[:, slot, :]
+        views = self.inbox.views                   # views[r][r, slot]: rank r's share, in rank r's inbox
+
+        def ready():
+            return row[L.S_STAMP] == want and all(views[r][r, slot, 7] == want for r in range(len(views)))
         t0 = time.perf_counter()
-        while row[L.S_STAMP] != want or not np.all(shares[:, 7] == want):
+        while not ready():
             if time.perf_counter() - t0 > timeout:
                 torch.cuda.current_stream(self.device).synchronize()
-                if row[L.S_STAMP] != want or not np.all(shares[:, 7] == want):
+                if not ready():
                     raise L.EspmError("scalar record %d was never completed by every rank (stamps %r / %r, expected %r)"
-                                      % (slot, row[L.S_STAMP], shares[:, 7].tolist(), want))
+                                      % (slot, row[L.S_STAMP], [float(views[r][r, slot, 7]) for r in range(len(views))],
+                                         want))
+        shares = np.stack([views[r][r, slot, :] for r in range(len(views))])
         out = row.copy()
         sh = shares.copy()
         for col, s in ((0, L.S_XLOGY), (1, L.S_LOGREG), (2, L.S_LAPL)):

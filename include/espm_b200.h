@@ -49,7 +49,8 @@ extern "C" {
 #define ESPM_PF_SFLAG 0            /* [r]: rank r published its S / H' statistics with this sequence number */
 #define ESPM_PF_MFLAG 16           /* [r]: rank r pushed its bisection trace mask with this sequence number */
 #define ESPM_PF_MASK  32           /* [4*r .. 4*r+3]: rank r's 128-bit trace mask */
-#define ESPM_PF_WORDS 128
+#define ESPM_PF_TFLAG 128          /* [32*r + c]: CTA c of rank r's espm_w_finish pushed its part of G^T S_r / the H' statistics */
+#define ESPM_PF_WORDS 640
 #define ESPM_NSCALARS 24          /* doubles per slot of the per-iteration scalar record */
 #define ESPM_MAXIT_DICHOTOMY 100  /* espm/conf.py:59 */
 
@@ -89,6 +90,10 @@ typedef enum espm_status {
 #define ESPM_FLAG_LS_PARTIAL  (1u << 20) /* pixel-sharded fit: espm_linesearch only leaves this rank's sums (4 + kp values,
                                           * then the kp row maxima of H') in row `px_blocks` of ls_part; the caller
                                           * combines the ranks and takes the gamma_ decision */
+#define ESPM_FLAG_NO_HSPEC    (1u << 21) /* espm_h_finish does not apply the previous lock-step count speculatively: espm_h_apply
+                                         * always replays (tests / diagnostics; the results are identical either way) */
+#define ESPM_FLAG_TIMING      (1u << 22) /* diagnostics: the small kernels leave %globaltimer stamps (ns, as doubles) in
+                                         * ESPM_S_T0 .. ESPM_S_T0 + 8 of the record they work on (scripts/timeline.py) */
 #define ESPM_FLAG_LINESEARCH  (1u << 18) /* smooth_nmf.py:376-386: gamma_ adapts from diff_surrogate; see sigma_dev */
 
 /* bits of the device-side error word (espm_state.dev_flags[0]) */
@@ -116,6 +121,8 @@ enum {
     ESPM_S_GW_FLAGS = 11, /* ESPM_DEV_GW_* bits of the GW produced for the NEXT H pass */
     ESPM_S_GAMMA = 12,    /* line search: gamma_ after this iteration's update (smooth_nmf.py:378-382) */
     ESPM_S_LS_D = 13,     /* line search: diff_surrogate(H_old, H_new) (surrogates.py:116-149) */
+    ESPM_S_T0 = 14,       /* .. 22: ESPM_FLAG_TIMING stamps -- h_apply start / after the mask wait, w_finish start / rows
+                           * pushed / flags seen / end, h_finish start / end */
     ESPM_S_STAMP = 23     /* espm_state.rec_stamp of the espm_h_finish that completed this record: written LAST, after a
                            * system-scope fence, so a host that sees the stamp in (pinned, device-mapped) memory sees
                            * the whole record without synchronising the stream */
@@ -203,16 +210,19 @@ typedef struct espm_state {
     uint32_t* bisect_mask;  /* 4 words: bit j set <=> max|f_j| > tol somewhere (lock-step trace) */
     uint32_t* dev_flags;    /* 8 words: [0] sticky ESPM_DEV_* error bits, [1] ESPM_DEV_GW_* of GW_next,
                              * [2] h_finish completion ticket, [3] grid-barrier counter of w_finish (start at 0),
-                             * [4] w_finish completion ticket, [5] w_finish "pushed" ticket (peer exchange) */
+                             * [4] w_finish completion ticket, [5] w_finish "pushed" ticket (peer exchange),
+                             * [6] lock-step count + 1 of the last espm_h_apply (the next espm_h_finish applies it
+                             * speculatively; 0: none), [7] the count + 1 the last espm_h_finish applied (0: none) */
     double* scalars;        /* ESPM_NSCALARS doubles: the record being filled.  Only ever WRITTEN by the kernels: it may
                              * live in pinned host memory (the host then polls ESPM_S_STAMP instead of synchronising) */
     double* coop_part;      /* ESPM_COOP_BLOCKS x (2*ESPM_MAX_K + 4) doubles: per-CTA partials of w_finish */
     /* ---- ESPM_FLAG_PEER: exchange between the pixel shards through CUDA-IPC peer memory over NVLink ----
      * No host-launched collective sits on the per-iteration path: the kernels signal and wait on flag words
      * (system-scope release/acquire) and move the few KiB that cross ranks with plain peer loads / stores.
-     *   - espm_w_finish PUSHES this rank's S and H' statistics into slot [rank] of every rank's receive buffer
-     *     (remote stores), raises its S flag on every rank, waits for all flags and folds the slots of its own
-     *     (local) buffer in rank order (identical everywhere, no remote load on the path);
+     *   - espm_w_finish PUSHES this rank's G^T S (m x k values; S itself, n x k, when G is the identity or the update
+     *     rule is not the plain KL one) and H' statistics into slot [rank] of every rank's receive buffer (remote
+     *     stores), raises its S flag on every rank, waits for all flags and folds the slots of its own (local) buffer
+     *     in rank order (identical everywhere, no remote load on the path);
      *   - the H update pushes its first / last image row into the neighbours' halo columns (Laplacian);
      *   - espm_h_finish pushes the 128-bit bisection trace mask to every rank, espm_h_apply waits for all. */
     int32_t rank;           /* this shard */
@@ -253,7 +263,9 @@ typedef struct espm_state {
     /* ---- ESPM_FLAG_PEER: record inboxes.  peer_rec[r] = rank r's inbox (pinned host memory of r's process, mapped into
      * this one with espm_host_register): [world][rec_cap][8] doubles.  espm_h_finish stores this rank's share
      * {sum X log Y, log-reg, Laplacian, rel_H, device flags, -, -, stamp} of record `rec_slot` into [rank][rec_slot] of
-     * every inbox; the hosts fold the shares.  rec_cap == 0: no inboxes (the caller gathers the records itself). */
+     * its OWN inbox (peer_rec[rank]; the other entries are not dereferenced) under the same system fence as the record;
+     * every host has every inbox mapped and folds the shares.  rec_cap == 0: no inboxes (the caller gathers the
+     * records itself). */
     double* peer_rec[ESPM_MAX_RANKS];
     int32_t rec_slot;
     int32_t rec_cap;
