@@ -125,9 +125,30 @@ class ClockSampler(threading.Thread):
                     self.source = "nvidia-smi"
             self._stop_evt.wait(0.002 if self._nvml is not None else 0.1)
 
+    def sample_while(self, running, every=0.001, limit=2000):
+        """Samples taken by the CALLING thread while ``running()`` is true (at least one).  Used right after the timed
+        iterations have been enqueued: the clocks are read while the GPU works through them, and no second host
+        thread competes with the enqueue (with 8 ranks in lock step, a host hiccup on one rank stalls all of them)."""
+        n = 0
+        while True:
+            try:
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
+            except Exception:
+                if self._nvml is not None:
+                    self._nvml = None
+                    self.source = "nvidia-smi"
+            n += 1
+            if not running() or n >= limit:
+                return
+            time.sleep(every)
+
     def stop(self):
         self._stop_evt.set()
-        self.join(timeout=5)
+        if self.is_alive():
+            self.join(timeout=5)
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples (NVML and nvidia-smi unavailable)"]}
         sm = sorted(s[0] for s in self.samples)
@@ -234,12 +255,6 @@ def run_image_batch(args, wl, prob, rank, world, local_rank, W, K, config):
         streams.append(st)
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    evs = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(4)) for _ in range(K)]
-    for tup in evs:
-        for e in tup:
-            e.record()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     main = torch.cuda.current_stream()
@@ -249,10 +264,12 @@ def run_image_batch(args, wl, prob, rank, world, local_rank, W, K, config):
         st.wait_event(e0)
         with torch.cuda.stream(st):
             l0 = eng.n_launches
-            eng.run_iterations(W + 1, K, events=evs if i == 0 else None)
+            eng.run_iterations(W + 1, K)
             launches += eng.n_launches - l0
         main.wait_stream(st)
     e1.record()
+    if sampler:
+        sampler.sample_while(lambda: not e1.query())
     barrier()
     clocks = sampler.stop() if sampler else None
     t_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -478,8 +495,6 @@ def main():
     eng.run_iterations(1, W)
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
     evs = pass_events(K)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -490,6 +505,8 @@ def main():
     e1.record()
     host_ms = (time.perf_counter() - t_host0) * 1e3 / K        # host time to ENQUEUE one iteration
     n_launches = eng.n_launches - launches0
+    if sampler:                   # clocks / throttle reasons while the GPU works through the timed iterations
+        sampler.sample_while(lambda: not e1.query())
     barrier()
     clocks = sampler.stop() if sampler else None
     ms = e0.elapsed_time(e1)

@@ -163,8 +163,19 @@ int espm_plan(espm_state* st) {
     if (rc) return rc;
     int dev = 0;
     ESPM_CUDA_CHECK(cudaGetDevice(&dev));
-    cudaDeviceProp prop;
-    ESPM_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+    // cudaGetDeviceProperties takes milliseconds (it queries everything); a fit plans once, but a fit of 20 iterations
+    // is only 15 ms of kernels -- keep the properties of every device after the first query
+    static cudaDeviceProp props[64];
+    static bool have[64] = {false};
+    if (dev < 0 || dev >= 64) {
+        set_error("device index %d out of range", dev);
+        return ESPM_ERR_BAD_ARG;
+    }
+    if (!have[dev]) {
+        ESPM_CUDA_CHECK(cudaGetDeviceProperties(&props[dev], dev));
+        have[dev] = true;
+    }
+    const cudaDeviceProp& prop = props[dev];
     if (prop.major < 10) {
         set_error("device %s is sm_%d%d; espm_b200 is built for sm_100a only", prop.name, prop.major, prop.minor);
         return ESPM_ERR_NO_DEVICE;

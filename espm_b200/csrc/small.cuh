@@ -1719,6 +1719,15 @@ __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_sta
             __syncthreads();
         }
     }
+    // T path: the column of G this thread needs in phase C does not depend on W' -- fetch it now, so that its L2 round
+    // trips overlap the synchronisation point instead of following it
+    constexpr int GPRE = 32;
+    TC gpre[GPRE];
+    const bool pre = tp && m <= GPRE && gthread < n;
+    if (pre) {
+#pragma unroll
+        for (int mm = 0; mm < GPRE; ++mm) gpre[mm] = (mm < m) ? Gt[(size_t)mm * n + gthread] : TC(0);
+    }
     // x / 0 in the W pass (updates.py:53-56): the caller redoes the step with ESPM_FLAG_CLAMP_Y
     if (__any_sync(0xffffffffu, nonfinite) && lane == 0)
         atomicOr(&st.dev_flags[0], ESPM_DEV_NONFINITE | ESPM_DEV_NONFINITE_W);
@@ -2012,6 +2021,15 @@ __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_sta
 #pragma unroll
                 for (int kk = 0; kk < KP; ++kk)
                     if (kk < k) v[kk] = Wsrc[(size_t)c * k + kk];
+            } else if (pre && c == gthread) {
+#pragma unroll
+                for (int mm = 0; mm < GPRE; ++mm) {
+                    if (mm < m) {
+#pragma unroll
+                        for (int kk = 0; kk < KP; ++kk)
+                            if (kk < k) v[kk] = fma(gpre[mm], Wsrc[(size_t)mm * k + kk], v[kk]);
+                    }
+                }
             } else {
 #pragma unroll 8
                 for (int mm = 0; mm < m; ++mm) {
@@ -2067,16 +2085,29 @@ __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_sta
     if (s_last) {
         __threadfence();
         TC* gwstats = reinterpret_cast<TC*>(st.gwstats_next);
-        if (threadIdx.x < 2 * KP) {
+        // one warp per column: lane b fetches CTA b's partial (ONE L2 round trip for the whole fold instead of gridDim
+        // dependent ones), butterfly sum in a fixed order
+        for (int v = warp; v < 2 * KP + 1; v += NWARPS) {
+            const int col = v < 2 * KP ? v : 2 * ESPM_MAX_K;      // last "column": the CTAs' flag words
             double a = 0.0;
-            for (int b = 0; b < (int)gridDim.x; ++b) a += __ldcg(st.coop_part + (size_t)b * W_COOP_STRIDE + threadIdx.x);
-            gwstats[threadIdx.x] = (TC)a;
+            uint32_t fb = 0u;
+            for (int b = lane; b < (int)gridDim.x; b += 32) {
+                const double x = __ldcg(st.coop_part + (size_t)b * W_COOP_STRIDE + col);
+                if (v < 2 * KP) a += x;
+                else fb |= (uint32_t)x;
+            }
+            if (v < 2 * KP) {
+                a = warp_sum(a);
+                if (lane == 0) gwstats[v] = (TC)a;
+            } else {
+                fb = __reduce_or_sync(0xffffffffu, fb);
+                if (lane == 0) s_err = fb;
+            }
         }
+        __syncthreads();
         if (threadIdx.x == 0) {
             time_stamp(st, 5);
-            uint32_t f = 0u;
-            for (int b = 0; b < (int)gridDim.x; ++b)
-                f |= (uint32_t)__ldcg(st.coop_part + (size_t)b * W_COOP_STRIDE + 2 * ESPM_MAX_K);
+            const uint32_t f = s_err;
             st.dev_flags[1] = f;
             st.scalars[ESPM_S_GW_FLAGS] = (double)f;
             if (!redundant_b) {   // scalars of the sliced phase B, folded in CTA order
