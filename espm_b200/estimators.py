@@ -250,7 +250,7 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
         # solve against the data on the host; when BOTH are missing (the reference's default call) the NNDSVD of
         # scikit-learn runs its randomized SVD on the device against the X the engine holds (init_device.py), so the
         # engine is created first, with placeholders, and receives the real factors afterwards.
-        device_init = (W is None and H is None and not distributed and config.device_init
+        device_init = (W is None and H is None and config.device_init
                        and self.n_components + 10 <= n < p)      # tall factorisations of init_device.py
         if device_init:
             c_np = np.result_type(Xv.dtype, *([] if G is None else [np.asarray(G).dtype]))

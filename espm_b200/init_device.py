@@ -30,11 +30,18 @@ def _norm(x):
 
 
 class _DeviceX:
-    """Products with the processed data matrix X_ (n x p) held as tile-major Xt [tile][n_pad][128]."""
+    """Products with the processed data matrix X_ (n x p) held as tile-major Xt [tile][n_pad][128].
+
+    Pixel-sharded fits (``eng.shard``): every rank holds the columns [j0, j1) of X_.  ``xt_times`` multiplies the local
+    slab and all-gathers the rows (the tall p x r panels are 15 MB at C3: every rank then factorises the SAME full
+    panel, so the algorithm and its pivoting are exactly the unsharded ones); ``x_times`` multiplies the local rows
+    of its argument and all-reduces the n x r result."""
 
     def __init__(self, eng):
         st = eng.st
-        self.n, self.p, self.n_pad, self.n_tiles = eng.n, eng.p_loc, st.n_pad, st.n_tiles
+        self.n, self.p_loc, self.n_pad, self.n_tiles = eng.n, eng.p_loc, st.n_pad, st.n_tiles
+        self.p, self.j0 = eng.p, eng.j0
+        self.shard = eng.shard
         self.dtype = torch.float64 if eng.c_code == L.F64 else torch.float32
         if eng.x_code == L.U8:          # compact count storage: a dense copy for the 16 GEMMs of the initialisation
             self.T3 = eng.Xt.view(st.n_tiles, st.n_pad, L.TILE_PX).to(self.dtype)
@@ -44,29 +51,55 @@ class _DeviceX:
         else:
             self.T3 = eng.Xt.view(st.n_tiles, st.n_pad, L.TILE_PX)
         self.device = eng.Xt.device
+        if self.shard is not None:
+            import torch.distributed as dist
+            self._dist = dist
+            sizes = [None] * self.shard.world
+            dist.all_gather_object(sizes, (int(self.j0), int(self.p_loc)), group=self.shard.group)
+            self.bounds = sizes                          # (j0, p_loc) of every rank
+            self.p_max = max(b[1] for b in sizes)
 
     def mean(self):
         # pad channels and pad pixels of Xt are zero
-        return float(self.T3.sum(dtype=torch.float64).item()) / (float(self.n) * float(self.p))
+        tot = self.T3.sum(dtype=torch.float64).reshape(1)
+        if self.shard is not None:
+            self.shard.allreduce_sum(tot)
+        return float(tot.item()) / (float(self.n) * float(self.p))
+
+    def _gather_rows(self, Y_loc):
+        """(p_loc x r) row blocks of every rank -> the full (p x r) matrix, on every rank."""
+        if self.shard is None:
+            return Y_loc
+        r = Y_loc.shape[1]
+        pad = torch.zeros(self.p_max, r, dtype=Y_loc.dtype, device=Y_loc.device)
+        pad[:self.p_loc] = Y_loc
+        parts = [torch.empty_like(pad) for _ in range(self.shard.world)]
+        self._dist.all_gather(parts, pad, group=self.shard.group)
+        out = torch.empty(self.p, r, dtype=Y_loc.dtype, device=Y_loc.device)
+        for (j0, pl), part in zip(self.bounds, parts):
+            out[j0:j0 + pl] = part[:pl]
+        return out
 
     def xt_times(self, Qn):
-        """X^T @ Qn for Qn (n x r) -> (p x r)."""
+        """X^T @ Qn for Qn (n x r) -> (p x r) (all pixels, on every rank)."""
         r = Qn.shape[1]
         Qp = torch.zeros(self.n_pad, r, dtype=self.dtype, device=self.device)
         Qp[:self.n] = Qn
         Y = torch.matmul(self.T3.transpose(1, 2), Qp)          # [tiles, 128, r]
-        return Y.reshape(self.n_tiles * L.TILE_PX, r)[:self.p]
+        return self._gather_rows(Y.reshape(self.n_tiles * L.TILE_PX, r)[:self.p_loc])
 
     def x_times(self, Qp):
         """X @ Qp for Qp (p x r) -> (n x r); tiles are folded in chunks to bound the temporary."""
         r = Qp.shape[1]
         P3 = torch.zeros(self.n_tiles * L.TILE_PX, r, dtype=self.dtype, device=self.device)
-        P3[:self.p] = Qp
+        P3[:self.p_loc] = Qp[self.j0:self.j0 + self.p_loc] if self.shard is not None else Qp
         P3 = P3.view(self.n_tiles, L.TILE_PX, r)
         out = torch.zeros(self.n_pad, r, dtype=self.dtype, device=self.device)
         step = 256
         for t0 in range(0, self.n_tiles, step):
             out += torch.matmul(self.T3[t0:t0 + step], P3[t0:t0 + step]).sum(0)
+        if self.shard is not None:
+            self.shard.allreduce_sum(out)
         return out[:self.n]
 
 
@@ -131,7 +164,7 @@ def initialize_nmf_device(eng, n_components, init=None, random_state=None):
     """``sklearn.decomposition._nmf._initialize_nmf(X_, n_components, init, random_state)`` with the SVD on the
     device.  Returns (W (n x k), H (k x p)) host arrays (the D and H of updates.py:179)."""
     from sklearn.utils import check_random_state
-    n, p = eng.n, eng.p_loc
+    n, p = eng.n, eng.p
     if init is not None and init != "random" and n_components > min(n, p):
         raise ValueError("init = '{}' can only be used when n_components <= min(n_samples, n_features)".format(init))
     if init is None:

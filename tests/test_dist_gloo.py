@@ -144,3 +144,43 @@ def test_shard_bounds_cover_image_rows():
     assert [shard_bounds(10, 0, 0, r, 3)[:2] for r in range(3)] == [(0, 4), (4, 7), (7, 10)]
     with pytest.raises(ValueError):
         shard_bounds(12, 3, 4, 0, 4)
+
+
+def _body_sharded_init(rank, world):
+    """NNDSVD initialisation against a pixel-SHARDED X (init_device.py): local products, all-gathered tall panels,
+    all-reduced n x r results.  CPU tensors + gloo stand in for the device + NCCL; the reference is scikit-learn's
+    _initialize_nmf on the whole matrix (updates.py:179)."""
+    import types
+    from sklearn.decomposition._nmf import _initialize_nmf
+    from espm_b200 import _lib as L
+    from espm_b200.dist import Shard, shard_bounds
+    from espm_b200.init_device import initialize_nmf_device
+    rng = np.random.default_rng(5)
+    n, nx, ny, k, m = 96, 21, 24, 3, 7            # 21 image rows: ragged shards
+    p = nx * ny
+    x = np.linspace(0, 1, n)
+    G = np.stack([np.exp(-0.5 * ((x - c) / 0.04) ** 2) for c in np.linspace(0.1, 0.9, m - 2)]
+                 + [np.exp(-3 * x) + 0.05, (1 - x) * 0.5 + 0.05], axis=1)
+    Ht = rng.uniform(size=(k, p)) ** 3
+    lam = G @ (rng.uniform(size=(m, k)) ** 2) @ (Ht / Ht.sum(0, keepdims=True))
+    X = rng.poisson(lam / lam.sum(0, keepdims=True) * 60.0).astype(np.float64) + 1e-14
+    j0, j1, _ = shard_bounds(p, nx, ny, rank, world)
+    p_loc = j1 - j0
+    n_pad, nt = (n + 31) // 32 * 32, (p_loc + 127) // 128
+    Xt = np.zeros((nt, n_pad, 128))
+    for t in range(nt):
+        w = min(128, p_loc - t * 128)
+        Xt[t, :n, :w] = X[:, j0 + t * 128:j0 + t * 128 + w]
+    eng = types.SimpleNamespace(n=n, p=p, p_loc=p_loc, j0=j0, shard=Shard(), Xt=torch.from_numpy(Xt.reshape(-1)),
+                                x_code=L.F64, c_code=L.F64, st=types.SimpleNamespace(n_pad=n_pad, n_tiles=nt))
+    for init in (None, "nndsvd", "random"):
+        Wd, Hd = initialize_nmf_device(eng, k, init, random_state=3)
+        Ws, Hs = _initialize_nmf(X, k, init=init, random_state=3)
+        assert Wd.shape == Ws.shape and Hd.shape == Hs.shape
+        assert np.max(np.abs(Wd - Ws)) <= 1e-10 * np.abs(Ws).max(), init
+        assert np.max(np.abs(Hd - Hs)) <= 1e-10 * np.abs(Hs).max(), init
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_nndsvd_init(tmp_path, world):
+    _run("_body_sharded_init", world, tmp_path)

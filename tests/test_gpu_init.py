@@ -94,7 +94,8 @@ def test_init_host_logic_with_cpu_tensors(dtype, tol):
         Xt[t, :n, :w] = Xp[:, t * 128:t * 128 + w]
     from espm_b200 import _lib as L
     code = L.F64 if dtype == np.float64 else L.F32
-    eng = types.SimpleNamespace(n=n, p_loc=p, Xt=torch.from_numpy(Xt.reshape(-1)), x_code=code, c_code=code,
+    eng = types.SimpleNamespace(n=n, p=p, p_loc=p, j0=0, shard=None, Xt=torch.from_numpy(Xt.reshape(-1)), x_code=code,
+                                c_code=code,
                                 st=types.SimpleNamespace(n_pad=n_pad, n_tiles=nt))
     for init in (None, "nndsvd", "nndsvdar", "random"):
         Wd, Hd = initialize_nmf_device(eng, k, init, random_state=3)

@@ -110,6 +110,27 @@ def _worker(rank, world, port, out_dir, peer):
             res[tag + "__H"] = est.H_
             res[tag + "__losses"] = np.array(est.losses_)
             res[tag + "__rel"] = np.array(est.rel_)
+        # default call, no W / H given (updates.py:179): the NNDSVD initialisation runs on the device against the SHARDED
+        # X (init_device.py: local products, all-gathered panels, all-reduced n x r results); rank 0 then repeats the
+        # fit unsharded in the same process
+        import espm_b200
+        X, G, _, _ = _data("simplex_H_lap_mu")
+        kw = dict(CASES["simplex_H_lap_mu"])
+
+        def default_fit():
+            est = SmoothNMF(n_components=3, G=G, shape_2d=(NX, NY), tol=0, no_stop_criterion=True, max_iter=5,
+                            verbose=0, random_state=0, **kw)
+            with contextlib.redirect_stdout(io.StringIO()):
+                est.fit_transform(X)
+            return est
+        est = default_fit()
+        res["init__W"], res["init__H"], res["init__losses"] = est.W_, est.H_, np.array(est.losses_)
+        if rank == 0:
+            keep = espm_b200.config.distributed
+            espm_b200.config.distributed = False
+            est1 = default_fit()
+            espm_b200.config.distributed = keep
+            res["init1__W"], res["init1__H"], res["init1__losses"] = est1.W_, est1.H_, np.array(est1.losses_)
         np.savez(os.path.join(out_dir, "rank%d.npz" % rank), **res)
     finally:
         dist.destroy_process_group()
@@ -149,6 +170,13 @@ def test_sharded_fit_matches_oracle(tmp_path, peer, world):
         for r in res[1:]:
             assert np.array_equal(res[0][tag + "__W"], r[tag + "__W"]), tag
             assert np.array_equal(res[0][tag + "__losses"], r[tag + "__losses"]), tag
+    # default initialisation on the device, sharded vs unsharded (fp64; the randomized subspace iteration is contractive)
+    r0 = res[0]
+    assert rel_err(r0["init__losses"], r0["init1__losses"]) < 1e-9
+    assert rel_err(r0["init__W"], r0["init1__W"]) < 1e-7
+    assert rel_err(r0["init__H"], r0["init1__H"]) < 1e-6
+    for r in res[1:]:
+        assert np.array_equal(r0["init__W"], r["init__W"])
 
 
 # ------------------------------------------------------------------------------------------------------------
