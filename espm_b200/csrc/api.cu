@@ -88,6 +88,9 @@ static int check_state(const espm_state* st) {
     return ESPM_OK;
 }
 
+#ifndef ESPM_L2PIN_MB_DEFAULT
+#define ESPM_L2PIN_MB_DEFAULT 0
+#endif
 static XPassArgs make_args(const espm_state* st, bool w_pass) {
     XPassArgs a;
     memset(&a, 0, sizeof(a));
@@ -116,6 +119,20 @@ static XPassArgs make_args(const espm_state* st, bool w_pass) {
     a.y_shift = (!w_pass && (st->flags & ESPM_FLAG_HQ)) ? st->log_shift : 0.0;
     a.n = st->n;
     a.p_loc = st->p_loc;
+    {
+        // L2-resident part of X (see XPassArgs::pin_tiles): ESPM_B200_L2PIN_MB megabytes of the tile-major image
+        static int pin_mb = -1;
+        if (pin_mb < 0) {
+            const char* e = getenv("ESPM_B200_L2PIN_MB");
+            pin_mb = e ? atoi(e) : ESPM_L2PIN_MB_DEFAULT;
+            if (pin_mb < 0) pin_mb = 0;
+        }
+        const size_t item = st->x_dtype == ESPM_F64 ? 8 : st->x_dtype == ESPM_F32 ? 4 : st->x_dtype == ESPM_U16 ? 2 : 1;
+        const size_t tile_bytes = (size_t)st->n_pad * TILE_PX * item;
+        long long t = tile_bytes ? (long long)(((size_t)pin_mb << 20) / tile_bytes) : 0;
+        if (t > st->n_tiles) t = st->n_tiles;
+        a.pin_tiles = (int)t;
+    }
     return a;
 }
 

@@ -765,8 +765,11 @@ __device__ __forceinline__ void h_scalars_block(const espm_state& st, double* sh
 // ------------------------------------------------------------------------------------------------
 // h_finish: per-pixel assembly (updates.py:132-152) + loss regularisers + rel_H + bisection trace
 // ------------------------------------------------------------------------------------------------
-template <typename TC, int KP>
-__global__ void __launch_bounds__(PX_THREADS, 4) h_finish_kernel(const espm_state st) {
+// OCC: CTAs per SM the kernel is compiled for.  4 (64 registers per thread) when the shard needs more than two CTAs per
+// SM; 2 (128 registers: no spills, no rematerialised conversions in the root search) when the whole grid fits in
+// 2 x #SM CTAs anyway -- the pixel shards of a multi-GPU fit, where the kernel is a pure latency chain.
+template <typename TC, int KP, int OCC>
+__global__ void __launch_bounds__(PX_THREADS, OCC) h_finish_kernel(const espm_state st) {
     pdl_wait();
     pdl_trigger();
     if (blockIdx.x == 0 && threadIdx.x == 0) time_stamp(st, 6);

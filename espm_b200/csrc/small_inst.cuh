@@ -50,7 +50,11 @@ static int small_launch_t(int op, const espm_state* st, cudaStream_t s) {
     const int kp = st->kp;
     switch (op) {
         case OP_H_FINISH:
-            ESPM_KP_SWITCH(kp, ESPM_CUDA_CHECK(launch_pdl(h_finish_kernel<TC, KP>, dim3(st->px_blocks), dim3(PX_THREADS), 0, s, *st)));
+            if (st->n_sms > 0 && st->px_blocks <= 2 * st->n_sms) {
+                ESPM_KP_SWITCH(kp, ESPM_CUDA_CHECK(launch_pdl(h_finish_kernel<TC, KP, 2>, dim3(st->px_blocks), dim3(PX_THREADS), 0, s, *st)));
+            } else {
+                ESPM_KP_SWITCH(kp, ESPM_CUDA_CHECK(launch_pdl(h_finish_kernel<TC, KP, 4>, dim3(st->px_blocks), dim3(PX_THREADS), 0, s, *st)));
+            }
             break;
         case OP_H_APPLY:
             ESPM_KP_SWITCH(kp, ESPM_CUDA_CHECK(launch_pdl(h_apply_kernel<TC, KP>, dim3(st->px_blocks), dim3(PX_THREADS), 0, s, *st)));

@@ -1,27 +1,56 @@
 """Synthetic STEM-EDXS spectrum images of the BASELINE.json shapes (no network, no hyperspy/exspy):
-an EDXS-like G (Gaussian x-ray lines + two bremsstrahlung columns), sphere phase maps and Poisson counts,
+an EDXS G (tabulated x-ray lines at 200 keV + two bremsstrahlung columns), sphere phase maps and Poisson counts,
 following the recipe of SURVEY.md section 8d (espm/datasets/base.py:13-68, models/edxs.py:163-254,
 weights/generate_weights.py:182-223).  Host-side NumPy for small cases, torch for device generation."""
 import numpy as np
 
 
+_TABLES = None
+
+
+def _tables():
+    """x-ray line energies / cross sections at 200 keV and the SDD efficiency curve of the reference's tables
+    (espm/tables/200keV_xrays.json, SDD_efficiency.txt), extracted by scripts/gen_xray_table.py."""
+    global _TABLES
+    if _TABLES is None:
+        import json
+        import os
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "edxs_tables.json")
+        with open(path) as fh:
+            _TABLES = json.load(fh)
+    return _TABLES
+
+
 def edxs_G(n, n_elements, seed, e_offset=0.2, e_scale=0.01, E0=200.0):
-    """G (n x (n_elements+2)): per element 1-4 Gaussian lines with width (0.01 E + 0.065)/2.3548, times a
-    smooth detector efficiency, plus two Lifshin-type bremsstrahlung columns; columns scaled to max 1."""
-    rng = np.random.default_rng(seed)
+    """G (n x (n_elements+2)) following SURVEY.md section 8d: energy axis x = linspace(offset, offset + n scale, n)
+    (models/base.py:215); per element the column sum_lines cs N(x; E_line, (0.01 E_line + 0.065) / 2.3548) D(E_line)
+    with the line energies and emission cross sections of espm/tables/200keV_xrays.json and the detector efficiency D
+    of SDD_efficiency.txt (models/edxs.py:56-110, EDXS_function.py:20-46; absorption == 1); plus the two
+    bremsstrahlung columns lifshin_b0 / lifshin_b1 (EDXS_function.py:159-172) times D(x); the element columns are
+    normalised by their mean sum, the two continuum columns by their own sums (models/edxs.py:246-252).
+    ``seed`` is unused (the element list is fixed: the first n_elements of the table's 25)."""
+    tb = _tables()
     x = np.linspace(e_offset, e_offset + n * e_scale, n)
-    det = 1.0 - np.exp(-x / 0.6) * 0.9            # low-energy roll-off of an SDD-like efficiency
+    ee = np.asarray(tb["sdd_efficiency"]["energy_keV"])
+    ev = np.asarray(tb["sdd_efficiency"]["efficiency"])
+
+    def det(e):
+        return np.interp(e, ee, ev)
+    Z = tb["elements"][:n_elements]
+    if len(Z) < n_elements:
+        raise ValueError("the table holds %d elements, %d requested" % (len(tb["elements"]), n_elements))
     G = np.zeros((n, n_elements + 2))
-    for e in range(n_elements):
-        for _ in range(rng.integers(1, 5)):
-            E = rng.uniform(x[0] + 0.3, x[-1] - 0.3)
+    for e, z in enumerate(Z):
+        for _, E, cs in tb["lines"][str(z)]:
+            if not (x[0] <= E <= x[-1]):
+                continue
             w = (0.01 * E + 0.065) / 2.3548
-            cs = rng.uniform(0.2, 1.0)
-            G[:, e] += cs * np.exp(-0.5 * ((x - E) / w) ** 2) * np.interp(E, x, det)
-    G[:, -2] = (E0 - x) / x * det
-    G[:, -1] = (E0 - x) ** 2 / (E0 * x) * det
-    G /= G.max(axis=0, keepdims=True)
-    return G
+            G[:, e] += cs * np.exp(-0.5 * ((x - E) / w) ** 2) / (w * np.sqrt(2 * np.pi)) * det(E)
+    G[:, -2] = (E0 - x) / (E0 * x) * (1.0 - (E0 - x) / E0) * det(x)
+    G[:, -1] = (E0 - x) ** 2 / (E0 * E0 * x) * det(x)
+    norms = G.sum(axis=0, keepdims=True)
+    norms[0, :-2] = np.mean(norms[0, :-2])
+    return G / norms
 
 
 def true_W(m, k, seed):

@@ -19,7 +19,20 @@ from espm_b200 import engine as E
 nx = ny = 512
 n, k, K = 2048, 4, 20
 prob = synth.make_problem(nx, ny, n, k, 25, seed=93)
-dev = torch.device("cuda", 0)
+rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+torch.cuda.set_device(dev)
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=dev)
+_print = print
+
+
+def print(*a, **k_):                      # noqa: A001 -- rank 0 speaks
+    if rank == 0:
+        _print(*a, **k_)
+
+
 X = synth.poisson_X_torch(prob, 0, nx * ny, 93, dev, torch.float32)
 Xh = torch.empty((n, nx * ny), dtype=torch.float32, pin_memory=True)
 Xh.copy_(X)
@@ -71,6 +84,19 @@ fit()
 plain = sorted(fit() for _ in range(5))
 print("un-instrumented fits: %s ms" % ", ".join("%.1f" % (t * 1e3) for t in plain))
 orig = {}
+if world > 1:
+    from espm_b200 import dist as D
+    for nm in ("setup_peer", "setup_inbox", "close"):
+        timed(D.PeerShard, nm)
+    mk0 = D.make_shard
+
+    def mk(*a, **kw_):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = mk0(*a, **kw_)
+        stages["make_shard"] = stages.get("make_shard", 0.0) + time.perf_counter() - t0
+        return out
+    D.make_shard = mk
 for nm in ("_stage_x", "_choose_storage", "_retile_x", "set_G", "_init_WH", "run_iterations", "evaluate", "read_records",
            "get_W", "get_H"):
     orig[nm] = timed(E.FitEngine, nm)
@@ -91,5 +117,9 @@ tot = sum(fit() for _ in range(R))
 print("instrumented fit: %.1f ms" % (tot / R * 1e3))
 for nm, t in sorted(stages.items(), key=lambda kv: -kv[1]):
     print("  %-18s %7.2f ms" % (nm, t / R * 1e3))
-sub = sum(stages.get(nm, 0.0) for nm in ("_stage_x", "_choose_storage", "_retile_x", "set_G", "_init_WH"))
+sub = sum(stages.get(nm, 0.0) for nm in ("_stage_x", "_choose_storage", "_retile_x", "set_G", "_init_WH", "setup_peer",
+                                         "setup_inbox"))
 print("  %-18s %7.2f ms" % ("__init__ (rest)", (stages["__init__ (all)"] - sub) / R * 1e3))
+if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()

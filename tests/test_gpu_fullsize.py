@@ -212,7 +212,7 @@ def test_loss_decreases_at_full_size():
     assert losses.shape == (10,) and np.all(np.isfinite(losses))
     assert np.all(np.diff(losses) < 0)
     assert np.max(np.abs(est.H_.sum(0) - 1.0)) <= 1.1e-5
-    assert est.W_.shape == (27, 4) and np.all(est.W_ >= 1e-14)
+    assert est.W_.shape == (27, 4) and np.all(est.W_ >= float(np.float32(1e-14)))
 
 
 def test_free_nmf_simplex_w_at_full_size():
@@ -238,7 +238,8 @@ def test_free_nmf_simplex_w_at_full_size():
     assert int(recs[0][L.S_DEV_FLAGS]) == 0 and int(recs[1][L.S_DEV_FLAGS]) == 0
     its = int(recs[1][L.S_BISECT_ITS_W])
     assert 5 < its < 80
-    assert np.all(np.isfinite(W1)) and np.all(W1 >= LS) and np.all(np.isfinite(H1)) and np.all(H1 >= LS)
+    lsf = float(dtype(LS))                # the clamp in the arithmetic type: float32(1e-14) is a hair below 1e-14
+    assert np.all(np.isfinite(W1)) and np.all(W1 >= lsf) and np.all(np.isfinite(H1)) and np.all(H1 >= lsf)
     assert np.max(np.abs(W1.sum(0) - 1.0)) <= TOL * 1.001 + 2e-6          # columns of W on the simplex
 
     dev = X.device
