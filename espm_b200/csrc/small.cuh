@@ -598,6 +598,21 @@ struct KlAnchorReplay {
     }
 };
 
+// "Far" midpoints of a root-anchored evaluator: while |new - nu*| exceeds every size threshold (and the rounding margin
+// mx), the evaluator's answer is {sign by side, |f| > tol} without looking at anything else -- see
+// KlAnchorEval::operator().  far_info() hands the trace loop the root and that distance (false: no such shortcut).
+template <typename E>
+__device__ __forceinline__ bool far_info(const E&, double&, double&) {
+    return false;
+}
+template <int KP>
+__device__ __forceinline__ bool far_info(const KlAnchorEval<KP>& ev, double& nu, double& dist) {
+    if (!ev.ok) return false;
+    nu = ev.nu;
+    dist = fmax(fmax(ev.eLhi, ev.eRhi), ev.mx);     // +inf when the size bounds are unusable: the fast loop never runs
+    return true;
+}
+
 template <typename E>
 __device__ __forceinline__ void bisect_trace_rec(double a, double b, const E& ev, int maxit, Mask128& bad, Mask128& dec,
                                                  uint32_t& seen, uint32_t& err) {
@@ -609,6 +624,31 @@ __device__ __forceinline__ void bisect_trace_rec(double a, double b, const E& ev
     int j = 0, widx = 0;
     uint32_t stat = 0u;
     uint32_t wb = 0u, wd = 0u, bit = 1u;    // bits of the current 32-iteration word
+    // Fast loop over the far midpoints (typically the first ~17 of ~21 iterations): a dozen instructions each instead
+    // of the general body below.  It takes exactly the decisions the general body would take: the evaluator returns
+    // {new > nu*, bad} there; the moved end is not within tol, so `a_ok && b_ok` stays false; nu* stays inside [a, b],
+    // so a stationary bracket (new == a or b) is at most one ulp from nu*, i.e. within mx, and ends this loop.
+    {
+        double nu_far = 0.0, dist = 0.0;
+        if (far_info(ev, nu_far, dist) && !(a_ok && b_ok)) {
+            while (j < maxit && j < 31) {
+                const double d = nw - nu_far;
+                if (!(fabs(d) > dist)) break;
+                wb |= bit;
+                if (d > 0.0) {
+                    b = nw;
+                    b_ok = false;
+                    wd |= bit;
+                } else {
+                    a = nw;
+                    a_ok = false;
+                }
+                nw = (a + b) * 0.5;
+                bit <<= 1;
+                ++j;
+            }
+        }
+    }
     for (; j < maxit; ++j) {
         const Cls c = ev(nw);
         if (c.bad) wb |= bit;
@@ -1676,7 +1716,7 @@ __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_sta
             TC acc[KP];
 #pragma unroll
             for (int kk = 0; kk < KP; ++kk) acc[kk] = TC(0);
-#pragma unroll 2
+#pragma unroll 4
             for (int c = threadIdx.x; c < n; c += W_COOP_THREADS) {
                 const TC g = Gt[(size_t)mm * n + c];
                 TC srow[KP];
@@ -1721,15 +1761,6 @@ __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_sta
             }
             __syncthreads();
         }
-    }
-    // T path: the column of G this thread needs in phase C does not depend on W' -- fetch it now, so that its L2 round
-    // trips overlap the synchronisation point instead of following it
-    constexpr int GPRE = 32;
-    TC gpre[GPRE];
-    const bool pre = tp && m <= GPRE && gthread < n;
-    if (pre) {
-#pragma unroll
-        for (int mm = 0; mm < GPRE; ++mm) gpre[mm] = (mm < m) ? Gt[(size_t)mm * n + gthread] : TC(0);
     }
     // x / 0 in the W pass (updates.py:53-56): the caller redoes the step with ESPM_FLAG_CLAMP_Y
     if (__any_sync(0xffffffffu, nonfinite) && lane == 0)
@@ -2024,15 +2055,6 @@ __global__ void __launch_bounds__(W_COOP_THREADS) w_finish_kernel(const espm_sta
 #pragma unroll
                 for (int kk = 0; kk < KP; ++kk)
                     if (kk < k) v[kk] = Wsrc[(size_t)c * k + kk];
-            } else if (pre && c == gthread) {
-#pragma unroll
-                for (int mm = 0; mm < GPRE; ++mm) {
-                    if (mm < m) {
-#pragma unroll
-                        for (int kk = 0; kk < KP; ++kk)
-                            if (kk < k) v[kk] = fma(gpre[mm], Wsrc[(size_t)mm * k + kk], v[kk]);
-                    }
-                }
             } else {
 #pragma unroll 8
                 for (int mm = 0; mm < m; ++mm) {
