@@ -406,7 +406,7 @@ def main():
         # the whole image when the host has the memory for the reference's n x p temporaries
         # (4 of them live at once: 8.6 GB fp32 / 17 GB fp64 at C3), else a crop scaled linearly in p
         full_gb = 6.0 * n * p * np_dtype().itemsize / 2 ** 30
-        rows = nx if (args.cpu_rows <= 0 and host_ram_gb() >= max(64.0, 2 * full_gb)) else min(max(args.cpu_rows, 1), nx)
+        rows = nx if (args.cpu_rows <= 0 and host_ram_gb() >= max(64.0, 2 * full_gb)) else min(args.cpu_rows if args.cpu_rows > 1 else 48, nx)
         if args.cpu_rows <= 0 and rows == nx and args.workload in ("C4", "C5"):
             rows = min(48, nx)                       # always crop-and-scale
         steps = max(1, min(K, 5 if rows == nx else 20))

@@ -88,6 +88,9 @@ static int check_state(const espm_state* st) {
     return ESPM_OK;
 }
 
+#ifndef ESPM_GWRES_DEFAULT
+#define ESPM_GWRES_DEFAULT 0
+#endif
 #ifndef ESPM_L2PIN_MB_DEFAULT
 #define ESPM_L2PIN_MB_DEFAULT 0
 #endif
@@ -119,6 +122,16 @@ static XPassArgs make_args(const espm_state* st, bool w_pass) {
     a.y_shift = (!w_pass && (st->flags & ESPM_FLAG_HQ)) ? st->log_shift : 0.0;
     a.n = st->n;
     a.p_loc = st->p_loc;
+    if (!w_pass) {
+        // resident GW: the planner appended the region to the H pass's shared memory (espm_plan)
+        XPassSizes z;
+        if (sizes_of(st, 1, &z) == ESPM_OK) {
+            const int csz = st->c_dtype == ESPM_F64 ? 8 : 4;
+            const int gw_al = (st->n_pad * st->kp * csz + 127) / 128 * 128;
+            const int extra = st->h_smem - (z.fixed + st->h_depth * z.h_stride + z.h_tail);
+            a.gw_res_off = (extra >= gw_al && extra > 0) ? st->h_smem - gw_al : 0;
+        }
+    }
     {
         // L2-resident part of X (see XPassArgs::pin_tiles): ESPM_B200_L2PIN_MB megabytes of the tile-major image
         static int pin_mb = -1;
@@ -229,8 +242,27 @@ int espm_plan(espm_state* st) {
         set_error("shared memory budget too small for the H pass (kp=%d)", st->kp);
         return ESPM_ERR_UNSUPPORTED;
     }
+    // GW resident in the H pass's shared memory (XPassArgs::gw_res_off) when all of it fits beside a ring of >= 3 stages
+    int gw_extra = 0;
+    {
+        static int on = -1;
+        if (on < 0) {
+            const char* e = getenv("ESPM_B200_GWRES");
+            on = e ? (atoi(e) != 0) : ESPM_GWRES_DEFAULT;
+        }
+        const int csz = st->c_dtype == ESPM_F64 ? 8 : 4;
+        const int gw_al = (st->n_pad * st->kp * csz + 127) / 128 * 128;
+        if (on && gw_al <= 40 * 1024) {
+            int d2 = (budget_for(z.h_occ) - z.fixed - z.h_tail - gw_al) / z.h_stride;
+            if (d2 > 8) d2 = 8;
+            if (d2 >= 3) {
+                if (d2 < depth) depth = d2;
+                gw_extra = gw_al;
+            }
+        }
+    }
     st->h_depth = depth;
-    st->h_smem = z.fixed + depth * z.h_stride + z.h_tail;
+    st->h_smem = z.fixed + depth * z.h_stride + z.h_tail + gw_extra;
     int occ = 0;
     {
         XPassLaunch l{XPASS_H, st->kp, 1, 1, st->h_smem, XMODE_KL};

@@ -35,6 +35,8 @@ struct XPassArgs {
     double log_shift;
     double y_shift;      // H pass: ratio = x / (y + y_shift); log_shift for algo="l2_surrogate" (updates.py:280), else 0
     int n, p_loc;        // real channel / pixel counts (the Frobenius loss masks the padding)
+    int gw_res_off;      // H pass, non-SAFE instances: byte offset in shared memory where the CTA keeps ALL rows of GW for the
+                         // whole pass (0: the GW rows of a stage travel with it, a second bulk copy per stage)
     int pin_tiles;       // X of the last pin_tiles tiles is fetched with the L2 evict_last policy by BOTH passes: that part
                          // of the image stays in the 126 MB L2 from pass to pass and is not read from HBM again
 };
@@ -245,6 +247,16 @@ h_pass_kernel(const XPassArgs a) {
     pdl_wait();
     pdl_trigger();
     if (blockIdx.x == 0 && threadIdx.x < 4 && a.bisect_mask) a.bisect_mask[threadIdx.x] = 0u;
+    // GW resident in shared memory for the whole pass (n_pad x KP values, 32 KiB at C3): one bulk copy per stage
+    // instead of two, and the 512 B of GW rows per stage are not fetched from L2 131072 times per pass
+    const bool gw_res = !SAFE && a.gw_res_off != 0;
+    const unsigned char* gwres = smem + a.gw_res_off;
+    if (gw_res) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(a.GW);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(smem + a.gw_res_off);
+        const int words = a.n_pad * KP * (int)sizeof(TC) / 4;
+        for (int i = threadIdx.x; i < words; i += XPASS_THREADS) dst[i] = src[i];
+    }
     __syncthreads();
 
     const int n_items = a.n_tiles * a.nsplit;
@@ -265,9 +277,10 @@ h_pass_kernel(const XPassArgs a) {
                     ring.acquire(pos);
                     const int slot = pos.slot;
                     unsigned char* sp = ring.stage(slot);
-                    mbar_expect_tx(&ring.full[slot], S::X_BYTES + S::GW_BYTES * (dual ? 2 : 1));
+                    mbar_expect_tx(&ring.full[slot], S::X_BYTES + (gw_res ? 0 : S::GW_BYTES * (dual ? 2 : 1)));
                     const TX* xsrc = reinterpret_cast<const TX*>(a.Xt) + ((size_t)tile * a.n_pad + (size_t)st * G::CS) * TILE_PX;
                     tma_bulk_g2s(sp, xsrc, S::X_BYTES, &ring.full[slot], tile >= pin0 ? pol_gw : pol_x);
+                    if (gw_res) continue;
                     const TC* gsrc = reinterpret_cast<const TC*>(a.GW) + (size_t)st * G::CS * KP;
                     tma_bulk_g2s(sp + S::X_BYTES, gsrc, S::GW_BYTES, &ring.full[slot], pol_gw);
                     if (dual) {
@@ -312,7 +325,7 @@ h_pass_kernel(const XPassArgs a) {
             for (int st = s0; st < s1; ++st, ring.next(pos)) {
                 ring.consumer_wait(pos);
                 const unsigned char* xs = ring.stage(pos.slot);
-                const unsigned char* gs = xs + S::X_BYTES;
+                const unsigned char* gs = gw_res ? gwres + (size_t)st * G::CS * KP * sizeof(TC) : xs + S::X_BYTES;
                 float2 xl2 = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int ci = 0; ci < G::CPW; ++ci) {
@@ -359,7 +372,7 @@ h_pass_kernel(const XPassArgs a) {
             for (int st = s0; st < s1; ++st, ring.next(pos)) {
                 ring.consumer_wait(pos);
                 const unsigned char* xs = ring.stage(pos.slot);
-                const unsigned char* gs = xs + S::X_BYTES;
+                const unsigned char* gs = gw_res ? gwres + (size_t)st * G::CS * KP * sizeof(TC) : xs + S::X_BYTES;
                 const unsigned char* gcs = gs + S::GW_BYTES_AL;
                 TC xl = TC(0);
                 float zl = 0.f;

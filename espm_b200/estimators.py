@@ -484,7 +484,10 @@ class SmoothNMF(TransformerMixin, BaseEstimator):
                 rel_w = rec[L.S_REL_W]
                 eng.enable_clamp()
                 if int(rec[L.S_DEV_FLAGS]) & L.DEV_NONFINITE_W:
+                    # back to iterate it - 1; its H update has to be rebuilt as well (the trace / ratio sums on the
+                    # device belong to a later evaluation by now), then the whole step is repeated with the clamp
                     eng.rollback()
+                    eng.evaluate(eng.max_records - 7)
                     eng.advance(it)
                     rel_w = None
                 eng.evaluate(it)
