@@ -34,6 +34,10 @@ WORKLOADS = {
     # kernels at the shard size that limits strong scaling (ncu cannot attach to a multi-rank run)
     "C3r8": dict(nx=64, ny=512, n=2048, k=4, n_elements=25,
                  kw=dict(simplex_H=True, simplex_W=False, lambda_L=2.0, mu=0.05)),
+    "C3r4": dict(nx=128, ny=512, n=2048, k=4, n_elements=25,
+                 kw=dict(simplex_H=True, simplex_W=False, lambda_L=2.0, mu=0.05)),
+    "C3r2": dict(nx=256, ny=512, n=2048, k=4, n_elements=25,
+                 kw=dict(simplex_H=True, simplex_W=False, lambda_L=2.0, mu=0.05)),
     # configs[3]: 1024x1024 px x 4096 ch (17.2 GB fp32), 5 phases + Laplacian; --algo l2_surrogate for the "L2" reading
     "C4": dict(nx=1024, ny=1024, n=4096, k=5, n_elements=25,
                kw=dict(simplex_H=True, simplex_W=False, lambda_L=2.0, mu=0.05)),
