@@ -22,4 +22,7 @@ PY
 }
 run 8 C3
 run 4 C3
+run 2 C3 --no-compact
 run 8 C4 --no-e2e --no-compact
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29514 scripts/timeline.py --workload C3 --out gpurun_out/${TAG}_timeline_c3_n4.json 2>&1 | tail -5
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29519 scripts/e2e_stages.py 2>&1 | grep -v "^\*\|OMP_NUM" | tail -22 | tee gpurun_out/${TAG}_e2e_stages_n8.log
