@@ -131,6 +131,17 @@ class Shard:
         allr = np.stack([g.cpu().numpy() for g in gathered])          # (world, m, NSCALARS)
         return combine_record_arrays(allr)
 
+    def gather_H_device(self, H_dev, sizes):
+        """Concatenate the H shards along pixels (rank order) from DEVICE slabs: one padded all-gather and one D2H copy.
+        ``sizes``: the pixel count of every rank (known to every rank from shard_bounds, no collective needed)."""
+        k, mx = H_dev.shape[0], max(sizes)
+        pad = torch.zeros(k, mx, dtype=H_dev.dtype, device=H_dev.device)
+        pad[:, :H_dev.shape[1]] = H_dev
+        out = torch.empty(self.world, k, mx, dtype=H_dev.dtype, device=H_dev.device)
+        dist.all_gather_into_tensor(out, pad, group=self.group)
+        host = out.cpu().numpy()
+        return np.concatenate([host[r][:, :s] for r, s in enumerate(sizes)], axis=1)
+
     def gather_H(self, H_local, p):
         """Concatenate the H shards along pixels (rank order)."""
         k = H_local.shape[0]
@@ -471,12 +482,20 @@ def _peer_capable(group):
     return all(oks)
 
 
+_PEER_CAPABLE = {}
+
+
 def make_shard(group=None):
     """PeerShard when the process group runs NCCL, every rank sits on the same host with peer access between the
-    devices and ESPM_B200_PEER != 0; else Shard (NCCL collectives).  The decision is collective."""
+    devices and ESPM_B200_PEER != 0; else Shard (NCCL collectives).  The decision is collective; the capability check
+    (two object collectives, ~2 ms at 8 ranks) is made once per process group and device."""
     import os
-    if dist.get_backend(group) == "nccl" and os.environ.get("ESPM_B200_PEER", "1") != "0" and _peer_capable(group):
-        return PeerShard(group=group)
+    if dist.get_backend(group) == "nccl" and os.environ.get("ESPM_B200_PEER", "1") != "0":
+        key = (id(group) if group is not None else None, dist.get_world_size(group), torch.cuda.current_device())
+        if key not in _PEER_CAPABLE:
+            _PEER_CAPABLE[key] = _peer_capable(group)
+        if _PEER_CAPABLE[key]:
+            return PeerShard(group=group)
     return Shard(group=group)
 
 

@@ -854,10 +854,17 @@ class FitEngine:
         return self.Hbuf[self.ih[1]][:, self.halo:self.halo + self.p_loc].cpu().numpy()
 
     def get_H(self):
-        Hl = self.get_H_local()
         if self.shard is not None:
-            return self.shard.gather_H(Hl, self.p)
-        return Hl
+            from .dist import shard_bounds
+            sizes = []
+            for r in range(self.world):
+                a, b, _ = shard_bounds(self.p, self.nx, self.ny, r, self.world)
+                sizes.append(b - a)
+            Hd = self.Hbuf[self.ih[1]][:, self.halo:self.halo + self.p_loc]
+            if Hd.is_cuda:
+                return self.shard.gather_H_device(Hd, sizes)
+            return self.shard.gather_H(self.get_H_local(), self.p)
+        return self.get_H_local()
 
     def get_GW(self):
         return self.GWbuf[self.iw[0]][:self.n, :self.k].cpu().numpy()
