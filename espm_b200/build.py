@@ -29,7 +29,7 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "--expt-relaxed-constexpr",
     "-Xcompiler", "-fPIC",
-]
+] + os.environ.get("ESPM_NVCC_EXTRA", "").split()      # experiments: extra -D switches (part of the build digest)
 
 
 def _digest():

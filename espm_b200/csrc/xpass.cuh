@@ -49,6 +49,10 @@ struct XPassArgs {
 //                 updates.py:263-301, the loss is 0.5 Frobenius_loss, base.py:197-198)
 constexpr int XMODE_KL = 0, XMODE_FROB = 1, XMODE_KL_FROB = 2;
 
+#ifndef ESPM_H_OCC_F64
+#define ESPM_H_OCC_F64 2
+#endif
+
 template <typename TX, typename TC, int KP, bool SAFE>
 struct XPassSmem {
     using G = PassGeom<TX, TC>;
@@ -70,10 +74,12 @@ struct XPassSmem {
     static constexpr int ACC_WORDS = G::CPW * KP * (FAST32 ? 2 : (int)sizeof(TC) / 4);
     static constexpr bool ACC_REG = ACC_WORDS <= 64;
     // CTAs per SM the kernels are compiled for (register budget: 96 regs/thread at 2, 168 at 1)
-    static constexpr int H_OCC = (KP * (int)sizeof(TC) <= 32) ? 2 : 1;
+    static constexpr int OCC_BASE = (KP * (int)sizeof(TC) <= 32) ? 2 : 1;
+    // fp64 H pass: ESPM_H_OCC_F64 = 1 trades half the warps for twice the registers (more independent DP chains per warp)
+    static constexpr int H_OCC = (OCC_BASE == 2 && sizeof(TC) == 8) ? ESPM_H_OCC_F64 : OCC_BASE;
     static constexpr int W_REGS_EST = (ACC_REG ? ACC_WORDS : KP * (int)sizeof(TC) / 4 * (FAST32 ? 2 : 1)) +
                                       KP * G::PPL * (int)sizeof(TC) / 4 + 36;
-    static constexpr int W_OCC = (H_OCC == 2 && W_REGS_EST <= 110) ? 2 : 1;
+    static constexpr int W_OCC = (OCC_BASE == 2 && W_REGS_EST <= 110) ? 2 : 1;
 };
 
 template <typename T, int N>
