@@ -482,16 +482,28 @@ def main():
         (the next kernel's prologue no longer overlaps the predecessor's tail): measured with scripts/timeline.py,
         events in EVERY iteration cost 18 us per iteration at C3 and 16 us (10 %) on an 1/8 shard, so the per-kernel
         durations are sampled inside the timed region instead of taken from every launch."""
-        evs = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(4))
-               if (i % EV_EVERY == EV_EVERY - 1 or (count < EV_EVERY and i == count - 1)) else None for i in range(count)]
+        evs = []
+        for i in range(count):
+            if not (i % EV_EVERY == EV_EVERY - 1 or (count < EV_EVERY and i == count - 1)):
+                evs.append(None)
+                continue
+            # alternate between the two passes, so that a sampled iteration carries two events, not four
+            if count < 2 * EV_EVERY:        # too few timed iterations to alternate: both passes on the sampled ones
+                evs.append(tuple(torch.cuda.Event(enable_timing=True) for _ in range(4)))
+                continue
+            w_turn = (i // EV_EVERY) % 2 == 1
+            pair = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            evs.append((pair[0], pair[1], None, None) if w_turn else (None, None, pair[0], pair[1]))
         for tup in evs:
             for e in (tup or ()):
-                e.record()              # creates the underlying cudaEvent_t
+                if e is not None:
+                    e.record()              # creates the underlying cudaEvent_t
         return evs
 
     def pass_ms(evs):
-        evs = [t for t in evs if t is not None]
-        return (float(np.mean([t[2].elapsed_time(t[3]) for t in evs])), float(np.mean([t[0].elapsed_time(t[1]) for t in evs])))
+        h = [t[2].elapsed_time(t[3]) for t in evs if t is not None and t[2] is not None]
+        w = [t[0].elapsed_time(t[1]) for t in evs if t is not None and t[0] is not None]
+        return float(np.mean(h)), float(np.mean(w))
 
     # The K timed iterations are issued by ONE call into the library (espm_run_iterations: the launches and the buffer
     # rotation of every iteration in native code), which is what SmoothNMF.fit_transform does as well.
@@ -549,8 +561,10 @@ def main():
                 "peak_source": peak_src,
                 "bytes_per_launch": bytes_launch,
                 "h_pass_ms": h_ms, "w_pass_ms": w_ms,
-                "launches_timed": "CUDA events around the X passes of every %d-th of the %d timed iterations (%d launches "
-                                  "each)" % (EV_EVERY, K, len([t for t in evs if t is not None])),
+                "launches_timed": "CUDA events around one X pass (H and W in turn) of every %d-th of the %d timed "
+                                  "iterations: %d H-pass and %d W-pass launches" % (
+                                      EV_EVERY, K, len([t for t in evs if t is not None and t[2] is not None]),
+                                      len([t for t in evs if t is not None and t[0] is not None])),
                 "h_pass_gbs": bytes_launch / (h_ms * 1e-3) / 1e9, "w_pass_gbs": bytes_launch / (w_ms * 1e-3) / 1e9,
                 "iteration_frac": (2 * bytes_launch / (ms / K * 1e-3) / 1e9) / peak, "kernel_ms": kernel_ms,
                 "host_enqueue_ms_per_step": host_ms}

@@ -711,7 +711,7 @@ class FitEngine:
         lp.records = self.records.data_ptr()
         ev_arr = None
         if events is not None:
-            ev_arr = (ctypes.c_void_p * (4 * n))(*[(None if tup is None else tup[i].cuda_event)
+            ev_arr = (ctypes.c_void_p * (4 * n))(*[(None if tup is None or tup[i] is None else tup[i].cuda_event)
                                                    for tup in events for i in range(4)])
             lp.ev = ctypes.cast(ev_arr, ctypes.c_void_p)
         for i in range(3):
