@@ -137,8 +137,13 @@ class Shard:
         k, mx = H_dev.shape[0], max(sizes)
         pad = torch.zeros(k, mx, dtype=H_dev.dtype, device=H_dev.device)
         pad[:, :H_dev.shape[1]] = H_dev
-        out = torch.empty(self.world, k, mx, dtype=H_dev.dtype, device=H_dev.device)
-        dist.all_gather_into_tensor(out, pad, group=self.group)
+        if dist.get_backend(self.group) == "nccl":
+            out = torch.empty(self.world, k, mx, dtype=H_dev.dtype, device=H_dev.device)
+            dist.all_gather_into_tensor(out, pad, group=self.group)
+        else:                                   # gloo (CPU tests): no all_gather_into_tensor
+            parts = [torch.empty_like(pad) for _ in range(self.world)]
+            dist.all_gather(parts, pad, group=self.group)
+            out = torch.stack(parts)
         host = out.cpu().numpy()
         return np.concatenate([host[r][:, :s] for r, s in enumerate(sizes)], axis=1)
 

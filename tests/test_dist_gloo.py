@@ -184,3 +184,26 @@ def _body_sharded_init(rank, world):
 @pytest.mark.parametrize("world", [2, 3])
 def test_sharded_nndsvd_init(tmp_path, world):
     _run("_body_sharded_init", world, tmp_path)
+
+
+def _body_gather_device(rank, world):
+    """Shard.gather_H_device (one padded all-gather + one copy; sizes from shard_bounds, no collective) against the
+    original gather_H on ragged shards."""
+    from espm_b200.dist import Shard, shard_bounds
+    nx, ny, k = 11, 6, 3
+    p = nx * ny
+    Hfull = torch.arange(k * p, dtype=torch.float32).reshape(k, p) * 0.5 + 1.0
+    sizes = []
+    for r in range(world):
+        a, b, _ = shard_bounds(p, nx, ny, r, world)
+        sizes.append(b - a)
+    j0, j1, _ = shard_bounds(p, nx, ny, rank, world)
+    sh = Shard()
+    out = sh.gather_H_device(Hfull[:, j0:j1].contiguous(), sizes)
+    ref = sh.gather_H(Hfull[:, j0:j1].numpy(), p)
+    assert out.shape == (k, p) and np.array_equal(out, Hfull.numpy()) and np.array_equal(out, ref)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gather_h_device(tmp_path, world):
+    _run("_body_gather_device", world, tmp_path)
