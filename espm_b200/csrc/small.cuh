@@ -1453,19 +1453,21 @@ __global__ void __launch_bounds__(256) colsum_g_kernel(const TC* Gt, int n, int 
 
 // ------------------------------------------------------------------------------------------------
 // w_finish: the W update (updates.py:58-76) + GW' for the next H pass, as ONE cooperative kernel of
-// W_COOP_BLOCKS CTAs.  Grid barriers cost ~4 us each at this size, so the phases are arranged to need as few as
-// possible (single GPU, no simplex_W, m k <= W_SM_MAX: ONE barrier; was four):
-//   phase 0 (all CTAs, optional)  H' row statistics (every CTA folds them for itself into shared memory: nothing below
-//                                 waits for another CTA's phase 0); sharded: push of the local S to every rank
-//   phase A (one CTA per row of G^T) num = W * (G^T S),  den = colsum(G) (x) rowsum(H'); S rows are folded from the
-//                                 partial slots on the fly when the fit is not sharded
-//   -- grid barrier --
-//   phase B                       W' = max(num/den, ls), fixed_W, rel_W: redundantly in every CTA (W' stays in shared
-//                                 memory, CTA 0 writes it out) unless simplex_W or a large m (then CTA 0 + a barrier)
-//   phase C (all CTAs)            GW' = G W' (+ pad rows, clamped copy), per-CTA column sums / flags
-//   phase D (last CTA to finish)  column sums in CTA order (deterministic), flags
-// Sharded fits (ESPM_FLAG_PEER) exchange S in phase 0 by PUSHING it into every rank's receive buffer (remote stores +
-// one flag per rank); phase A folds the ranks' slots on the fly.  No additional grid barrier.
+// W_COOP_BLOCKS CTAs with ONE synchronisation point in the common case (plain KL rule, real G, no simplex_W,
+// m k <= W_SM_MAX -- the "T path"):
+//   before   one CTA per row of G^T: T[mm][:] = sum_c G[c][mm] S[c][:], S folded from the W-pass partial slots on the
+//            fly; the last CTA folds the H' row statistics meanwhile.  Sharded: the k values of the row and the
+//            statistics are PUSHED into slot [rank] of every rank's receive buffer, then the CTA raises its own flag word
+//            on every rank
+//   sync     one GPU: grid barrier.  Sharded: wait for the world x gridDim flag words (which is also the grid barrier)
+//   after    W' = max(W * T / (colsum(G) (x) rowsum(H')), ls), fixed_W, rel_W: redundantly in every CTA from T (the ranks'
+//            slots folded in rank order) and the statistics -- W' stays in shared memory, CTA 0 writes it out;
+//            GW' = G W' (+ pad rows, clamped copy), per-CTA column sums / flags; the last CTA to finish folds the column
+//            sums (one warp per column, fixed order) and the flags
+// Other rules (identity G, Bregman, projected gradient, Frobenius): num / denum are formed before the barrier
+// (`entry`), sharded fits push S itself (n x k) in phase 0 and fold the ranks' slots in phase A; simplex_W adds the
+// lock-step bisection over the columns (trace, barrier, replay, barrier); m k > W_SM_MAX slices W' over the CTAs (one more
+// barrier).
 // ------------------------------------------------------------------------------------------------
 constexpr int W_COOP_BLOCKS = 32;
 constexpr int W_COOP_THREADS = 256;
