@@ -209,6 +209,29 @@ def cpu_baseline(prob, wl, rows, steps, seed, np_dtype, threads=None):
     return its * p_crop / (nx * ny), its, dt, kind, blas
 
 
+EV_EVERY = 4
+
+
+def event_plan(count, make_event):
+    """Which of the `count` timed iterations carry CUDA events around an X pass: entry i is None or a 4-tuple
+    (w_pass start, w_pass end, h_pass start, h_pass end) whose members may be None.  An event between two kernels breaks
+    their programmatic dependent launch (the next kernel's prologue no longer overlaps the predecessor's tail): measured
+    with scripts/timeline.py, events in EVERY iteration cost 18 us per iteration at C3 and 16 us (10 %) on an 1/8 shard.
+    So every EV_EVERY-th iteration is sampled, and a sampled iteration carries the events of ONE pass (H and W in turn)
+    -- unless there are too few iterations to alternate, then both."""
+    evs = []
+    for i in range(count):
+        if not (i % EV_EVERY == EV_EVERY - 1 or (count < EV_EVERY and i == count - 1)):
+            evs.append(None)
+        elif count < 2 * EV_EVERY:
+            evs.append(tuple(make_event() for _ in range(4)))
+        elif (i // EV_EVERY) % 2 == 1:
+            evs.append((make_event(), make_event(), None, None))
+        else:
+            evs.append((None, None, make_event(), make_event()))
+    return evs
+
+
 def host_ram_gb():
     try:
         import psutil
@@ -474,26 +497,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    EV_EVERY = 4
-
     def pass_events(count):
-        """4 CUDA events (w_pass start / end, h_pass start / end) for the native loop to record around the X passes of
-        every EV_EVERY-th timed iteration.  An event between two kernels breaks their programmatic dependent launch
-        (the next kernel's prologue no longer overlaps the predecessor's tail): measured with scripts/timeline.py,
-        events in EVERY iteration cost 18 us per iteration at C3 and 16 us (10 %) on an 1/8 shard, so the per-kernel
-        durations are sampled inside the timed region instead of taken from every launch."""
-        evs = []
-        for i in range(count):
-            if not (i % EV_EVERY == EV_EVERY - 1 or (count < EV_EVERY and i == count - 1)):
-                evs.append(None)
-                continue
-            # alternate between the two passes, so that a sampled iteration carries two events, not four
-            if count < 2 * EV_EVERY:        # too few timed iterations to alternate: both passes on the sampled ones
-                evs.append(tuple(torch.cuda.Event(enable_timing=True) for _ in range(4)))
-                continue
-            w_turn = (i // EV_EVERY) % 2 == 1
-            pair = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-            evs.append((pair[0], pair[1], None, None) if w_turn else (None, None, pair[0], pair[1]))
+        evs = event_plan(count, lambda: torch.cuda.Event(enable_timing=True))
         for tup in evs:
             for e in (tup or ()):
                 if e is not None:

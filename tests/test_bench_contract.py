@@ -49,3 +49,24 @@ def test_gpu_arm_fails_loudly_without_a_device():
     out = _run(["--workload", "C1", "--steps", "1", "--no-e2e", "--no-cpu-baseline"], timeout=900)
     assert out.returncode != 0
     assert "{\"metric\"" not in out.stdout
+
+
+def test_event_plan_samples_every_fourth_iteration():
+    """bench.event_plan: which timed iterations carry CUDA events (an event between two kernels costs their PDL overlap,
+    so the launches are sampled); every plan must time both passes at least once."""
+    sys.path.insert(0, ROOT)
+    import bench
+    mk = object
+    for count in (1, 2, 3, 4, 5, 7, 8, 20, 50):
+        plan = bench.event_plan(count, mk)
+        assert len(plan) == count
+        h = [t for t in plan if t is not None and t[2] is not None]
+        w = [t for t in plan if t is not None and t[0] is not None]
+        assert h and w, count
+        for t in plan:
+            if t is not None:
+                assert (t[0] is None) == (t[1] is None) and (t[2] is None) == (t[3] is None)
+    p20 = bench.event_plan(20, mk)
+    assert [i for i, t in enumerate(p20) if t is not None] == [3, 7, 11, 15, 19]
+    assert sum(t is not None and t[2] is not None for t in p20) == 3 and sum(t is not None and t[0] is not None for t in p20) == 2
+    assert all(t is None or (t[0] is None) != (t[2] is None) for t in p20)      # one pass per sampled iteration
