@@ -48,9 +48,25 @@ def test_constants_match_header():
         assert m and int(m.group(1)) == val, name
     for name in ("SIMPLEX_H", "SIMPLEX_W", "G_IDENTITY", "CLAMP_Y", "LOSS_DUAL", "FIXED_H", "FIXED_W", "MU",
                  "LAPLACIAN", "HAVE_HPREV", "SIMPLEX_ROWS", "HQ", "FUSED_WREDUCE", "PEER", "BMD", "PG", "L2", "L2_H",
-                 "LINESEARCH", "EVAL_ONLY"):
+                 "LINESEARCH", "EVAL_ONLY", "LS_PARTIAL", "NO_HSPEC", "TIMING"):
         m = re.search(r"#define\s+ESPM_FLAG_%s\s+\(1u << (\d+)\)" % name, header)
         assert m and (1 << int(m.group(1))) == getattr(_lib, "FLAG_" + name), name
+    # no two flags share a bit
+    bits = [int(b) for b in re.findall(r"#define\s+ESPM_FLAG_\w+\s+\(1u << (\d+)\)", header)]
+    assert len(bits) == len(set(bits))
+    # layout of the peer flag block and the record slots added in round 2
+    for name, val in (("ESPM_PF_SFLAG", _lib.PF_SFLAG), ("ESPM_PF_MFLAG", _lib.PF_MFLAG), ("ESPM_PF_MASK", _lib.PF_MASK),
+                      ("ESPM_PF_TFLAG", _lib.PF_TFLAG), ("ESPM_PF_WORDS", _lib.PF_WORDS),
+                      ("ESPM_COOP_BLOCKS", _lib.COOP_BLOCKS)):
+        m = re.search(r"#define\s+%s\s+(\d+)" % name, header)
+        assert m and int(m.group(1)) == val, name
+    max_ranks = int(re.search(r"#define\s+ESPM_MAX_RANKS\s+(\d+)", header).group(1))
+    assert _lib.PF_TFLAG + 32 * max_ranks <= _lib.PF_WORDS and _lib.COOP_BLOCKS <= 32      # one flag word per (rank, CTA)
+    assert _lib.PF_MASK + 4 * max_ranks <= _lib.PF_TFLAG
+    for name, val in (("ESPM_S_T0", _lib.S_T0), ("ESPM_S_STAMP", _lib.S_STAMP)):
+        m = re.search(r"%s\s*=\s*(\d+)" % name, header)
+        assert m and int(m.group(1)) == val, name
+    assert _lib.S_LS_D < _lib.S_T0 and _lib.S_T0 + 8 < _lib.S_STAMP < _lib.NSCALARS
 
 
 def test_no_cpu_fallback(lib):
