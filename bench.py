@@ -721,7 +721,12 @@ def main():
                "final_loss": float(est.losses_[-1]),
                "h2d_gbs_lower_bound": x_bytes_total / world / dt / 1e9,
                "default_mode": {"value": iters_d[1] / dt_d * (world if replicas else 1), "unit": "it/s",
-                                "n_iter": iters_d, "walls": walls_d, "ratio_to_batch_mode": (iters_d[1] / dt_d) / (K / dt),
+                                "n_iter": iters_d, "walls": walls_d,
+                                # comparable only when the stop tests let all K iterations run (a fit that stops early
+                                # spreads the same upload over fewer iterations)
+                                "ratio_to_batch_mode": ((iters_d[1] / dt_d) / (K / dt)
+                                                        if min(iters_d) == K else None),
+                                "stopped_early": bool(min(iters_d) < K),
                                 "what": "same fit with the reference's default tol=1e-4, verbose=1: ordered stop tests "
                                         "after every iteration, records polled from pinned host memory"}}
 
